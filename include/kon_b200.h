@@ -1,0 +1,184 @@
+/*
+ * kon_b200.h -- C-ABI of libkon_b200.so: hand-written sm_100a kernels for the CTR
+ * hot path of TIXhjq/ML_Function (`kon.model.ctr_model`).
+ *
+ * The reference has no native code and no FFI: its hot path is Keras layers whose
+ * arithmetic runs inside TensorFlow 2.1.  Each entry point below replaces the TF op
+ * stream one reference `call` dispatches (cited as IL/BL/CL = interactive_layer.py /
+ * behavior_layer.py / core_layer.py under kon/model/ctr_model/layer/...), and is what
+ * a maintainer would bind from Python with ctypes.
+ *
+ * Conventions
+ *   - Tensors cross the boundary as `const DLTensor*` (DLPack ABI struct: plain
+ *     pointers, sizes and strides -- no framework types).  The caller owns every
+ *     buffer, output and workspace; the library never allocates device memory,
+ *     never keeps a pointer past the call, never calls a DLPack deleter and never
+ *     synchronises the device.  All work is enqueued on `stream` (a cudaStream_t).
+ *   - Return value: 0 on success, negative KON_E* on failure; the message is in the
+ *     thread-local `kon_last_error()`.  Nothing throws across the ABI.
+ *   - Shapes/dtypes/devices/alignment are validated on the host before any launch.
+ *   - There is no CPU implementation behind any of these symbols.
+ */
+#ifndef KON_B200_H_
+#define KON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- DLPack tensor (ABI-identical to dlpack.h's DLTensor; defined here so that the
+ *      header is self-contained; skipped when dlpack.h was included first) ---------- */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0, kDLUInt = 1, kDLFloat = 2, kDLBfloat = 4 } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void*      data;
+  DLDevice   device;
+  int32_t    ndim;
+  DLDataType dtype;
+  int64_t*   shape;
+  int64_t*   strides;      /* in elements; NULL = compact row-major */
+  uint64_t   byte_offset;
+} DLTensor;
+#endif
+
+#define KON_ABI_VERSION 1
+
+enum {
+  KON_OK = 0,
+  KON_EINVAL = -1,       /* bad shape / dtype / stride / alignment / null pointer */
+  KON_EDEVICE = -2,      /* tensor not on a CUDA device, or devices differ */
+  KON_EUNSUPPORTED = -3, /* legal request outside what the kernels cover */
+  KON_ECUDA = -4,        /* CUDA runtime error at launch */
+  KON_EWORKSPACE = -5    /* workspace too small */
+};
+
+int         kon_abi_version(void);
+const char* kon_last_error(void);
+/* SM count / arch of the device the tensors live on (for host-side grid sizing). */
+int         kon_device_info(int device_id, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ============================ a1-a3: embeddings ================================== */
+/* Replaces the 26 Keras `Embedding` gathers (+Cast) of SparseEmbed.call (IL:225-242),
+ * the optional field `Add` (IL:233-234) and SeqBaseLayer's sum-pool (BL:45-46).
+ *
+ *   arena   [R, dim] f32   every field's table back to back (rows of field f start at
+ *                          field_row_offset[f]; field_row_offset has n_fields+1 entries
+ *                          and lives on the HOST)
+ *   ids     [B, F] or [B, F, L]  int32 | int64, compact
+ *   out     [B, F, dim] f32; strides of dims 0 and 1 are free (so it may be a window of
+ *                          a wider [B, 13+F*dim] concat buffer, CL:49-55), dim 2 compact
+ *   L > 1   sums the L rows of a bag in order l = 0..L-1 (BL:46)
+ *   flags   KON_EMBED_SUM_FIELDS: out is [B, dim] = sum over f, left to right (IL:233)
+ *   oob     optional [1] int32 device counter incremented per out-of-range id (such
+ *           lookups return zeros, as TF's GPU gather does; TF-CPU raises)
+ */
+#define KON_EMBED_SUM_FIELDS 1
+int kon_embed_fwd(const DLTensor* arena, const DLTensor* ids, const int64_t* field_row_offset,
+                  int32_t n_fields, DLTensor* out, DLTensor* oob, int32_t flags, void* stream);
+
+/* a4: embedding backward (implicit in Model.fit; TF: IndexedSlices -> unique +
+ * unsorted_segment_sum).  Sort-then-segment, deterministic.
+ *
+ *   d_out        [B, F, dim] f32, free strides on dims 0/1 (stride 0 on dim 1 = the
+ *                gradient of a field-summed lookup)
+ *   ids          as in kon_embed_fwd
+ *   unique_rows  [N] int32 out (arena row ids, ascending), N = B*F*L
+ *   grads        [N, dim] f32 out; row u is the summed gradient of unique_rows[u]
+ *   n_unique     [1] int32 out (device)
+ *   workspace    [>= kon_embed_bwd_workspace_bytes(N, dim)] uint8
+ */
+size_t kon_embed_bwd_workspace_bytes(int64_t n_lookups, int32_t dim);
+int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+                  int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                  DLTensor* workspace, void* stream);
+
+/* Sparse row-wise SGD on the arena: w[r] -= lr * (g + 2*l2*w[r]) for the n_unique rows
+ * (the L2 term is the reference's embeddings_regularizer, IL:217, applied lazily). */
+int kon_embed_sgd(DLTensor* arena, const DLTensor* unique_rows, const DLTensor* grads,
+                  const DLTensor* n_unique, float lr, float l2, void* stream);
+/* Sparse row-wise (lazy) Adam on the arena; m, v are [R, dim] f32 state, step >= 1. */
+int kon_embed_adam(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTensor* unique_rows,
+                   const DLTensor* grads, const DLTensor* n_unique, float lr, float beta1,
+                   float beta2, float eps, float l2, int32_t step, void* stream);
+
+/* ============================ a5-a6: FM ========================================== */
+/* Replaces InnerLayer's 325 tf.multiply + sequential Add (IL:59-66) and FmLayer's Add
+ * of the linear terms (IL:161-170) by one pass:
+ *   out[b,:] = sum_{i<j} v[b,i,:]*v[b,j,:] + sum_f lin[b,f]
+ *   v [B,F,k] f32 (free strides on dims 0/1), lin [B,F] f32 or NULL, out [B,k] f32. */
+int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out, void* stream);
+/* dv[b,f,:] = g[b,:] * (S[b,:] - v[b,f,:]);  dlin[b,f] = sum_k g[b,k]  (dlin may be NULL) */
+int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin, void* stream);
+
+/* ============================ a7: DCN cross ====================================== */
+/* Replaces CrossLayer.call (IL:275-282): x_{l+1} = x0 * (x_l . w_l) + x_l + b_l.
+ *   x0 [B,D] f32, w,b [L,D] f32 (the reference's L `[D,1]` kernels / biases stacked),
+ *   out [B,D] f32 (the reference returns it as [B,D,1]),
+ *   s [B,L] f32 out: the per-sample scalars x_l . w_l, saved for the backward. */
+int kon_cross_fwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b, DLTensor* out,
+                  DLTensor* s, void* stream);
+size_t kon_cross_bwd_workspace_bytes(int64_t batch, int32_t dim, int32_t layers, int device_id);
+int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b, const DLTensor* s,
+                  const DLTensor* g, DLTensor* dx0, DLTensor* dw, DLTensor* db,
+                  DLTensor* workspace, void* stream);
+
+/* ============================ a8: xDeepFM CIN ==================================== */
+/* Replaces CIN.call (IL:310-327) up to and including the per-layer sum pooling; the
+ * Dense(1) logit layer (IL:325) stays with the caller.
+ *
+ *   x0       [B, m, D] f32 compact           (Concatenate(axis=1) of the field embeddings, MD:131)
+ *   w[l]     [H_{l-1}*m, H_l] f32            Keras Conv1D kernel [1,C,N] without its leading 1;
+ *                                            channel c = h*m + i (IL:317-318); H_0 = m
+ *   bias[l]  [H_l] f32
+ *   pooled   [B, n_layers*D] f32 out         concat over layers of sum_o z_l[b,d,o] (IL:322-323)
+ *   saved    [>= kon_cin_saved_bytes] uint8  activations kept for the backward (z_l)
+ *   precision KON_CIN_FP32: fp32 CUDA-core arithmetic (parity mode, 1e-5)
+ *             KON_CIN_BF16: bf16 operands on tcgen05 tensor cores, fp32 accumulate (2e-2)
+ */
+#define KON_CIN_FP32 0
+#define KON_CIN_BF16 1
+#define KON_CIN_MAX_LAYERS 8
+size_t kon_cin_saved_bytes(int64_t batch, int32_t m, int32_t D, const int32_t* layer_sizes,
+                           int32_t n_layers, int32_t precision);
+size_t kon_cin_workspace_bytes(int64_t batch, int32_t m, int32_t D, const int32_t* layer_sizes,
+                               int32_t n_layers, int32_t precision, int device_id);
+int kon_cin_fwd(const DLTensor* x0, const DLTensor* const* w, const DLTensor* const* bias,
+                int32_t n_layers, DLTensor* pooled, DLTensor* saved, DLTensor* workspace,
+                int32_t precision, void* stream);
+/* d_pooled [B, n_layers*D] -> dx0 [B,m,D], dw[l] like w[l], dbias[l] like bias[l]. */
+int kon_cin_bwd(const DLTensor* x0, const DLTensor* const* w, const DLTensor* const* bias,
+                int32_t n_layers, const DLTensor* d_pooled, const DLTensor* saved,
+                DLTensor* dx0, DLTensor* const* dw, DLTensor* const* dbias,
+                DLTensor* workspace, int32_t precision, void* stream);
+
+/* ============================ a9-a10: AutoInt attention ========================== */
+/* Replaces MultHeadAttentionLayer.call (BL:356-377) + ProductAttentionLayer.call
+ * (BL:292-311) + the Add/ReLU the wrapping DnnLayer applies (CL:205-216):
+ *   Q = X Wq, K = X Wk, (V = K, BL:360), S = sigmoid(Q K^T [/ sqrt(d)]),
+ *   O = S K, Y = ReLU(LN_{eps}(O) * gamma + beta + X Wr)
+ *   x [B,F,kin] f32; wq,wk,wr [kin,H,d] f32; gamma,beta [d] f32; y [H,B,F,d] f32.
+ * flags select the reference's ctor switches. */
+#define KON_ATTN_USE_SCALE 1   /* use_scale (BL:296-297)              */
+#define KON_ATTN_USE_LN    2   /* use_ln    (BL:368-369), eps = 1e-3  */
+#define KON_ATTN_USE_RES   4   /* use_res   (BL:365-366) + Add (CL:212) */
+#define KON_ATTN_RELU      8   /* DnnLayer's activation (CL:216)      */
+int kon_attn_fwd(const DLTensor* x, const DLTensor* wq, const DLTensor* wk, const DLTensor* wr,
+                 const DLTensor* gamma, const DLTensor* beta, DLTensor* y, float ln_eps,
+                 int32_t flags, void* stream);
+size_t kon_attn_bwd_workspace_bytes(int64_t batch, int32_t fields, int32_t kin, int32_t heads,
+                                    int32_t d, int device_id);
+int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTensor* wk, const DLTensor* wr,
+                 const DLTensor* gamma, const DLTensor* beta, const DLTensor* gy, DLTensor* dx,
+                 DLTensor* dwq, DLTensor* dwk, DLTensor* dwr, DLTensor* dgamma, DLTensor* dbeta,
+                 DLTensor* workspace, float ln_eps, int32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KON_B200_H_ */

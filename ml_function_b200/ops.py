@@ -1,0 +1,283 @@
+"""torch.autograd bindings of the C-ABI kernels (one Function per reference ``call``).
+
+Forward = the ``kon_*_fwd`` entry point, backward = ``kon_*_bwd``; torch only owns
+the buffers and the stream.  Nothing here computes on the CPU or with torch ops:
+inputs that are not CUDA tensors raise ``KonError`` from the library's own checks.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- #
+# embeddings (a1-a4)
+# --------------------------------------------------------------------------- #
+class SparseGrad:
+    """Result of kon_embed_bwd: ``rows[:n]`` ascending unique arena rows and their summed
+    gradients ``grads[:n]``; ``n`` stays on the device (no host sync)."""
+
+    __slots__ = ("rows", "grads", "n")
+
+    def __init__(self, rows, grads, n):
+        self.rows, self.grads, self.n = rows, grads, n
+
+    def to_dense(self, n_rows: int) -> torch.Tensor:
+        n = int(self.n.item())
+        dense = torch.zeros(n_rows, self.grads.shape[1], dtype=self.grads.dtype, device=self.grads.device)
+        dense.index_add_(0, self.rows[:n].long(), self.grads[:n])
+        return dense
+
+
+def embed_fwd_raw(arena, ids, field_row_offset: Sequence[int], sum_fields=False, out=None, oob=None):
+    lib = L.lib()
+    F = ids.shape[1]
+    dim = arena.shape[1]
+    if out is None:
+        shape = (ids.shape[0], dim) if sum_fields else (ids.shape[0], F, dim)
+        out = torch.empty(shape, dtype=arena.dtype, device=arena.device)
+    offs = L.i64_array(list(field_row_offset))
+    a, i, o, ob = L._arg(arena), L._arg(ids), L._arg(out), L._arg(oob)
+    L.check(lib.kon_embed_fwd(a.ptr, i.ptr, offs, F, o.ptr, L._p(ob),
+                              L.KON_EMBED_SUM_FIELDS if sum_fields else 0, L.stream_ptr(arena.device)),
+            "kon_embed_fwd")
+    return out
+
+
+def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int]) -> SparseGrad:
+    """d_out [B,F,dim] (any strides on dims 0/1, e.g. an expanded [B,1,dim])."""
+    lib = L.lib()
+    F = ids.shape[1]
+    dim = d_out.shape[2]
+    n = ids.numel()
+    dev = d_out.device
+    rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.kon_embed_bwd_workspace_bytes(n, dim), dev)
+    offs = L.i64_array(list(field_row_offset))
+    a = [L._arg(t) for t in (d_out, ids, rows, grads, nu, ws)]
+    L.check(lib.kon_embed_bwd(a[0].ptr, a[1].ptr, offs, F, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
+                              L.stream_ptr(dev)), "kon_embed_bwd")
+    return SparseGrad(rows, grads, nu)
+
+
+class _EmbedLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, arena, ids, field_row_offset, sum_fields):
+        out = embed_fwd_raw(arena.detach(), ids, field_row_offset, sum_fields)
+        ctx.save_for_backward(ids)
+        ctx.arena = arena
+        ctx.offs = field_row_offset
+        ctx.sum_fields = sum_fields
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        arena = ctx.arena
+        if arena.requires_grad:
+            if ctx.sum_fields:   # [B,dim] -> every field sees the same gradient (stride 0)
+                g3 = g.contiguous().unsqueeze(1).expand(g.shape[0], ids.shape[1], g.shape[1])
+            else:
+                g3 = g.contiguous()
+            sg = embed_bwd_raw(g3, ids, ctx.offs)
+            if not hasattr(arena, "kon_sparse_grads"):
+                arena.kon_sparse_grads = []
+            arena.kon_sparse_grads.append(sg)
+        return None, None, None, None
+
+
+def embed_lookup(arena, ids, field_row_offset, sum_fields=False):
+    """Gather (and bag-sum) rows of ``arena``; the gradient of ``arena`` is delivered
+    sparsely as ``arena.kon_sparse_grads`` (list of SparseGrad) and ``arena.grad`` stays
+    None -- a dense [R,dim] gradient is never materialised."""
+    return _EmbedLookup.apply(arena, ids, tuple(field_row_offset), sum_fields)
+
+
+def embed_sgd(arena, sg: SparseGrad, lr: float, l2: float = 0.0):
+    lib = L.lib()
+    a = [L._arg(t) for t in (arena, sg.rows, sg.grads, sg.n)]
+    L.check(lib.kon_embed_sgd(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, lr, l2, L.stream_ptr(arena.device)),
+            "kon_embed_sgd")
+
+
+def embed_adam(arena, m, v, sg: SparseGrad, lr, beta1, beta2, eps, l2, step):
+    lib = L.lib()
+    a = [L._arg(t) for t in (arena, m, v, sg.rows, sg.grads, sg.n)]
+    L.check(lib.kon_embed_adam(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr, lr, beta1,
+                               beta2, eps, l2, step, L.stream_ptr(arena.device)), "kon_embed_adam")
+
+
+# --------------------------------------------------------------------------- #
+# FM (a5-a6)
+# --------------------------------------------------------------------------- #
+class _Fm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, lin):
+        lib = L.lib()
+        out = torch.empty((v.shape[0], v.shape[2]), dtype=v.dtype, device=v.device)
+        a, b, o = L._arg(v), L._arg(lin), L._arg(out)
+        L.check(lib.kon_fm_fwd(a.ptr, L._p(b), o.ptr, L.stream_ptr(v.device)), "kon_fm_fwd")
+        ctx.save_for_backward(v)
+        ctx.has_lin = lin is not None
+        ctx.lin_shape = None if lin is None else lin.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        (v,) = ctx.saved_tensors
+        g = g.contiguous()
+        dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+        dlin = torch.empty(ctx.lin_shape, dtype=v.dtype, device=v.device) if ctx.has_lin else None
+        a, b, c, d = L._arg(v), L._arg(g), L._arg(dv), L._arg(dlin)
+        L.check(lib.kon_fm_bwd(a.ptr, b.ptr, c.ptr, L._p(d), L.stream_ptr(v.device)), "kon_fm_bwd")
+        return dv, dlin
+
+
+def fm(v: torch.Tensor, lin: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """v [B,F,k], lin [B,F] or None -> [B,k]  (FmLayer / InnerLayer(use_add=True))."""
+    return _Fm.apply(v, lin)
+
+
+# --------------------------------------------------------------------------- #
+# DCN cross (a7)
+# --------------------------------------------------------------------------- #
+class _Cross(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, w, b):
+        lib = L.lib()
+        w, b = w.contiguous(), b.contiguous()
+        if x0.stride(-1) != 1:
+            x0 = x0.contiguous()
+        out = torch.empty(x0.shape, dtype=x0.dtype, device=x0.device)
+        s = torch.empty((x0.shape[0], w.shape[0]), dtype=x0.dtype, device=x0.device)
+        a = [L._arg(t) for t in (x0, w, b, out, s)]
+        L.check(lib.kon_cross_fwd(*[t.ptr for t in a], L.stream_ptr(x0.device)), "kon_cross_fwd")
+        ctx.save_for_backward(x0, w, b, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        x0, w, b, s = ctx.saved_tensors
+        if g.stride(-1) != 1:
+            g = g.contiguous()
+        dev = x0.device
+        dx0 = torch.empty(x0.shape, dtype=x0.dtype, device=dev)
+        dw = torch.empty_like(w)
+        db = torch.empty_like(b)
+        ws = _ws(lib.kon_cross_bwd_workspace_bytes(x0.shape[0], x0.shape[1], w.shape[0], dev.index or 0), dev)
+        a = [L._arg(t) for t in (x0, w, b, s, g, dx0, dw, db, ws)]
+        L.check(lib.kon_cross_bwd(*[t.ptr for t in a], L.stream_ptr(dev)), "kon_cross_bwd")
+        return dx0, dw, db
+
+
+def cross(x0, w, b):
+    """x0 [B,D], w/b [L,D] -> x_L [B,D]  (CrossLayer)."""
+    return _Cross.apply(x0, w, b)
+
+
+# --------------------------------------------------------------------------- #
+# CIN (a8)
+# --------------------------------------------------------------------------- #
+class _Cin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, precision, n_layers, *wb):
+        lib = L.lib()
+        ws_ = [t.contiguous() for t in wb[:n_layers]]
+        bs_ = [t.contiguous() for t in wb[n_layers:]]
+        x0 = x0.contiguous()
+        B, m, D = x0.shape
+        dev = x0.device
+        hs = L.i32_array([w.shape[1] for w in ws_])
+        pooled = torch.empty((B, n_layers * D), dtype=torch.float32, device=dev)
+        saved = _ws(lib.kon_cin_saved_bytes(B, m, D, hs, n_layers, precision), dev)
+        work = _ws(lib.kon_cin_workspace_bytes(B, m, D, hs, n_layers, precision, dev.index or 0), dev)
+        wa, wk = L.tensor_array(ws_)
+        ba, bk = L.tensor_array(bs_)
+        a = [L._arg(t) for t in (x0, pooled, saved, work)]
+        L.check(lib.kon_cin_fwd(a[0].ptr, wa, ba, n_layers, a[1].ptr, a[2].ptr, a[3].ptr, precision,
+                                L.stream_ptr(dev)), "kon_cin_fwd")
+        ctx.save_for_backward(x0, saved, *ws_, *bs_)
+        ctx.precision, ctx.n_layers = precision, n_layers
+        ctx.work = work
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        x0, saved = ctx.saved_tensors[:2]
+        nl = ctx.n_layers
+        ws_ = list(ctx.saved_tensors[2:2 + nl])
+        bs_ = list(ctx.saved_tensors[2 + nl:])
+        dev = x0.device
+        g = g.contiguous()
+        dx0 = torch.empty_like(x0)
+        dws = [torch.empty_like(w) for w in ws_]
+        dbs = [torch.empty_like(b) for b in bs_]
+        wa, k1 = L.tensor_array(ws_)
+        ba, k2 = L.tensor_array(bs_)
+        dwa, k3 = L.tensor_array(dws)
+        dba, k4 = L.tensor_array(dbs)
+        a = [L._arg(t) for t in (x0, g, saved, dx0, ctx.work)]
+        L.check(lib.kon_cin_bwd(a[0].ptr, wa, ba, nl, a[1].ptr, a[2].ptr, a[3].ptr, dwa, dba, a[4].ptr,
+                                ctx.precision, L.stream_ptr(dev)), "kon_cin_bwd")
+        return (dx0, None, None, *dws, *dbs)
+
+
+def cin(x0, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], precision: int = L.KON_CIN_FP32):
+    """x0 [B,m,D], weights[l] [H_{l-1}*m, H_l], biases[l] [H_l] -> pooled [B, L*D]."""
+    return _Cin.apply(x0, precision, len(weights), *weights, *biases)
+
+
+# --------------------------------------------------------------------------- #
+# AutoInt attention (a9-a10)
+# --------------------------------------------------------------------------- #
+class _Attn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wq, wk, wr, gamma, beta, flags, eps):
+        lib = L.lib()
+        x, wq, wk = x.contiguous(), wq.contiguous(), wk.contiguous()
+        wr = None if wr is None else wr.contiguous()
+        H, d = wq.shape[1], wq.shape[2]
+        y = torch.empty((H, x.shape[0], x.shape[1], d), dtype=x.dtype, device=x.device)
+        a = [L._arg(t) for t in (x, wq, wk, wr, gamma, beta, y)]
+        L.check(lib.kon_attn_fwd(*[L._p(t) for t in a], eps, flags, L.stream_ptr(x.device)), "kon_attn_fwd")
+        ctx.save_for_backward(x, wq, wk, wr, gamma, beta)
+        ctx.flags, ctx.eps = flags, eps
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.lib()
+        x, wq, wk, wr, gamma, beta = ctx.saved_tensors
+        dev = x.device
+        gy = gy.contiguous()
+        dx = torch.empty_like(x)
+        dwq, dwk = torch.empty_like(wq), torch.empty_like(wk)
+        dwr = None if wr is None else torch.empty_like(wr)
+        dg = None if gamma is None else torch.empty_like(gamma)
+        db = None if beta is None else torch.empty_like(beta)
+        ws = _ws(lib.kon_attn_bwd_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], wq.shape[1],
+                                                  wq.shape[2], dev.index or 0), dev)
+        a = [L._arg(t) for t in (x, wq, wk, wr, gamma, beta, gy, dx, dwq, dwk, dwr, dg, db, ws)]
+        L.check(lib.kon_attn_bwd(*[L._p(t) for t in a], ctx.eps, ctx.flags, L.stream_ptr(dev)), "kon_attn_bwd")
+        return dx, dwq, dwk, dwr, dg, db, None, None
+
+
+def attention(x, wq, wk, wr=None, gamma=None, beta=None, use_scale=True, use_ln=True, use_res=True,
+              relu=True, eps: float = 1e-3):
+    """x [B,F,kin]; w* [kin,H,d] -> [H,B,F,d] = ReLU(LN(sigmoid(QK^T/sqrt d) K) + X Wr)."""
+    flags = ((L.KON_ATTN_USE_SCALE if use_scale else 0) | (L.KON_ATTN_USE_LN if use_ln else 0) |
+             (L.KON_ATTN_USE_RES if use_res else 0) | (L.KON_ATTN_RELU if relu else 0))
+    return _Attn.apply(x, wq, wk, wr if use_res else None, gamma if use_ln else None,
+                       beta if use_ln else None, flags, eps)

@@ -1,0 +1,327 @@
+"""-m gpu parity tests: every kernel through the C-ABI against the CPU oracle.
+
+Tolerances (north_star): bit-exact for lookups / unique rows / routing; 1e-5 relative
+(norm-relative, judged against the fp64 evaluation of the oracle) for fp32 arithmetic;
+2e-2 for the bf16 tensor-core CIN.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_rel, gen, make_ids, make_tables, offsets, rel_err
+from oracle import kon_oracle as ko
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-5
+
+
+def _ops():
+    from ml_function_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------ embeddings
+@pytest.mark.parametrize("dim", [16, 32, 8, 4, 12, 1, 3])
+@pytest.mark.parametrize("idt", [torch.int32, torch.int64])
+def test_embed_fwd_bitexact(dim, idt):
+    ops = _ops()
+    g = gen(dim)
+    rows = [7, 1, 300, 5000, 3, 64, 1000]
+    B = 1237
+    tables = make_tables(rows, dim, g)
+    ids = make_ids(B, rows, g, dtype=idt)
+    ref = ko.sparse_embed([ids[:, f:f + 1] for f in range(len(rows))], tables, use_flatten=False)
+    ref = torch.cat(ref, dim=1)                                   # [B,F,dim]
+    arena = torch.cat(tables, 0).to(DEV)
+    out = ops.embed_fwd_raw(arena, ids.to(DEV), offsets(rows))
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_embed_fwd_large_tiles_and_strided_out():
+    ops = _ops()
+    g = gen(1)
+    rows = [50000, 9, 777, 123456]
+    B, dim = 40000, 16                                            # many tiles, ragged tail
+    tables = make_tables(rows, dim, g)
+    ids = make_ids(B, rows, g)
+    ref = torch.cat(ko.sparse_embed([ids[:, f:f + 1] for f in range(4)], tables, use_flatten=False), 1)
+    arena = torch.cat(tables, 0).to(DEV)
+    wide = torch.full((B, 16 + 4 * dim), -7.0, device=DEV)        # [dense pad | 4 fields]
+    view = wide[:, 16:].view(B, 4, dim)
+    ops.embed_fwd_raw(arena, ids.to(DEV), offsets(rows), out=view)
+    assert torch.equal(view.cpu(), ref)
+    assert torch.all(wide[:, :16] == -7.0)
+
+
+@pytest.mark.parametrize("L", [2, 5, 90])
+def test_embed_bag_sum(L):
+    ops = _ops()
+    g = gen(L)
+    rows = [11, 2000, 3]
+    B, dim = 257, 16
+    tables = make_tables(rows, dim, g)
+    ids = make_ids(B, rows, g, L=L)
+    emb = ko.sparse_embed([ids[:, f] for f in range(3)], tables, use_flatten=False)   # [B,L,dim]
+    # sequential l = 0..L-1 (the fp32 order the kernel promises)
+    ref = []
+    for e in emb:
+        acc = e[:, 0].clone()
+        for l in range(1, L):
+            acc = acc + e[:, l]
+        ref.append(acc.unsqueeze(1))
+    ref = torch.cat(ref, 1)
+    arena = torch.cat(tables, 0).to(DEV)
+    out = ops.embed_fwd_raw(arena, ids.to(DEV), offsets(rows))
+    assert torch.equal(out.cpu(), ref)
+    # and against the reference op (tf.reduce_sum, order unspecified) within fp32 tolerance
+    ref2 = torch.cat(ko.seq_base_layer(emb), 1)
+    assert_rel(out, ref2.double(), FP32_TOL, "bag sum")
+
+
+def test_embed_sum_fields_linear():
+    ops = _ops()
+    g = gen(3)
+    rows = [5, 100, 7, 1000, 2]
+    B = 513
+    tables = make_tables(rows, 1, g)
+    ids = make_ids(B, rows, g)
+    lst = ko.sparse_embed([ids[:, f:f + 1] for f in range(5)], tables, use_flatten=False, use_add=True)
+    arena = torch.cat(tables, 0).to(DEV)
+    out = ops.embed_fwd_raw(arena, ids.to(DEV), offsets(rows), sum_fields=True)
+    assert torch.equal(out.cpu(), lst[:, 0, :])
+
+
+def test_embed_oob_counts_and_zeros():
+    ops = _ops()
+    rows = [4, 4]
+    arena = torch.ones(8, 16, device=DEV)
+    ids = torch.tensor([[0, 3], [4, -1], [1, 2]], dtype=torch.int32, device=DEV)
+    oob = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = ops.embed_fwd_raw(arena, ids, offsets(rows), oob=oob)
+    assert oob.item() == 2
+    assert torch.all(out[1] == 0) and torch.all(out[0] == 1) and torch.all(out[2] == 1)
+
+
+def _check_embed_bwd(rows, B, dim, L=None, seed=0, idt=torch.int32):
+    ops = _ops()
+    g = gen(seed)
+    F = len(rows)
+    ids = make_ids(B, rows, g, L=L, dtype=idt)
+    d_out = torch.randn(B, F, dim, generator=g)
+    sg = ops.embed_bwd_raw(d_out.to(DEV), ids.to(DEV), offsets(rows))
+    n = int(sg.n.item())
+    off = offsets(rows)
+    exp_rows, exp_grads = [], []
+    for f in range(F):
+        idf = ids[:, f].reshape(B, -1).numpy()
+        Lf = idf.shape[1]
+        gf = d_out[:, f].numpy()[:, None, :].repeat(Lf, axis=1).reshape(B * Lf, dim)
+        u, gr = ko.embedding_grad(idf.reshape(-1), gf, rows[f])
+        exp_rows.append(u + off[f])
+        exp_grads.append(gr)
+    exp_rows = np.concatenate(exp_rows)
+    exp_grads = np.concatenate(exp_grads)
+    assert n == exp_rows.shape[0]
+    assert np.array_equal(sg.rows[:n].cpu().numpy().astype(np.int64), exp_rows)    # routing: bit-exact
+    got = sg.grads[:n].cpu().numpy()
+    counts = np.concatenate([np.bincount(ids[:, f].reshape(-1).numpy(), minlength=rows[f])[
+        np.unique(ids[:, f].reshape(-1).numpy())] for f in range(F)])
+    single = counts == 1
+    assert np.array_equal(got[single], exp_grads[single])        # one contribution: bit-exact
+    scale = np.abs(exp_grads).max()
+    assert np.abs(got - exp_grads).max() <= 1e-5 * scale + 1e-30
+
+
+@pytest.mark.parametrize("dim", [16, 32, 8, 1])
+def test_embed_bwd_mixed_cardinalities(dim):
+    # tiny tables -> runs thousands long (cross-window and cross-CTA stitching), big -> singletons
+    _check_embed_bwd([3, 70000, 10, 1, 500, 100000, 27], 6001, dim, seed=dim)
+
+
+def test_embed_bwd_int64_and_bags():
+    _check_embed_bwd([5, 3000, 2], 700, 16, L=4, seed=9, idt=torch.int64)
+
+
+def test_embed_bwd_single_row_table_long_run():
+    _check_embed_bwd([1], 50000, 16, seed=4)    # one run spanning ~49 CTAs
+
+
+def test_embed_bwd_tiny():
+    _check_embed_bwd([4, 4], 1, 16, seed=5)
+    _check_embed_bwd([4, 4], 17, 16, seed=6)
+
+
+def test_embed_autograd_and_sgd():
+    ops = _ops()
+    g = gen(11)
+    rows = [6, 50, 3]
+    B, dim = 64, 16
+    tables = make_tables(rows, dim, g)
+    ids = make_ids(B, rows, g)
+    arena = torch.nn.Parameter(torch.cat(tables, 0).to(DEV))
+    out = ops.embed_lookup(arena, ids.to(DEV), offsets(rows))
+    w = torch.randn(B, 3, dim, generator=g).to(DEV)
+    (out * w).sum().backward()
+    assert arena.grad is None and len(arena.kon_sparse_grads) == 1
+    dense = arena.kon_sparse_grads[0].to_dense(sum(rows))
+    ref_t = [t.clone().requires_grad_(True) for t in tables]
+    ref = torch.cat(ko.sparse_embed([ids[:, f:f + 1] for f in range(3)], ref_t, use_flatten=False), 1)
+    (ref * w.cpu()).sum().backward()
+    ref_dense = torch.cat([t.grad for t in ref_t], 0)
+    assert_rel(dense, ref_dense.double(), FP32_TOL, "embedding grad")
+    before = arena.detach().clone()
+    ops.embed_sgd(arena.data, arena.kon_sparse_grads[0], lr=0.5, l2=0.0)
+    assert_rel(arena.detach(), (before - 0.5 * dense).double(), 1e-6, "sgd")
+
+
+# ------------------------------------------------------------------ FM
+@pytest.mark.parametrize("F,k,B", [(26, 16, 1000), (26, 8, 77), (5, 32, 33), (3, 6, 10), (26, 16, 1)])
+def test_fm_fwd_bwd(F, k, B):
+    ops = _ops()
+    g = gen(F * k)
+    v = torch.randn(B, F, k, generator=g)
+    lin = torch.randn(B, F, generator=g)
+
+    def oracle(v_, lin_):
+        return ko.fm_layer([v_[:, f:f + 1] for f in range(F)], [lin_[:, f:f + 1, None] for f in range(F)])[:, 0]
+
+    v64, l64 = v.double().requires_grad_(True), lin.double().requires_grad_(True)
+    y64 = oracle(v64, l64)
+    wgt = torch.randn(B, k, generator=g)
+    (y64 * wgt.double()).sum().backward()
+    y32 = oracle(v, lin)
+    vc, lc = v.to(DEV).requires_grad_(True), lin.to(DEV).requires_grad_(True)
+    y = ops.fm(vc, lc)
+    (y * wgt.to(DEV)).sum().backward()
+    e_ref = rel_err(y32, y64)
+    e = assert_rel(y, y64, FP32_TOL, "fm fwd")
+    assert e <= max(4 * e_ref, 2e-6), (e, e_ref)   # no worse than the reference's own fp32 order
+    assert_rel(vc.grad, v64.grad, FP32_TOL, "fm dv")
+    assert_rel(lc.grad, l64.grad, FP32_TOL, "fm dlin")
+
+
+def test_fm_strided_view_and_no_linear():
+    ops = _ops()
+    g = gen(5)
+    B, F, k = 300, 26, 16
+    wide = torch.randn(B, 16 + F * k, generator=g).to(DEV)
+    v = wide[:, 16:].view(B, F, k)
+    y = ops.fm(v, None)
+    ref = ko.inner_layer([v.cpu().double()[:, f:f + 1] for f in range(F)], use_add=True)[:, 0]
+    assert_rel(y, ref, FP32_TOL, "fm strided")
+
+
+# ------------------------------------------------------------------ Cross
+@pytest.mark.parametrize("B,D,L", [(513, 845, 6), (64, 429, 3), (7, 33, 1), (100, 1024, 8), (9, 5, 2)])
+def test_cross_fwd_bwd(B, D, L):
+    ops = _ops()
+    g = gen(D)
+    x = torch.randn(B, D, generator=g)
+    w = torch.randn(L, D, generator=g) * (1.0 / D ** 0.5)
+    b = torch.randn(L, D, generator=g) * 0.1
+    wgt = torch.randn(B, D, generator=g)
+
+    def run(dt):
+        xx = x.to(dt).requires_grad_(True)
+        ww = w.to(dt).requires_grad_(True)
+        bb = b.to(dt).requires_grad_(True)
+        y = ko.cross_layer(xx, [ww[i][:, None] for i in range(L)], [bb[i][:, None] for i in range(L)])[..., 0]
+        (y * wgt.to(dt)).sum().backward()
+        return y, xx.grad, ww.grad, bb.grad
+
+    y64, dx64, dw64, db64 = run(torch.float64)
+    xc = x.to(DEV).requires_grad_(True)
+    wc = w.to(DEV).requires_grad_(True)
+    bc = b.to(DEV).requires_grad_(True)
+    y = ops.cross(xc, wc, bc)
+    (y * wgt.to(DEV)).sum().backward()
+    assert_rel(y, y64, FP32_TOL, "cross fwd")
+    assert_rel(xc.grad, dx64, FP32_TOL, "cross dx0")
+    assert_rel(wc.grad, dw64, FP32_TOL, "cross dw")
+    assert_rel(bc.grad, db64, FP32_TOL, "cross db")
+
+
+# ------------------------------------------------------------------ CIN (fp32 parity mode)
+def _cin_case(B, m, D, hs, seed):
+    g = gen(seed)
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    ws, bs = [], []
+    prev = m
+    for h in hs:
+        ws.append(torch.randn(prev * m, h, generator=g) * (1.0 / (prev * m) ** 0.5))
+        bs.append(torch.randn(h, generator=g) * 0.1)
+        prev = h
+    wgt = torch.randn(B, len(hs) * D, generator=g)
+    return x0, ws, bs, wgt
+
+
+def _cin_oracle(x0, ws, bs, wgt, dt):
+    xx = x0.to(dt).requires_grad_(True)
+    ww = [w.to(dt).requires_grad_(True) for w in ws]
+    bb = [b.to(dt).requires_grad_(True) for b in bs]
+    pooled = ko.cin(xx, [w[None] for w in ww], bb, return_pooled=True)
+    (pooled * wgt.to(dt)).sum().backward()
+    return pooled, xx.grad, [w.grad for w in ww], [b.grad for b in bb]
+
+
+@pytest.mark.parametrize("B,m,D,hs", [(37, 26, 16, [20, 12, 8]), (8, 5, 4, [7]), (130, 26, 16, [200, 200])])
+def test_cin_fp32_fwd_bwd(B, m, D, hs):
+    ops = _ops()
+    x0, ws, bs, wgt = _cin_case(B, m, D, hs, seed=B)
+    p64, dx64, dw64, db64 = _cin_oracle(x0, ws, bs, wgt, torch.float64)
+    xc = x0.to(DEV).requires_grad_(True)
+    wc = [w.to(DEV).requires_grad_(True) for w in ws]
+    bc = [b.to(DEV).requires_grad_(True) for b in bs]
+    pooled = ops.cin(xc, wc, bc, precision=0)
+    (pooled * wgt.to(DEV)).sum().backward()
+    assert_rel(pooled, p64, FP32_TOL, "cin pooled")
+    assert_rel(xc.grad, dx64, FP32_TOL, "cin dx0")
+    for l in range(len(hs)):
+        assert_rel(wc[l].grad, dw64[l], FP32_TOL, f"cin dw{l}")
+        assert_rel(bc[l].grad, db64[l], FP32_TOL, f"cin db{l}")
+
+
+# ------------------------------------------------------------------ AutoInt attention
+@pytest.mark.parametrize("B,F,kin,H,d", [(129, 26, 16, 2, 8), (33, 26, 16, 3, 8), (5, 7, 24, 3, 8),
+                                         (64, 32, 8, 1, 4), (17, 26, 16, 2, 16)])
+@pytest.mark.parametrize("flags", [(True, True, True, True), (False, False, False, False), (True, True, False, True)])
+def test_attention_fwd_bwd(B, F, kin, H, d, flags):
+    ops = _ops()
+    use_scale, use_ln, use_res, relu = flags
+    g = gen(B + F)
+    x = torch.randn(B, F, kin, generator=g)
+    wq = torch.randn(kin, H, d, generator=g) * 0.3
+    wk = torch.randn(kin, H, d, generator=g) * 0.3
+    wr = torch.randn(kin, H, d, generator=g) * 0.3
+    gam = 1 + 0.1 * torch.randn(d, generator=g)
+    bet = 0.1 * torch.randn(d, generator=g)
+    wgt = torch.randn(H, B, F, d, generator=g)
+
+    def run(dt):
+        t = [a.to(dt).requires_grad_(True) for a in (x, wq, wk, wr, gam, bet)]
+        out = ko.mult_head_attention(t[0], t[1], t[2], t[3], t[4], t[5], use_scale=use_scale,
+                                     use_res=use_res, use_ln=use_ln)
+        if H == 1:
+            atten, res = out.unsqueeze(0), (torch.tensordot(t[0], t[3], dims=1).permute(2, 0, 1, 3) if use_res else [])
+        else:
+            atten, res = out
+        y = ko.keras_add([res, atten]) if use_res else atten
+        if relu:
+            y = torch.relu(y)
+        (y * wgt.to(dt)).sum().backward()
+        return y, [a.grad for a in t]
+
+    y64, g64 = run(torch.float64)
+    tc = [a.to(DEV).requires_grad_(True) for a in (x, wq, wk, wr, gam, bet)]
+    y = ops.attention(tc[0], tc[1], tc[2], tc[3], tc[4], tc[5], use_scale=use_scale, use_ln=use_ln,
+                      use_res=use_res, relu=relu)
+    (y * wgt.to(DEV)).sum().backward()
+    assert_rel(y, y64, FP32_TOL, "attn fwd")
+    names = ["dx", "dwq", "dwk", "dwr", "dgamma", "dbeta"]
+    for i, nm in enumerate(names):
+        if nm == "dwr" and not use_res:
+            continue
+        if nm in ("dgamma", "dbeta") and not use_ln:
+            continue
+        assert_rel(tc[i].grad, g64[i], 2e-5 if relu else FP32_TOL, f"attn {nm}")
