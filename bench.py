@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- train-step throughput of the CTR hot path on synthetic Criteo-shaped data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model xdeepfm|deepfm|dcn|autoint|fm]
+    python bench.py --impl reference ...      # the reference-equivalent CPU path (oracle port)
+
+A "step" = one full training step (embedding gather -> interaction layers + MLP -> loss ->
+backward incl. the sort-then-segment embedding scatter-add -> Adam on dense weights and
+row-wise Adam on the touched embedding rows) over one batch of 65,536 synthetic samples
+(26 sparse + 13 dense).  Metric: train samples/s (BASELINE.json), whole job over all ranks.
+
+One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM.  ``e2e``: the same step
+through the public API with the batch coming from pinned host memory (H2D inside the timed
+region) and the loss read back (D2H).  ``roofline``: the dominant kernel family, timed live
+with CUDA events on the launching stream inside the timed region.  ``cpu_baseline``: the
+oracle port (torch-CPU restatement of the reference layers; TensorFlow is not installable
+here) on a bounded sample of the same workload on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CRITEO_ROWS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27,
+               14992, 5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+N_DENSE = 13
+
+MODEL_CFG = {
+    # name: (emb dim, description)  -- BASELINE.json configs[1..4]
+    "deepfm": dict(k=16, desc="DeepFM, 26 sparse + 13 dense, emb 16, MLP 256-128-64"),
+    "dcn": dict(k=32, desc="DCN-v1, 6 CrossLayers, emb 32, MLP 256-128-64"),
+    "xdeepfm": dict(k=16, desc="xDeepFM, CIN [200,200,200] bf16 tcgen05, emb 16, MLP 256-128-64"),
+    "autoint": dict(k=16, desc="AutoInt, 3 layers x 2 heads x d=8, emb 16"),
+    "fm": dict(k=16, desc="FM, emb 16"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per op per step (DESIGN.md "Roofline accounting")
+# ------------------------------------------------------------------------------------------
+def algo_work(model, B, k, conv=(200, 200, 200), cross_layers=6, heads=2, d=8, kin=16):
+    F, p = 26, 4
+    W = (F * k + N_DENSE + 3) // 4 * 4
+    w = {
+        "embed_fwd": ("hbm", B * F * (4 + 2 * k * p)),
+        "embed_bwd": ("hbm", B * F * (4 + k * p) + B * F * (k * p + 4)),       # worst case all rows unique
+        "fm_fwd": ("hbm", B * (F * k * p + F * p + k * p)),
+        "fm_bwd": ("hbm", B * (k * p + 2 * F * k * p + F * p)),
+        "cross_fwd": ("hbm", B * (2 * W * p + 4 * cross_layers)),
+        "cross_bwd": ("hbm", B * 3 * W * p),
+        "attn_fwd": ("hbm", B * (F * kin * p + heads * F * d * p)),
+        "attn_bwd": ("hbm", B * (2 * F * kin * p + heads * F * d * p)),
+    }
+    hp, fl = F, 0
+    for n in conv:
+        fl += 2 * B * k * hp * F * n
+        hp = n
+    w["cin_fwd"] = ("tensor", fl)
+    w["cin_bwd"] = ("tensor", 2 * fl)
+    return w
+
+
+def sample_clocks_start(path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        f = open(path, "w")
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                stdout=f, stderr=subprocess.DEVNULL), f
+    except Exception:
+        return None, None
+
+
+def sample_clocks_stop(proc, f, path, dev_index):
+    if proc is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    proc.terminate()
+    try:
+        proc.wait(timeout=5)
+    except Exception:
+        proc.kill()
+    f.close()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in open(path):
+        c = [x.strip() for x in line.split(",")]
+        if len(c) < 9 or not c[0].isdigit() or int(c[0]) != dev_index:
+            continue
+        try:
+            sm.append(float(c[1])); mx.append(float(c[2]))
+        except ValueError:
+            continue
+        for n, v in zip(names, c[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(n)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    sm.sort()
+    # "under load": upper half of the samples (the sampler also sees the idle edges)
+    load = sm[len(sm) // 2:]
+    return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic data
+# ------------------------------------------------------------------------------------------
+def synth_batches(n, B, rows, seed, sigmoid_head, zipf=False, pin=True):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        cols = []
+        for r in rows:
+            if zipf:
+                u = torch.rand(B, generator=g, dtype=torch.float64)
+                c = (torch.exp(u * torch.log(torch.tensor(float(r) + 1.0))) - 1.0).long().clamp_(0, r - 1)
+            else:
+                c = torch.randint(0, r, (B,), generator=g)
+            cols.append(c)
+        ids = torch.stack(cols, 1).to(torch.int32).contiguous()
+        dense = torch.rand(B, N_DENSE, generator=g)
+        y = (torch.rand(B, generator=g) < 0.25).float()
+        labels = y.view(B, 1) if sigmoid_head else torch.stack([1 - y, y], 1)       # to_categorical, DP:359
+        t = (dense.contiguous(), ids, labels.contiguous())
+        if pin:
+            t = tuple(x.pin_memory() for x in t)
+        out.append(t)
+    return out
+
+
+def build_model(name, device, cin_precision="bf16", rows=CRITEO_ROWS, mlp_dtype=None):
+    import torch
+    from ml_function_b200 import layers as KL
+    from ml_function_b200 import models as KM
+    k = MODEL_CFG[name]["k"]
+    sparse = [KL.make_sparse_fea(str(14 + i), r, cross_unit=k) for i, r in enumerate(rows)]
+    dense = [KL.denseFea(str(1 + i), None) for i in range(N_DENSE)]
+    fea = KM.FeatureInput(sparse, dense, useLinear=True, useAddLinear=(name == "xdeepfm"), device=device)
+    if name == "deepfm":
+        m = KM.DeepFM(fea)
+    elif name == "dcn":
+        m = KM.DCN(fea, cross_hidden=6)
+    elif name == "xdeepfm":
+        m = KM.XDeepFM(fea, cin_precision=cin_precision)
+    elif name == "autoint":
+        m = KM.AutoInt(fea, attention_dim=8, attention_head_dim=2, n_layers=3)
+    else:
+        m = KM.FM(fea)
+    if mlp_dtype is not None and hasattr(m, "dnn"):
+        m.dnn.compute_dtype = mlp_dtype
+    return m
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the same model (reference-equivalent CPU path)
+# ------------------------------------------------------------------------------------------
+def oracle_params(name, rows, k, gen):
+    import torch
+    from oracle import kon_oracle as ko
+    p = {}
+    F = len(rows)
+    for f, r in enumerate(rows):
+        p[f"emb_{f}"] = ko.glorot_uniform((r, k), gen)
+        p[f"lin_{f}"] = (torch.rand(r, 1, generator=gen) - 0.5) * 0.1
+    D = N_DENSE + F * k
+    dims = [D, 256, 128, 64]
+    for i in range(3):
+        p[f"dnn_w{i}"] = ko.glorot_uniform((dims[i], dims[i + 1]), gen)
+        p[f"dnn_b{i}"] = ko.glorot_uniform((dims[i + 1],), gen)
+    if name == "deepfm":
+        p["head_w"], p["head_b"] = ko.glorot_uniform((k + 64, 2), gen), torch.zeros(2)
+    elif name == "fm":
+        p["head_w"], p["head_b"] = ko.glorot_uniform((k, 2), gen), torch.zeros(2)
+    elif name == "dcn":
+        for i in range(6):
+            p[f"outer_weight_{i}"] = ko.glorot_uniform((D, 1), gen)
+            p[f"outer_bias_{i}"] = torch.zeros(D, 1)
+        p["head_w"], p["head_b"] = ko.glorot_uniform((D + 64, 2), gen), torch.zeros(2)
+    elif name == "xdeepfm":
+        hp = F
+        for i, n in enumerate((200, 200, 200)):
+            p[f"cin_w{i}"] = ko.glorot_uniform((1, hp * F, n), gen)
+            p[f"cin_b{i}"] = torch.zeros(n)
+            hp = n
+        p["cin_logit_w"], p["cin_logit_b"] = ko.glorot_uniform((3 * k, 1), gen), torch.zeros(1)
+        p["dnn_logit_w"], p["dnn_logit_b"] = ko.glorot_uniform((64, 1), gen), torch.zeros(1)
+    elif name == "autoint":
+        H, d = 2, 8
+        for w in ("query_w", "key_w", "res_w"):
+            p[w] = ko.glorot_uniform((k, H, d), gen)
+        p["ln_gamma"], p["ln_beta"] = torch.ones(d), torch.zeros(d)
+        p["head_w"], p["head_b"] = ko.glorot_uniform((H * F * d, 2), gen), torch.zeros(2)
+    return p
+
+
+def oracle_step(name, p, dense, ids, labels, lr=1e-3):
+    """fwd + bwd + SGD on the touched parameters, reference op order (oracle/kon_oracle.py)."""
+    import torch
+    from oracle import kon_oracle as ko
+    fn = {"fm": ko.model_fm, "deepfm": ko.model_deepfm, "xdeepfm": ko.model_xdeepfm, "autoint": ko.model_autoint,
+          "dcn": lambda p_, d_, i_: ko.model_dcn(p_, d_, i_, cross_hidden=6)}[name]
+    for t in p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    out = fn(p, dense, ids)
+    loss = ko.binary_crossentropy(labels.view(out.shape), out)
+    loss.backward()
+    with torch.no_grad():
+        for key, t in p.items():
+            if t.grad is None:
+                continue
+            if key.startswith(("emb_", "lin_")):          # TF: IndexedSlices -> sparse apply
+                f = int(key.split("_")[1])
+                rows_ = torch.unique(ids[:, f].long())
+                t[rows_] -= lr * t.grad[rows_]
+            else:
+                t -= lr * t.grad
+    return float(loss.detach())
+
+
+def cpu_arm(name, sample_B, steps, warmup, seed=2020, small_tables=True):
+    """Times the oracle port on all host cores.  Embedding tables are capped at 200k rows per
+    field for the CPU arm (a dense [R,k] autograd gradient per table is what TF's Keras path
+    with the L2 regulariser materialises too, but 2 GB of it per step would only measure
+    memset); ids are drawn in the capped range."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows = [min(r, 200_000) for r in CRITEO_ROWS] if small_tables else CRITEO_ROWS
+    k = MODEL_CFG[name]["k"]
+    g = torch.Generator().manual_seed(seed)
+    p = oracle_params(name, rows, k, g)
+    batches = synth_batches(2, sample_B, rows, seed, name == "xdeepfm", pin=False)
+    for i in range(warmup):
+        d, ids, y = batches[i % 2]
+        oracle_step(name, p, d, ids, y)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        d, ids, y = batches[i % 2]
+        oracle_step(name, p, d, ids, y)
+    dt = time.perf_counter() - t0
+    return sample_B * steps / dt, dt / steps, torch.get_num_threads()
+
+
+CPU_SAMPLE_B = {"xdeepfm": 1024, "deepfm": 16384, "dcn": 16384, "autoint": 16384, "fm": 16384}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.model
+    sb = CPU_SAMPLE_B[name]
+    v, s_per_step, cores = cpu_arm(name, sb, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "train samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": MODEL_CFG[name]["desc"], "batch_per_step": sb},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {sb} (oracle port, reference op order, torch-CPU "
+                                   f"fp32; tables capped at 200k rows/field)"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from ml_function_b200 import _lib, ops
+    from ml_function_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dctx = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from ml_function_b200.parallel import DistContext
+        dctx = DistContext(dist.group.WORLD, dev)
+    lib = _lib.lib()
+    name = args.model
+    B = args.batch
+    k = MODEL_CFG[name]["k"]
+    mlp_dtype = {"bf16": torch.bfloat16, "f32": None}[args.mlp_dtype]
+    torch.manual_seed(2020)
+    model = build_model(name, dev, cin_precision=args.cin_precision, mlp_dtype=mlp_dtype)
+    if dctx is not None:
+        dctx.attach(model)
+    trainer = Trainer(model, lr=1e-3, dist_ctx=dctx)
+    host = synth_batches(args.n_batches, B, CRITEO_ROWS, 2020 + rank, name == "xdeepfm", zipf=(args.ids == "zipf"))
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident(i):
+        d, ids, y = resident[i % len(resident)]
+        return trainer.step(d, ids, y)
+
+    stage = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        hb = host[i % len(host)]
+        st = stage[i % 2]
+        for dst, src in zip(st, hb):
+            dst.copy_(src, non_blocking=True)
+        loss = trainer.step(*st)
+        loss_host.copy_(loss.view(1), non_blocking=True)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    # ---- resident-input timing (value) with live per-op events + clocks --------------------
+    clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
+    os.makedirs(os.path.dirname(clk_path), exist_ok=True)
+    proc, f = sample_clocks_start(clk_path) if rank == 0 else (None, None)
+    ops.PROFILE = {}
+    l0 = lib.kon_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.kon_launch_count() - l0
+    prof = ops.profile_summary()
+    ops.PROFILE = None
+    # ---- end-to-end timing (H2D + step + D2H) ---------------------------------------------
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sample_clocks_stop(proc, f, clk_path, local) if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    work = algo_work(name, B, k)
+    kernels = {}
+    for op, (calls, mean_ms) in prof.items():
+        if op not in work:
+            continue
+        bound, amount = work[op]
+        per_step_calls = calls / args.steps
+        # ops called more than once per step (e.g. the two embedding arenas, stacked attention
+        # layers) share the per-step algorithmic work evenly in this accounting
+        rate = amount / (mean_ms * 1e-3 * per_step_calls) if op.startswith(("cin", "cross", "fm")) or per_step_calls <= 1 \
+            else amount / (mean_ms * 1e-3)
+        if bound == "hbm":
+            kernels[op] = {"bound": "hbm", "ms": mean_ms, "calls_per_step": per_step_calls,
+                           "achieved": rate / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": rate / 1e9 / pk["hbm"]}
+        else:
+            kernels[op] = {"bound": "tensor", "ms": mean_ms, "calls_per_step": per_step_calls,
+                           "achieved": rate / 1e12, "peak": pk["tc_sust"], "unit": "TFLOP/s",
+                           "frac": rate / 1e12 / pk["tc_sust"]}
+    dom = max((o for o in kernels), key=lambda o: kernels[o]["ms"] * kernels[o]["calls_per_step"], default=None)
+    roof = None
+    if dom is not None:
+        kd = kernels[dom]
+        roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
+                "frac": kd["frac"], "traffic": None, "peak_source": pk["src"] + (" (sustained)" if kd["bound"] == "tensor" else ""),
+                "share_of_step": kd["ms"] * kd["calls_per_step"] / (ms / args.steps)}
+    total = B * world * args.steps
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    # CPU baseline on rank 0, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        sb = CPU_SAMPLE_B[name]
+        v, s_step, cores = cpu_arm(name, sb, args.cpu_steps, 1)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_steps} steps of batch {sb} (oracle port of the reference layers, torch-CPU fp32, "
+                         f"fwd+bwd+SGD; tables capped at 200k rows/field)"}
+    line = {
+        "metric": "train samples/s", "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if (name == "xdeepfm" and args.cin_precision == "bf16") else ("bf16" if mlp_dtype else "f32"),
+        "data": "synthetic",
+        "config": {"workload": MODEL_CFG[name]["desc"], "batch_per_gpu": B, "global_batch": B * world, "emb_dim": k,
+                   "tables": "Criteo-Kaggle cardinalities (33.76M rows)", "ids": args.ids,
+                   "optimizer": "Adam (dense, fused) + row-wise lazy Adam (embeddings)",
+                   "mlp_dtype": args.mlp_dtype, "cache": "working set per step (>1 GB) exceeds the 126 MB L2; "
+                   f"{args.n_batches} distinct batches rotate",
+                   "parallelism": "single GPU" if world == 1 else dctx.describe()},
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="xdeepfm", choices=list(MODEL_CFG))
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--cin-precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--n-batches", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

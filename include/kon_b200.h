@@ -60,6 +60,9 @@ enum {
 
 int         kon_abi_version(void);
 const char* kon_last_error(void);
+/* Number of kernels of THIS library launched by the process so far (every __global__ of
+ * libkon_b200 counts once per launch; CUB primitives called by kon_embed_bwd do not). */
+long long   kon_launch_count(void);
 /* SM count / arch of the device the tensors live on (for host-side grid sizing). */
 int         kon_device_info(int device_id, int* sm_count, int* cc_major, int* cc_minor);
 

@@ -125,6 +125,7 @@ def lib():
     sigs = {
         "kon_abi_version": (ctypes.c_int, []),
         "kon_last_error": (ctypes.c_char_p, []),
+        "kon_launch_count": (ctypes.c_longlong, []),
         "kon_device_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)] + [ctypes.POINTER(ctypes.c_int)] * 2),
         "kon_embed_fwd": (ctypes.c_int, [T, T, i64p, i32, T, T, i32, vp]),
         "kon_embed_bwd_workspace_bytes": (sz, [i64, i32]),
@@ -155,7 +156,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "kon_abi_version", "kon_last_error", "kon_device_info", "kon_embed_fwd",
+    "kon_abi_version", "kon_last_error", "kon_launch_count", "kon_device_info", "kon_embed_fwd",
     "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_sgd", "kon_embed_adam",
     "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",

@@ -1,4 +1,5 @@
 // libkon_b200 C-ABI plumbing: version, thread-local error string, device attribute cache.
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -9,6 +10,9 @@ char* tls_error_buf() {
   static thread_local char buf[kErrLen] = {0};
   return buf;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count_of(int device_id) {
   static std::mutex mu;
@@ -27,6 +31,10 @@ int sm_count_of(int device_id) {
 }  // namespace kon
 
 extern "C" int kon_abi_version(void) { return KON_ABI_VERSION; }
+
+extern "C" long long kon_launch_count(void) {
+  return kon::g_launches.load(std::memory_order_relaxed);
+}
 
 extern "C" const char* kon_last_error(void) { return kon::tls_error_buf(); }
 

@@ -38,8 +38,11 @@ inline int fail(int code, const char* fmt, ...) {
                          cudaGetErrorString(_e), __FILE__, __LINE__);               \
   } while (0)
 
+void count_launch();   // abi.cu: bumps the process-wide launch counter (kon_launch_count)
+
 #define KON_LAUNCH_CHECK(name)                                                      \
   do {                                                                              \
+    ::kon::count_launch();                                                          \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess)                                                          \
       return ::kon::fail(KON_ECUDA, "launch of %s failed: %s", name,                \

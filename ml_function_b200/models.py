@@ -1,0 +1,253 @@
+"""The reference's CTR model builders on the B200 kernels: ``FM``, ``DeepFM``, ``DCN``,
+``XDeepFM``, ``AutoInt`` (kon/model/ctr_model/model/models.py = MD:36-41, 80-106, 121-138,
+150-165) and ``data_prepare.FeatureInput`` / ``InputFeature`` (kon/utils/data_prepare.py =
+DP:39-76).
+
+A builder takes an ``InputFeature`` exactly as in the reference and returns a module whose
+``forward(dense_inputs, sparse_inputs)`` accepts either the reference's lists of per-feature
+``[B,1]`` tensors or packed ``dense [B,n_dense]`` float32 / ``ids [B,F]`` int32|int64.
+
+Data layout in HBM: one row-major concat buffer ``xcat [B, W]`` per step,
+``W = F*k + n_dense`` rounded up to a multiple of 4 floats.  Columns ``[0, F*k)`` hold the
+field embeddings (written in place by the gather kernel, 16-B aligned rows), then the dense
+features, then zero padding.  ``xcat[:, :F*k].view(B,F,k)`` is the FM / CIN / attention
+input and ``xcat`` itself the MLP / Cross input -- no concat copy.  The reference's
+``StackLayer`` order is dense-first (MD:86); weights in reference order are permuted once at
+load time (``load_reference_params``), which changes nothing but the physical column order.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import ops
+from .layers import (CIN, CrossLayer, DnnLayer, FieldList, FmLayer, MergeScoreLayer, MultHeadAttentionLayer,
+                     ScoreLayer, SparseEmbed, StackLayer, denseFea, pack_ids, sparseFea)
+
+
+class InputFeature(object):
+    """DP:39-49 (fields kept; the Keras Input placeholders have no torch counterpart, the
+    embed entries are the ``SparseEmbed`` layers themselves)."""
+
+    def __init__(self, denseInfo=None, sparseInfo=None, seqInfo=None, denseInputs=None, sparseInputs=None,
+                 seqInputs=None, linearEmbed=None, sparseEmbed=None, seqEmbedList=None):
+        self.dense_info = denseInfo
+        self.sparse_info = sparseInfo
+        self.seq_info = seqInfo
+        self.dense_inputs = denseInputs
+        self.sparse_inputs = sparseInputs
+        self.seq_inputs = seqInputs
+        self.linear_embed = linearEmbed
+        self.sparse_embed = sparseEmbed
+        self.seq_embed_list = seqEmbedList
+
+
+def FeatureInput(sparseInfo: list = None, denseInfo: list = None, seqInfo=None, useLinear: bool = False,
+                 useAddLinear: bool = False, useFlattenLinear: bool = False, useFlattenSparse: bool = False,
+                 device="cuda") -> InputFeature:
+    """``data_prepare.FeatureInput`` (DP:65-76)."""
+    linearEmbed = sparseEmbed = None
+    if useLinear:
+        linearEmbed = SparseEmbed(sparseInfo, use_flatten=useFlattenLinear, is_linear=True,
+                                  use_add=useAddLinear, device=device)
+    if sparseInfo:
+        sparseEmbed = SparseEmbed(sparseInfo, use_flatten=useFlattenSparse, device=device)
+    return InputFeature(denseInfo, sparseInfo, seqInfo, None, None, None, linearEmbed, sparseEmbed, [None, None])
+
+
+def _pack_dense(dense_inputs) -> torch.Tensor:
+    if isinstance(dense_inputs, torch.Tensor):
+        return dense_inputs
+    return torch.cat([t.reshape(t.shape[0], 1) for t in dense_inputs], dim=1)
+
+
+class _CtrModel(nn.Module):
+    """Shared front end: ids/dense -> the concat buffer and its views."""
+
+    def __init__(self, inputFea: InputFeature):
+        super().__init__()
+        self.sparse_embed: SparseEmbed = inputFea.sparse_embed
+        self.linear_embed: Optional[SparseEmbed] = inputFea.linear_embed
+        self.n_dense = len(inputFea.dense_info or [])
+        self.F = len(inputFea.sparse_info)
+        self.k = self.sparse_embed.dim
+        self.Fk = self.F * self.k
+        self.W = (self.Fk + self.n_dense + 3) // 4 * 4
+
+    # ---- physical <-> reference column order -------------------------------------------
+    def ref_to_phys_rows(self, w_ref: torch.Tensor) -> torch.Tensor:
+        """Rows of a reference-order ``[n_dense + F*k, ...]`` weight -> physical ``[W, ...]``."""
+        nd = self.n_dense
+        pad = torch.zeros((self.W - self.Fk - nd,) + tuple(w_ref.shape[1:]), dtype=w_ref.dtype, device=w_ref.device)
+        return torch.cat([w_ref[nd:], w_ref[:nd], pad], dim=0).contiguous()
+
+    def front(self, dense_inputs, sparse_inputs):
+        ids = pack_ids(sparse_inputs)
+        dense = _pack_dense(dense_inputs) if self.n_dense else None
+        xcat = self.sparse_embed.lookup_concat(ids, dense, self.W)
+        v = xcat[:, :self.Fk].view(ids.shape[0], self.F, self.k)
+        return ids, xcat, v
+
+    def sparse_parameters(self) -> List[nn.Parameter]:
+        ps = [self.sparse_embed.arena]
+        if self.linear_embed is not None:
+            ps.append(self.linear_embed.arena)
+        return ps
+
+    def dense_parameters(self) -> List[nn.Parameter]:
+        sp = {id(p) for p in self.sparse_parameters()}
+        return [p for p in self.parameters() if id(p) not in sp]
+
+
+class FM(_CtrModel):
+    """MD:36-41: ``Dense(2,softmax)(squeeze(FmLayer([sparse_embed, linear_embed])))``."""
+
+    def __init__(self, inputFea: InputFeature = None):
+        super().__init__(inputFea)
+        self.fm = FmLayer()
+        self.head = MergeScoreLayer(use_merge=False)
+
+    def forward(self, dense_inputs, sparse_inputs):
+        ids = pack_ids(sparse_inputs)
+        v = self.sparse_embed.lookup(ids)
+        lin = self.linear_embed.lookup(ids)
+        fm_ = self.fm([v, lin])
+        return self.head(fm_.squeeze(1))
+
+    def load_reference_params(self, p: Dict[str, torch.Tensor]):
+        _load_embeds(self, p)
+        self.head.load_reference_weights(p["head_w"], p["head_b"])
+
+
+class DeepFM(_CtrModel):
+    """MD:80-90."""
+
+    def __init__(self, inputFea: InputFeature = None, hidden_units=None):
+        super().__init__(inputFea)
+        self.hidden_units = hidden_units if hidden_units is not None else [256, 128, 64]
+        self.fm = FmLayer()
+        self.dnn = DnnLayer(hidden_units=self.hidden_units)
+        self.head = MergeScoreLayer()
+
+    def forward(self, dense_inputs, sparse_inputs):
+        ids, xcat, v = self.front(dense_inputs, sparse_inputs)
+        lin = self.linear_embed.lookup(ids)
+        fm_ = self.fm([v, lin])
+        dnn_ = self.dnn(xcat)
+        return self.head([fm_, dnn_])
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        n = len(self.hidden_units)
+        ks = [p[f"dnn_w{i}"] for i in range(n)]
+        ks[0] = self.ref_to_phys_rows(ks[0])
+        self.dnn.load_reference_weights(ks, [p[f"dnn_b{i}"] for i in range(n)])
+        self.head.load_reference_weights(p["head_w"], p["head_b"])
+
+
+class DCN(_CtrModel):
+    """MD:92-106."""
+
+    def __init__(self, inputFea: InputFeature = None, hidden_units=None, cross_hidden=3):
+        super().__init__(inputFea)
+        self.hidden_units = hidden_units if hidden_units is not None else [256, 128, 64]
+        self.cross = CrossLayer(cross_hidden=cross_hidden)
+        self.dnn = DnnLayer(hidden_units=self.hidden_units)
+        self.head = MergeScoreLayer()
+
+    def forward(self, dense_inputs, sparse_inputs):
+        ids, xcat, v = self.front(dense_inputs, sparse_inputs)
+        cross_fea = self.cross(xcat)                       # [B,W,1]
+        deep_fea = self.dnn(xcat)
+        return self.head([cross_fea, deep_fea])
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        n, L = len(self.hidden_units), self.cross.cross_hidden
+        ks = [p[f"dnn_w{i}"] for i in range(n)]
+        ks[0] = self.ref_to_phys_rows(ks[0])
+        self.dnn.load_reference_weights(ks, [p[f"dnn_b{i}"] for i in range(n)])
+        self.cross.load_reference_weights([self.ref_to_phys_rows(p[f"outer_weight_{i}"]) for i in range(L)],
+                                          [self.ref_to_phys_rows(p[f"outer_bias_{i}"]) for i in range(L)])
+        D = self.n_dense + self.Fk
+        hw = p["head_w"]
+        self.head.load_reference_weights(torch.cat([self.ref_to_phys_rows(hw[:D]), hw[D:]], 0), p["head_b"])
+
+
+class XDeepFM(_CtrModel):
+    """MD:121-138, with ``FeatureInput(useLinear=True, useAddLinear=True)`` (the only wiring
+    under which ``ScoreLayer(use_add=True)([linear, cin, dnn])`` is well formed).  Output
+    ``sigmoid`` ``[B,1,1]``."""
+
+    def __init__(self, inputFea: InputFeature = None, conv_size=None, hidden_units=None, cin_precision="bf16"):
+        super().__init__(inputFea)
+        self.conv_size = conv_size if conv_size is not None else [200, 200, 200]
+        self.hidden_units = hidden_units if hidden_units is not None else [256, 128, 64]
+        self.cin = CIN(conv_size=self.conv_size, output_dim=1, precision=cin_precision)
+        self.dnn = DnnLayer(hidden_units=self.hidden_units, output_dim=1)
+        self.score = ScoreLayer(use_add=True)
+
+    def logit(self, dense_inputs, sparse_inputs):
+        ids, xcat, v = self.front(dense_inputs, sparse_inputs)
+        linear = ops.embed_lookup(self.linear_embed.arena, ids, self.linear_embed.field_row_offset, True)
+        cin_out = self.cin(v)                              # [B,1]
+        dnn_out = self.dnn(xcat)                           # [B,1]
+        return ScoreLayer.summed([linear.unsqueeze(1), cin_out, dnn_out])   # [B,1,1]
+
+    def forward(self, dense_inputs, sparse_inputs):
+        return torch.sigmoid(self.logit(dense_inputs, sparse_inputs))
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        n, nc = len(self.hidden_units), len(self.conv_size)
+        ks = [p[f"dnn_w{i}"] for i in range(n)]
+        ks[0] = self.ref_to_phys_rows(ks[0])
+        self.dnn.load_reference_weights(ks, [p[f"dnn_b{i}"] for i in range(n)], p["dnn_logit_w"], p["dnn_logit_b"])
+        self.cin.load_reference_weights([p[f"cin_w{i}"] for i in range(nc)], [p[f"cin_b{i}"] for i in range(nc)],
+                                        p["cin_logit_w"], p["cin_logit_b"])
+
+
+class AutoInt(_CtrModel):
+    """MD:150-165.  ``n_layers > 1`` stacks blocks by re-packing ``[H,B,F,d] -> [B,F,H*d]``
+    (standard AutoInt; an extension, the reference wires exactly one block)."""
+
+    def __init__(self, inputFea: InputFeature = None, attention_dim=8, attention_head_dim=3, n_layers=1):
+        super().__init__(inputFea)
+        self.blocks = nn.ModuleList([
+            DnnLayer(res_unit=1, other_dense=[MultHeadAttentionLayer(
+                attention_dim=attention_dim, attention_head_dim=attention_head_dim, use_ln=True,
+                atten_mask_mod=1)]) for _ in range(n_layers)])
+        self.head = MergeScoreLayer(use_merge=False)
+
+    def forward(self, dense_inputs, sparse_inputs):
+        ids = pack_ids(sparse_inputs)
+        x = self.sparse_embed.lookup(ids)                  # StackLayer(use_flat=False, axis=1)
+        for i, blk in enumerate(self.blocks):
+            a = blk(x)                                     # [H,B,F,d]
+            if i + 1 < len(self.blocks):
+                x = a.permute(1, 2, 0, 3).reshape(a.shape[1], a.shape[2], -1).contiguous()
+        final = a.permute(1, 0, 2, 3).reshape(a.shape[1], -1)   # MD:162: heads side by side
+        return self.head(final)
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        self.blocks[0].other_dense[0].load_reference_weights(p["query_w"], p["key_w"], p["res_w"],
+                                                             p["ln_gamma"], p["ln_beta"])
+        self.head.load_reference_weights(p["head_w"], p["head_b"])
+
+
+def _load_embeds(model: _CtrModel, p):
+    F = model.F
+    model.sparse_embed.load_reference_weights([p[f"emb_{f}"] for f in range(F)])
+    if model.linear_embed is not None:
+        model.linear_embed.load_reference_weights([p[f"lin_{f}"] for f in range(F)])
+
+
+def keras_binary_crossentropy(y_true: torch.Tensor, y_pred: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """``compile(loss=binary_crossentropy)`` (example/ctr_example/un_seq.py:61) on
+    probabilities: clip, mean over the last axis, mean over the batch."""
+    p = torch.clamp(y_pred, eps, 1 - eps)
+    bce = -(y_true * torch.log(p + eps) + (1 - y_true) * torch.log(1 - p + eps))
+    return bce.mean(dim=-1).mean()

@@ -13,6 +13,40 @@ import torch
 from . import _lib as L
 
 
+# Per-op device timing for bench.py's roofline: when PROFILE is a dict, every C-ABI call below
+# is bracketed by CUDA events recorded on the launching (current) stream.
+PROFILE = None
+
+
+class _prof:
+    __slots__ = ("name", "e0")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
+def profile_summary():
+    """-> {op: (calls, mean ms)} from the events collected in PROFILE (synchronises)."""
+    torch.cuda.synchronize()
+    out = {}
+    for k, evs in (PROFILE or {}).items():
+        ts = [a.elapsed_time(b) for a, b in evs]
+        out[k] = (len(ts), sum(ts) / max(len(ts), 1))
+    return out
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -45,9 +79,10 @@ def embed_fwd_raw(arena, ids, field_row_offset: Sequence[int], sum_fields=False,
         out = torch.empty(shape, dtype=arena.dtype, device=arena.device)
     offs = L.i64_array(list(field_row_offset))
     a, i, o, ob = L._arg(arena), L._arg(ids), L._arg(out), L._arg(oob)
-    L.check(lib.kon_embed_fwd(a.ptr, i.ptr, offs, F, o.ptr, L._p(ob),
-                              L.KON_EMBED_SUM_FIELDS if sum_fields else 0, L.stream_ptr(arena.device)),
-            "kon_embed_fwd")
+    with _prof("embed_fwd"):
+        L.check(lib.kon_embed_fwd(a.ptr, i.ptr, offs, F, o.ptr, L._p(ob),
+                                  L.KON_EMBED_SUM_FIELDS if sum_fields else 0, L.stream_ptr(arena.device)),
+                "kon_embed_fwd")
     return out
 
 
@@ -64,8 +99,9 @@ def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int]) -> SparseGrad:
     ws = _ws(lib.kon_embed_bwd_workspace_bytes(n, dim), dev)
     offs = L.i64_array(list(field_row_offset))
     a = [L._arg(t) for t in (d_out, ids, rows, grads, nu, ws)]
-    L.check(lib.kon_embed_bwd(a[0].ptr, a[1].ptr, offs, F, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
-                              L.stream_ptr(dev)), "kon_embed_bwd")
+    with _prof("embed_bwd"):
+        L.check(lib.kon_embed_bwd(a[0].ptr, a[1].ptr, offs, F, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
+                                  L.stream_ptr(dev)), "kon_embed_bwd")
     return SparseGrad(rows, grads, nu)
 
 
@@ -105,15 +141,17 @@ def embed_lookup(arena, ids, field_row_offset, sum_fields=False):
 def embed_sgd(arena, sg: SparseGrad, lr: float, l2: float = 0.0):
     lib = L.lib()
     a = [L._arg(t) for t in (arena, sg.rows, sg.grads, sg.n)]
-    L.check(lib.kon_embed_sgd(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, lr, l2, L.stream_ptr(arena.device)),
-            "kon_embed_sgd")
+    with _prof("embed_sgd"):
+        L.check(lib.kon_embed_sgd(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, lr, l2, L.stream_ptr(arena.device)),
+                "kon_embed_sgd")
 
 
 def embed_adam(arena, m, v, sg: SparseGrad, lr, beta1, beta2, eps, l2, step):
     lib = L.lib()
     a = [L._arg(t) for t in (arena, m, v, sg.rows, sg.grads, sg.n)]
-    L.check(lib.kon_embed_adam(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr, lr, beta1,
-                               beta2, eps, l2, step, L.stream_ptr(arena.device)), "kon_embed_adam")
+    with _prof("embed_adam"):
+        L.check(lib.kon_embed_adam(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr, lr, beta1,
+                                   beta2, eps, l2, step, L.stream_ptr(arena.device)), "kon_embed_adam")
 
 
 # --------------------------------------------------------------------------- #
@@ -125,7 +163,8 @@ class _Fm(torch.autograd.Function):
         lib = L.lib()
         out = torch.empty((v.shape[0], v.shape[2]), dtype=v.dtype, device=v.device)
         a, b, o = L._arg(v), L._arg(lin), L._arg(out)
-        L.check(lib.kon_fm_fwd(a.ptr, L._p(b), o.ptr, L.stream_ptr(v.device)), "kon_fm_fwd")
+        with _prof("fm_fwd"):
+            L.check(lib.kon_fm_fwd(a.ptr, L._p(b), o.ptr, L.stream_ptr(v.device)), "kon_fm_fwd")
         ctx.save_for_backward(v)
         ctx.has_lin = lin is not None
         ctx.lin_shape = None if lin is None else lin.shape
@@ -139,7 +178,8 @@ class _Fm(torch.autograd.Function):
         dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
         dlin = torch.empty(ctx.lin_shape, dtype=v.dtype, device=v.device) if ctx.has_lin else None
         a, b, c, d = L._arg(v), L._arg(g), L._arg(dv), L._arg(dlin)
-        L.check(lib.kon_fm_bwd(a.ptr, b.ptr, c.ptr, L._p(d), L.stream_ptr(v.device)), "kon_fm_bwd")
+        with _prof("fm_bwd"):
+            L.check(lib.kon_fm_bwd(a.ptr, b.ptr, c.ptr, L._p(d), L.stream_ptr(v.device)), "kon_fm_bwd")
         return dv, dlin
 
 
@@ -161,7 +201,8 @@ class _Cross(torch.autograd.Function):
         out = torch.empty(x0.shape, dtype=x0.dtype, device=x0.device)
         s = torch.empty((x0.shape[0], w.shape[0]), dtype=x0.dtype, device=x0.device)
         a = [L._arg(t) for t in (x0, w, b, out, s)]
-        L.check(lib.kon_cross_fwd(*[t.ptr for t in a], L.stream_ptr(x0.device)), "kon_cross_fwd")
+        with _prof("cross_fwd"):
+            L.check(lib.kon_cross_fwd(*[t.ptr for t in a], L.stream_ptr(x0.device)), "kon_cross_fwd")
         ctx.save_for_backward(x0, w, b, s)
         return out
 
@@ -177,7 +218,8 @@ class _Cross(torch.autograd.Function):
         db = torch.empty_like(b)
         ws = _ws(lib.kon_cross_bwd_workspace_bytes(x0.shape[0], x0.shape[1], w.shape[0], dev.index or 0), dev)
         a = [L._arg(t) for t in (x0, w, b, s, g, dx0, dw, db, ws)]
-        L.check(lib.kon_cross_bwd(*[t.ptr for t in a], L.stream_ptr(dev)), "kon_cross_bwd")
+        with _prof("cross_bwd"):
+            L.check(lib.kon_cross_bwd(*[t.ptr for t in a], L.stream_ptr(dev)), "kon_cross_bwd")
         return dx0, dw, db
 
 
@@ -205,8 +247,9 @@ class _Cin(torch.autograd.Function):
         wa, wk = L.tensor_array(ws_)
         ba, bk = L.tensor_array(bs_)
         a = [L._arg(t) for t in (x0, pooled, saved, work)]
-        L.check(lib.kon_cin_fwd(a[0].ptr, wa, ba, n_layers, a[1].ptr, a[2].ptr, a[3].ptr, precision,
-                                L.stream_ptr(dev)), "kon_cin_fwd")
+        with _prof("cin_fwd"):
+            L.check(lib.kon_cin_fwd(a[0].ptr, wa, ba, n_layers, a[1].ptr, a[2].ptr, a[3].ptr, precision,
+                                    L.stream_ptr(dev)), "kon_cin_fwd")
         ctx.save_for_backward(x0, saved, *ws_, *bs_)
         ctx.precision, ctx.n_layers = precision, n_layers
         ctx.work = work
@@ -229,8 +272,9 @@ class _Cin(torch.autograd.Function):
         dwa, k3 = L.tensor_array(dws)
         dba, k4 = L.tensor_array(dbs)
         a = [L._arg(t) for t in (x0, g, saved, dx0, ctx.work)]
-        L.check(lib.kon_cin_bwd(a[0].ptr, wa, ba, nl, a[1].ptr, a[2].ptr, a[3].ptr, dwa, dba, a[4].ptr,
-                                ctx.precision, L.stream_ptr(dev)), "kon_cin_bwd")
+        with _prof("cin_bwd"):
+            L.check(lib.kon_cin_bwd(a[0].ptr, wa, ba, nl, a[1].ptr, a[2].ptr, a[3].ptr, dwa, dba, a[4].ptr,
+                                    ctx.precision, L.stream_ptr(dev)), "kon_cin_bwd")
         return (dx0, None, None, *dws, *dbs)
 
 
@@ -251,7 +295,8 @@ class _Attn(torch.autograd.Function):
         H, d = wq.shape[1], wq.shape[2]
         y = torch.empty((H, x.shape[0], x.shape[1], d), dtype=x.dtype, device=x.device)
         a = [L._arg(t) for t in (x, wq, wk, wr, gamma, beta, y)]
-        L.check(lib.kon_attn_fwd(*[L._p(t) for t in a], eps, flags, L.stream_ptr(x.device)), "kon_attn_fwd")
+        with _prof("attn_fwd"):
+            L.check(lib.kon_attn_fwd(*[L._p(t) for t in a], eps, flags, L.stream_ptr(x.device)), "kon_attn_fwd")
         ctx.save_for_backward(x, wq, wk, wr, gamma, beta)
         ctx.flags, ctx.eps = flags, eps
         return y
@@ -270,7 +315,8 @@ class _Attn(torch.autograd.Function):
         ws = _ws(lib.kon_attn_bwd_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], wq.shape[1],
                                                   wq.shape[2], dev.index or 0), dev)
         a = [L._arg(t) for t in (x, wq, wk, wr, gamma, beta, gy, dx, dwq, dwk, dwr, dg, db, ws)]
-        L.check(lib.kon_attn_bwd(*[L._p(t) for t in a], ctx.eps, ctx.flags, L.stream_ptr(dev)), "kon_attn_bwd")
+        with _prof("attn_bwd"):
+            L.check(lib.kon_attn_bwd(*[L._p(t) for t in a], ctx.eps, ctx.flags, L.stream_ptr(dev)), "kon_attn_bwd")
         return dx, dwq, dwk, dwr, dg, db, None, None
 
 
@@ -281,3 +327,46 @@ def attention(x, wq, wk, wr=None, gamma=None, beta=None, use_scale=True, use_ln=
              (L.KON_ATTN_USE_RES if use_res else 0) | (L.KON_ATTN_RELU if relu else 0))
     return _Attn.apply(x, wq, wk, wr if use_res else None, gamma if use_ln else None,
                        beta if use_ln else None, flags, eps)
+
+
+# --------------------------------------------------------------------------- #
+# a11: the concat buffer (StackLayer without the copy)
+# --------------------------------------------------------------------------- #
+class _EmbedConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, arena, ids, field_row_offset, dense, width):
+        B, F = ids.shape[0], ids.shape[1]
+        dim = arena.shape[1]
+        Fk = F * dim
+        nd = 0 if dense is None else dense.shape[1]
+        assert width % 4 == 0 and width >= Fk + nd
+        xcat = torch.empty((B, width), dtype=arena.dtype, device=arena.device)
+        embed_fwd_raw(arena.detach(), ids, field_row_offset, False, out=xcat[:, :Fk].view(B, F, dim))
+        if nd:
+            xcat[:, Fk:Fk + nd] = dense
+        if width > Fk + nd:
+            xcat[:, Fk + nd:] = 0
+        ctx.save_for_backward(ids)
+        ctx.arena, ctx.offs, ctx.Fk, ctx.nd = arena, field_row_offset, Fk, nd
+        ctx.dense_grad = dense is not None and dense.requires_grad
+        return xcat
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        arena = ctx.arena
+        B, F = ids.shape[0], ids.shape[1]
+        if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
+            g = g.contiguous()
+        if arena.requires_grad:
+            sg = embed_bwd_raw(g[:, :ctx.Fk].view(B, F, ctx.Fk // F), ids, ctx.offs)
+            if not hasattr(arena, "kon_sparse_grads"):
+                arena.kon_sparse_grads = []
+            arena.kon_sparse_grads.append(sg)
+        gd = g[:, ctx.Fk:ctx.Fk + ctx.nd] if ctx.dense_grad else None
+        return None, None, None, gd, None
+
+
+def embed_lookup_concat(arena, ids, field_row_offset, dense, width):
+    """-> xcat [B,width] = [F*dim embedding columns | dense | zero pad] (see models.py)."""
+    return _EmbedConcat.apply(arena, ids, tuple(field_row_offset), dense, width)

@@ -1,0 +1,81 @@
+"""One training step of a CTR model the way ``model.compile(loss=binary_crossentropy,
+optimizer='adam'); model.fit(...)`` runs it in the reference (example/ctr_example/
+un_seq.py:61-62): forward, loss, backward, optimizer.
+
+Dense parameters: ``torch.optim.Adam(fused=True)``.  Embedding arenas: the sparse gradient
+``(unique rows, summed grads)`` from ``kon_embed_bwd`` goes straight into the row-wise
+(lazy) Adam kernel ``kon_embed_adam`` together with the reference's L2 term (IL:217) -- the
+dense ``[R,dim]`` gradient Keras materialises is never formed.
+
+Multi-GPU (one process per GPU, see ``parallel.py``): dense grads are all-reduced in one flat
+bucket; the embedding exchange is handled inside the sharded embedding layer.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .models import XDeepFM, keras_binary_crossentropy
+
+
+class SparseAdam:
+    """Row-wise lazy Adam state for one arena."""
+
+    def __init__(self, arena: torch.nn.Parameter, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, l2=0.0):
+        self.arena = arena
+        self.m = torch.zeros_like(arena.data)
+        self.v = torch.zeros_like(arena.data)
+        self.lr, self.beta1, self.beta2, self.eps, self.l2 = lr, beta1, beta2, eps, l2
+        self.t = 0
+
+    def step(self):
+        sgs = getattr(self.arena, "kon_sparse_grads", None)
+        if not sgs:
+            return
+        self.t += 1
+        for sg in sgs:
+            ops.embed_adam(self.arena.data, self.m, self.v, sg, self.lr, self.beta1, self.beta2, self.eps,
+                           self.l2, self.t)
+        self.arena.kon_sparse_grads = []
+
+
+class Trainer:
+    def __init__(self, model, lr: float = 1e-3, dist_ctx=None):
+        self.model = model
+        self.dist = dist_ctx
+        dense = model.dense_parameters()
+        self._dense_params = dense
+        self.dense_opt = None
+        self.lr = lr
+        self.sparse_opts = []
+        for emb in (model.sparse_embed, model.linear_embed):
+            if emb is not None:
+                self.sparse_opts.append(SparseAdam(emb.arena, lr=lr, l2=emb.emb_reg))
+        self.is_sigmoid = isinstance(model, XDeepFM)
+
+    def _ensure_dense_opt(self):
+        if self.dense_opt is None:      # lazily: layers build their weights on first call
+            self._dense_params = self.model.dense_parameters()
+            self.dense_opt = torch.optim.Adam(self._dense_params, lr=self.lr, eps=1e-7, fused=True)
+
+    def loss(self, dense, ids, labels):
+        out = self.model(dense, ids)
+        return keras_binary_crossentropy(labels.view(out.shape), out)
+
+    def step(self, dense, ids, labels) -> torch.Tensor:
+        """labels: one-hot ``[B,2]`` (``to_categorical``, DP:359) for the softmax(2) heads,
+        ``[B,1]`` for XDeepFM's sigmoid head.  Returns the (device) loss."""
+        for so in self.sparse_opts:
+            so.arena.kon_sparse_grads = []
+        loss = self.loss(dense, ids, labels)
+        self._ensure_dense_opt()
+        self.dense_opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.dist is not None:
+            self.dist.allreduce_dense_grads(self._dense_params)
+        self.dense_opt.step()
+        for so in self.sparse_opts:
+            so.step()
+        return loss.detach()

@@ -40,7 +40,12 @@ import torch
 
 def keras_add(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     """``tf.keras.layers.Add``: left-to-right sequential sum with broadcasting
-    of size-1 dims (TF ``_Merge._merge_function``: ``out = x[0]; out += x[i]``)."""
+    of size-1 dims (TF ``_Merge._merge_function``: ``out = x[0]; out += x[i]``).
+    Inputs of lower rank are first expanded at axis 1 until all ranks match
+    (``_Merge.call``: "expand each of them at axis=1"), e.g. ``[B,1,1] + [B,1]``
+    is ``[B,1,1]``, not numpy's right-aligned ``[B,B,1]``."""
+    nd = max(t.dim() for t in tensors)
+    tensors = [t.reshape(tuple(t.shape[:1]) + (1,) * (nd - t.dim()) + tuple(t.shape[1:])) for t in tensors]
     out = tensors[0]
     for t in tensors[1:]:
         out = out + t

@@ -1,0 +1,99 @@
+"""-m "not gpu": the C-ABI library loads and exports every symbol include/kon_b200.h declares,
+rejects CPU tensors loudly (no fallback), and the host-side layer logic."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from ml_function_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    return _lib
+
+
+def test_header_symbols_all_exported():
+    L = _lib()
+    hdr = open(os.path.join(ROOT, "include", "kon_b200.h")).read()
+    declared = set(re.findall(r"\b(kon_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in kon_b200.h but not exported"
+    assert declared == set(L.EXPORTED_SYMBOLS)
+    assert lib.kon_abi_version() == 1
+
+
+def test_cpu_tensors_are_rejected_not_computed():
+    L = _lib()
+    from ml_function_b200 import ops
+    v = torch.randn(4, 3, 8)
+    with pytest.raises(L.KonError, match="not a CUDA tensor"):
+        ops.fm(v, None)
+    with pytest.raises(L.KonError):
+        ops.embed_fwd_raw(torch.randn(10, 4), torch.zeros(2, 1, dtype=torch.int32), [0, 10])
+    with pytest.raises(L.KonError):
+        ops.cross(torch.randn(4, 8), torch.randn(2, 8), torch.randn(2, 8))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    L = _lib()
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libkon_b200.so")
+    with pytest.raises(L.KonError, match="no CPU or PyTorch fallback"):
+        L.lib()
+
+
+def test_workspace_queries_need_no_gpu():
+    L = _lib()
+    lib = L.lib()
+    assert lib.kon_embed_bwd_workspace_bytes(65536 * 26, 16) > 65536 * 26 * 20
+    hs = L.i32_array([200, 200, 200])
+    assert lib.kon_cin_saved_bytes(128, 26, 16, hs, 3, L.KON_CIN_FP32) == 128 * 16 * 600 * 4
+
+
+def test_pack_ids_reference_call_convention():
+    from ml_function_b200.layers import pack_ids
+    cols = [torch.tensor([[1.0], [2.0], [3.0]]), torch.tensor([[0.0], [5.0], [7.0]])]   # float32 Keras Inputs (DP:290)
+    ids = pack_ids(cols)
+    assert ids.dtype == torch.int32 and ids.shape == (3, 2) and ids[2, 1] == 7
+    seq = [torch.zeros(3, 5, dtype=torch.int64), torch.ones(3, 5, dtype=torch.int64)]
+    assert pack_ids(seq).shape == (3, 2, 5)
+
+
+def test_sparse_fea_fields_match_reference():
+    from ml_function_b200.layers import make_sparse_fea, sparseFea
+    assert sparseFea._fields == ('fea_name', 'word_size', 'input_dim', 'cross_unit', 'linear_unit', 'pre_weight',
+                                 'mask_zero', 'is_trainable', 'input_length', 'sample_num', 'batch_size', 'emb_reg')
+    f = make_sparse_fea("14", 100)
+    assert f.cross_unit == 8 and f.linear_unit == 1 and f.emb_reg == 1e-8 and f.input_length == 1
+
+
+def test_ref_to_phys_row_permutation():
+    from ml_function_b200 import layers as KL, models as KM
+    sp = [KL.make_sparse_fea(str(i), 5, cross_unit=4) for i in range(3)]
+    de = [KL.denseFea(str(i), None) for i in range(13)]
+    fea = KM.FeatureInput(sp, de, useLinear=True, device="cpu")
+    m = KM.DeepFM(fea, hidden_units=[8, 4])
+    assert m.W == 28 and m.Fk == 12
+    w = torch.arange(25, dtype=torch.float32).view(25, 1)
+    ph = m.ref_to_phys_rows(w)
+    assert ph.shape == (28, 1)
+    assert ph[:12, 0].tolist() == list(range(13, 25)) and ph[12:25, 0].tolist() == list(range(13))
+    assert ph[25:].abs().sum() == 0
+
+
+def test_bench_reference_arm_line():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "fm",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0

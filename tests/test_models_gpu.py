@@ -1,0 +1,184 @@
+"""-m gpu: the committed golden vectors and whole models (reference builders) through the
+C-ABI, forward and backward, against the CPU oracle with identical injected weights."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_rel, gen, offsets, rel_err
+from oracle import kon_oracle as ko
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "kon_golden.npz"))
+
+
+def _g(name):
+    return torch.from_numpy(GOLD[name]).to(DEV)
+
+
+def test_golden_vectors_through_the_abi():
+    from ml_function_b200 import _lib as L, ops
+    offs = offsets(GOLD["emb_rows"].tolist())
+    ids = _g("emb_ids")
+    out = ops.embed_fwd_raw(_g("emb_tables"), ids, offs)
+    assert torch.equal(out.cpu(), torch.from_numpy(GOLD["emb_out"]))               # bit-exact lookup
+    sg = ops.embed_bwd_raw(_g("emb_dout"), ids, offs)
+    n = int(sg.n.item())
+    assert np.array_equal(sg.rows[:n].cpu().numpy(), GOLD["emb_unique_rows"])       # bit-exact routing
+    assert_rel(sg.grads[:n], torch.from_numpy(GOLD["emb_grads"]), 1e-6, "golden emb grads")
+    lin = ops.embed_fwd_raw(_g("emb_lins"), ids, offs)
+    assert_rel(ops.fm(out, lin[..., 0]), torch.from_numpy(GOLD["fm_out_f64"]), 1e-5, "golden fm")
+    cw, cb = _g("cross_w")[..., 0].contiguous(), _g("cross_b")[..., 0].contiguous()
+    assert_rel(ops.cross(_g("cross_x"), cw, cb), torch.from_numpy(GOLD["cross_out"][..., 0]), 1e-5, "golden cross")
+    pooled = ops.cin(_g("cin_x0"), [_g("cin_w0")[0], _g("cin_w1")[0]], [_g("cin_b0"), _g("cin_b1")], L.KON_CIN_FP32)
+    assert_rel(pooled, torch.from_numpy(GOLD["cin_pooled_f64"]), 1e-5, "golden cin")
+    y = ops.attention(_g("attn_x"), _g("attn_wq"), _g("attn_wk"), _g("attn_wr"), _g("attn_gamma"), _g("attn_beta"))
+    assert_rel(y, torch.from_numpy(GOLD["attn_out"]), 1e-5, "golden attention")
+
+
+# ---------------------------------------------------------------------------------------
+def _params(name, rows, k, g, hidden=(24, 16, 8), conv=(10, 9, 8), heads=2, d=4, cross=3):
+    F = len(rows)
+    p = {}
+    for f, r in enumerate(rows):
+        p[f"emb_{f}"] = torch.randn(r, k, generator=g) * 0.5
+        p[f"lin_{f}"] = torch.randn(r, 1, generator=g) * 0.5
+    D = 13 + F * k
+    dims = [D] + list(hidden)
+    for i in range(3):
+        p[f"dnn_w{i}"] = ko.glorot_uniform((dims[i], dims[i + 1]), g)
+        p[f"dnn_b{i}"] = torch.randn(dims[i + 1], generator=g) * 0.1
+    if name == "fm":
+        p["head_w"], p["head_b"] = ko.glorot_uniform((k, 2), g), torch.randn(2, generator=g) * 0.1
+    if name == "deepfm":
+        p["head_w"], p["head_b"] = ko.glorot_uniform((k + hidden[-1], 2), g), torch.randn(2, generator=g) * 0.1
+    if name == "dcn":
+        for i in range(cross):
+            p[f"outer_weight_{i}"] = ko.glorot_uniform((D, 1), g)
+            p[f"outer_bias_{i}"] = torch.randn(D, 1, generator=g) * 0.05
+        p["head_w"], p["head_b"] = ko.glorot_uniform((D + hidden[-1], 2), g), torch.zeros(2)
+    if name == "xdeepfm":
+        hp = F
+        for i, n in enumerate(conv):
+            p[f"cin_w{i}"] = ko.glorot_uniform((1, hp * F, n), g)
+            p[f"cin_b{i}"] = torch.randn(n, generator=g) * 0.05
+            hp = n
+        p["cin_logit_w"], p["cin_logit_b"] = ko.glorot_uniform((len(conv) * k, 1), g), torch.zeros(1)
+        p["dnn_logit_w"], p["dnn_logit_b"] = ko.glorot_uniform((hidden[-1], 1), g), torch.zeros(1)
+    if name == "autoint":
+        for w in ("query_w", "key_w", "res_w"):
+            p[w] = ko.glorot_uniform((k, heads, d), g)
+        p["ln_gamma"], p["ln_beta"] = torch.rand(d, generator=g) + 0.5, torch.randn(d, generator=g) * 0.1
+        p["head_w"], p["head_b"] = ko.glorot_uniform((heads * F * d, 2), g), torch.zeros(2)
+    return p
+
+
+def _build(name, rows, k, p, cin_precision="fp32", hidden=(24, 16, 8), conv=(10, 9, 8)):
+    from ml_function_b200 import layers as KL, models as KM
+    sp = [KL.make_sparse_fea(str(14 + i), r, cross_unit=k) for i, r in enumerate(rows)]
+    de = [KL.denseFea(str(1 + i), None) for i in range(13)]
+    fea = KM.FeatureInput(sp, de, useLinear=True, useAddLinear=(name == "xdeepfm"), device=DEV)
+    m = {"fm": lambda: KM.FM(fea), "deepfm": lambda: KM.DeepFM(fea, hidden_units=list(hidden)),
+         "dcn": lambda: KM.DCN(fea, hidden_units=list(hidden), cross_hidden=3),
+         "xdeepfm": lambda: KM.XDeepFM(fea, conv_size=list(conv), hidden_units=list(hidden), cin_precision=cin_precision),
+         "autoint": lambda: KM.AutoInt(fea, attention_dim=4, attention_head_dim=2)}[name]()
+    m.load_reference_params({k_: v.to(DEV) for k_, v in p.items()})
+    return m
+
+
+ORACLE = {"fm": ko.model_fm, "deepfm": ko.model_deepfm, "dcn": ko.model_dcn, "xdeepfm": ko.model_xdeepfm,
+          "autoint": ko.model_autoint}
+
+
+@pytest.mark.parametrize("name", ["fm", "deepfm", "dcn", "xdeepfm", "autoint"])
+def test_model_forward_backward_matches_oracle(name):
+    from ml_function_b200.models import keras_binary_crossentropy
+    g = gen(11)
+    rows = [7, 300, 5, 41, 2, 1000]
+    B, k = 517, 8
+    p = _params(name, rows, k, g)
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32)
+    dense = torch.rand(B, 13, generator=g)
+    y = (torch.rand(B, generator=g) < 0.3).float()
+    labels = y.view(B, 1, 1) if name == "xdeepfm" else torch.stack([1 - y, y], 1)
+    # oracle in fp64 = truth; in fp32 = the reference's own arithmetic (its error sets the scale)
+    p64 = {k_: v.double().requires_grad_(True) for k_, v in p.items()}
+    out64 = ORACLE[name](p64, dense.double(), ids)
+    loss64 = ko.binary_crossentropy(labels.double(), out64)
+    loss64.backward()
+    out32 = ORACLE[name](p, dense, ids)
+    model = _build(name, rows, k, p)
+    out = model(dense.to(DEV), ids.to(DEV))
+    assert out.shape == out64.shape
+    e_ref = rel_err(out32, out64)
+    e = assert_rel(out, out64, max(1e-5, 4 * e_ref), f"{name} forward")
+    loss = keras_binary_crossentropy(labels.to(DEV), out)
+    loss.backward()
+    assert abs(loss.item() - loss64.item()) < 1e-5 * max(1.0, abs(loss64.item()))
+    # sparse gradient of the embedding arena == dense oracle gradient, row for row
+    offs = offsets(rows)
+    sgs = model.sparse_embed.arena.kon_sparse_grads
+    assert len(sgs) == 1 and model.sparse_embed.arena.grad is None
+    dense_g = sgs[0].to_dense(offs[-1]).cpu()
+    ref_g = torch.cat([p64[f"emb_{f}"].grad for f in range(len(rows))])
+    assert_rel(dense_g, ref_g, 2e-5, f"{name} embedding grad")
+    n = int(sgs[0].n.item())
+    touched = torch.unique((ids.long() + torch.tensor(offs[:-1])).reshape(-1))
+    assert torch.equal(sgs[0].rows[:n].cpu().long(), touched)                       # bit-exact routing
+    if name in ("fm", "deepfm", "xdeepfm"):
+        lg = model.linear_embed.arena.kon_sparse_grads[0].to_dense(offs[-1]).cpu()
+        assert_rel(lg, torch.cat([p64[f"lin_{f}"].grad for f in range(len(rows))]), 2e-5, f"{name} linear grad")
+    # a few dense weights
+    if name == "dcn":
+        ref_w = torch.stack([model.ref_to_phys_rows(p64[f"outer_weight_{i}"].grad)[:, 0] for i in range(3)])
+        assert_rel(model.cross.kernel.grad, ref_w, 2e-5, "dcn cross kernel grad")
+    if name == "xdeepfm":
+        for i in range(3):
+            assert_rel(model.cin.conv_kernels[i].grad, p64[f"cin_w{i}"].grad, 2e-5, f"cin_w{i} grad")
+            assert_rel(model.cin.conv_biases[i].grad, p64[f"cin_b{i}"].grad, 2e-5, f"cin_b{i} grad")
+    if name == "autoint":
+        att = model.blocks[0].other_dense[0]
+        assert_rel(att.query_w.grad, p64["query_w"].grad, 2e-5, "query_w grad")
+        assert_rel(att.key_w.grad, p64["key_w"].grad, 2e-5, "key_w grad")
+        assert att.value_w.grad is None                                             # never read (BL:360)
+    if name in ("deepfm", "dcn", "xdeepfm"):
+        assert_rel(model.dnn.kernels[0].grad, model.ref_to_phys_rows(p64["dnn_w0"].grad), 2e-5, "dnn_w0 grad")
+
+
+def test_reference_list_call_convention():
+    """Model called the way the reference calls it: lists of per-feature [B,1] tensors, ids as
+    float32 (DP:290-292)."""
+    g = gen(5)
+    rows = [9, 30, 4]
+    B, k = 64, 8
+    p = _params("deepfm", rows, k, g)
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1)
+    dense = torch.rand(B, 13, generator=g)
+    model = _build("deepfm", rows, k, p)
+    a = model(dense.to(DEV), ids.to(torch.int32).to(DEV))
+    b = model([dense[:, j:j + 1].to(DEV) for j in range(13)], [ids[:, f:f + 1].float().to(DEV) for f in range(3)])
+    assert torch.equal(a, b)
+
+
+def test_train_step_updates_only_touched_rows_and_lowers_loss():
+    from ml_function_b200.train import Trainer
+    g = gen(9)
+    rows = [50, 3000, 7]
+    B, k = 1024, 8
+    p = _params("deepfm", rows, k, g)
+    model = _build("deepfm", rows, k, p)
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).to(DEV)
+    dense = torch.rand(B, 13, generator=g).to(DEV)
+    y = (torch.rand(B, generator=g) < 0.3).float()
+    labels = torch.stack([1 - y, y], 1).to(DEV)
+    tr = Trainer(model, lr=1e-2)
+    before = model.sparse_embed.arena.detach().clone()
+    l0 = tr.step(dense, ids, labels).item()
+    for _ in range(20):
+        l1 = tr.step(dense, ids, labels).item()
+    assert l1 < l0
+    changed = (model.sparse_embed.arena.detach() != before).any(dim=1).nonzero().flatten().cpu()
+    touched = torch.unique((ids.cpu().long() + torch.tensor(offsets(rows)[:-1])).reshape(-1))
+    assert torch.equal(changed, touched)

@@ -1,0 +1,140 @@
+"""-m "not gpu": the oracle against its fp64 closed forms, torch autograd, and the committed
+golden vectors (tests/golden/make_golden.py).  The reference has no tests of its own."""
+import itertools
+import os
+
+import numpy as np
+import torch
+
+from helpers import gen, rel_err
+from oracle import kon_oracle as ko
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "kon_golden.npz"))
+
+
+def _t(name):
+    return torch.from_numpy(GOLD[name])
+
+
+def test_golden_embedding_and_grad():
+    rows = GOLD["emb_rows"].tolist()
+    offs = np.concatenate([[0], np.cumsum(rows)])
+    tabs = [_t("emb_tables")[offs[f]:offs[f + 1]] for f in range(3)]
+    ids = _t("emb_ids")
+    out = torch.cat(ko.sparse_embed([ids[:, f:f + 1] for f in range(3)], tabs, use_flatten=False), 1)
+    assert torch.equal(out, _t("emb_out"))
+    ur, ug = [], []
+    for f in range(3):
+        u, g = ko.embedding_grad(GOLD["emb_ids"][:, f], GOLD["emb_dout"][:, f], rows[f])
+        ur.append(u + offs[f]); ug.append(g)
+    assert np.array_equal(np.concatenate(ur), GOLD["emb_unique_rows"])
+    assert np.array_equal(np.concatenate(ug), GOLD["emb_grads"])
+    # against autograd of the gather
+    w = torch.cat(tabs).clone().requires_grad_(True)
+    gl = (ids.long() + torch.tensor(offs[:3])).reshape(-1)
+    (w[gl].reshape(-1, 3, 8) * _t("emb_dout")).sum().backward()
+    dense = np.zeros_like(GOLD["emb_tables"]); dense[GOLD["emb_unique_rows"]] = GOLD["emb_grads"]
+    assert rel_err(w.grad, torch.from_numpy(dense)) < 1e-6
+
+
+def test_golden_fm_and_closed_form():
+    rows = GOLD["emb_rows"].tolist()
+    offs = np.concatenate([[0], np.cumsum(rows)])
+    ids = _t("emb_ids")
+    idl = [ids[:, f:f + 1] for f in range(3)]
+    emb = ko.sparse_embed(idl, [_t("emb_tables")[offs[f]:offs[f + 1]] for f in range(3)], use_flatten=False)
+    lin = ko.sparse_embed(idl, [_t("emb_lins")[offs[f]:offs[f + 1]] for f in range(3)], use_flatten=False)
+    y = ko.fm_layer(emb, lin)
+    assert y.shape == (33, 1, 8)                       # the "FM" keeps the embedding axis (IL:161-170)
+    assert torch.equal(y[:, 0], _t("fm_out"))
+    assert rel_err(y[:, 0], _t("fm_out_f64")) < 1e-5
+
+
+def test_fm_pair_order_and_count():
+    g = gen(3)
+    xs = [torch.randn(4, 1, 3, generator=g, dtype=torch.float64) for _ in range(26)]
+    pairs = ko.inner_layer(xs)
+    assert len(pairs) == 325
+    assert torch.equal(pairs[1], xs[0] * xs[2])         # itertools.combinations order
+    v = torch.cat(xs, 1)
+    ref = ko.fm_closed_form(v, torch.zeros(4, 26, dtype=torch.float64))
+    assert rel_err(ko.inner_layer(xs, use_add=True)[:, 0], ref) < 1e-12
+
+
+def test_golden_cross():
+    x, w, b = _t("cross_x"), _t("cross_w"), _t("cross_b")
+    out = ko.cross_layer(x, list(w), list(b))
+    assert out.shape == (33, 29, 1)
+    assert torch.equal(out, _t("cross_out"))
+    # closed form in fp64
+    x0 = x.double(); xl = x0
+    for l in range(3):
+        s = (xl * w[l, :, 0].double()).sum(1, keepdim=True)
+        xl = x0 * s + xl + b[l, :, 0].double()
+    assert rel_err(out[..., 0], xl) < 1e-5
+
+
+def test_golden_cin_mirror_equals_closed_form():
+    x0 = _t("cin_x0")
+    ws, bs = [_t("cin_w0"), _t("cin_w1")], [_t("cin_b0"), _t("cin_b1")]
+    pooled = ko.cin(x0, ws, bs, return_pooled=True)
+    assert pooled.shape == (33, 2 * 4)                 # pools over the feature maps -> [B,D] per layer
+    assert torch.equal(pooled, _t("cin_pooled"))
+    cf, zs = ko.cin_closed_form(x0.double(), [w.double() for w in ws], [b.double() for b in bs])
+    assert rel_err(cf, _t("cin_pooled_f64")) < 1e-12
+    assert rel_err(pooled, cf) < 1e-5
+    # channel index is h*m + i (IL:317-318): perturb one weight and watch the right product move
+    m, h, i, o = 5, 2, 3, 1
+    w2 = ws[0].double().clone(); w2[0, h * m + i, o] += 1.0
+    _, z2 = ko.cin_closed_form(x0.double(), [w2, ws[1].double()], [b.double() for b in bs])
+    dz = z2[0] - zs[0]
+    expect = x0[:, h].double() * x0[:, i].double()      # layer 1: pre == x0
+    assert rel_err(dz[:, :, o], expect) < 1e-12
+
+
+def test_golden_attention_block_semantics():
+    x, wq, wk, wr = _t("attn_x"), _t("attn_wq"), _t("attn_wk"), _t("attn_wr")
+    gam, bet = _t("attn_gamma"), _t("attn_beta")
+    y = ko.autoint_block(x, wq, wk, wr, gam, bet)
+    assert y.shape == (2, 33, 6, 4)
+    assert torch.equal(y, _t("attn_out"))
+    # sigmoid (not softmax), V = X key_w, LN eps 1e-3 before the residual, ReLU last
+    xd = x.double()
+    for h in range(2):
+        q, k = xd @ wq[:, h].double(), xd @ wk[:, h].double()
+        s = torch.sigmoid(q @ k.transpose(1, 2) / 2.0)
+        o = s @ k
+        mu, var = o.mean(-1, keepdim=True), o.var(-1, unbiased=False, keepdim=True)
+        ln = (o - mu) / torch.sqrt(var + 1e-3) * gam.double() + bet.double()
+        ref = torch.relu(ln + xd @ wr[:, h].double())
+        assert rel_err(y[h], ref) < 1e-5
+
+
+def test_keras_add_rank_expansion():
+    a, b = torch.ones(5, 1, 1), torch.ones(5, 1)
+    assert ko.keras_add([a, b]).shape == (5, 1, 1)
+
+
+def test_oracle_models_run_and_shapes():
+    g = gen(7)
+    rows = [5, 9, 4]
+    B, k = 12, 4
+    p = {}
+    for f, r in enumerate(rows):
+        p[f"emb_{f}"] = torch.randn(r, k, generator=g); p[f"lin_{f}"] = torch.randn(r, 1, generator=g)
+    D = 13 + 3 * k
+    dims = [D, 8, 6, 5]
+    for i in range(3):
+        p[f"dnn_w{i}"] = torch.randn(dims[i], dims[i + 1], generator=g) * 0.2
+        p[f"dnn_b{i}"] = torch.randn(dims[i + 1], generator=g) * 0.1
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1)
+    dense = torch.rand(B, 13, generator=g)
+    p["head_w"], p["head_b"] = torch.randn(k + 5, 2, generator=g), torch.zeros(2)
+    assert ko.model_deepfm(p, dense, ids).shape == (B, 2)
+    hp = 3
+    for i, n in enumerate((4, 3, 2)):
+        p[f"cin_w{i}"] = torch.randn(1, hp * 3, n, generator=g) * 0.3; p[f"cin_b{i}"] = torch.zeros(n); hp = n
+    p["cin_logit_w"], p["cin_logit_b"] = torch.randn(3 * k, 1, generator=g), torch.zeros(1)
+    p["dnn_logit_w"], p["dnn_logit_b"] = torch.randn(5, 1, generator=g), torch.zeros(1)
+    out = ko.model_xdeepfm(p, dense, ids)
+    assert out.shape == (B, 1, 1) and float(out.min()) > 0 and float(out.max()) < 1
