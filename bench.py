@@ -82,7 +82,7 @@ def sample_clocks_start(path):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
         f = open(path, "w")
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                 stdout=f, stderr=subprocess.DEVNULL), f
     except Exception:
         return None, None

@@ -487,6 +487,9 @@ class ScoreLayer(nn.Module):
 
     @staticmethod
     def summed(inputs):
+        # Keras Add: lower-rank inputs are expanded at axis 1 until all ranks match (_Merge.call)
+        nd = max(t.dim() for t in inputs)
+        inputs = [t.reshape(tuple(t.shape[:1]) + (1,) * (nd - t.dim()) + tuple(t.shape[1:])) for t in inputs]
         out = inputs[0]
         for t in inputs[1:]:
             out = out + t

@@ -79,7 +79,7 @@ def embed_fwd_raw(arena, ids, field_row_offset: Sequence[int], sum_fields=False,
         out = torch.empty(shape, dtype=arena.dtype, device=arena.device)
     offs = L.i64_array(list(field_row_offset))
     a, i, o, ob = L._arg(arena), L._arg(ids), L._arg(out), L._arg(oob)
-    with _prof("embed_fwd"):
+    with _prof("embed_fwd" if dim > 1 else "embed_fwd_lin"):
         L.check(lib.kon_embed_fwd(a.ptr, i.ptr, offs, F, o.ptr, L._p(ob),
                                   L.KON_EMBED_SUM_FIELDS if sum_fields else 0, L.stream_ptr(arena.device)),
                 "kon_embed_fwd")
@@ -99,7 +99,7 @@ def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int]) -> SparseGrad:
     ws = _ws(lib.kon_embed_bwd_workspace_bytes(n, dim), dev)
     offs = L.i64_array(list(field_row_offset))
     a = [L._arg(t) for t in (d_out, ids, rows, grads, nu, ws)]
-    with _prof("embed_bwd"):
+    with _prof("embed_bwd" if dim > 1 else "embed_bwd_lin"):
         L.check(lib.kon_embed_bwd(a[0].ptr, a[1].ptr, offs, F, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
                                   L.stream_ptr(dev)), "kon_embed_bwd")
     return SparseGrad(rows, grads, nu)
