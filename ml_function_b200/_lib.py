@@ -15,7 +15,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkon_b200.so")
+# KON_B200_LIB selects an experimental build of the same library (kernel-parameter sweeps)
+LIB_PATH = os.environ.get("KON_B200_LIB") or os.path.join(_HERE, "libkon_b200.so")
 
 KON_EMBED_SUM_FIELDS = 1
 KON_CIN_FP32, KON_CIN_BF16 = 0, 1

@@ -29,12 +29,28 @@ namespace kon {
 
 namespace {
 
-constexpr int kTcThreads = 320;
-constexpr int kG = 3;        // k-steps (of 16) per A slot and per B stage
-constexpr int kNS = 2;       // A slots per sub-tile
-constexpr int kS = 8;        // B stages
+#ifndef KON_TC_SUB
+#define KON_TC_SUB 2
+#endif
+constexpr int kSub = KON_TC_SUB;           // 128-row sub-tiles per CTA sharing every B stage
+constexpr int kProdWarps = 4 * kSub;
+constexpr int kTcThreads = 32 * (kProdWarps + 2);
+#ifndef KON_TC_G
+#define KON_TC_G 3
+#endif
+#ifndef KON_TC_NS
+#define KON_TC_NS (KON_TC_SUB == 2 ? 2 : 12)
+#endif
+#ifndef KON_TC_S
+#define KON_TC_S 8
+#endif
+constexpr int kG = KON_TC_G;     // k-steps (of 16) per A slot and per B stage
+constexpr int kNS = KON_TC_NS;   // A slots per sub-tile (8*kG*kNS <= 48 TMEM columns)
+constexpr int kS = KON_TC_S;     // B stages
 constexpr int kMaxN = 208;
+// TMEM columns: kSub == 2: D0 [0,208) A0 [208,256) D1 [256,464) A1 [464,512);  kSub == 1: D0 [0,208) A0 [208,496)
 constexpr uint32_t kColD0 = 0, kColA0 = 208, kColD1 = 256, kColA1 = 464;
+static_assert(8 * kG * kNS <= (kSub == 2 ? 48 : 304), "A ring does not fit in tensor memory");
 
 __host__ __device__ constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
 __host__ __device__ constexpr int lcm_(int a, int b) { return a / gcd_(a, b) * b; }
@@ -54,7 +70,7 @@ __device__ __forceinline__ float bf16_to_f32(unsigned short u) { return __uint_a
 
 struct Barriers {
   uint64_t b_full[kS], b_empty[kS];
-  uint64_t a_full[2][kNS], a_empty[2][kNS];
+  uint64_t a_full[kSub][kNS], a_empty[kSub][kNS];
   uint64_t d_full;
   uint32_t tmem_base;
 };
@@ -100,7 +116,7 @@ struct FwdArgs {
   long long rows;               // B*D
   int D, Hp, N, N8, nk;
   uint32_t kblk;                // bytes per k-step block of wpack
-  long long n_pairs;            // ceil(rows / 256)
+  long long n_pairs;            // ceil(rows / (128*kSub))
 };
 
 template <int MF>
@@ -111,17 +127,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   static_assert(MF % 2 == 0, "field count must be even (bf16x2 pairs never straddle an h)");
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Barriers bars;
+  __shared__ float s_bias[kMaxN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < kMaxN; i += kTcThreads) s_bias[i] = i < a.N ? a.bias[i] : 0.f;
 
   if (tid == 0) {
     for (int i = 0; i < kS; ++i) { mbar_init(&bars.b_full[i], 1); mbar_init(&bars.b_empty[i], 1); }
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < kSub; ++s)
       for (int i = 0; i < kNS; ++i) { mbar_init(&bars.a_full[s][i], 4); mbar_init(&bars.a_empty[s][i], 1); }
     mbar_init(&bars.d_full, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tc::tmem_alloc(&bars.tmem_base, 512);
+  if (warp == kProdWarps) tc::tmem_alloc(&bars.tmem_base, 512);
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
@@ -130,7 +148,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   const int n_groups = (a.nk + kG - 1) / kG;
   const uint32_t stage_bytes = kG * a.kblk;
 
-  if (warp < 8) {
+  if (warp < kProdWarps) {
     // ================= producers + epilogue =================================================
     const int sub = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -140,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
     uint32_t a_it = 0;   // A-slot uses so far (ring position)
     uint32_t tile_it = 0;
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x, ++tile_it) {
-      const long long r = pair * 256 + sub * 128 + (warp & 3) * 32 + lane;
+      const long long r = pair * (128 * kSub) + sub * 128 + (warp & 3) * 32 + lane;
       const bool valid = r < a.rows;
       const long long b = valid ? r / a.D : 0;
       const int d = valid ? (int)(r - b * a.D) : 0;
@@ -152,21 +170,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
         const float hi = valid ? __ldg(xrow + (long long)(2 * i + 1) * a.D) : 0.f;
         x2[i] = tc::pack_bf16(lo, hi);
       }
+      // pre[r,h] for the PH feature maps of a period, fetched one period ahead.  The raw loads
+      // land in distinct registers and are only touched (broadcast to bf16x2) a period later, so
+      // the L2 latency hides behind ~13 k-steps of work; out-of-range h reads a clamped address
+      // and is zeroed by the mask instead of branching around the load.
       const unsigned short* prow = a.pre ? a.pre + b * (long long)a.Hp * a.D + d : nullptr;
-      auto load_pre = [&](int h) -> uint32_t {
-        if (!valid || h >= a.Hp) return 0u;
-        if (prow) return bf16_bcast_raw(__ldg(prow + (long long)h * a.D));
-        return bf16_bcast(__ldg(xrow + (long long)h * a.D));
+      auto load_raw = [&](int h) -> uint32_t {
+        const int hc = min(h, a.Hp - 1);
+        if (prow) return (uint32_t)__ldg(prow + (long long)hc * a.D);
+        return __float_as_uint(__ldg(xrow + (long long)hc * a.D));
       };
-      uint32_t cur[PH], nxt[PH];
+      auto to_bcast = [&](uint32_t raw, int h) -> uint32_t {
+        if (!valid || h >= a.Hp) return 0u;
+        return prow ? bf16_bcast_raw((unsigned short)raw) : bf16_bcast(__uint_as_float(raw));
+      };
+      uint32_t cur[PH], nraw[PH];
 #pragma unroll
-      for (int j = 0; j < PH; ++j) cur[j] = load_pre(j);
+      for (int j = 0; j < PH; ++j) nraw[j] = load_raw(j);
 
       int ks_global = 0;     // k-step index within this tile
       int cnt = 0;           // k-steps written into the current slot
       for (int per = 0; per < n_periods; ++per) {
 #pragma unroll
-        for (int j = 0; j < PH; ++j) nxt[j] = load_pre((per + 1) * PH + j);
+        for (int j = 0; j < PH; ++j) cur[j] = to_bcast(nraw[j], per * PH + j);
+#pragma unroll
+        for (int j = 0; j < PH; ++j) nraw[j] = load_raw((per + 1) * PH + j);
 #pragma unroll
         for (int j = 0; j < PK; ++j) {
           if (ks_global < a.nk) {
@@ -196,35 +224,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < PH; ++j) cur[j] = nxt[j];
       }
       // ---- epilogue: z = D + bias; pooled = sum_o z; z^T (bf16) -> zt ---------------------
       mbar_wait(&bars.d_full, tile_it & 1);
       tc::fence_after();
       float rsum = 0.f;
       unsigned short* zrow = a.zt + b * (long long)a.N * a.D + d;       // zt[b,o,d] = zrow[o*D]
-      for (int o0 = 0; o0 < a.N8 * 8; o0 += 8) {
+      const int n_full = a.N & ~15;
+      for (int o0 = 0; o0 < n_full; o0 += 16) {
+        uint32_t v[16];
+        tc::ld16(tmem + lane_base + colD + o0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+          const float z0 = __uint_as_float(v[q]) + s_bias[o0 + q];
+          const float z1 = __uint_as_float(v[q + 1]) + s_bias[o0 + q + 1];
+          rsum += z0;
+          rsum += z1;
+          const uint32_t pk = tc::pack_bf16(z0, z1);
+          if (valid) {
+            zrow[(long long)(o0 + q) * a.D] = (unsigned short)(pk & 0xffffu);
+            zrow[(long long)(o0 + q + 1) * a.D] = (unsigned short)(pk >> 16);
+          }
+        }
+      }
+      for (int o0 = n_full; o0 < a.N; o0 += 8) {     // tail: N % 16 in {8} or ragged
         uint32_t v[8];
         tc::ld8(tmem + lane_base + colD + o0, v);
         tc::wait_ld();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int o = o0 + q;
-          if (o < a.N) {
-            const float z = __uint_as_float(v[q]) + __ldg(a.bias + o);
+          if (o0 + q < a.N) {
+            const float z = __uint_as_float(v[q]) + s_bias[o0 + q];
             rsum += z;
-            if (valid) {
-              const __nv_bfloat16 zb = __float2bfloat16_rn(z);
-              zrow[(long long)o * a.D] = *reinterpret_cast<const unsigned short*>(&zb);
-            }
+            if (valid) zrow[(long long)(o0 + q) * a.D] = (unsigned short)(tc::pack_bf16(z, 0.f) & 0xffffu);
           }
         }
       }
       if (valid) a.pooled[b * a.pooled_stride + a.pooled_col0 + d] = rsum;
       tc::fence_before();   // our tcgen05.ld are complete (wait_ld) before the next tile's a_full arrive
     }
-  } else if (warp == 8) {
+  } else if (warp == kProdWarps) {
     // ================= MMA issuer ===========================================================
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_bf16(128, a.N8 * 8, 0, 0);
@@ -240,7 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
           const uint32_t slot = a_it % kNS;
           const uint32_t apar = (a_it / kNS) & 1;
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
+          for (int sub = 0; sub < kSub; ++sub) {
             mbar_wait(&bars.a_full[sub][slot], apar);
             tc::fence_after();
             const uint32_t dcol = tmem + (sub ? kColD1 : kColD0);
@@ -276,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == kProdWarps) tc::tmem_dealloc(tmem, 512);
 }
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -368,7 +408,7 @@ int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias,
     a.N8 = L.N8[l];
     a.nk = L.nk[l];
     a.kblk = 2u * L.N8[l] * 128u;
-    a.n_pairs = (rows + 255) / 256;
+    a.n_pairs = (rows + 128 * kSub - 1) / (128 * kSub);
     const int grid = (int)std::min<long long>(a.n_pairs, sms);
     cin_fwd_tc_kernel<26><<<grid, kTcThreads, smem, st>>>(a);
     KON_LAUNCH_CHECK("cin_fwd_tc_kernel");
