@@ -21,59 +21,13 @@
 //   * TMEM map (512 columns): D0 [0,N) | A ring 0 [208,256) | D1 [256,256+N) | A ring 1 [464,512)
 //   * no swizzle: operands are stored as 8x8 core matrices (128 contiguous bytes); the layouts
 //     and descriptor fields were pinned on hardware with tools/tc_probe.cu.
-#include <cuda_bf16.h>
-
-#include "tc_ptx.cuh"
+#include "cin_tc_common.cuh"
 
 namespace kon {
 
+using namespace tcs;
+
 namespace {
-
-#ifndef KON_TC_SUB
-#define KON_TC_SUB 2
-#endif
-constexpr int kSub = KON_TC_SUB;           // 128-row sub-tiles per CTA sharing every B stage
-constexpr int kProdWarps = 4 * kSub;
-constexpr int kTcThreads = 32 * (kProdWarps + 2);
-#ifndef KON_TC_G
-#define KON_TC_G 3
-#endif
-#ifndef KON_TC_NS
-#define KON_TC_NS (KON_TC_SUB == 2 ? 2 : 12)
-#endif
-#ifndef KON_TC_S
-#define KON_TC_S 8
-#endif
-constexpr int kG = KON_TC_G;     // k-steps (of 16) per A slot and per B stage
-constexpr int kNS = KON_TC_NS;   // A slots per sub-tile (8*kG*kNS <= 48 TMEM columns)
-constexpr int kS = KON_TC_S;     // B stages
-constexpr int kMaxN = 208;
-// TMEM columns: kSub == 2: D0 [0,208) A0 [208,256) D1 [256,464) A1 [464,512);  kSub == 1: D0 [0,208) A0 [208,496)
-constexpr uint32_t kColD0 = 0, kColA0 = 208, kColD1 = 256, kColA1 = 464;
-static_assert(8 * kG * kNS <= (kSub == 2 ? 48 : 304), "A ring does not fit in tensor memory");
-
-__host__ __device__ constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
-__host__ __device__ constexpr int lcm_(int a, int b) { return a / gcd_(a, b) * b; }
-
-__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf16_bcast(float x) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const uint32_t u = *reinterpret_cast<const unsigned short*>(&h);
-  return u | (u << 16);
-}
-__device__ __forceinline__ uint32_t bf16_bcast_raw(unsigned short u) { return (uint32_t)u | ((uint32_t)u << 16); }
-__device__ __forceinline__ float bf16_to_f32(unsigned short u) { return __uint_as_float((uint32_t)u << 16); }
-
-struct Barriers {
-  uint64_t b_full[kS], b_empty[kS];
-  uint64_t a_full[kSub][kNS], a_empty[kSub][kNS];
-  uint64_t d_full;
-  uint32_t tmem_base;
-};
 
 // ---------------------------------------------------------------------------------------------
 // Weight packing: W[C,N] fp32 (Keras Conv1D kernel, row c = h*m+i) -> bf16 core-matrix blocks.
@@ -132,21 +86,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < kMaxN; i += kTcThreads) s_bias[i] = i < a.N ? a.bias[i] : 0.f;
 
-  if (tid == 0) {
-    for (int i = 0; i < kS; ++i) { mbar_init(&bars.b_full[i], 1); mbar_init(&bars.b_empty[i], 1); }
-    for (int s = 0; s < kSub; ++s)
-      for (int i = 0; i < kNS; ++i) { mbar_init(&bars.a_full[s][i], 4); mbar_init(&bars.a_empty[s][i], 1); }
-    mbar_init(&bars.d_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == kProdWarps) tc::tmem_alloc(&bars.tmem_base, 512);
-  tc::fence_before();
-  __syncthreads();
-  tc::fence_after();
+  stream_init(bars, tid, warp);
   const uint32_t tmem = bars.tmem_base;
-
-  const int n_groups = (a.nk + kG - 1) / kG;
-  const uint32_t stage_bytes = kG * a.kblk;
 
   if (warp < kProdWarps) {
     // ================= producers + epilogue =================================================
@@ -155,7 +96,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
     const uint32_t colD = sub ? kColD1 : kColD0;
     const uint32_t colA = sub ? kColA1 : kColA0;
     const int n_periods = (a.Hp + PH - 1) / PH;
-    uint32_t a_it = 0;   // A-slot uses so far (ring position)
+    SlotWriter sw;
     uint32_t tile_it = 0;
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x, ++tile_it) {
       const long long r = pair * (128 * kSub) + sub * 128 + (warp & 3) * 32 + lane;
@@ -189,7 +130,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
       for (int j = 0; j < PH; ++j) nraw[j] = load_raw(j);
 
       int ks_global = 0;     // k-step index within this tile
-      int cnt = 0;           // k-steps written into the current slot
       for (int per = 0; per < n_periods; ++per) {
 #pragma unroll
         for (int j = 0; j < PH; ++j) cur[j] = to_bcast(nraw[j], per * PH + j);
@@ -198,30 +138,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
 #pragma unroll
         for (int j = 0; j < PK; ++j) {
           if (ks_global < a.nk) {
-            const uint32_t slot = a_it % kNS;
-            if (cnt == 0) {
-              mbar_wait(&bars.a_empty[sub][slot], ((a_it / kNS) & 1) ^ 1);
-              tc::fence_after();
-            }
             uint32_t w[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              constexpr int dummy = 0;
-              (void)dummy;
               const int cl = 16 * j + 2 * q;            // compile-time after unrolling
               w[q] = hmul2_bf16(cur[cl / MF], x2[(cl % MF) / 2]);
             }
-            tc::st8(tmem + lane_base + colA + slot * (8 * kG) + 8 * cnt, w);
-            ++cnt;
             ++ks_global;
-            if (cnt == kG || ks_global == a.nk) {
-              tc::wait_st();
-              tc::fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&bars.a_full[sub][slot]);
-              cnt = 0;
-              ++a_it;
-            }
+            sw.put(bars, sub, tmem + lane_base + colA, w, ks_global == a.nk, lane);
           }
         }
       }
@@ -267,51 +191,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   } else if (warp == kProdWarps) {
     // ================= MMA issuer ===========================================================
     if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16(128, a.N8 * 8, 0, 0);
-      const uint32_t lbo = (uint32_t)a.N8 * 128, sbo = 128;
-      uint32_t a_it = 0, b_it = 0;
-      for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
-        for (int g = 0; g < n_groups; ++g) {
-          const int gk = min(kG, a.nk - g * kG);
-          const uint32_t bs = b_it % kS;
-          mbar_wait(&bars.b_full[bs], (b_it / kS) & 1);
-          tc::fence_after();
-          const uint64_t bdesc0 = tc::smem_desc(smem_u32(smem + bs * stage_bytes), lbo, sbo);
-          const uint32_t slot = a_it % kNS;
-          const uint32_t apar = (a_it / kNS) & 1;
-#pragma unroll
-          for (int sub = 0; sub < kSub; ++sub) {
-            mbar_wait(&bars.a_full[sub][slot], apar);
-            tc::fence_after();
-            const uint32_t dcol = tmem + (sub ? kColD1 : kColD0);
-            const uint32_t acol = tmem + (sub ? kColA1 : kColA0) + slot * (8 * kG);
-            for (int ks = 0; ks < gk; ++ks)
-              tc::mma_ts(dcol, acol + 8 * ks, bdesc0 + (uint64_t)((ks * a.kblk) >> 4), idesc,
-                         (g > 0 || ks > 0) ? 1u : 0u);
-            tc::commit(&bars.a_empty[sub][slot]);
-          }
-          tc::commit(&bars.b_empty[bs]);
-          ++a_it;
-          ++b_it;
-        }
-        tc::commit(&bars.d_full);
-      }
+      const long long n_items = a.n_pairs > blockIdx.x ? (a.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      stream_mma_role(bars, smem, tmem, n_items, a.nk, a.kblk, tc::idesc_bf16(128, a.N8 * 8, 0, 0),
+                      (uint32_t)a.N8 * 128, 128);
     }
   } else {
     // ================= B loader =============================================================
     if (lane == 0) {
-      uint32_t b_it = 0;
-      for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
-        for (int g = 0; g < n_groups; ++g) {
-          const int gk = min(kG, a.nk - g * kG);
-          const uint32_t bs = b_it % kS;
-          mbar_wait(&bars.b_empty[bs], ((b_it / kS) & 1) ^ 1);
-          const uint32_t bytes = gk * a.kblk;
-          mbar_expect_tx(&bars.b_full[bs], bytes);
-          bulk_g2s(smem + bs * stage_bytes, a.wpack + (size_t)g * stage_bytes, bytes, &bars.b_full[bs]);
-          ++b_it;
-        }
-      }
+      const long long n_items = a.n_pairs > blockIdx.x ? (a.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      stream_loader_role(bars, smem, n_items, a.nk, a.kblk, [&](long long) { return a.wpack; });
     }
   }
   tc::fence_before();
@@ -319,51 +207,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   if (warp == kProdWarps) tc::tmem_dealloc(tmem, 512);
 }
 
-size_t align256(size_t x) { return (x + 255) / 256 * 256; }
-
-struct TcLayout {
-  int nl;
-  int Hp[KON_CIN_MAX_LAYERS], N[KON_CIN_MAX_LAYERS], N8[KON_CIN_MAX_LAYERS], nk[KON_CIN_MAX_LAYERS];
-  size_t wpack_off[KON_CIN_MAX_LAYERS], wpack_bytes[KON_CIN_MAX_LAYERS];
-  size_t zt_off[KON_CIN_MAX_LAYERS];
-  size_t saved_total, work_total;
-};
-
-int tc_layout(int64_t B, int m, int D, const int32_t* hs, int nl, TcLayout* L) {
-  if (m != 26) return -1;
-  const int LCM = lcm_(16, m), PH = LCM / m, PK = LCM / 16;
-  L->nl = nl;
-  size_t so = 0, wo = 0;
-  int hp = m;
-  for (int l = 0; l < nl; ++l) {
-    if (hs[l] > kMaxN) return -2;
-    L->Hp[l] = hp;
-    L->N[l] = hs[l];
-    L->N8[l] = (hs[l] + 7) / 8;
-    L->nk[l] = (hp + PH - 1) / PH * PK;
-    L->wpack_bytes[l] = (size_t)L->nk[l] * 2 * L->N8[l] * 128;
-    L->wpack_off[l] = wo;
-    wo = align256(wo + L->wpack_bytes[l]);
-    L->zt_off[l] = so;
-    so = align256(so + (size_t)B * hs[l] * D * 2);
-    hp = hs[l];
-  }
-  L->saved_total = so ? so : 256;
-  L->work_total = wo ? wo : 256;
-  return 0;
-}
-
 }  // namespace
 
 size_t cin_tc_saved_bytes(int64_t B, int m, int D, const int32_t* hs, int nl) {
   TcLayout L;
-  if (tc_layout(B, m, D, hs, nl, &L) != 0) return 256;
+  if (tc_layout(B, m, D, hs, nl, 148, &L) != 0) return 256;
   return L.saved_total;
 }
 
 size_t cin_tc_workspace_bytes(int64_t B, int m, int D, const int32_t* hs, int nl, int sms) {
   TcLayout L;
-  if (tc_layout(B, m, D, hs, nl, &L) != 0) return 256;
+  if (tc_layout(B, m, D, hs, nl, sms, &L) != 0) return 256;
   return L.work_total;
 }
 
@@ -371,15 +225,13 @@ int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias,
                const int32_t* hs, int64_t B, int m, int D, float* pooled, void* saved,
                void* workspace, int sms, cudaStream_t st) {
   TcLayout L;
-  const int rc = tc_layout(B, m, D, hs, nl, &L);
-  KON_REQUIRE(rc != -1, KON_EUNSUPPORTED, "KON_CIN_BF16 supports m = 26 fields (got %d); use KON_CIN_FP32", m);
-  KON_REQUIRE(rc == 0, KON_EUNSUPPORTED, "KON_CIN_BF16 supports layer sizes <= %d", kMaxN);
+  KON_TRY(tc_check_layout(tc_layout(B, m, D, hs, nl, sms, &L), m, D));
   KON_REQUIRE(((uintptr_t)workspace & 255u) == 0 && ((uintptr_t)saved & 255u) == 0, KON_EINVAL,
               "saved / workspace must be 256-B aligned");
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   unsigned char* sv = static_cast<unsigned char*>(saved);
   const long long rows = B * D;
-  const size_t smem = (size_t)kS * kG * 2 * ((kMaxN + 7) / 8) * 128;
+  const size_t smem = stream_smem_bytes();
   static bool attr_done = false;
   if (!attr_done) {
     KON_CUDA(cudaFuncSetAttribute(cin_fwd_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -414,12 +266,6 @@ int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias,
     KON_LAUNCH_CHECK("cin_fwd_tc_kernel");
   }
   return KON_OK;
-}
-
-int cin_tc_bwd(const float*, const float* const*, const float* const*, int, const int32_t*, int64_t,
-               int, int, const float*, const void*, float*, float* const*, float* const*, void*, int,
-               cudaStream_t) {
-  return fail(KON_EUNSUPPORTED, "KON_CIN_BF16 backward not built yet");
 }
 
 }  // namespace kon

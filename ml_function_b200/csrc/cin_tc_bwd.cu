@@ -1,0 +1,557 @@
+// a8 backward on tcgen05 (KON_CIN_BF16).  Per layer l (last to first), with dZ_l[r,o] the
+// gradient of z_l (pooled-grad broadcast over o, IL:322, plus dpre_{l+1}):
+//
+//   dW kernel  (stream skeleton of cin_tc_common.cuh):
+//       dW_l[c,o] = sum_r A[r,c] dZ_l[r,o],   A[r,c] = pre[r,h] x0[r,i]  regenerated on the fly.
+//       GEMM with M-side = c (TMEM lane = c, 2 x 128 lanes per CTA), N = o, K = rows.  One k-step
+//       (16 rows) is one sample's 16 embedding coordinates, so lane c multiplies two contiguous
+//       32-byte vectors pre[b,h,:] * x0[b,i,:] (bf16x2 HMUL2) and stores them to the TMEM ring.
+//       B operand = dZ_l in a blocked 8x8 layout (MN-major core matrices) streamed with bulk copies.
+//       An all-ones lane c == C yields dbias.  Work = (c-tile pair) x (row slice); the slices'
+//       partial sums are reduced by a second kernel in a fixed order (deterministic).
+//   dA kernel:
+//       dA[r,c] = sum_o dZ_l[r,o] W_l[c,o]  (never stored), contracted in the epilogue:
+//       dpre_l[r,h] = sum_i dA[r,h*m+i] x0[r,i],   dx0[r,i] += sum_h dA[r,h*m+i] pre[r,h].
+//       A operand = the dZ tile, written once per 128-row tile into TMEM (13 k-steps);
+//       B operand = chunks of 4*m = 104 weight rows (K-major), 13 MMAs per chunk and sub-tile;
+//       the two sub-tiles ping-pong: while the row warps of one contract their 104 accumulator
+//       columns (packed fp32x2 FMAs), the tensor core fills the other's.
+//       dZ_{l-1} = dpre_l + pooled-grad broadcast is written in the blocked layout the next
+//       iteration's two kernels consume.
+#include "cin_tc_common.cuh"
+
+namespace kon {
+
+using namespace tcs;
+
+namespace {
+
+static_assert(kSub == 2, "the backward kernels are written for two 128-lane sub-tiles per CTA");
+
+// ---------------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cin_x0_bf16_kernel(const float* __restrict__ x0, unsigned short* __restrict__ out, long long n) {
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < n;
+       i += (long long)gridDim.x * blockDim.x * 2) {
+    const float a = x0[i], b = (i + 1 < n) ? x0[i + 1] : 0.f;
+    const uint32_t pk = tc::pack_bf16(a, b);
+    if (i + 1 < n) *reinterpret_cast<uint32_t*>(out + i) = pk;
+    else out[i] = (unsigned short)(pk & 0xffffu);
+  }
+}
+
+// blocked dZ: [rows/8][N8][8 rows][8 cols] bf16; element (r,o) at ((r/8)*N8 + o/8)*128 + (r%8)*16 + (o%8)*2
+__global__ void __launch_bounds__(256)
+cin_dz_init_kernel(const float* __restrict__ gpool, int gstride, int gcol, long long rows, int D, int N,
+                   int N8, unsigned char* __restrict__ dz) {
+  const long long total = rows * N8;      // one 16-byte unit per (row, column group)
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    // consecutive idx -> consecutive 16-byte units of the blocked buffer
+    const int r7 = (int)(idx & 7);
+    const long long t = idx >> 3;
+    const int o8 = (int)(t % N8);
+    const long long rg = t / N8;
+    const long long r = rg * 8 + r7;
+    const long long b = r / D;
+    const float g = gpool[b * gstride + gcol + (int)(r - b * D)];
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = o8 * 8 + 2 * q;
+      w[q] = tc::pack_bf16(o < N ? g : 0.f, o + 1 < N ? g : 0.f);
+    }
+    *reinterpret_cast<uint4*>(dz + idx * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// dA B operand, K-major B[n = c_local][k = o], chunk j = weight rows [CH*j, CH*j+CH):
+//   offset = j*chunk + s*(2*CH8*128) + kg*CH8*128 + (c_local/8)*128 + (c%8)*16 + (o%8)*2,  o = 16s + 8kg + o%8
+__global__ void __launch_bounds__(256)
+cin_pack_w_bwd_kernel(const float* __restrict__ W, int C, int N, int CH8, int nkA, int n_chunks,
+                      __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)n_chunks * nkA * 2 * CH8 * 64;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int o7 = (int)(idx & 7);
+    const int c7 = (int)((idx >> 3) & 7);
+    long long t = idx >> 6;
+    const int n8 = (int)(t % CH8);
+    t /= CH8;
+    const int kg = (int)(t & 1);
+    t >>= 1;
+    const int s = (int)(t % nkA);
+    const long long j = t / nkA;
+    const long long c = j * (CH8 * 8) + n8 * 8 + c7;
+    const int o = 16 * s + 8 * kg + o7;
+    float v = 0.f;
+    if (c < C && o < N) v = W[c * N + o];
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// dW[c,o] = sum_slices part[s][c][o] (c < C);  dbias[o] = sum_slices part[s][C][o]
+__global__ void __launch_bounds__(256)
+cin_dw_reduce_kernel(const float* __restrict__ part, int n_slices, long long slice_stride, int Npad, int C,
+                     int N, float* __restrict__ dW, float* __restrict__ dbias) {
+  const long long total = (long long)(C + 1) * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / N;
+    const int o = (int)(idx - c * N);
+    const float* p = part + c * Npad + o;
+    float acc = 0.f;
+    for (int s = 0; s < n_slices; ++s) acc += p[s * slice_stride];
+    if (c < C) dW[idx] = acc;
+    else dbias[o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW: stream kernel, lanes = c
+// ---------------------------------------------------------------------------------------------
+struct DwArgs {
+  const unsigned short* pre;   // [B,Hp,D] bf16
+  const unsigned short* x0b;   // [B,m,D] bf16
+  const unsigned char* dz;     // blocked, kblk bytes per k-step (16 rows)
+  float* part;                 // [n_slices][n_cp*256][Npad]
+  int D, Hp, N8, C, n_cp, n_slices;
+  uint32_t kblk;
+  long long nks_total, ks_per_slice;
+};
+
+template <int MF>
+__global__ void __launch_bounds__(kTcThreads, 1) cin_dw_tc_kernel(const DwArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ Barriers bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stream_init(bars, tid, warp);
+  const uint32_t tmem = bars.tmem_base;
+
+  const int cp = blockIdx.x % a.n_cp;
+  const int slice = blockIdx.x / a.n_cp;
+  const long long ks0 = slice * a.ks_per_slice;
+  const long long nk_ll = min(a.ks_per_slice, a.nks_total - ks0);
+  const int nk = nk_ll > 0 ? (int)nk_ll : 0;
+  const int Npad = a.N8 * 8;
+
+  if (warp < kProdWarps) {
+    const int sub = warp >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t colD = sub ? kColD1 : kColD0;
+    const uint32_t colA = sub ? kColA1 : kColA0;
+    const int c = cp * (128 * kSub) + sub * 128 + (warp & 3) * 32 + lane;
+    const int mode = c < a.C ? 2 : (c == a.C ? 1 : 0);          // product / ones (dbias) / zero
+    const int h = mode == 2 ? c / MF : 0, i = mode == 2 ? c % MF : 0;
+    const int ksD = a.D / 16;                                   // k-steps per sample
+    auto addr = [&](long long ks, const unsigned short* base, int H, int row) -> const uint4* {
+      const long long b = ks / ksD;
+      const int d0 = (int)(ks - b * ksD) * 16;
+      return reinterpret_cast<const uint4*>(base + (b * H + row) * (long long)a.D + d0);
+    };
+    if (nk > 0) {
+      SlotWriter sw;
+      const int n_groups = (nk + kG - 1) / kG;
+      uint4 nb[kG][4];
+      auto load_group = [&](int g) {
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+          long long ks = ks0 + (long long)g * kG + u;
+          if (ks >= ks0 + nk) ks = ks0 + nk - 1;                 // clamped (value unused)
+          const uint4* pp = addr(ks, a.pre, a.Hp, h);
+          const uint4* xp = addr(ks, a.x0b, MF, i);
+          nb[u][0] = __ldg(pp); nb[u][1] = __ldg(pp + 1);
+          nb[u][2] = __ldg(xp); nb[u][3] = __ldg(xp + 1);
+        }
+      };
+      load_group(0);
+      for (int g = 0; g < n_groups; ++g) {
+        uint4 cb[kG][4];
+#pragma unroll
+        for (int u = 0; u < kG; ++u)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cb[u][q] = nb[u][q];
+        if (g + 1 < n_groups) load_group(g + 1);
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+          const int kl = g * kG + u;
+          if (kl < nk) {
+            uint32_t w[8];
+            if (mode == 2) {
+              w[0] = hmul2_bf16(cb[u][0].x, cb[u][2].x); w[1] = hmul2_bf16(cb[u][0].y, cb[u][2].y);
+              w[2] = hmul2_bf16(cb[u][0].z, cb[u][2].z); w[3] = hmul2_bf16(cb[u][0].w, cb[u][2].w);
+              w[4] = hmul2_bf16(cb[u][1].x, cb[u][3].x); w[5] = hmul2_bf16(cb[u][1].y, cb[u][3].y);
+              w[6] = hmul2_bf16(cb[u][1].z, cb[u][3].z); w[7] = hmul2_bf16(cb[u][1].w, cb[u][3].w);
+            } else {
+              const uint32_t v = mode == 1 ? 0x3F803F80u : 0u;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) w[q] = v;
+            }
+            sw.put(bars, sub, tmem + lane_base + colA, w, kl == nk - 1, lane);
+          }
+        }
+      }
+      // ---- epilogue: this lane's accumulator row -> partial buffer --------------------------
+      mbar_wait(&bars.d_full, 0);
+      tc::fence_after();
+      float* prow = a.part + ((long long)slice * a.n_cp * (128 * kSub) + c) * Npad;
+      for (int o0 = 0; o0 < Npad; o0 += 8) {
+        uint32_t v[8];
+        tc::ld8(tmem + lane_base + colD + o0, v);
+        tc::wait_ld();
+        *reinterpret_cast<uint4*>(prow + o0) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4*>(prow + o0 + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      // empty slice: contribute zeros so that the reduction can read every slice
+      float* prow = a.part + ((long long)slice * a.n_cp * (128 * kSub) + c) * Npad;
+      for (int o0 = 0; o0 < Npad; o0 += 4) *reinterpret_cast<uint4*>(prow + o0) = make_uint4(0, 0, 0, 0);
+    }
+  } else if (warp == kProdWarps) {
+    if (lane == 0 && nk > 0)
+      stream_mma_role(bars, smem, tmem, 1, nk, a.kblk, tc::idesc_bf16(128, Npad, 0, 1),
+                      (uint32_t)a.N8 * 128, 128);
+  } else {
+    if (lane == 0 && nk > 0)
+      stream_loader_role(bars, smem, 1, nk, a.kblk, [&](long long) { return a.dz + (size_t)ks0 * a.kblk; });
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == kProdWarps) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dA: chunked GEMM with contracting epilogue
+// ---------------------------------------------------------------------------------------------
+constexpr int kDaS = 4;                       // weight-chunk stages
+constexpr uint32_t kDaColA0 = 0, kDaColD0 = 104, kDaColA1 = 256, kDaColD1 = 360;
+
+struct DaBarriers {
+  uint64_t b_full[kDaS], b_empty[kDaS];
+  uint64_t a_full[2], a_empty[2], d_full[2], d_empty[2];
+  uint32_t tmem_base;
+};
+
+struct DaArgs {
+  const unsigned char* dz;       // blocked dZ_l
+  const unsigned char* wpack;    // n_chunks chunks
+  const unsigned short* x0b;     // [B,m,D] bf16
+  const unsigned short* pre;     // [B,Hp,D] bf16 (layer 0: == x0b)
+  float* dx0;                    // [B,m,D] fp32, accumulated
+  unsigned char* dz_prev;        // blocked dZ_{l-1} (N8p column groups) or nullptr on layer 0
+  const float* gpool;            // d_pooled [B, gstride]
+  int gstride, gcol_prev;
+  long long rows, n_pairs;
+  int D, Hp, N8, N8p, n_chunks, nkA;
+  uint32_t chunk_bytes;
+};
+
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+#if KON_NO_FFMA2
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.y = fmaf(a.y, b.y, acc.y);
+#else
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(rc));
+#endif
+}
+
+template <int MF>
+__global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
+  constexpr int CH = kDaChunkH * MF;          // accumulator columns per chunk (104)
+  static_assert(CH % 8 == 0 && CH <= 152 && MF % 2 == 0, "chunk shape");
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ DaBarriers bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kDaS; ++i) { mbar_init(&bars.b_full[i], 1); mbar_init(&bars.b_empty[i], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.a_full[s], 4); mbar_init(&bars.a_empty[s], 1);
+      mbar_init(&bars.d_full[s], 1); mbar_init(&bars.d_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&bars.tmem_base, 512);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = bars.tmem_base;
+  const long long n_items = a.n_pairs > blockIdx.x ? (a.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t kstep_bytes = 2u * (CH / 8) * 128u;
+
+  if (warp < 8) {
+    const int sub = warp >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t colA = sub ? kDaColA1 : kDaColA0;
+    const uint32_t colD = sub ? kDaColD1 : kDaColD0;
+    uint32_t d_use = 0;
+    uint32_t tile_it = 0;
+    for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x, ++tile_it) {
+      const long long r = pair * 256 + sub * 128 + (warp & 3) * 32 + lane;
+      const bool valid = r < a.rows;
+      const long long b = valid ? r / a.D : 0;
+      const int d = valid ? (int)(r - b * a.D) : 0;
+      // ---- A operand: this row of dZ_l, bf16, into TMEM (once per tile) ----------------------
+      mbar_wait(&bars.a_empty[sub], (tile_it & 1) ^ 1);
+      tc::fence_after();
+      {
+        const long long rc = valid ? r : 0;
+        const uint4* zr = reinterpret_cast<const uint4*>(a.dz + ((rc >> 3) * a.N8) * 128 + (rc & 7) * 16);
+        for (int s = 0; s < a.nkA; ++s) {
+          uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+          if (valid) {
+            lo = __ldg(zr + (2 * s) * 8);                         // column group 2s   (128 B apart)
+            if (2 * s + 1 < a.N8) hi = __ldg(zr + (2 * s + 1) * 8);
+          }
+          const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          tc::st8(tmem + lane_base + colA + 8 * s, w);
+        }
+        tc::wait_st();
+        tc::fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.a_full[sub]);
+      }
+      // ---- per-row constants -------------------------------------------------------------------
+      const unsigned short* xrow = a.x0b + b * (long long)MF * a.D + d;      // x0[b,i,d] = xrow[i*D]
+      const unsigned short* prow = a.pre + b * (long long)a.Hp * a.D + d;    // pre[b,h,d] = prow[h*D]
+      float2 x2[MF / 2], dx2[MF / 2];
+#pragma unroll
+      for (int i = 0; i < MF / 2; ++i) {
+        x2[i].x = bf16_to_f32(__ldg(xrow + (long long)(2 * i) * a.D));
+        x2[i].y = bf16_to_f32(__ldg(xrow + (long long)(2 * i + 1) * a.D));
+        dx2[i] = make_float2(0.f, 0.f);
+      }
+      const float gp = (a.dz_prev && valid) ? a.gpool[b * a.gstride + a.gcol_prev + d] : 0.f;
+      unsigned short praw[kDaChunkH];
+#pragma unroll
+      for (int q = 0; q < kDaChunkH; ++q) praw[q] = __ldg(prow + (long long)min(q, a.Hp - 1) * a.D);
+
+      for (int j = 0; j < a.n_chunks; ++j, ++d_use) {
+        float2 pb[kDaChunkH], dp[kDaChunkH];
+#pragma unroll
+        for (int q = 0; q < kDaChunkH; ++q) {
+          const int h = j * kDaChunkH + q;
+          const float p = (h < a.Hp) ? bf16_to_f32(praw[q]) : 0.f;
+          pb[q] = make_float2(p, p);
+          dp[q] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < kDaChunkH; ++q)
+          praw[q] = __ldg(prow + (long long)min((j + 1) * kDaChunkH + q, a.Hp - 1) * a.D);
+
+        mbar_wait(&bars.d_full[sub], d_use & 1);
+        tc::fence_after();
+        // 104 accumulator columns: column q -> (hh, i) = (q / MF, q % MF); pairs never straddle an h
+#pragma unroll
+        for (int q0 = 0; q0 < CH; q0 += 32) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          uint32_t v[32];
+          if (q0 + 32 <= CH) {
+            tc::ld32(tmem + lane_base + colD + q0, v);
+          } else {
+            tc::ld8(tmem + lane_base + colD + q0, v);            // CH - q0 == 8 for MF == 26
+          }
+          tc::wait_ld();
+          if (q0 + 32 > CH) {                                     // all loads of this chunk are done
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.d_empty[sub]);
+          }
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            if (q0 + q < CH) {
+              const int col = q0 + q;
+              const int hh = col / MF, ii = (col % MF) / 2;
+              const float2 val = make_float2(__uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+              ffma2(dp[hh], val, x2[ii]);
+              ffma2(dx2[ii], val, pb[hh]);
+            }
+          }
+        }
+        // ---- dpre of this chunk's 4 feature maps -------------------------------------------------
+        if (valid) {
+          if (a.dz_prev) {
+            uint32_t w2[2];
+#pragma unroll
+            for (int q = 0; q < kDaChunkH; q += 2) {
+              const int h = j * kDaChunkH + q;
+              const float v0 = h < a.Hp ? dp[q].x + dp[q].y + gp : 0.f;
+              const float v1 = h + 1 < a.Hp ? dp[q + 1].x + dp[q + 1].y + gp : 0.f;
+              w2[q / 2] = tc::pack_bf16(v0, v1);
+            }
+            const int h0 = j * kDaChunkH;
+            if (h0 < a.N8p * 8) {
+              unsigned char* dst = a.dz_prev + ((r >> 3) * a.N8p + (h0 >> 3)) * 128 + (r & 7) * 16 + (h0 & 7) * 2;
+              *reinterpret_cast<uint2*>(dst) = make_uint2(w2[0], w2[1]);
+            }
+          } else {
+            // layer 0: pre == x0, so dpre lands in dx0[b,h,d]
+#pragma unroll
+            for (int q = 0; q < kDaChunkH; ++q) {
+              const int h = j * kDaChunkH + q;
+              if (h < a.Hp) {
+                float* p = a.dx0 + (b * MF + h) * (long long)a.D + d;
+                *p += dp[q].x + dp[q].y;
+              }
+            }
+          }
+        }
+      }
+      if (valid) {
+        float* dxr = a.dx0 + b * (long long)MF * a.D + d;
+#pragma unroll
+        for (int i = 0; i < MF / 2; ++i) {
+          dxr[(long long)(2 * i) * a.D] += dx2[i].x;
+          dxr[(long long)(2 * i + 1) * a.D] += dx2[i].y;
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_bf16(128, CH, 0, 0);
+      const uint32_t lbo = (CH / 8) * 128, sbo = 128;
+      uint32_t bs = 0, bph = 0, d_use = 0;
+      for (long long it = 0; it < n_items; ++it) {
+        mbar_wait(&bars.a_full[0], it & 1);
+        mbar_wait(&bars.a_full[1], it & 1);
+        tc::fence_after();
+        for (int j = 0; j < a.n_chunks; ++j, ++d_use) {
+          mbar_wait(&bars.b_full[bs], bph);
+          tc::fence_after();
+          const uint64_t bdesc0 = tc::smem_desc(smem_u32(smem + bs * a.chunk_bytes), lbo, sbo);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            mbar_wait(&bars.d_empty[sub], (d_use & 1) ^ 1);
+            tc::fence_after();
+            const uint32_t dcol = tmem + (sub ? kDaColD1 : kDaColD0);
+            const uint32_t acol = tmem + (sub ? kDaColA1 : kDaColA0);
+            for (int ks = 0; ks < a.nkA; ++ks)
+              tc::mma_ts(dcol, acol + 8 * ks, bdesc0 + (uint64_t)((ks * kstep_bytes) >> 4), idesc, ks > 0 ? 1u : 0u);
+            tc::commit(&bars.d_full[sub]);
+          }
+          tc::commit(&bars.b_empty[bs]);
+          if (++bs == kDaS) { bs = 0; bph ^= 1; }
+        }
+        tc::commit(&bars.a_empty[0]);
+        tc::commit(&bars.a_empty[1]);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      uint32_t bs = 0, bph = 0;
+      for (long long it = 0; it < n_items; ++it) {
+        for (int j = 0; j < a.n_chunks; ++j) {
+          mbar_wait(&bars.b_empty[bs], bph ^ 1);
+          mbar_expect_tx(&bars.b_full[bs], a.chunk_bytes);
+          bulk_g2s(smem + bs * a.chunk_bytes, a.wpack + (size_t)j * a.chunk_bytes, a.chunk_bytes, &bars.b_full[bs]);
+          if (++bs == kDaS) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+int grid_of(long long total, int sms, int mult = 8) {
+  return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sms * mult));
+}
+
+}  // namespace
+
+int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias, int nl,
+               const int32_t* hs, int64_t B, int m, int D, const float* d_pooled, const void* saved,
+               float* dx0, float* const* dw, float* const* dbias, void* workspace, int sms,
+               cudaStream_t st) {
+  TcLayout L;
+  KON_TRY(tc_check_layout(tc_layout(B, m, D, hs, nl, sms, &L), m, D));
+  KON_REQUIRE(((uintptr_t)workspace & 255u) == 0 && ((uintptr_t)saved & 255u) == 0, KON_EINVAL,
+              "saved / workspace must be 256-B aligned");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const unsigned char* sv = static_cast<const unsigned char*>(saved);
+  const long long rows = B * D;
+  const size_t smem_stream = stream_smem_bytes();
+  const size_t smem_da = (size_t)kDaS * 13 * 2 * (kDaChunkH * 26 / 8) * 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+    KON_CUDA(cudaFuncSetAttribute(cin_da_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_da));
+    attr_done = true;
+  }
+  unsigned short* x0b = reinterpret_cast<unsigned short*>(ws + L.x0b_off);
+  const long long nx = B * m * D;
+  cin_x0_bf16_kernel<<<grid_of(nx / 2 + 1, sms), 256, 0, st>>>(x0, x0b, nx);
+  KON_LAUNCH_CHECK("cin_x0_bf16_kernel");
+  KON_CUDA(cudaMemsetAsync(dx0, 0, (size_t)nx * 4, st));
+  bool ragged = false;
+  for (int l = 0; l < nl; ++l) {
+    const long long tot = (long long)L.n_chunks[l] * L.nkA[l] * 2 * (kDaChunkH * m / 8) * 64;
+    cin_pack_w_bwd_kernel<<<grid_of(tot, sms), 256, 0, st>>>(w[l], L.Hp[l] * m, L.N[l], kDaChunkH * m / 8, L.nkA[l],
+                                                            L.n_chunks[l], reinterpret_cast<__nv_bfloat16*>(ws + L.wbwd_off[l]));
+    KON_LAUNCH_CHECK("cin_pack_w_bwd_kernel");
+    if (L.N[l] % 8) ragged = true;
+  }
+  if (ragged) KON_CUDA(cudaMemsetAsync(ws + L.dz_off[0], 0, 2 * L.dz_bytes, st));
+  int cur = 0;
+  cin_dz_init_kernel<<<grid_of(rows * L.N8[nl - 1], sms), 256, 0, st>>>(d_pooled, nl * D, (nl - 1) * D, rows, D, L.N[nl - 1],
+                                                                       L.N8[nl - 1], ws + L.dz_off[cur]);
+  KON_LAUNCH_CHECK("cin_dz_init_kernel");
+  for (int l = nl - 1; l >= 0; --l) {
+    const unsigned short* pre = l == 0 ? x0b : reinterpret_cast<const unsigned short*>(sv + L.zt_off[l - 1]);
+    // ---- dW_l, dbias_l ----------------------------------------------------------------------
+    DwArgs q;
+    q.pre = pre;
+    q.x0b = x0b;
+    q.dz = ws + L.dz_off[cur];
+    q.part = reinterpret_cast<float*>(ws + L.part_off);
+    q.D = D;
+    q.Hp = L.Hp[l];
+    q.N8 = L.N8[l];
+    q.C = L.Hp[l] * m;
+    q.n_cp = L.n_cp[l];
+    q.n_slices = L.n_slices[l];
+    q.kblk = 2u * L.N8[l] * 128u;
+    q.nks_total = rows / 16;
+    q.ks_per_slice = (q.nks_total + q.n_slices - 1) / q.n_slices;
+    cin_dw_tc_kernel<26><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
+    KON_LAUNCH_CHECK("cin_dw_tc_kernel");
+    const int Npad = L.N8[l] * 8;
+    cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
+        q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
+    KON_LAUNCH_CHECK("cin_dw_reduce_kernel");
+    // ---- dpre_l -> dZ_{l-1}, dx0 ------------------------------------------------------------------
+    DaArgs p;
+    p.dz = ws + L.dz_off[cur];
+    p.wpack = ws + L.wbwd_off[l];
+    p.x0b = x0b;
+    p.pre = pre;
+    p.dx0 = dx0;
+    p.dz_prev = l == 0 ? nullptr : ws + L.dz_off[cur ^ 1];
+    p.gpool = d_pooled;
+    p.gstride = nl * D;
+    p.gcol_prev = (l - 1) * D;
+    p.rows = rows;
+    p.n_pairs = (rows + 255) / 256;
+    p.D = D;
+    p.Hp = L.Hp[l];
+    p.N8 = L.N8[l];
+    p.N8p = l == 0 ? 0 : L.N8[l - 1];
+    p.n_chunks = L.n_chunks[l];
+    p.nkA = L.nkA[l];
+    p.chunk_bytes = L.chunk_bytes[l];
+    cin_da_tc_kernel<26><<<(int)std::min<long long>(p.n_pairs, sms), 320, smem_da, st>>>(p);
+    KON_LAUNCH_CHECK("cin_da_tc_kernel");
+    cur ^= 1;
+  }
+  return KON_OK;
+}
+
+}  // namespace kon

@@ -56,3 +56,41 @@ def test_cin_bf16_unsupported_shapes_fail_loudly():
     x0, ws, bs = _case(4, 5, 16, [8], 1)
     with pytest.raises(L.KonError, match="m = 26"):
         ops.cin(x0.to(DEV), [w[0].to(DEV) for w in ws], [b.to(DEV) for b in bs], L.KON_CIN_BF16)
+
+
+@pytest.mark.parametrize("B,D,hs", [(40, 16, [200, 200, 200]), (33, 16, [200, 104]), (16, 16, [64, 40]),
+                                    (300, 16, [8, 200]), (2, 32, [200, 200])])
+def test_cin_bf16_backward(B, D, hs):
+    from ml_function_b200 import _lib as L, ops
+    x0, ws, bs = _case(B, 26, D, hs, 7 * B + len(hs))
+    g = gen(B)
+    gout = torch.randn(B, len(hs) * D, generator=g)
+    xd = x0.double().requires_grad_(True)
+    wd = [w.double().requires_grad_(True) for w in ws]
+    bd = [b.double().requires_grad_(True) for b in bs]
+    ref, _ = ko.cin_closed_form(xd, wd, bd)
+    (ref * gout.double()).sum().backward()
+    xg = x0.to(DEV).requires_grad_(True)
+    wg = [w[0].to(DEV).requires_grad_(True) for w in ws]
+    bg = [b.to(DEV).requires_grad_(True) for b in bs]
+    out = ops.cin(xg, wg, bg, L.KON_CIN_BF16)
+    (out * gout.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert_rel(xg.grad, xd.grad, BF16_TOL, "cin bf16 dx0")
+    for l in range(len(hs)):
+        assert_rel(wg[l].grad, wd[l].grad[0], BF16_TOL, f"cin bf16 dW{l}")
+        assert_rel(bg[l].grad, bd[l].grad, BF16_TOL, f"cin bf16 dbias{l}")
+
+
+def test_cin_bf16_backward_is_deterministic():
+    from ml_function_b200 import _lib as L, ops
+    x0, ws, bs = _case(64, 26, 16, [200, 200], 3)
+    res = []
+    for _ in range(2):
+        xg = x0.to(DEV).requires_grad_(True)
+        wg = [w[0].to(DEV).requires_grad_(True) for w in ws]
+        bg = [b.to(DEV).requires_grad_(True) for b in bs]
+        ops.cin(xg, wg, bg, L.KON_CIN_BF16).sum().backward()
+        res.append([xg.grad.clone()] + [w.grad.clone() for w in wg] + [b.grad.clone() for b in bg])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
