@@ -137,6 +137,10 @@ class SparseEmbed(nn.Module):
         """packed ids ``[B,F]`` / ``[B,F,L]`` -> ``[B,F,dim]`` (bag-summed over L)."""
         return ops.embed_lookup(self.arena, ids, self.field_row_offset, False)
 
+    def lookup_sum(self, ids: torch.Tensor) -> torch.Tensor:
+        """packed ids -> ``[B,dim]`` = sum over fields, left to right (Keras Add, IL:233-234)."""
+        return ops.embed_lookup(self.arena, ids, self.field_row_offset, True)
+
     def lookup_concat(self, ids: torch.Tensor, dense: Optional[torch.Tensor], width: int) -> torch.Tensor:
         """-> ``xcat [B,width]`` = field embeddings | dense features | zero pad, the gather
         kernel writing the embedding window in place (CL:49-55 without the concat copy)."""
@@ -212,8 +216,8 @@ class FmLayer(nn.Module):
         if not self.use_add:
             raise L.KonError("FmLayer(use_add=False) is not on the B200 hot path")
         v = pack_fields(inputs[0])
-        lin = pack_fields(inputs[1])                       # [B,F,1]
-        lin = lin.reshape(lin.shape[0], -1)                # [B,F]
+        lin = pack_fields(inputs[1])                       # [B,F,1] (or an already reduced [B,F'])
+        lin = lin.reshape(lin.shape[0], -1)                # only the sum over fields enters the result
         return ops.fm(v, lin).unsqueeze(1)
 
 

@@ -112,7 +112,7 @@ class FM(_CtrModel):
     def forward(self, dense_inputs, sparse_inputs):
         ids = pack_ids(sparse_inputs)
         v = self.sparse_embed.lookup(ids)
-        lin = self.linear_embed.lookup(ids)
+        lin = self.linear_embed.lookup_sum(ids)            # FmLayer only uses sum_f lin[b,f]
         fm_ = self.fm([v, lin])
         return self.head(fm_.squeeze(1))
 
@@ -133,7 +133,7 @@ class DeepFM(_CtrModel):
 
     def forward(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
-        lin = self.linear_embed.lookup(ids)
+        lin = self.linear_embed.lookup_sum(ids)
         fm_ = self.fm([v, lin])
         dnn_ = self.dnn(xcat)
         return self.head([fm_, dnn_])
@@ -191,7 +191,7 @@ class XDeepFM(_CtrModel):
 
     def logit(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
-        linear = ops.embed_lookup(self.linear_embed.arena, ids, self.linear_embed.field_row_offset, True)
+        linear = self.linear_embed.lookup_sum(ids)         # [B,1] (useAddLinear, IL:233-234)
         cin_out = self.cin(v)                              # [B,1]
         dnn_out = self.dnn(xcat)                           # [B,1]
         return ScoreLayer.summed([linear.unsqueeze(1), cin_out, dnn_out])   # [B,1,1]

@@ -1,0 +1,325 @@
+"""Multi-GPU execution of the CTR hot path: one process per GPU, ``torch.distributed`` (NCCL
+over NVLink 5 / NVSwitch on the B200 box, gloo in the CPU unit tests of the routing logic).
+
+The reference is single-process (no distributed code at all); this is the scale-out
+of the same step:
+
+* dense interaction + MLP weights are replicated, the batch is split (data parallel), dense
+  gradients are summed with ONE flat-bucket ``all_reduce`` per step;
+* embedding tables are sharded: small tables table-wise (whole table on one rank, greedy by
+  lookup count), tables with >= ``row_wise_min_rows`` rows row-wise (row r lives on rank
+  ``r % N`` at local row ``r // N``).  ids are all-gathered (4 B per lookup vs 4k B of payload);
+  every owner gathers for the GLOBAL batch with the same ``kon_embed_fwd`` kernel, then
+
+      table-wise part : ``all_to_all_single``  -> each rank gets its samples' rows
+      row-wise part   : ``reduce_scatter``      (non-owned ids gather zeros, the sum assembles)
+
+  and the backward mirrors it (``all_to_all_single`` / ``all_gather`` of dOut, then the local
+  sort-then-segment ``kon_embed_bwd``; non-owned ids carry no gradient).
+  The first-order (dim-1) tables only ever enter the models through their sum over fields, so
+  each rank sums its own fields/rows and one tiny ``reduce_scatter`` finishes the job.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class ShardPlan:
+    """Which rank owns which (field, row)."""
+
+    def __init__(self, rows: Sequence[int], world: int, row_wise_min_rows: int = 1_000_000):
+        self.rows = [int(r) for r in rows]
+        self.world = world
+        F = len(self.rows)
+        self.rw_fields = [f for f in range(F) if world > 1 and self.rows[f] >= row_wise_min_rows]
+        self.tw_fields = [f for f in range(F) if f not in self.rw_fields]
+        # greedy: every table-wise field costs the same number of lookups; place big tables first
+        load = [0] * world
+        mem = [0] * world
+        self.tw_owner = {}
+        for f in sorted(self.tw_fields, key=lambda f: -self.rows[f]):
+            p = min(range(world), key=lambda q: (load[q], mem[q]))
+            self.tw_owner[f] = p
+            load[p] += 1
+            mem[p] += self.rows[f]
+        self.tw_of_rank = [[f for f in self.tw_fields if self.tw_owner[f] == p] for p in range(world)]
+        # field order after the exchange ("rank-major"): rank 0's tw fields, rank 1's, ..., then rw fields
+        self.exchange_order = [f for p in range(world) for f in self.tw_of_rank[p]] + self.rw_fields
+        inv = [0] * F
+        for pos, f in enumerate(self.exchange_order):
+            inv[f] = pos
+        self.to_global = inv            # emb_global[:, f] = emb_exchange[:, to_global[f]]
+
+    def local_rows(self, rank: int, f: int) -> int:
+        if f in self.rw_fields:
+            return (self.rows[f] - rank + self.world - 1) // self.world
+        return self.rows[f]
+
+    def local_offsets(self, rank: int):
+        """(tw offsets [n_tw+1], rw offsets [n_rw+1]) into the rank's arena (tw tables first)."""
+        o = [0]
+        for f in self.tw_of_rank[rank]:
+            o.append(o[-1] + self.local_rows(rank, f))
+        tw = list(o)
+        o = [tw[-1]]
+        for f in self.rw_fields:
+            o.append(o[-1] + self.local_rows(rank, f))
+        return tw, o
+
+    def describe(self) -> str:
+        return (f"dp{self.world} dense + sharded embeddings ({len(self.tw_fields)} table-wise, "
+                f"{len(self.rw_fields)} row-wise fields)")
+
+
+# ------------------------------------------------------------------------------------------
+# collectives (NCCL on GPU; gloo lacks reduce_scatter, so the CPU tests use all_reduce + slice)
+# ------------------------------------------------------------------------------------------
+def _reduce_scatter(out: torch.Tensor, inp: torch.Tensor, group):
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out, inp, group=group)
+    else:
+        t = inp.clone()
+        dist.all_reduce(t, group=group)
+        n = out.numel()
+        out.copy_(t.reshape(-1)[dist.get_rank(group) * n:(dist.get_rank(group) + 1) * n].view_as(out))
+
+
+def _all_gather(out: torch.Tensor, inp: torch.Tensor, group):
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, inp, group=group)
+    else:
+        parts = [torch.empty_like(inp) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, inp, group=group)
+        out.copy_(torch.cat([p.reshape(-1) for p in parts]).view_as(out))
+
+
+def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits, group):
+    dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+
+
+class _ShardedLookup(torch.autograd.Function):
+    """ids_local [B_l,F] -> emb [B_l,F,k] in global field order."""
+
+    @staticmethod
+    def forward(ctx, arena, ids_local, sh: "ShardedEmbed"):
+        plan, g, N, rank = sh.plan, sh.group, sh.world, sh.rank
+        B_l, F = ids_local.shape
+        k = arena.shape[1]
+        dev = arena.device
+        ids_all = torch.empty((N * B_l, F), dtype=ids_local.dtype, device=dev)
+        _all_gather(ids_all, ids_local.contiguous(), g)
+        ids_tw, ids_rw = sh.local_ids(ids_all)
+        n_tw, n_rw = len(plan.tw_of_rank[rank]), len(plan.rw_fields)
+        chunks = []
+        if len(plan.tw_fields):
+            send = sh.lookup_fn(arena, ids_tw, sh.tw_offs) if n_tw else torch.empty((N * B_l, 0, k), device=dev)
+            in_splits = [B_l * n_tw * k] * N
+            out_splits = [B_l * len(plan.tw_of_rank[p]) * k for p in range(N)]
+            recv = torch.empty(sum(out_splits), dtype=arena.dtype, device=dev)
+            _all_to_all(recv, send.reshape(-1), out_splits, in_splits, g)
+            o = 0
+            for p in range(N):
+                if out_splits[p]:
+                    chunks.append(recv[o:o + out_splits[p]].view(B_l, len(plan.tw_of_rank[p]), k))
+                o += out_splits[p]
+        if n_rw:
+            part = sh.lookup_fn(arena, ids_rw, sh.rw_offs)                   # [B_g, n_rw, k], zeros where not owned
+            mine = torch.empty((B_l, n_rw, k), dtype=arena.dtype, device=dev)
+            _reduce_scatter(mine, part, g)
+            chunks.append(mine)
+        ex = chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=1)     # exchange (rank-major) order
+        emb = ex.index_select(1, sh.to_global)
+        ctx.sh, ctx.arena = sh, arena
+        ctx.save_for_backward(ids_tw, ids_rw)
+        ctx.B_l = B_l
+        return emb
+
+    @staticmethod
+    def backward(ctx, gout):
+        sh, arena = ctx.sh, ctx.arena
+        ids_tw, ids_rw = ctx.saved_tensors
+        plan, g, N, rank = sh.plan, sh.group, sh.world, sh.rank
+        B_l, k = ctx.B_l, arena.shape[1]
+        dev = arena.device
+        gex = gout.index_select(1, sh.to_exchange)                            # [B_l, F, k] exchange order
+        n_tw, n_rw = len(plan.tw_of_rank[rank]), len(plan.rw_fields)
+        n_tw_all = len(plan.tw_fields)
+        grads = []
+        if n_tw_all:
+            # slab p of the exchange order goes back to rank p
+            send = torch.cat([gex[:, o:o + c].reshape(-1) for o, c in sh.tw_slabs])
+            in_splits = [B_l * len(plan.tw_of_rank[p]) * k for p in range(N)]
+            out_splits = [B_l * n_tw * k] * N
+            recv = torch.empty(sum(out_splits), dtype=gout.dtype, device=dev)
+            _all_to_all(recv, send.contiguous(), out_splits, in_splits, g)
+            if n_tw:
+                grads.append((recv.view(N * B_l, n_tw, k), ids_tw, sh.tw_offs))
+        if n_rw:
+            mine = gex[:, n_tw_all:].contiguous()
+            full = torch.empty((N * B_l, n_rw, k), dtype=gout.dtype, device=dev)
+            _all_gather(full, mine, g)
+            grads.append((full, ids_rw, sh.rw_offs))
+        if arena.requires_grad:
+            if not hasattr(arena, "kon_sparse_grads"):
+                arena.kon_sparse_grads = []
+            for gg, ii, oo in grads:
+                arena.kon_sparse_grads.append(sh.scatter_fn(gg, ii, oo))
+        return None, None, None
+
+
+class _ShardedSum(torch.autograd.Function):
+    """ids_local [B_l,F] -> sum over fields of the dim-1 (first-order) tables, [B_l, dim]."""
+
+    @staticmethod
+    def forward(ctx, arena, ids_local, sh: "ShardedEmbed"):
+        g, N = sh.group, sh.world
+        B_l, F = ids_local.shape
+        dev = arena.device
+        ids_all = torch.empty((N * B_l, F), dtype=ids_local.dtype, device=dev)
+        _all_gather(ids_all, ids_local.contiguous(), g)
+        ids_tw, ids_rw = sh.local_ids(ids_all)
+        ids_loc = torch.cat([ids_tw, ids_rw], dim=1).contiguous()
+        part = sh.lookup_fn(arena, ids_loc, sh.all_offs, True)                # [B_g, dim]
+        mine = torch.empty((B_l, arena.shape[1]), dtype=arena.dtype, device=dev)
+        _reduce_scatter(mine, part, g)
+        ctx.sh, ctx.arena, ctx.B_l = sh, arena, B_l
+        ctx.save_for_backward(ids_loc)
+        return mine
+
+    @staticmethod
+    def backward(ctx, gout):
+        sh, arena = ctx.sh, ctx.arena
+        (ids_loc,) = ctx.saved_tensors
+        N = sh.world
+        full = torch.empty((N * ctx.B_l, gout.shape[1]), dtype=gout.dtype, device=gout.device)
+        _all_gather(full, gout.contiguous(), sh.group)
+        if arena.requires_grad:
+            g3 = full.unsqueeze(1).expand(full.shape[0], ids_loc.shape[1], full.shape[1])
+            if not hasattr(arena, "kon_sparse_grads"):
+                arena.kon_sparse_grads = []
+            arena.kon_sparse_grads.append(sh.scatter_fn(g3, ids_loc, sh.all_offs))
+        return None, None, None
+
+
+def _kon_lookup(arena, ids, offs, sum_fields=False):
+    from . import ops
+    return ops.embed_fwd_raw(arena.detach(), ids, offs, sum_fields)
+
+
+def _kon_scatter(g, ids, offs):
+    from . import ops
+    if g.stride(-1) != 1 or g.stride(0) % 4 or (g.stride(1) % 4 and g.stride(1) != 0):
+        g = g.contiguous()
+    return ops.embed_bwd_raw(g, ids, offs)
+
+
+class ShardedEmbed(nn.Module):
+    """Drop-in for ``layers.SparseEmbed`` on one rank of a sharded job (same ``lookup`` /
+    ``lookup_concat`` / ``lookup_sum`` surface; ``arena`` holds this rank's tables and shards)."""
+
+    def __init__(self, sparse_info: list, plan: ShardPlan, group, device, is_linear=False, seed=2020,
+                 lookup_fn: Callable = _kon_lookup, scatter_fn: Callable = _kon_scatter):
+        super().__init__()
+        self.plan, self.group = plan, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.is_linear = is_linear
+        self.lookup_fn, self.scatter_fn = lookup_fn, scatter_fn
+        dims = {(i.linear_unit if is_linear else i.cross_unit) for i in sparse_info}
+        assert len(dims) == 1
+        self.dim = dims.pop()
+        self.emb_reg = 0.0 if is_linear else float(sparse_info[0].emb_reg or 0.0)
+        tw, rw = plan.local_offsets(self.rank)
+        self.tw_offs, self.rw_offs = tuple(tw), tuple(rw)
+        self.all_offs = tuple(tw + rw[1:])
+        self.field_row_offset = self.all_offs
+        n_local = rw[-1]
+        arena = torch.empty(max(n_local, 1), self.dim, device=device, dtype=torch.float32)
+        gd = torch.Generator(device=device).manual_seed(seed + 7919 * self.rank)
+        fields = plan.tw_of_rank[self.rank] + plan.rw_fields
+        for j, f in enumerate(fields):
+            lim = 0.05 if is_linear else (6.0 / (plan.rows[f] + self.dim)) ** 0.5
+            arena[self.all_offs[j]:self.all_offs[j + 1]].uniform_(-lim, lim, generator=gd)
+        self.arena = nn.Parameter(arena)
+        self.register_buffer("to_global", torch.tensor(plan.to_global, dtype=torch.long, device=device), persistent=False)
+        self.register_buffer("to_exchange", torch.tensor(plan.exchange_order, dtype=torch.long, device=device), persistent=False)
+        self.register_buffer("tw_idx", torch.tensor(plan.tw_of_rank[self.rank], dtype=torch.long, device=device), persistent=False)
+        self.register_buffer("rw_idx", torch.tensor(plan.rw_fields, dtype=torch.long, device=device), persistent=False)
+        o, slabs = 0, []
+        for p in range(self.world):
+            slabs.append((o, len(plan.tw_of_rank[p])))
+            o += len(plan.tw_of_rank[p])
+        self.tw_slabs = slabs
+
+    def local_ids(self, ids_all: torch.Tensor):
+        """Global ids of the global batch -> this rank's (table-wise ids, row-wise local ids or -1)."""
+        ids_tw = ids_all.index_select(1, self.tw_idx).contiguous()
+        r = ids_all.index_select(1, self.rw_idx)
+        own = (r % self.world) == self.rank
+        ids_rw = torch.where(own, torch.div(r, self.world, rounding_mode="floor"), torch.full_like(r, -1)).contiguous()
+        return ids_tw, ids_rw
+
+    def load_global_tables(self, tables: Sequence[torch.Tensor]):
+        """Scatter full (global) tables into this rank's shard (tests / checkpoint import)."""
+        with torch.no_grad():
+            fields = self.plan.tw_of_rank[self.rank] + self.plan.rw_fields
+            for j, f in enumerate(fields):
+                t = tables[f].to(self.arena.device)
+                if f in self.plan.rw_fields:
+                    t = t[self.rank::self.world]
+                self.arena[self.all_offs[j]:self.all_offs[j + 1]].copy_(t)
+
+    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        return _ShardedLookup.apply(self.arena, ids, self)
+
+    def lookup_sum(self, ids: torch.Tensor) -> torch.Tensor:
+        return _ShardedSum.apply(self.arena, ids, self)
+
+    def lookup_concat(self, ids: torch.Tensor, dense: Optional[torch.Tensor], width: int) -> torch.Tensor:
+        emb = self.lookup(ids)
+        B, F, k = emb.shape
+        parts = [emb.reshape(B, F * k)]
+        if dense is not None:
+            parts.append(dense)
+        pad = width - F * k - (0 if dense is None else dense.shape[1])
+        if pad:
+            parts.append(torch.zeros((B, pad), dtype=emb.dtype, device=emb.device))
+        return torch.cat(parts, dim=1)
+
+
+class DistContext:
+    def __init__(self, group, device, row_wise_min_rows: int = 1_000_000):
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.row_wise_min_rows = row_wise_min_rows
+        self.plan: Optional[ShardPlan] = None
+
+    def attach(self, model):
+        """Replace the model's replicated embedding layers by sharded ones (in place)."""
+        info = model.sparse_embed.sparse_info
+        self.plan = ShardPlan([i.word_size for i in info], self.world, self.row_wise_min_rows)
+        dev = self.device
+        old = model.sparse_embed
+        model.sparse_embed = ShardedEmbed(info, self.plan, self.group, dev, is_linear=False, seed=old.seed)
+        if model.linear_embed is not None:
+            model.linear_embed = ShardedEmbed(info, self.plan, self.group, dev, is_linear=True, seed=old.seed)
+        del old
+        return model
+
+    def allreduce_dense_grads(self, params: List[torch.nn.Parameter]):
+        gs = [p.grad for p in params if p.grad is not None]
+        if not gs:
+            return
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        dist.all_reduce(flat, group=self.group)
+        o = 0
+        for g in gs:
+            n = g.numel()
+            g.copy_(flat[o:o + n].view_as(g))
+            o += n
+
+    def describe(self) -> str:
+        return self.plan.describe() if self.plan else f"dp{self.world}"

@@ -72,9 +72,12 @@ class Trainer:
         loss = self.loss(dense, ids, labels)
         self._ensure_dense_opt()
         self.dense_opt.zero_grad(set_to_none=True)
-        loss.backward()
         if self.dist is not None:
+            # global loss = mean over ranks of the local means; grads are summed across ranks
+            (loss / self.dist.world).backward()
             self.dist.allreduce_dense_grads(self._dense_params)
+        else:
+            loss.backward()
         self.dense_opt.step()
         for so in self.sparse_opts:
             so.step()
