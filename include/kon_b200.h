@@ -114,9 +114,11 @@ int kon_embed_adam(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTensor* un
 /* Replaces InnerLayer's 325 tf.multiply + sequential Add (IL:59-66) and FmLayer's Add
  * of the linear terms (IL:161-170) by one pass:
  *   out[b,:] = sum_{i<j} v[b,i,:]*v[b,j,:] + sum_f lin[b,f]
- *   v [B,F,k] f32 (free strides on dims 0/1), lin [B,F] f32 or NULL, out [B,k] f32. */
+ *   v [B,F,k] f32 (free strides on dims 0/1), out [B,k] f32,
+ *   lin [B,Fl] f32 or NULL: Fl = F for the reference's per-field list; any Fl >= 1 is accepted
+ *   (only the sum over lin's fields enters, e.g. an already reduced [B,1]). */
 int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out, void* stream);
-/* dv[b,f,:] = g[b,:] * (S[b,:] - v[b,f,:]);  dlin[b,f] = sum_k g[b,k]  (dlin may be NULL) */
+/* dv[b,f,:] = g[b,:] * (S[b,:] - v[b,f,:]);  dlin[b,f] = sum_k g[b,k]  (dlin [B,Fl] or NULL) */
 int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin, void* stream);
 
 /* ============================ a7: DCN cross ====================================== */

@@ -53,7 +53,7 @@ struct Vec<1> {
 template <int V>
 __global__ void __launch_bounds__(256)
 fm_fwd_kernel(const float* __restrict__ v, long long sb, long long sf, const float* __restrict__ lin,
-              long long lsb, long long lsf, float* __restrict__ out, long long B, int F, int cpr) {
+              long long lsb, long long lsf, int Fl, float* __restrict__ out, long long B, int F, int cpr) {
   const long long total = B * cpr;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -74,7 +74,7 @@ fm_fwd_kernel(const float* __restrict__ v, long long sb, long long sf, const flo
     }
     if (lin) {   // Keras Add: ((cross + lin_0) + lin_1) + ...  (IL:166)
       const float* lp = lin + b * lsb;
-      for (int f = 0; f < F; ++f) acc.adds(__ldg(lp + f * lsf));
+      for (int f = 0; f < Fl; ++f) acc.adds(__ldg(lp + f * lsf));
     }
     acc.store(out + b * (long long)cpr * V + c * V);
   }
@@ -86,7 +86,7 @@ template <int V>
 __global__ void __launch_bounds__(256)
 fm_bwd_kernel(const float* __restrict__ v, long long sb, long long sf, const float* __restrict__ g,
               float* __restrict__ dv, long long dsb, long long dsf, float* __restrict__ dlin,
-              long long dlsb, long long dlsf, long long B, int F, int cpr, int cpr_pad) {
+              long long dlsb, long long dlsf, int Fl, long long B, int F, int cpr, int cpr_pad) {
   const long long total = B * cpr_pad;
   const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of 32
   for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -122,7 +122,7 @@ fm_bwd_kernel(const float* __restrict__ v, long long sb, long long sf, const flo
       for (int o = 1; o < cpr_pad; o <<= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
       if (on && c == 0) {
         float* dl = dlin + b * dlsb;
-        for (int f = 0; f < F; ++f) dl[f * dlsf] = gs;
+        for (int f = 0; f < Fl; ++f) dl[f * dlsf] = gs;
       }
     }
   }
@@ -155,10 +155,12 @@ extern "C" int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out,
               KON_EINVAL, "out must be compact float32 [B,k]");
   const float* lp = nullptr;
   long long lsb = 0, lsf = 0;
+  int Fl = 0;
   if (lin) {
     KON_TRY(check_cuda_tensor(lin, "lin", dev));
-    KON_REQUIRE(is_f32(lin) && lin->ndim == 2 && lin->shape[0] == B && lin->shape[1] == F,
-                KON_EINVAL, "lin must be float32 [B,F]");
+    KON_REQUIRE(is_f32(lin) && lin->ndim == 2 && lin->shape[0] == B && lin->shape[1] >= 1,
+                KON_EINVAL, "lin must be float32 [B,Fl], Fl >= 1");
+    Fl = (int)lin->shape[1];
     lp = data_ptr<float>(lin);
     lsb = stride_of(lin, 0);
     lsf = stride_of(lin, 1);
@@ -175,11 +177,11 @@ extern "C" int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out,
     const int cpr = (int)(k / 4);
     const long long total = B * cpr;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
-    fm_fwd_kernel<4><<<grid, 256, 0, st>>>(vp, sb, sf, lp, lsb, lsf, op, B, (int)F, cpr);
+    fm_fwd_kernel<4><<<grid, 256, 0, st>>>(vp, sb, sf, lp, lsb, lsf, Fl, op, B, (int)F, cpr);
   } else {
     const long long total = B * k;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
-    fm_fwd_kernel<1><<<grid, 256, 0, st>>>(vp, sb, sf, lp, lsb, lsf, op, B, (int)F, (int)k);
+    fm_fwd_kernel<1><<<grid, 256, 0, st>>>(vp, sb, sf, lp, lsb, lsf, Fl, op, B, (int)F, (int)k);
   }
   KON_LAUNCH_CHECK("fm_fwd_kernel");
   return KON_OK;
@@ -198,10 +200,12 @@ extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DL
               "dv must have the shape of v");
   float* dlp = nullptr;
   long long dlsb = 0, dlsf = 0;
+  int Fl = 0;
   if (dlin) {
     KON_TRY(check_cuda_tensor(dlin, "dlin", dev));
-    KON_REQUIRE(is_f32(dlin) && dlin->ndim == 2 && dlin->shape[0] == B && dlin->shape[1] == F,
-                KON_EINVAL, "dlin must be float32 [B,F]");
+    KON_REQUIRE(is_f32(dlin) && dlin->ndim == 2 && dlin->shape[0] == B && dlin->shape[1] >= 1,
+                KON_EINVAL, "dlin must be float32 [B,Fl], Fl >= 1");
+    Fl = (int)dlin->shape[1];
     dlp = data_ptr<float>(dlin);
     dlsb = stride_of(dlin, 0);
     dlsf = stride_of(dlin, 1);
@@ -221,7 +225,7 @@ extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DL
     const int cpr = (int)(k / 4), cpr_pad = pow2_ge_i(cpr);
     const long long total = B * cpr_pad;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
-    fm_bwd_kernel<4><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, B,
+    fm_bwd_kernel<4><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
                                            (int)F, cpr, cpr_pad);
   } else {
     KON_REQUIRE(k <= 32, KON_EUNSUPPORTED,
@@ -230,7 +234,7 @@ extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DL
     const int cpr = (int)k, cpr_pad = pow2_ge_i(cpr);
     const long long total = B * cpr_pad;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
-    fm_bwd_kernel<1><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, B,
+    fm_bwd_kernel<1><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
                                            (int)F, cpr, cpr_pad);
   }
   KON_LAUNCH_CHECK("fm_bwd_kernel");
