@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
     }
   } else if (warp == kProdWarps) {
     // ================= MMA issuer ===========================================================
-    if (lane == 0) {
+    {
       const long long n_items = a.n_pairs > blockIdx.x ? (a.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       stream_mma_role(bars, smem, tmem, n_items, a.nk, a.kblk, tc::idesc_bf16(128, a.N8 * 8, 0, 0),
                       (uint32_t)a.N8 * 128, 128);

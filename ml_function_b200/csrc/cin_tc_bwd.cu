@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_dw_tc_kernel(const DwArgs a
       for (int o0 = 0; o0 < Npad; o0 += 4) *reinterpret_cast<uint4*>(prow + o0) = make_uint4(0, 0, 0, 0);
     }
   } else if (warp == kProdWarps) {
-    if (lane == 0 && nk > 0)
+    if (nk > 0)
       stream_mma_role(bars, smem, tmem, 1, nk, a.kblk, tc::idesc_bf16(128, Npad, 0, 1),
                       (uint32_t)a.N8 * 128, 128);
   } else {
@@ -414,10 +414,13 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    // MMA role: warp-uniform control flow, one elected lane issues (see stream_mma_role)
+    {
       const uint32_t idesc = tc::idesc_bf16(128, CH, 0, 0);
       const uint32_t lbo = (CH / 8) * 128, sbo = 128;
+      const uint32_t kadv = kstep_bytes >> 4;
       uint32_t bs = 0, bph = 0, d_use = 0;
+      const bool leader = tc::elect_one();
       for (long long it = 0; it < n_items; ++it) {
         mbar_wait(&bars.a_full[0], it & 1);
         mbar_wait(&bars.a_full[1], it & 1);
@@ -432,15 +435,24 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
             tc::fence_after();
             const uint32_t dcol = tmem + (sub ? kDaColD1 : kDaColD0);
             const uint32_t acol = tmem + (sub ? kDaColA1 : kDaColA0);
-            for (int ks = 0; ks < a.nkA; ++ks)
-              tc::mma_ts(dcol, acol + 8 * ks, bdesc0 + (uint64_t)((ks * kstep_bytes) >> 4), idesc, ks > 0 ? 1u : 0u);
-            tc::commit(&bars.d_full[sub]);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < 13; ++ks)
+                if (ks < a.nkA)
+                  tc::mma_ts(dcol, acol + 8 * ks, bdesc0 + (uint64_t)(ks * kadv), idesc, ks > 0 ? 1u : 0u);
+              tc::commit(&bars.d_full[sub]);
+            }
+            __syncwarp();
           }
-          tc::commit(&bars.b_empty[bs]);
+          if (leader) tc::commit(&bars.b_empty[bs]);
+          __syncwarp();
           if (++bs == kDaS) { bs = 0; bph ^= 1; }
         }
-        tc::commit(&bars.a_empty[0]);
-        tc::commit(&bars.a_empty[1]);
+        if (leader) {
+          tc::commit(&bars.a_empty[0]);
+          tc::commit(&bars.a_empty[1]);
+        }
+        __syncwarp();
       }
     }
   } else {
