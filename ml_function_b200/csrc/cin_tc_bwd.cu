@@ -42,6 +42,22 @@ cin_x0_bf16_kernel(const float* __restrict__ x0, unsigned short* __restrict__ ou
   }
 }
 
+// x0 fp32 [B,m,16] -> bf16 [B][2][m][8]: the two 16-byte halves of every field's 16 coordinates are
+// stored in separate planes, so that 32 lanes reading 32 different fields hit 32 different banks.
+__global__ void __launch_bounds__(256)
+cin_x0_halves_kernel(const float* __restrict__ x0, unsigned short* __restrict__ out, long long B, int m) {
+  const long long total = B * m * 16;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx & 15);
+    const long long t = idx >> 4;
+    const int i = (int)(t % m);
+    const long long b = t / m;
+    const __nv_bfloat16 v = __float2bfloat16_rn(x0[idx]);
+    out[b * (m * 16) + (d >> 3) * (m * 8) + i * 8 + (d & 7)] = *reinterpret_cast<const unsigned short*>(&v);
+  }
+}
+
 // blocked dZ: [rows/8][N8][8 rows][8 cols] bf16; element (r,o) at ((r/8)*N8 + o/8)*128 + (r%8)*16 + (o%8)*2
 __global__ void __launch_bounds__(256)
 cin_dz_init_kernel(const float* __restrict__ gpool, int gstride, int gcol, long long rows, int D, int N,
@@ -115,6 +131,7 @@ cin_dw_reduce_kernel(const float* __restrict__ part, int n_slices, long long sli
 struct DwArgs {
   const unsigned short* pre;   // [B,Hp,D] bf16
   const unsigned short* x0b;   // [B,m,D] bf16
+  const unsigned short* x0h;   // [B,2,m,8] bf16 (D == 16 only): staged path
   const unsigned char* dz;     // blocked, kblk bytes per k-step (16 rows)
   float* part;                 // [n_slices][n_cp*256][Npad]
   int D, Hp, N8, C, n_cp, n_slices;
@@ -122,13 +139,23 @@ struct DwArgs {
   long long nks_total, ks_per_slice;
 };
 
+// kStaged (D == 16): the loader thread also bulk-copies, per k-step (= one sample b), the slab
+// pre[b, h_lo..h_hi, :] (<= 11 rows x 32 B) and x0h[b] (832 B) into the B stage; the row warps read
+// their two 32-byte vectors from shared memory (29-cycle latency) instead of chasing L2 with
+// per-lane global loads, and release the stage together with the MMA (b_empty count 9).
+constexpr int kDwNH = 11;
 template <int MF>
+constexpr uint32_t dw_stage_bytes(uint32_t kblk) { return kG * (kblk + kDwNH * 32u + MF * 32u); }
+
+template <int MF, bool kStaged>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_dw_tc_kernel(const DwArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Barriers bars;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  stream_init(bars, tid, warp);
+  stream_init(bars, tid, warp, kStaged ? 1 + kProdWarps : 1);
   const uint32_t tmem = bars.tmem_base;
+  const uint32_t stage_stride = kStaged ? dw_stage_bytes<MF>(a.kblk) : kG * a.kblk;
+  const uint32_t offP = kG * a.kblk, offX = offP + kG * kDwNH * 32u;
 
   const int cp = blockIdx.x % a.n_cp;
   const int slice = blockIdx.x / a.n_cp;
@@ -146,53 +173,101 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_dw_tc_kernel(const DwArgs a
     const int mode = c < a.C ? 2 : (c == a.C ? 1 : 0);          // product / ones (dbias) / zero
     const int h = mode == 2 ? c / MF : 0, i = mode == 2 ? c % MF : 0;
     const int ksD = a.D / 16;                                   // k-steps per sample
-    auto addr = [&](long long ks, const unsigned short* base, int H, int row) -> const uint4* {
-      const long long b = ks / ksD;
-      const int d0 = (int)(ks - b * ksD) * 16;
-      return reinterpret_cast<const uint4*>(base + (b * H + row) * (long long)a.D + d0);
-    };
-    if (nk > 0) {
+    if (nk > 0 && kStaged) {
       SlotWriter sw;
       const int n_groups = (nk + kG - 1) / kG;
-      uint4 nb[kG][4];
-      auto load_group = [&](int g) {
+      const int h_lo = (cp * (128 * kSub)) / MF;
+      const uint32_t myP = offP + (uint32_t)(h - h_lo) * 32u, myX = offX + (uint32_t)i * 16u;
+      uint32_t bs = 0, bph = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const int gk = min(kG, nk - g * kG);
+        mbar_wait(&bars.b_full[bs], bph);
+        const unsigned char* st = smem + bs * stage_stride;
+        uint32_t w[kG][8];
 #pragma unroll
         for (int u = 0; u < kG; ++u) {
-          long long ks = ks0 + (long long)g * kG + u;
-          if (ks >= ks0 + nk) ks = ks0 + nk - 1;                 // clamped (value unused)
-          const uint4* pp = addr(ks, a.pre, a.Hp, h);
-          const uint4* xp = addr(ks, a.x0b, MF, i);
-          nb[u][0] = __ldg(pp); nb[u][1] = __ldg(pp + 1);
-          nb[u][2] = __ldg(xp); nb[u][3] = __ldg(xp + 1);
+          if (mode == 2) {
+            const uint4 p0 = *reinterpret_cast<const uint4*>(st + myP + u * (kDwNH * 32));
+            const uint4 p1 = *reinterpret_cast<const uint4*>(st + myP + u * (kDwNH * 32) + 16);
+            const uint4 x0 = *reinterpret_cast<const uint4*>(st + myX + u * (MF * 32));
+            const uint4 x1 = *reinterpret_cast<const uint4*>(st + myX + u * (MF * 32) + MF * 16);
+            w[u][0] = hmul2_bf16(p0.x, x0.x); w[u][1] = hmul2_bf16(p0.y, x0.y);
+            w[u][2] = hmul2_bf16(p0.z, x0.z); w[u][3] = hmul2_bf16(p0.w, x0.w);
+            w[u][4] = hmul2_bf16(p1.x, x1.x); w[u][5] = hmul2_bf16(p1.y, x1.y);
+            w[u][6] = hmul2_bf16(p1.z, x1.z); w[u][7] = hmul2_bf16(p1.w, x1.w);
+          } else {
+            const uint32_t v = mode == 1 ? 0x3F803F80u : 0u;
+#pragma unroll
+            for (int z = 0; z < 8; ++z) w[u][z] = v;
+          }
         }
-      };
-      load_group(0);
-      for (int g = 0; g < n_groups; ++g) {
-        uint4 cb[kG][4];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.b_empty[bs]);               // our reads of this stage are done
+        if (++bs == kS) { bs = 0; bph ^= 1; }
 #pragma unroll
         for (int u = 0; u < kG; ++u)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) cb[u][q] = nb[u][q];
-        if (g + 1 < n_groups) load_group(g + 1);
+          if (u < gk) sw.put(bars, sub, tmem + lane_base + colA, w[u], g * kG + u == nk - 1, lane);
+      }
+    } else if (nk > 0) {
+      SlotWriter sw;
+      const int n_groups = (nk + kG - 1) / kG;
+      // running element offsets of the NEXT k-step to fetch: sample-major, 16 coordinates per k-step
+      long long bq = ks0 / ksD;
+      int dq = (int)(ks0 - bq * ksD);
+      const unsigned short* pp = a.pre + (bq * a.Hp + h) * (long long)a.D + dq * 16;
+      const unsigned short* xp = a.x0b + (bq * MF + i) * (long long)a.D + dq * 16;
+      const long long p_wrap = (long long)a.Hp * a.D - a.D + 16;   // last k-step of a sample -> first of the next
+      const long long x_wrap = (long long)MF * a.D - a.D + 16;
+      int fetched = 0;                                             // k-steps fetched so far
+      constexpr int kPF = 2;                                       // groups in flight ahead of the compute
+      uint4 nb[kPF][kG][4];
+      auto load_group = [&](int slot) {
 #pragma unroll
         for (int u = 0; u < kG; ++u) {
-          const int kl = g * kG + u;
-          if (kl < nk) {
-            uint32_t w[8];
-            if (mode == 2) {
-              w[0] = hmul2_bf16(cb[u][0].x, cb[u][2].x); w[1] = hmul2_bf16(cb[u][0].y, cb[u][2].y);
-              w[2] = hmul2_bf16(cb[u][0].z, cb[u][2].z); w[3] = hmul2_bf16(cb[u][0].w, cb[u][2].w);
-              w[4] = hmul2_bf16(cb[u][1].x, cb[u][3].x); w[5] = hmul2_bf16(cb[u][1].y, cb[u][3].y);
-              w[6] = hmul2_bf16(cb[u][1].z, cb[u][3].z); w[7] = hmul2_bf16(cb[u][1].w, cb[u][3].w);
-            } else {
-              const uint32_t v = mode == 1 ? 0x3F803F80u : 0u;
+          if (fetched < nk) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(pp);
+            const uint4* x4 = reinterpret_cast<const uint4*>(xp);
+            nb[slot][u][0] = __ldg(p4); nb[slot][u][1] = __ldg(p4 + 1);
+            nb[slot][u][2] = __ldg(x4); nb[slot][u][3] = __ldg(x4 + 1);
+            ++fetched;
+            if (++dq == ksD) { dq = 0; pp += p_wrap; xp += x_wrap; }
+            else { pp += 16; xp += 16; }
+          }
+        }
+      };
 #pragma unroll
-              for (int q = 0; q < 8; ++q) w[q] = v;
+      for (int q = 0; q < kPF; ++q) load_group(q);
+      for (int g0 = 0; g0 < n_groups; g0 += kPF) {
+#pragma unroll
+        for (int q = 0; q < kPF; ++q) {
+          const int g = g0 + q;
+          if (g < n_groups) {
+            uint32_t w[kG][8];
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {
+              if (mode == 2) {
+                const uint4 p0 = nb[q][u][0], p1 = nb[q][u][1], x0 = nb[q][u][2], x1 = nb[q][u][3];
+                w[u][0] = hmul2_bf16(p0.x, x0.x); w[u][1] = hmul2_bf16(p0.y, x0.y);
+                w[u][2] = hmul2_bf16(p0.z, x0.z); w[u][3] = hmul2_bf16(p0.w, x0.w);
+                w[u][4] = hmul2_bf16(p1.x, x1.x); w[u][5] = hmul2_bf16(p1.y, x1.y);
+                w[u][6] = hmul2_bf16(p1.z, x1.z); w[u][7] = hmul2_bf16(p1.w, x1.w);
+              } else {
+                const uint32_t v = mode == 1 ? 0x3F803F80u : 0u;
+#pragma unroll
+                for (int z = 0; z < 8; ++z) w[u][z] = v;
+              }
             }
-            sw.put(bars, sub, tmem + lane_base + colA, w, kl == nk - 1, lane);
+            load_group(q);                                          // refill this slot: group g + kPF
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {
+              const int kl = g * kG + u;
+              if (kl < nk) sw.put(bars, sub, tmem + lane_base + colA, w[u], kl == nk - 1, lane);
+            }
           }
         }
       }
+    }
+    if (nk > 0) {
       // ---- epilogue: this lane's accumulator row -> partial buffer --------------------------
       mbar_wait(&bars.d_full, 0);
       tc::fence_after();
@@ -212,10 +287,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_dw_tc_kernel(const DwArgs a
   } else if (warp == kProdWarps) {
     if (nk > 0)
       stream_mma_role(bars, smem, tmem, 1, nk, a.kblk, tc::idesc_bf16(128, Npad, 0, 1),
-                      (uint32_t)a.N8 * 128, 128);
+                      (uint32_t)a.N8 * 128, 128, stage_stride);
   } else {
-    if (lane == 0 && nk > 0)
-      stream_loader_role(bars, smem, 1, nk, a.kblk, [&](long long) { return a.dz + (size_t)ks0 * a.kblk; });
+    if (lane == 0 && nk > 0) {
+      if (!kStaged) {
+        stream_loader_role(bars, smem, 1, nk, a.kblk, [&](long long) { return a.dz + (size_t)ks0 * a.kblk; });
+      } else {
+        const int n_groups = (nk + kG - 1) / kG;
+        const int h_lo = (cp * (128 * kSub)) / MF;
+        const int h_hi = min(a.Hp - 1, (cp * (128 * kSub) + 128 * kSub - 1) / MF);
+        const uint32_t pbytes = h_hi >= h_lo ? (uint32_t)(h_hi - h_lo + 1) * 32u : 0u;   // 0: only the bias lane
+        uint32_t bs = 0, bph = 0;
+        for (int g = 0; g < n_groups; ++g) {
+          const int gk = min(kG, nk - g * kG);
+          const long long k0 = ks0 + (long long)g * kG;            // == first sample of the group (D == 16)
+          mbar_wait(&bars.b_empty[bs], bph ^ 1);
+          unsigned char* st = smem + bs * stage_stride;
+          mbar_expect_tx(&bars.b_full[bs], gk * (a.kblk + pbytes + MF * 32u));
+          bulk_g2s(st, a.dz + (size_t)k0 * a.kblk, gk * a.kblk, &bars.b_full[bs]);
+          bulk_g2s(st + offX, a.x0h + (size_t)k0 * (MF * 16), gk * MF * 32u, &bars.b_full[bs]);
+          for (int u = 0; u < gk && pbytes; ++u)
+            bulk_g2s(st + offP + u * (kDwNH * 32), a.pre + ((size_t)(k0 + u) * a.Hp + h_lo) * 16, pbytes,
+                     &bars.b_full[bs]);
+          if (++bs == kS) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
   }
   tc::fence_before();
   __syncthreads();
@@ -491,10 +588,12 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
   const unsigned char* sv = static_cast<const unsigned char*>(saved);
   const long long rows = B * D;
   const size_t smem_stream = stream_smem_bytes();
+  const size_t smem_dw = (size_t)kS * dw_stage_bytes<26>(2u * ((kMaxN + 7) / 8) * 128u);
   const size_t smem_da = (size_t)kDaS * 13 * 2 * (kDaChunkH * 26 / 8) * 128;
   static bool attr_done = false;
   if (!attr_done) {
-    KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+    KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+    KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw));
     KON_CUDA(cudaFuncSetAttribute(cin_da_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_da));
     attr_done = true;
   }
@@ -502,6 +601,11 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
   const long long nx = B * m * D;
   cin_x0_bf16_kernel<<<grid_of(nx / 2 + 1, sms), 256, 0, st>>>(x0, x0b, nx);
   KON_LAUNCH_CHECK("cin_x0_bf16_kernel");
+  unsigned short* x0h = reinterpret_cast<unsigned short*>(ws + L.x0h_off);
+  if (D == 16) {
+    cin_x0_halves_kernel<<<grid_of(nx, sms), 256, 0, st>>>(x0, x0h, B, m);
+    KON_LAUNCH_CHECK("cin_x0_halves_kernel");
+  }
   KON_CUDA(cudaMemsetAsync(dx0, 0, (size_t)nx * 4, st));
   bool ragged = false;
   for (int l = 0; l < nl; ++l) {
@@ -522,6 +626,7 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     DwArgs q;
     q.pre = pre;
     q.x0b = x0b;
+    q.x0h = x0h;
     q.dz = ws + L.dz_off[cur];
     q.part = reinterpret_cast<float*>(ws + L.part_off);
     q.D = D;
@@ -533,7 +638,8 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     q.kblk = 2u * L.N8[l] * 128u;
     q.nks_total = rows / 16;
     q.ks_per_slice = (q.nks_total + q.n_slices - 1) / q.n_slices;
-    cin_dw_tc_kernel<26><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
+    if (D == 16) cin_dw_tc_kernel<26, true><<<q.n_cp * q.n_slices, kTcThreads, smem_dw, st>>>(q);
+    else cin_dw_tc_kernel<26, false><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
     KON_LAUNCH_CHECK("cin_dw_tc_kernel");
     const int Npad = L.N8[l] * 8;
     cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(

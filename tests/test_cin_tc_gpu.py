@@ -59,7 +59,7 @@ def test_cin_bf16_unsupported_shapes_fail_loudly():
 
 
 @pytest.mark.parametrize("B,D,hs", [(40, 16, [200, 200, 200]), (33, 16, [200, 104]), (16, 16, [64, 40]),
-                                    (300, 16, [8, 200]), (2, 32, [200, 200])])
+                                    (300, 16, [8, 200]), (2, 32, [200, 200]), (20, 16, [128, 64])])
 def test_cin_bf16_backward(B, D, hs):
     from ml_function_b200 import _lib as L, ops
     x0, ws, bs = _case(B, 26, D, hs, 7 * B + len(hs))

@@ -7,7 +7,7 @@
 //     bit1  B operand: 0 = K-major, 1 = MN-major (no swizzle)
 //     bit2  swap LBO/SBO in the descriptors (hypothesis test)
 //     bit3  TMEM A packing: 0 = low half-word holds the even k, 1 = the odd k
-//     bit4  timing mode: issue 2048 MMAs back to back and report cycles per MMA
+//     bit4  timing mode: issue 16384 MMAs back to back (K = 64) and report cycles per MMA
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -96,21 +96,29 @@ __global__ void __launch_bounds__(128) probe_kernel(Params p) {
   // ---- MMA ------------------------------------------------------------------------------
   const uint32_t idesc = tc::idesc_bf16(128, N, 0, b_mn ? 1 : 0);
   long long t0 = 0;
-  if (tid == 0) {
-    const int reps = timing ? 2048 / (K / 16) : 1;
+  if (warp == 0) {
+    // warp-uniform control flow, one elected lane issues (keeps operands in uniform registers)
+    const bool leader = tc::elect_one();
+    const int reps = timing ? 4096 : 1;
+    const uint64_t da0 = swap ? tc::smem_desc(smem_u32(sA), sboA, lboA) : tc::smem_desc(smem_u32(sA), lboA, sboA);
+    const uint64_t db0 = swap ? tc::smem_desc(smem_u32(sB), sboB, lboB) : tc::smem_desc(smem_u32(sB), lboB, sboB);
+    const uint32_t adv_a = (2 * lboA) >> 4, adv_b = (2 * lboB) >> 4;
     t0 = clock64();
     for (int r = 0; r < reps; ++r) {
-      for (int s = 0; s < K / 16; ++s) {
-        const uint32_t aaddr = smem_u32(sA) + s * 2 * lboA;
-        const uint32_t baddr = smem_u32(sB) + s * 2 * lboB;
-        const uint64_t da = swap ? tc::smem_desc(aaddr, sboA, lboA) : tc::smem_desc(aaddr, lboA, sboA);
-        const uint64_t db = swap ? tc::smem_desc(baddr, sboB, lboB) : tc::smem_desc(baddr, lboB, sboB);
-        const uint32_t acc = (s > 0 || r > 0) ? 1u : 0u;
-        if (a_tmem) tc::mma_ts(tmem + d_col, tmem + a_col + 8 * s, db, idesc, acc);
-        else        tc::mma_ss(tmem + d_col, da, db, idesc, acc);
+      if (leader) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {            // K == 64 in timing mode
+          if (s < K / 16) {
+            const uint32_t acc = (s > 0 || r > 0) ? 1u : 0u;
+            if (a_tmem) tc::mma_ts(tmem + d_col, tmem + a_col + 8 * s, db0 + (uint64_t)(s * adv_b), idesc, acc);
+            else        tc::mma_ss(tmem + d_col, da0 + (uint64_t)(s * adv_a), db0 + (uint64_t)(s * adv_b), idesc, acc);
+          }
+        }
       }
+      __syncwarp();
     }
-    tc::commit(&bar);
+    if (leader) tc::commit(&bar);
+    __syncwarp();
   }
   mbar_wait(&bar, 0);
   tc::fence_after();
@@ -162,7 +170,7 @@ int main(int argc, char** argv) {
   double maxerr = 0, maxref = 0;
   for (size_t i = 0; i < D.size(); ++i) { maxerr = fmax(maxerr, fabs((double)D[i] - R[i])); maxref = fmax(maxref, fabs((double)R[i])); }
   if (variant & 16) {
-    const int n_mma = (2048 / (K / 16)) * (K / 16);
+    const int n_mma = 4096 * (K / 16 < 4 ? K / 16 : 4);
     printf("variant %d N %d K %d: TIMING %lld cycles for %d MMAs = %.1f cyc/MMA\n", variant, N, K, cyc, n_mma, (double)cyc / n_mma);
   } else {
     printf("variant %d N %d K %d: max|err| %.4g (max|ref| %.3g) %s\n", variant, N, K, maxerr, maxref,
