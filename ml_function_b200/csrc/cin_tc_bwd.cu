@@ -337,6 +337,7 @@ struct DaArgs {
   const unsigned short* x0b;     // [B,m,D] bf16
   const unsigned short* pre;     // [B,Hp,D] bf16 (layer 0: == x0b)
   float* dx0;                    // [B,m,D] fp32, accumulated
+  float* dpre0;                  // [B,m,D] fp32 scratch: layer 0's dpre (pre == x0), folded into dx0 per tile
   unsigned char* dz_prev;        // blocked dZ_{l-1} (N8p column groups) or nullptr on layer 0
   const float* gpool;            // d_pooled [B, gstride]
   int gstride, gcol_prev;
@@ -398,16 +399,21 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
       mbar_wait(&bars.a_empty[sub], (tile_it & 1) ^ 1);
       tc::fence_after();
       {
+        // all 16-byte units of the row are requested before the first one is used (one exposed
+        // HBM latency per tile instead of one per k-step)
         const long long rc = valid ? r : 0;
         const uint4* zr = reinterpret_cast<const uint4*>(a.dz + ((rc >> 3) * a.N8) * 128 + (rc & 7) * 16);
-        for (int s = 0; s < a.nkA; ++s) {
-          uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-          if (valid) {
-            lo = __ldg(zr + (2 * s) * 8);                         // column group 2s   (128 B apart)
-            if (2 * s + 1 < a.N8) hi = __ldg(zr + (2 * s + 1) * 8);
+        uint4 zq[26];
+#pragma unroll
+        for (int q = 0; q < 26; ++q)
+          zq[q] = (valid && q < a.N8) ? __ldg(zr + q * 8) : make_uint4(0, 0, 0, 0);   // column group q (128 B apart)
+#pragma unroll
+        for (int s = 0; s < 13; ++s) {
+          if (s < a.nkA) {
+            const uint32_t w[8] = {zq[2 * s].x, zq[2 * s].y, zq[2 * s].z, zq[2 * s].w,
+                                   zq[2 * s + 1].x, zq[2 * s + 1].y, zq[2 * s + 1].z, zq[2 * s + 1].w};
+            tc::st8(tmem + lane_base + colA + 8 * s, w);
           }
-          const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          tc::st8(tmem + lane_base + colA + 8 * s, w);
         }
         tc::wait_st();
         tc::fence_before();
@@ -493,20 +499,29 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
 #pragma unroll
             for (int q = 0; q < kDaChunkH; ++q) {
               const int h = j * kDaChunkH + q;
-              if (h < a.Hp) {
-                float* p = a.dx0 + (b * MF + h) * (long long)a.D + d;
-                *p += dp[q].x + dp[q].y;
-              }
+              if (h < a.Hp)      // plain store now, one batched read-modify-write at the end of the tile
+                a.dpre0[(b * MF + h) * (long long)a.D + d] = dp[q].x + dp[q].y;
             }
           }
         }
       }
       if (valid) {
         float* dxr = a.dx0 + b * (long long)MF * a.D + d;
+        float old[MF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) old[i] = dxr[(long long)i * a.D];          // all loads first
+        if (!a.dz_prev) {                                                       // layer 0: + dpre (written by this thread)
+          const float* dq = a.dpre0 + b * (long long)MF * a.D + d;
+          float t[MF];
+#pragma unroll
+          for (int i = 0; i < MF; ++i) t[i] = dq[(long long)i * a.D];
+#pragma unroll
+          for (int i = 0; i < MF; ++i) old[i] += t[i];
+        }
 #pragma unroll
         for (int i = 0; i < MF / 2; ++i) {
-          dxr[(long long)(2 * i) * a.D] += dx2[i].x;
-          dxr[(long long)(2 * i + 1) * a.D] += dx2[i].y;
+          dxr[(long long)(2 * i) * a.D] = old[2 * i] + dx2[i].x;
+          dxr[(long long)(2 * i + 1) * a.D] = old[2 * i + 1] + dx2[i].y;
         }
       }
     }
@@ -652,6 +667,7 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     p.x0b = x0b;
     p.pre = pre;
     p.dx0 = dx0;
+    p.dpre0 = reinterpret_cast<float*>(ws + L.dpre0_off);
     p.dz_prev = l == 0 ? nullptr : ws + L.dz_off[cur ^ 1];
     p.gpool = d_pooled;
     p.gstride = nl * D;
