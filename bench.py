@@ -76,6 +76,16 @@ def algo_work(model, B, k, conv=(200, 200, 200), cross_layers=6, heads=2, d=8, k
     return w
 
 
+# library kernel -> (op whose algorithmic work it carries, share of that op's work)
+KERNEL_WORK = {
+    "cin_fwd_tc_kernel": ("cin_fwd", 1.0),
+    "cin_dw_tc_kernel": ("cin_bwd", 0.5),          # dW GEMM = 1x forward FLOPs
+    "cin_da_tc_kernel": ("cin_bwd", 0.5),          # dA GEMM = 1x forward FLOPs
+    "embed_fwd_vec_kernel": ("embed_fwd", 1.0),
+    "embed_reduce_kernel": ("embed_bwd", 1.0),
+}
+
+
 def sample_clocks_start(path):
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -358,11 +368,15 @@ def run_gpu(args):
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
     proc, f = sample_clocks_start(clk_path) if rank == 0 else (None, None)
     ops.PROFILE = {}
+    lib.kon_profile_reset()
+    lib.kon_profile_enable(1)
     l0 = lib.kon_launch_count()
     ms = timed(step_resident, args.steps)
     launches = lib.kon_launch_count() - l0
+    lib.kon_profile_enable(0)
     prof = ops.profile_summary()
     ops.PROFILE = None
+    kprof = {kn: _lib.profile_read(kn) for kn in KERNEL_WORK}
     # ---- end-to-end timing (H2D + step + D2H) ---------------------------------------------
     for i in range(2):
         step_e2e(i)
@@ -392,13 +406,41 @@ def run_gpu(args):
             kernels[op] = {"bound": "tensor", "ms": mean_ms, "calls_per_step": per_step_calls,
                            "achieved": rate / 1e12, "peak": pk["tc_sust"], "unit": "TFLOP/s",
                            "frac": rate / 1e12 / pk["tc_sust"]}
-    dom = max((o for o in kernels), key=lambda o: kernels[o]["ms"] * kernels[o]["calls_per_step"], default=None)
+    # ---- per-kernel roofline: each main kernel is bracketed by CUDA events inside the library
+    # (kon_profile_*), on the launching stream, inside the timed region ------------------------
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic_tab = json.load(open(tpath))
+    kstats = {}
+    for kn, (tot_ms, n) in kprof.items():
+        if n == 0:
+            continue
+        op, share = KERNEL_WORK[kn]
+        if op not in work:
+            continue
+        bound, amount = work[op]
+        amount = amount * share                     # algorithmic work of this kernel family per step
+        per_step_ms = tot_ms / args.steps
+        rate = amount / (per_step_ms * 1e-3)
+        peak = pk["hbm"] if bound == "hbm" else pk["tc_sust"]
+        scale = 1e9 if bound == "hbm" else 1e12
+        lps = n / args.steps
+        kstats[kn] = {"bound": bound, "launches_per_step": lps, "ms_per_launch": per_step_ms / lps,
+                      "work_per_launch": amount / lps, "achieved": rate / scale, "peak": peak,
+                      "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": rate / scale / peak,
+                      "share_of_step": per_step_ms / (ms / args.steps)}
+    dom = max(kstats, key=lambda kn: kstats[kn]["share_of_step"], default=None)
     roof = None
     if dom is not None:
-        kd = kernels[dom]
+        kd = kstats[dom]
+        tr = traffic_tab.get(dom, {}).get(name)
         roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
-                "frac": kd["frac"], "traffic": None, "peak_source": pk["src"] + (" (sustained)" if kd["bound"] == "tensor" else ""),
-                "share_of_step": kd["ms"] * kd["calls_per_step"] / (ms / args.steps)}
+                "frac": kd["frac"], "traffic": tr,
+                "peak_source": pk["src"] + (" (sustained: timed inside a long step)" if kd["bound"] == "tensor" else ""),
+                "launches_per_step": kd["launches_per_step"], "ms_per_launch": kd["ms_per_launch"],
+                "work_per_launch": kd["work_per_launch"], "share_of_step": kd["share_of_step"],
+                "note": "achieved = algorithmic work of the kernel's launches in a step / their summed CUDA-event time"}
     total = B * world * args.steps
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     # CPU baseline on rank 0, bounded sample
@@ -426,7 +468,8 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
-        "kernels": kernels,
+        "kernel_stats": kstats,
+        "op_stats": kernels,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -63,6 +63,15 @@ const char* kon_last_error(void);
 /* Number of kernels of THIS library launched by the process so far (every __global__ of
  * libkon_b200 counts once per launch; CUB primitives called by kon_embed_bwd do not). */
 long long   kon_launch_count(void);
+/* Per-kernel device timing for roofline reports.  While enabled, entry points that launch
+ * several kernels (kon_cin_fwd/bwd, kon_embed_fwd/bwd) bracket their main kernels with CUDA
+ * events recorded on the caller's stream (not usable under stream capture).  kon_profile_read
+ * synchronises on the recorded events and returns the summed duration and the launch count of
+ * one kernel name ("cin_fwd_tc_kernel", "cin_dw_tc_kernel", "cin_da_tc_kernel",
+ * "embed_fwd_vec_kernel", "embed_bwd_sort", "embed_reduce_kernel"). */
+int         kon_profile_enable(int on);
+int         kon_profile_reset(void);
+int         kon_profile_read(const char* kernel, double* total_ms, long long* launches);
 /* SM count / arch of the device the tensors live on (for host-side grid sizing). */
 int         kon_device_info(int device_id, int* sm_count, int* cc_major, int* cc_minor);
 

@@ -127,6 +127,9 @@ def lib():
         "kon_abi_version": (ctypes.c_int, []),
         "kon_last_error": (ctypes.c_char_p, []),
         "kon_launch_count": (ctypes.c_longlong, []),
+        "kon_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+        "kon_profile_reset": (ctypes.c_int, []),
+        "kon_profile_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
         "kon_device_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)] + [ctypes.POINTER(ctypes.c_int)] * 2),
         "kon_embed_fwd": (ctypes.c_int, [T, T, i64p, i32, T, T, i32, vp]),
         "kon_embed_bwd_workspace_bytes": (sz, [i64, i32]),
@@ -157,12 +160,20 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "kon_abi_version", "kon_last_error", "kon_launch_count", "kon_device_info", "kon_embed_fwd",
+    "kon_abi_version", "kon_last_error", "kon_launch_count", "kon_profile_enable", "kon_profile_reset",
+    "kon_profile_read", "kon_device_info", "kon_embed_fwd",
     "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_sgd", "kon_embed_adam",
     "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",
 )
+
+
+def profile_read(kernel: str):
+    """-> (total ms, launches) of one kernel name recorded since kon_profile_reset()."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+    check(lib().kon_profile_read(kernel.encode(), ctypes.byref(ms), ctypes.byref(n)), "kon_profile_read")
+    return ms.value, n.value
 
 
 def check(rc: int, what: str):

@@ -262,7 +262,10 @@ int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias,
     a.kblk = 2u * L.N8[l] * 128u;
     a.n_pairs = (rows + 128 * kSub - 1) / (128 * kSub);
     const int grid = (int)std::min<long long>(a.n_pairs, sms);
-    cin_fwd_tc_kernel<26><<<grid, kTcThreads, smem, st>>>(a);
+    {
+      ProfileScope ps("cin_fwd_tc_kernel", st);
+      cin_fwd_tc_kernel<26><<<grid, kTcThreads, smem, st>>>(a);
+    }
     KON_LAUNCH_CHECK("cin_fwd_tc_kernel");
   }
   return KON_OK;

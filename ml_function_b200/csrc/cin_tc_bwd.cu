@@ -653,8 +653,11 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     q.kblk = 2u * L.N8[l] * 128u;
     q.nks_total = rows / 16;
     q.ks_per_slice = (q.nks_total + q.n_slices - 1) / q.n_slices;
-    if (D == 16) cin_dw_tc_kernel<26, true><<<q.n_cp * q.n_slices, kTcThreads, smem_dw, st>>>(q);
-    else cin_dw_tc_kernel<26, false><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
+    {
+      ProfileScope ps("cin_dw_tc_kernel", st);
+      if (D == 16) cin_dw_tc_kernel<26, true><<<q.n_cp * q.n_slices, kTcThreads, smem_dw, st>>>(q);
+      else cin_dw_tc_kernel<26, false><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
+    }
     KON_LAUNCH_CHECK("cin_dw_tc_kernel");
     const int Npad = L.N8[l] * 8;
     cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
@@ -681,7 +684,10 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     p.n_chunks = L.n_chunks[l];
     p.nkA = L.nkA[l];
     p.chunk_bytes = L.chunk_bytes[l];
-    cin_da_tc_kernel<26><<<(int)std::min<long long>(p.n_pairs, sms), 320, smem_da, st>>>(p);
+    {
+      ProfileScope ps("cin_da_tc_kernel", st);
+      cin_da_tc_kernel<26><<<(int)std::min<long long>(p.n_pairs, sms), 320, smem_da, st>>>(p);
+    }
     KON_LAUNCH_CHECK("cin_da_tc_kernel");
     cur ^= 1;
   }

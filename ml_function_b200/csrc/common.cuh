@@ -56,6 +56,24 @@ void count_launch();   // abi.cu: bumps the process-wide launch counter (kon_lau
   } while (0)
 
 // ----------------------------------------------------------------------------------
+// optional per-kernel device timing (kon_profile_*): the entry points that launch several
+// kernels bracket their main kernels with CUDA events on the caller's stream
+// ----------------------------------------------------------------------------------
+bool profile_on();                                                  // abi.cu
+void profile_begin(const char* name, cudaStream_t st, void** tok);  // abi.cu
+void profile_end(void* tok, cudaStream_t st);                       // abi.cu
+struct ProfileScope {
+  void* tok = nullptr;
+  cudaStream_t st;
+  ProfileScope(const char* name, cudaStream_t s) : st(s) {
+    if (profile_on()) profile_begin(name, s, &tok);
+  }
+  ~ProfileScope() {
+    if (tok) profile_end(tok, st);
+  }
+};
+
+// ----------------------------------------------------------------------------------
 // DLTensor checks
 // ----------------------------------------------------------------------------------
 inline bool is_dtype(const DLTensor* t, int code, int bits) {

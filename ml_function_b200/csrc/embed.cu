@@ -552,6 +552,7 @@ static int launch_fwd_vec(int lpr, int grid, size_t smem, cudaStream_t st, const
     embed_fwd_vec_kernel<IdT, N><<<grid, kFwdThreads, smem, st>>>(arena, ids, ft, F, L, vpr,    \
                                                                   n_bags, bpt, out, sb, sf, oob); \
     break;
+  ProfileScope ps("embed_fwd_vec_kernel", st);
   switch (lpr) {
     KON_FWD_CASE(1)
     KON_FWD_CASE(2)
@@ -789,8 +790,11 @@ extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
   KON_LAUNCH_CHECK("embed_keys_kernel");
 
   size_t cub_bytes = l.cub_bytes;
-  KON_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, vals_in,
-                                           vals_out, (int)n, 0, end_bit, st));
+  {
+    ProfileScope ps("embed_bwd_sort", st);
+    KON_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, vals_in,
+                                             vals_out, (int)n, 0, end_bit, st));
+  }
   cub_bytes = l.cub_bytes;
   auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), RunHead{keys_out});
   KON_CUDA(cub::DeviceScan::InclusiveSum(ws + l.cub, cub_bytes, it, segidx, (int)n, st));
@@ -831,6 +835,7 @@ extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
                 "d_out rows must be 16-B aligned");
   }
   const size_t smem = 2 * (size_t)kRedThreads * 16;
+  ProfileScope ps_red("embed_reduce_kernel", st);
 #define KON_RED_CASE(N)                                                                  \
   case N:                                                                                \
     embed_reduce_kernel<N><<<l.n_cta, kRedThreads, smem, st>>>(a);                       \
