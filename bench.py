@@ -21,6 +21,10 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# NCCL's version/debug banner goes to stdout by default; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import subprocess
 import sys
 import time

@@ -31,21 +31,24 @@ from torch import nn
 class ShardPlan:
     """Which rank owns which (field, row)."""
 
-    def __init__(self, rows: Sequence[int], world: int, row_wise_min_rows: int = 1_000_000):
+    def __init__(self, rows: Sequence[int], world: int, row_wise_min_rows: int = 50_000_000):
         self.rows = [int(r) for r in rows]
         self.world = world
         F = len(self.rows)
         self.rw_fields = [f for f in range(F) if world > 1 and self.rows[f] >= row_wise_min_rows]
         self.tw_fields = [f for f in range(F) if f not in self.rw_fields]
-        # greedy: every table-wise field costs the same number of lookups; place big tables first
-        load = [0] * world
-        mem = [0] * world
+        # Every table-wise field costs the same number of lookups per step, so ranks are balanced by
+        # field COUNT; contiguous blocks of fields per rank keep the exchanged layout identical to the
+        # model's field order (no permutation copy after the all-to-all).
         self.tw_owner = {}
-        for f in sorted(self.tw_fields, key=lambda f: -self.rows[f]):
-            p = min(range(world), key=lambda q: (load[q], mem[q]))
-            self.tw_owner[f] = p
-            load[p] += 1
-            mem[p] += self.rows[f]
+        n_tw = len(self.tw_fields)
+        base, extra = divmod(n_tw, world)
+        pos = 0
+        for p in range(world):
+            cnt = base + (1 if p < extra else 0)
+            for f in self.tw_fields[pos:pos + cnt]:
+                self.tw_owner[f] = p
+            pos += cnt
         self.tw_of_rank = [[f for f in self.tw_fields if self.tw_owner[f] == p] for p in range(world)]
         # field order after the exchange ("rank-major"): rank 0's tw fields, rank 1's, ..., then rw fields
         self.exchange_order = [f for p in range(world) for f in self.tw_of_rank[p]] + self.rw_fields
@@ -53,6 +56,7 @@ class ShardPlan:
         for pos, f in enumerate(self.exchange_order):
             inv[f] = pos
         self.to_global = inv            # emb_global[:, f] = emb_exchange[:, to_global[f]]
+        self.identity_order = self.exchange_order == list(range(F))
 
     def local_rows(self, rank: int, f: int) -> int:
         if f in self.rw_fields:
@@ -110,9 +114,7 @@ class _ShardedLookup(torch.autograd.Function):
         B_l, F = ids_local.shape
         k = arena.shape[1]
         dev = arena.device
-        ids_all = torch.empty((N * B_l, F), dtype=ids_local.dtype, device=dev)
-        _all_gather(ids_all, ids_local.contiguous(), g)
-        ids_tw, ids_rw = sh.local_ids(ids_all)
+        ids_tw, ids_rw = sh.exchange_ids(ids_local)
         n_tw, n_rw = len(plan.tw_of_rank[rank]), len(plan.rw_fields)
         chunks = []
         if len(plan.tw_fields):
@@ -132,7 +134,7 @@ class _ShardedLookup(torch.autograd.Function):
             _reduce_scatter(mine, part, g)
             chunks.append(mine)
         ex = chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=1)     # exchange (rank-major) order
-        emb = ex.index_select(1, sh.to_global)
+        emb = ex if plan.identity_order else ex.index_select(1, sh.to_global)
         ctx.sh, ctx.arena = sh, arena
         ctx.save_for_backward(ids_tw, ids_rw)
         ctx.B_l = B_l
@@ -145,7 +147,7 @@ class _ShardedLookup(torch.autograd.Function):
         plan, g, N, rank = sh.plan, sh.group, sh.world, sh.rank
         B_l, k = ctx.B_l, arena.shape[1]
         dev = arena.device
-        gex = gout.index_select(1, sh.to_exchange)                            # [B_l, F, k] exchange order
+        gex = gout if plan.identity_order else gout.index_select(1, sh.to_exchange)   # exchange order
         n_tw, n_rw = len(plan.tw_of_rank[rank]), len(plan.rw_fields)
         n_tw_all = len(plan.tw_fields)
         grads = []
@@ -179,9 +181,7 @@ class _ShardedSum(torch.autograd.Function):
         g, N = sh.group, sh.world
         B_l, F = ids_local.shape
         dev = arena.device
-        ids_all = torch.empty((N * B_l, F), dtype=ids_local.dtype, device=dev)
-        _all_gather(ids_all, ids_local.contiguous(), g)
-        ids_tw, ids_rw = sh.local_ids(ids_all)
+        ids_tw, ids_rw = sh.exchange_ids(ids_local)
         ids_loc = torch.cat([ids_tw, ids_rw], dim=1).contiguous()
         part = sh.lookup_fn(arena, ids_loc, sh.all_offs, True)                # [B_g, dim]
         mine = torch.empty((B_l, arena.shape[1]), dtype=arena.dtype, device=dev)
@@ -253,13 +253,35 @@ class ShardedEmbed(nn.Module):
             slabs.append((o, len(plan.tw_of_rank[p])))
             o += len(plan.tw_of_rank[p])
         self.tw_slabs = slabs
+        self.tw_idx_of = [torch.tensor(plan.tw_of_rank[p], dtype=torch.long, device=device) for p in range(self.world)]
 
-    def local_ids(self, ids_all: torch.Tensor):
-        """Global ids of the global batch -> this rank's (table-wise ids, row-wise local ids or -1)."""
-        ids_tw = ids_all.index_select(1, self.tw_idx).contiguous()
-        r = ids_all.index_select(1, self.rw_idx)
-        own = (r % self.world) == self.rank
-        ids_rw = torch.where(own, torch.div(r, self.world, rounding_mode="floor"), torch.full_like(r, -1)).contiguous()
+    def exchange_ids(self, ids_local: torch.Tensor):
+        """Local ids ``[B_l,F]`` -> this rank's lookups for the GLOBAL batch:
+        (table-wise ids ``[B_g, n_tw_loc]``, row-wise local row ids ``[B_g, n_rw]`` with -1 where the
+        row lives on another rank).  Each owner only receives the columns it owns (all-to-all of
+        4 B ids), the row-wise columns are all-gathered."""
+        N, g, plan = self.world, self.group, self.plan
+        B_l = ids_local.shape[0]
+        dev = ids_local.device
+        n_loc = len(plan.tw_of_rank[self.rank])
+        if len(plan.tw_fields):
+            send = torch.cat([ids_local[:, o:o + c].reshape(-1) if plan.identity_order else
+                              ids_local.index_select(1, self.tw_idx_of[p]).reshape(-1)
+                              for p, (o, c) in enumerate(self.tw_slabs)])
+            recv = torch.empty(N * B_l * n_loc, dtype=ids_local.dtype, device=dev)
+            _all_to_all(recv, send, [B_l * n_loc] * N, [B_l * c for _, c in self.tw_slabs], g)
+            ids_tw = recv.view(N * B_l, n_loc)
+        else:
+            ids_tw = torch.empty((N * B_l, 0), dtype=ids_local.dtype, device=dev)
+        n_rw = len(plan.rw_fields)
+        if n_rw:
+            mine = ids_local.index_select(1, self.rw_idx).contiguous()
+            r = torch.empty((N * B_l, n_rw), dtype=ids_local.dtype, device=dev)
+            _all_gather(r, mine, g)
+            own = (r % N) == self.rank
+            ids_rw = torch.where(own, torch.div(r, N, rounding_mode="floor"), torch.full_like(r, -1)).contiguous()
+        else:
+            ids_rw = torch.empty((N * B_l, 0), dtype=ids_local.dtype, device=dev)
         return ids_tw, ids_rw
 
     def load_global_tables(self, tables: Sequence[torch.Tensor]):
@@ -291,7 +313,7 @@ class ShardedEmbed(nn.Module):
 
 
 class DistContext:
-    def __init__(self, group, device, row_wise_min_rows: int = 1_000_000):
+    def __init__(self, group, device, row_wise_min_rows: int = 50_000_000):
         self.group, self.device = group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.row_wise_min_rows = row_wise_min_rows

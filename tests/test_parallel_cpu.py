@@ -97,11 +97,14 @@ def test_shard_plan_covers_every_row_once():
     rows = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27,
             14992, 5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
     for world in (1, 2, 4, 8):
-        p = ShardPlan(rows, world)
-        assert sorted(p.exchange_order) == list(range(26))
-        for f in range(26):
-            assert sum(p.local_rows(r, f) for r in range(world) if f in p.rw_fields or p.tw_owner[f] == r) == rows[f]
-        if world == 8:
-            assert len(p.rw_fields) == 5
+        for thr in (50_000_000, 1_000_000):
+            p = ShardPlan(rows, world, row_wise_min_rows=thr)
+            assert sorted(p.exchange_order) == list(range(26))
+            for f in range(26):
+                assert sum(p.local_rows(r, f) for r in range(world) if f in p.rw_fields or p.tw_owner[f] == r) == rows[f]
             cnt = [len(x) for x in p.tw_of_rank]
-            assert max(cnt) - min(cnt) <= 1
+            assert max(cnt) - min(cnt) <= 1                      # balanced by lookup count
+            if thr == 50_000_000:                                # Criteo: everything table-wise, contiguous blocks
+                assert p.rw_fields == [] and p.identity_order
+            elif world == 8:
+                assert len(p.rw_fields) == 5
