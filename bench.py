@@ -496,10 +496,29 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at
+    # stderr (NCCL / C libraries print banners straight to fd 1), and is restored for the result.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    buf = io.StringIO()
+    real_stdout, sys.stdout = sys.stdout, buf
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_gpu(args)
+    finally:
+        sys.stdout = real_stdout
+        os.dup2(saved, 1)
+        os.close(saved)
+    out = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    for l in buf.getvalue().splitlines():
+        if not l.startswith("{"):
+            print(l, file=sys.stderr)
+    if out:
+        print(out[-1], flush=True)
 
 
 if __name__ == "__main__":

@@ -126,6 +126,135 @@ cin_dw_reduce_kernel(const float* __restrict__ part, int n_slices, long long sli
 }
 
 // ---------------------------------------------------------------------------------------------
+// Last layer: the reference pools over the feature maps (IL:322), so dZ_L[r,o] = g[r] for every o and
+// the two backward GEMMs of the LAST layer collapse:
+//     dA[r,c] = g[r] * wsum[c],  wsum[c] = sum_o W[c,o]
+//     dpre[r,h] = g[r] * sum_i wsum[h*m+i] x0[r,i]          dx0[r,i] += g[r] * sum_h wsum[h*m+i] pre[r,h]
+//     dW[c,o]  = v[c] for every o,  v = A^T g   (computed by the dW kernel with a 16-column B operand)
+// ---------------------------------------------------------------------------------------------
+constexpr int kTRow = 28;     // wsum rows padded to 28 floats (16-byte aligned rows, 2 zero columns)
+
+// T[h*28 + i] = sum_o W[(h*m+i)*N + o]; one warp per weight row
+__global__ void __launch_bounds__(256)
+cin_wsum_kernel(const float* __restrict__ W, int C, int N, int m, int Hp8, float* __restrict__ T) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)Hp8 * kTRow;
+  for (long long t = w0; t < total; t += nw) {
+    const int h = (int)(t / kTRow), i = (int)(t - (long long)h * kTRow);
+    const long long c = (long long)h * m + i;
+    float acc = 0.f;
+    if (i < m && c < C)
+      for (int o = lane; o < N; o += 32) acc += W[c * N + o];
+    acc = warp_sum(acc);
+    if (lane == 0) T[t] = acc;
+  }
+}
+
+struct LastDaArgs {
+  const unsigned short* x0b;   // [B,m,D] bf16
+  const unsigned short* pre;   // [B,Hp,D] bf16
+  const float* T;              // [Hp8, 28]
+  const float* gpool;          // d_pooled [B, gstride]
+  int gstride, gcol, gcol_prev;
+  unsigned char* dz_prev;      // blocked, N8p column groups
+  float* dx0;                  // [B,m,D] accumulated
+  long long rows;
+  int D, Hp, Hp8, N8p;
+};
+
+__device__ __forceinline__ void ffma2_acc(float2& acc, const float2 a, const float2 b) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(rc));
+}
+
+template <int MF>
+__global__ void __launch_bounds__(256) cin_last_da_kernel(const LastDaArgs a) {
+  static_assert(MF <= kTRow && MF % 2 == 0, "field count");
+  extern __shared__ __align__(16) float sT[];                  // [Hp8][28]
+  for (int i = threadIdx.x; i < a.Hp8 * kTRow; i += blockDim.x) sT[i] = a.T[i];
+  __syncthreads();
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < a.rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const long long b = r / a.D;
+    const int d = (int)(r - b * a.D);
+    const unsigned short* xrow = a.x0b + b * (long long)MF * a.D + d;
+    const unsigned short* prow = a.pre + b * (long long)a.Hp * a.D + d;
+    float2 x[kTRow / 2], dx[kTRow / 2];
+#pragma unroll
+    for (int i = 0; i < kTRow / 2; ++i) {
+      x[i].x = 2 * i < MF ? bf16_to_f32(__ldg(xrow + (long long)(2 * i) * a.D)) : 0.f;
+      x[i].y = 2 * i + 1 < MF ? bf16_to_f32(__ldg(xrow + (long long)(2 * i + 1) * a.D)) : 0.f;
+      dx[i] = make_float2(0.f, 0.f);
+    }
+    const float g = a.gpool[b * a.gstride + a.gcol + d];
+    const float gprev = a.gpool[b * a.gstride + a.gcol_prev + d];
+    unsigned short praw[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) praw[q] = __ldg(prow + (long long)min(q, a.Hp - 1) * a.D);
+    for (int h0 = 0; h0 < a.Hp8; h0 += 8) {
+      float pv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pv[q] = (h0 + q < a.Hp) ? bf16_to_f32(praw[q]) * g : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) praw[q] = __ldg(prow + (long long)min(h0 + 8 + q, a.Hp - 1) * a.D);
+      uint32_t outw[4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4* trow = reinterpret_cast<const float4*>(sT + (h0 + q) * kTRow);
+        float2 s2 = make_float2(0.f, 0.f);
+        const float2 gp2 = make_float2(pv[q], pv[q]);
+#pragma unroll
+        for (int z = 0; z < kTRow / 4; ++z) {
+          const float4 t = trow[z];
+          ffma2_acc(s2, make_float2(t.x, t.y), x[2 * z]);
+          ffma2_acc(s2, make_float2(t.z, t.w), x[2 * z + 1]);
+          ffma2_acc(dx[2 * z], make_float2(t.x, t.y), gp2);
+          ffma2_acc(dx[2 * z + 1], make_float2(t.z, t.w), gp2);
+        }
+        const float v = (h0 + q < a.Hp) ? g * (s2.x + s2.y) + gprev : 0.f;
+        if (q & 1) outw[q >> 1] = tc::pack_bf16(__uint_as_float(outw[q >> 1]), v);
+        else outw[q >> 1] = __float_as_uint(v);
+      }
+      if ((h0 >> 3) < a.N8p)
+        *reinterpret_cast<uint4*>(a.dz_prev + ((r >> 3) * a.N8p + (h0 >> 3)) * 128 + (r & 7) * 16) =
+            make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    }
+    float* dxr = a.dx0 + b * (long long)MF * a.D + d;
+    float old[MF];
+#pragma unroll
+    for (int i = 0; i < MF; ++i) old[i] = dxr[(long long)i * a.D];
+#pragma unroll
+    for (int i = 0; i < MF / 2; ++i) {
+      dxr[(long long)(2 * i) * a.D] = old[2 * i] + dx[i].x;
+      dxr[(long long)(2 * i + 1) * a.D] = old[2 * i + 1] + dx[i].y;
+    }
+  }
+}
+
+// dW[c,o] = sum_slices part[s][c][0] for every o (c < C);  dbias[o] = sum_slices part[s][C][0]
+__global__ void __launch_bounds__(256)
+cin_dw_reduce_bcast_kernel(const float* __restrict__ part, int n_slices, long long slice_stride, int Npad,
+                           int C, int N, float* __restrict__ dW, float* __restrict__ dbias) {
+  const long long total = (long long)(C + 1) * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / N;
+    const int o = (int)(idx - c * N);
+    const float* p = part + c * Npad;
+    float acc = 0.f;
+    for (int s = 0; s < n_slices; ++s) acc += p[s * slice_stride];
+    if (c < C) dW[idx] = acc;
+    else dbias[o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dW: stream kernel, lanes = c
 // ---------------------------------------------------------------------------------------------
 struct DwArgs {
@@ -632,9 +761,13 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
   }
   if (ragged) KON_CUDA(cudaMemsetAsync(ws + L.dz_off[0], 0, 2 * L.dz_bytes, st));
   int cur = 0;
-  cin_dz_init_kernel<<<grid_of(rows * L.N8[nl - 1], sms), 256, 0, st>>>(d_pooled, nl * D, (nl - 1) * D, rows, D, L.N[nl - 1],
-                                                                       L.N8[nl - 1], ws + L.dz_off[cur]);
-  KON_LAUNCH_CHECK("cin_dz_init_kernel");
+  const bool shortcut = nl >= 2 && L.N8[nl - 1] >= 2;   // last layer's dZ is constant over o: no GEMM needed (see cin_last_da_kernel)
+  {
+    const int lN = shortcut ? 16 : L.N[nl - 1], lN8 = shortcut ? 2 : L.N8[nl - 1];
+    cin_dz_init_kernel<<<grid_of(rows * lN8, sms), 256, 0, st>>>(d_pooled, nl * D, (nl - 1) * D, rows, D, lN, lN8,
+                                                                ws + L.dz_off[cur]);
+    KON_LAUNCH_CHECK("cin_dz_init_kernel");
+  }
   for (int l = nl - 1; l >= 0; --l) {
     const unsigned short* pre = l == 0 ? x0b : reinterpret_cast<const unsigned short*>(sv + L.zt_off[l - 1]);
     // ---- dW_l, dbias_l ----------------------------------------------------------------------
@@ -646,11 +779,12 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     q.part = reinterpret_cast<float*>(ws + L.part_off);
     q.D = D;
     q.Hp = L.Hp[l];
-    q.N8 = L.N8[l];
+    const bool sc = shortcut && l == nl - 1;
+    q.N8 = sc ? 2 : L.N8[l];
     q.C = L.Hp[l] * m;
     q.n_cp = L.n_cp[l];
     q.n_slices = L.n_slices[l];
-    q.kblk = 2u * L.N8[l] * 128u;
+    q.kblk = 2u * q.N8 * 128u;
     q.nks_total = rows / 16;
     q.ks_per_slice = (q.nks_total + q.n_slices - 1) / q.n_slices;
     {
@@ -659,10 +793,43 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
       else cin_dw_tc_kernel<26, false><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
     }
     KON_LAUNCH_CHECK("cin_dw_tc_kernel");
-    const int Npad = L.N8[l] * 8;
-    cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
-        q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
+    const int Npad = q.N8 * 8;
+    if (sc)
+      cin_dw_reduce_bcast_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
+          q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
+    else
+      cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
+          q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
     KON_LAUNCH_CHECK("cin_dw_reduce_kernel");
+    if (sc) {
+      const int Hp8 = (L.Hp[l] + 7) / 8 * 8;
+      float* T = reinterpret_cast<float*>(ws + L.part_off + L.part_bytes - align256((size_t)(kMaxN + 8) * kTRow * 4));
+      cin_wsum_kernel<<<grid_of((long long)Hp8 * kTRow * 32, sms), 256, 0, st>>>(w[l], q.C, L.N[l], m, Hp8, T);
+      KON_LAUNCH_CHECK("cin_wsum_kernel");
+      LastDaArgs z;
+      z.x0b = x0b;
+      z.pre = pre;
+      z.T = T;
+      z.gpool = d_pooled;
+      z.gstride = nl * D;
+      z.gcol = l * D;
+      z.gcol_prev = (l - 1) * D;
+      z.dz_prev = ws + L.dz_off[cur ^ 1];
+      z.dx0 = dx0;
+      z.rows = rows;
+      z.D = D;
+      z.Hp = L.Hp[l];
+      z.Hp8 = Hp8;
+      z.N8p = L.N8[l - 1];
+      {
+        ProfileScope ps("cin_last_da_kernel", st);
+        cin_last_da_kernel<26><<<(int)std::min<long long>((rows + 255) / 256, (long long)sms * 4), 256,
+                                 (size_t)Hp8 * kTRow * 4, st>>>(z);
+      }
+      KON_LAUNCH_CHECK("cin_last_da_kernel");
+      cur ^= 1;
+      continue;
+    }
     // ---- dpre_l -> dZ_{l-1}, dx0 ------------------------------------------------------------------
     DaArgs p;
     p.dz = ws + L.dz_off[cur];
