@@ -237,6 +237,155 @@ __global__ void __launch_bounds__(256) cin_last_da_kernel(const LastDaArgs a) {
   }
 }
 
+// v[h,i] = sum_b sum_d pre[b,h,d] * (x0[b,i,d] g[b,d])   (D == 16): per sample one m16n8k16 k-step.
+// Warp w owns the 16 feature maps h = 16w..16w+15 and all 4 n-tiles (i < 32); A fragments come
+// straight from the bf16 z^T rows in global memory, B = x0*g is built per sample in shared memory.
+// (Legacy mma.sync on purpose: 5.4 GFMA of side work, HBM-bound on the 419 MB of `pre`.)
+constexpr int kLdwBatch = 4;            // samples per __syncthreads
+constexpr int kLdwRow = 24;             // bf16 per padded smem row (12 words: conflict-free fragment reads)
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct LastDwArgs {
+  const unsigned short* x0b;   // [B,m,16] bf16
+  const unsigned short* pre;   // [B,Hp,16] bf16
+  const float* gpool;
+  int gstride, gcol;
+  float* part;                 // [grid][Hp16][32] fp32 partial v  (+ [grid] partial sum of g after it)
+  float* gsum;                 // [grid]
+  long long B;
+  int Hp, m;
+};
+
+__global__ void __launch_bounds__(416) cin_last_dw_kernel(const LastDwArgs a) {
+  __shared__ __align__(16) unsigned short sX[2][kLdwBatch][32 * kLdwRow];
+  __shared__ float s_g[13];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int n_mt = (a.Hp + 15) / 16;
+  const long long per = (a.B + gridDim.x - 1) / gridDim.x;
+  const long long b0 = blockIdx.x * per, b1 = min(a.B, b0 + per);
+  // zero the padded rows (i >= m) once
+  for (int i = tid; i < 2 * kLdwBatch * 32 * kLdwRow; i += blockDim.x) (&sX[0][0][0])[i] = 0;
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[n][q] = 0.f;
+  float gacc = 0.f;
+  const int h_lo = min(warp * 16 + g8, a.Hp - 1), h_hi = min(warp * 16 + g8 + 8, a.Hp - 1);
+  const bool lo_on = warp * 16 + g8 < a.Hp, hi_on = warp * 16 + g8 + 8 < a.Hp;
+  const int xi = tid / 16, xd = tid % 16;        // this thread's element of x0*g (416 = 26*16 threads)
+  auto fill = [&](long long bb, int buf) {
+#pragma unroll
+    for (int u = 0; u < kLdwBatch; ++u) {
+      const long long b = bb + u;
+      float v = 0.f;
+      if (b < b1 && xi < a.m) {
+        const float gv = a.gpool[b * a.gstride + a.gcol + xd];
+        v = bf16_to_f32(__ldg(a.x0b + (b * a.m + xi) * 16 + xd)) * gv;
+        if (xi == 0) gacc += gv;
+      }
+      const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+      sX[buf][u][xi * kLdwRow + xd] = *reinterpret_cast<const unsigned short*>(&hv);
+    }
+  };
+  auto load_a = [&](long long bb, uint32_t (*af)[4]) {
+#pragma unroll
+    for (int u = 0; u < kLdwBatch; ++u) {
+      const long long b = min(bb + u, a.B - 1);
+      const uint32_t* plo = reinterpret_cast<const uint32_t*>(a.pre + (b * a.Hp + h_lo) * 16);
+      const uint32_t* phi = reinterpret_cast<const uint32_t*>(a.pre + (b * a.Hp + h_hi) * 16);
+      af[u][0] = __ldg(plo + t4);
+      af[u][1] = __ldg(phi + t4);
+      af[u][2] = __ldg(plo + t4 + 4);
+      af[u][3] = __ldg(phi + t4 + 4);
+    }
+  };
+  uint32_t an[kLdwBatch][4];
+  if (b0 < b1) {
+    fill(b0, 0);
+    if (warp < n_mt) load_a(b0, an);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (long long bb = b0; bb < b1; bb += kLdwBatch, buf ^= 1) {
+    uint32_t ac[kLdwBatch][4];
+#pragma unroll
+    for (int u = 0; u < kLdwBatch; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ac[u][q] = an[u][q];
+    if (bb + kLdwBatch < b1) {
+      fill(bb + kLdwBatch, buf ^ 1);
+      if (warp < n_mt) load_a(bb + kLdwBatch, an);
+    }
+    if (warp < n_mt) {
+#pragma unroll
+      for (int u = 0; u < kLdwBatch; ++u) {
+        if (bb + u < b1) {
+          uint32_t af[4] = {lo_on ? ac[u][0] : 0u, hi_on ? ac[u][1] : 0u, lo_on ? ac[u][2] : 0u, hi_on ? ac[u][3] : 0u};
+          const uint32_t* xs = reinterpret_cast<const uint32_t*>(&sX[buf][u][0]);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const uint32_t bq0 = xs[(n * 8 + g8) * (kLdwRow / 2) + t4];
+            const uint32_t bq1 = xs[(n * 8 + g8) * (kLdwRow / 2) + t4 + 4];
+            mma_bf16_16816(acc[n], af, bq0, bq1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // partial results: part[cta][h][i], h < Hp16 = 16*n_mt, i < 32
+  if (warp < n_mt) {
+    float* p = a.part + ((long long)blockIdx.x * n_mt * 16 + warp * 16) * 32;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      p[(g8) * 32 + n * 8 + 2 * t4] = acc[n][0];
+      p[(g8) * 32 + n * 8 + 2 * t4 + 1] = acc[n][1];
+      p[(g8 + 8) * 32 + n * 8 + 2 * t4] = acc[n][2];
+      p[(g8 + 8) * 32 + n * 8 + 2 * t4 + 1] = acc[n][3];
+    }
+  }
+  // sum of g over this CTA's samples (threads with xi == 0 hold one coordinate each)
+  gacc = warp_sum(gacc);
+  if (lane == 0) s_g[warp] = gacc;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 13; ++w) t += s_g[w];
+    a.gsum[blockIdx.x] = t;
+  }
+}
+
+// dW[c,o] = sum_cta part[cta][h][i] for every o;  dbias[o] = sum_cta gsum[cta]
+__global__ void __launch_bounds__(256)
+cin_last_dw_reduce_kernel(const float* __restrict__ part, const float* __restrict__ gsum, int n_cta, int Hp16,
+                          int m, int C, int N, float* __restrict__ dW, float* __restrict__ dbias) {
+  const long long total = (long long)(C + 1) * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / N;
+    const int o = (int)(idx - c * N);
+    float acc = 0.f;
+    if (c < C) {
+      const int h = (int)(c / m), i = (int)(c % m);
+      const float* p = part + (long long)h * 32 + i;
+      for (int s = 0; s < n_cta; ++s) acc += p[(long long)s * Hp16 * 32];
+      dW[idx] = acc;
+    } else {
+      for (int s = 0; s < n_cta; ++s) acc += gsum[s];
+      dbias[o] = acc;
+    }
+  }
+}
+
 // dW[c,o] = sum_slices part[s][c][0] for every o (c < C);  dbias[o] = sum_slices part[s][C][0]
 __global__ void __launch_bounds__(256)
 cin_dw_reduce_bcast_kernel(const float* __restrict__ part, int n_slices, long long slice_stride, int Npad,
@@ -446,6 +595,137 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_dw_tc_kernel(const DwArgs a
   tc::fence_before();
   __syncthreads();
   if (warp == kProdWarps) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW, D == 16, second generation: 16 row warps in two sets.  Set s fills the A slot s of its
+// sub-tile for the groups g = s, s+2, ... (with kNS == 2 a set always owns the same slot), so the
+// chain  stage wait -> LDS -> HMUL2 -> slot wait -> tcgen05.st -> wait::st -> arrive  of one group
+// overlaps with the other set's chain instead of serialising every group of a lane quarter.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDw2Prod = 16;
+constexpr int kDw2Threads = 32 * (kDw2Prod + 2);
+
+template <int MF>
+__global__ void __launch_bounds__(kDw2Threads, 1) cin_dw2_tc_kernel(const DwArgs a) {
+  static_assert(kNS == 2 && kSub == 2, "two producer sets <-> two A slots");
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ Barriers bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kS; ++i) { mbar_init(&bars.b_full[i], 1); mbar_init(&bars.b_empty[i], 1 + 8); }
+    for (int s = 0; s < kSub; ++s)
+      for (int i = 0; i < kNS; ++i) { mbar_init(&bars.a_full[s][i], 4); mbar_init(&bars.a_empty[s][i], 1); }
+    mbar_init(&bars.d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kDw2Prod) tc::tmem_alloc(&bars.tmem_base, 512);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = bars.tmem_base;
+  const uint32_t stage_stride = dw_stage_bytes<MF>(a.kblk);
+  const uint32_t offP = kG * a.kblk, offX = offP + kG * kDwNH * 32u;
+
+  const int cp = blockIdx.x % a.n_cp;
+  const int slice = blockIdx.x / a.n_cp;
+  const long long ks0 = slice * a.ks_per_slice;
+  const long long nk_ll = min(a.ks_per_slice, a.nks_total - ks0);
+  const int nk = nk_ll > 0 ? (int)nk_ll : 0;
+  const int Npad = a.N8 * 8;
+  const int n_groups = (nk + kG - 1) / kG;
+
+  if (warp < kDw2Prod) {
+    const int set = warp >> 3, w8 = warp & 7, sub = w8 >> 2, quarter = w8 & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t colD = sub ? kColD1 : kColD0;
+    const uint32_t colA = (sub ? kColA1 : kColA0) + set * (8 * kG);
+    const int c = cp * 256 + sub * 128 + quarter * 32 + lane;
+    const int mode = c < a.C ? 2 : (c == a.C ? 1 : 0);          // product / ones (dbias) / zero
+    const int h = mode == 2 ? c / MF : 0, i = mode == 2 ? c % MF : 0;
+    const int h_lo = (cp * 256) / MF;
+    const uint32_t myP = offP + (uint32_t)(h - h_lo) * 32u, myX = offX + (uint32_t)i * 16u;
+    float* prow = a.part + ((long long)slice * a.n_cp * 256 + c) * Npad;
+    if (nk > 0) {
+      for (int g = set; g < n_groups; g += 2) {
+        const int gk = min(kG, nk - g * kG);
+        const uint32_t bs = g % kS, bph = (g / kS) & 1, use = g >> 1;
+        mbar_wait(&bars.b_full[bs], bph);
+        const unsigned char* st = smem + bs * stage_stride;
+        uint32_t w[kG][8];
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+          if (mode == 2) {
+            const uint4 p0 = *reinterpret_cast<const uint4*>(st + myP + u * (kDwNH * 32));
+            const uint4 p1 = *reinterpret_cast<const uint4*>(st + myP + u * (kDwNH * 32) + 16);
+            const uint4 x0 = *reinterpret_cast<const uint4*>(st + myX + u * (MF * 32));
+            const uint4 x1 = *reinterpret_cast<const uint4*>(st + myX + u * (MF * 32) + MF * 16);
+            w[u][0] = hmul2_bf16(p0.x, x0.x); w[u][1] = hmul2_bf16(p0.y, x0.y);
+            w[u][2] = hmul2_bf16(p0.z, x0.z); w[u][3] = hmul2_bf16(p0.w, x0.w);
+            w[u][4] = hmul2_bf16(p1.x, x1.x); w[u][5] = hmul2_bf16(p1.y, x1.y);
+            w[u][6] = hmul2_bf16(p1.z, x1.z); w[u][7] = hmul2_bf16(p1.w, x1.w);
+          } else {
+            const uint32_t v = mode == 1 ? 0x3F803F80u : 0u;
+#pragma unroll
+            for (int z = 0; z < 8; ++z) w[u][z] = v;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.b_empty[bs]);               // our reads of this stage are done
+        mbar_wait(&bars.a_empty[sub][set], (use & 1) ^ 1);
+        tc::fence_after();
+#pragma unroll
+        for (int u = 0; u < kG; ++u)
+          if (u < gk) tc::st8(tmem + lane_base + colA + 8 * u, w[u]);
+        tc::wait_st();
+        tc::fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.a_full[sub][set]);
+      }
+      // ---- epilogue: the two sets split this lane's accumulator row by 8-column chunks ---------
+      mbar_wait(&bars.d_full, 0);
+      tc::fence_after();
+      for (int o0 = set * 8; o0 < Npad; o0 += 16) {
+        uint32_t v[8];
+        tc::ld8(tmem + lane_base + colD + o0, v);
+        tc::wait_ld();
+        *reinterpret_cast<uint4*>(prow + o0) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4*>(prow + o0 + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      for (int o0 = set * 8; o0 < Npad; o0 += 16) {
+        *reinterpret_cast<uint4*>(prow + o0) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(prow + o0 + 4) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  } else if (warp == kDw2Prod) {
+    if (nk > 0)
+      stream_mma_role(bars, smem, tmem, 1, nk, a.kblk, tc::idesc_bf16(128, Npad, 0, 1),
+                      (uint32_t)a.N8 * 128, 128, stage_stride);
+  } else {
+    if (lane == 0 && nk > 0) {
+      const int h_lo = (cp * 256) / MF;
+      const int h_hi = min(a.Hp - 1, (cp * 256 + 255) / MF);
+      const uint32_t pbytes = h_hi >= h_lo ? (uint32_t)(h_hi - h_lo + 1) * 32u : 0u;   // 0: only the bias lane
+      uint32_t bs = 0, bph = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const int gk = min(kG, nk - g * kG);
+        const long long k0 = ks0 + (long long)g * kG;              // == first sample of the group (D == 16)
+        mbar_wait(&bars.b_empty[bs], bph ^ 1);
+        unsigned char* st = smem + bs * stage_stride;
+        mbar_expect_tx(&bars.b_full[bs], gk * (a.kblk + pbytes + MF * 32u));
+        bulk_g2s(st, a.dz + (size_t)k0 * a.kblk, gk * a.kblk, &bars.b_full[bs]);
+        bulk_g2s(st + offX, a.x0h + (size_t)k0 * (MF * 16), gk * MF * 32u, &bars.b_full[bs]);
+        for (int u = 0; u < gk && pbytes; ++u)
+          bulk_g2s(st + offP + u * (kDwNH * 32), a.pre + ((size_t)(k0 + u) * a.Hp + h_lo) * 16, pbytes,
+                   &bars.b_full[bs]);
+        if (++bs == kS) { bs = 0; bph ^= 1; }
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == kDw2Prod) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -738,6 +1018,7 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
   if (!attr_done) {
     KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
     KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw));
+    KON_CUDA(cudaFuncSetAttribute(cin_dw2_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw));
     KON_CUDA(cudaFuncSetAttribute(cin_da_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_da));
     attr_done = true;
   }
@@ -771,6 +1052,31 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
   for (int l = nl - 1; l >= 0; --l) {
     const unsigned short* pre = l == 0 ? x0b : reinterpret_cast<const unsigned short*>(sv + L.zt_off[l - 1]);
     // ---- dW_l, dbias_l ----------------------------------------------------------------------
+    const bool sc = shortcut && l == nl - 1;
+    const bool sc_mma = sc && D == 16;          // v = A^T g with mma.sync (cin_last_dw_kernel)
+    if (sc_mma) {
+      LastDwArgs z;
+      z.x0b = x0b;
+      z.pre = pre;
+      z.gpool = d_pooled;
+      z.gstride = nl * D;
+      z.gcol = l * D;
+      z.part = reinterpret_cast<float*>(ws + L.part_off);
+      const int n_cta = (int)std::min<long long>(B, sms);
+      const int Hp16 = (L.Hp[l] + 15) / 16 * 16;
+      z.gsum = z.part + (long long)n_cta * Hp16 * 32;
+      z.B = B;
+      z.Hp = L.Hp[l];
+      z.m = m;
+      {
+        ProfileScope ps("cin_last_dw_kernel", st);
+        cin_last_dw_kernel<<<n_cta, 416, 0, st>>>(z);
+      }
+      KON_LAUNCH_CHECK("cin_last_dw_kernel");
+      cin_last_dw_reduce_kernel<<<grid_of((long long)(L.Hp[l] * m + 1) * L.N[l], sms), 256, 0, st>>>(
+          z.part, z.gsum, n_cta, Hp16, m, L.Hp[l] * m, L.N[l], dw[l], dbias[l]);
+      KON_LAUNCH_CHECK("cin_last_dw_reduce_kernel");
+    }
     DwArgs q;
     q.pre = pre;
     q.x0b = x0b;
@@ -779,7 +1085,6 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     q.part = reinterpret_cast<float*>(ws + L.part_off);
     q.D = D;
     q.Hp = L.Hp[l];
-    const bool sc = shortcut && l == nl - 1;
     q.N8 = sc ? 2 : L.N8[l];
     q.C = L.Hp[l] * m;
     q.n_cp = L.n_cp[l];
@@ -787,20 +1092,22 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     q.kblk = 2u * q.N8 * 128u;
     q.nks_total = rows / 16;
     q.ks_per_slice = (q.nks_total + q.n_slices - 1) / q.n_slices;
-    {
-      ProfileScope ps("cin_dw_tc_kernel", st);
-      if (D == 16) cin_dw_tc_kernel<26, true><<<q.n_cp * q.n_slices, kTcThreads, smem_dw, st>>>(q);
-      else cin_dw_tc_kernel<26, false><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
-    }
-    KON_LAUNCH_CHECK("cin_dw_tc_kernel");
     const int Npad = q.N8 * 8;
-    if (sc)
-      cin_dw_reduce_bcast_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
-          q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
-    else
-      cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
-          q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
-    KON_LAUNCH_CHECK("cin_dw_reduce_kernel");
+    if (!sc_mma) {
+      {
+        ProfileScope ps("cin_dw_tc_kernel", st);
+        if (D == 16) cin_dw2_tc_kernel<26><<<q.n_cp * q.n_slices, kDw2Threads, smem_dw, st>>>(q);
+        else cin_dw_tc_kernel<26, false><<<q.n_cp * q.n_slices, kTcThreads, smem_stream, st>>>(q);
+      }
+      KON_LAUNCH_CHECK("cin_dw_tc_kernel");
+      if (sc)
+        cin_dw_reduce_bcast_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
+            q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
+      else
+        cin_dw_reduce_kernel<<<grid_of((long long)(q.C + 1) * L.N[l], sms), 256, 0, st>>>(
+            q.part, q.n_slices, (long long)q.n_cp * 256 * Npad, Npad, q.C, L.N[l], dw[l], dbias[l]);
+      KON_LAUNCH_CHECK("cin_dw_reduce_kernel");
+    }
     if (sc) {
       const int Hp8 = (L.Hp[l] + 7) / 8 * 8;
       float* T = reinterpret_cast<float*>(ws + L.part_off + L.part_bytes - align256((size_t)(kMaxN + 8) * kTRow * 4));
