@@ -71,20 +71,27 @@ def algo_work(model, B, k, conv=(200, 200, 200), cross_layers=6, heads=2, d=8, k
         "attn_fwd": ("hbm", B * (F * kin * p + heads * F * d * p)),
         "attn_bwd": ("hbm", B * (2 * F * kin * p + heads * F * d * p)),
     }
-    hp, fl = F, 0
+    hp, fl, per_layer = F, 0, []
     for n in conv:
-        fl += 2 * B * k * hp * F * n
+        per_layer.append(2 * B * k * hp * F * n)
+        fl += per_layer[-1]
         hp = n
     w["cin_fwd"] = ("tensor", fl)
-    w["cin_bwd"] = ("tensor", 2 * fl)
+    w["cin_bwd"] = ("tensor", 2 * fl)        # dense-GEMM definition (dW + dA of every layer)
+    # what the two backward GEMM kernels actually execute: the LAST layer's dZ is constant over the
+    # feature maps (the reference pools over them, IL:322), so its dW / dA GEMMs are replaced by a
+    # rank-1 shortcut (cin_last_dw_kernel / cin_last_da_kernel) and only layers 0..L-2 run as GEMMs
+    gemm_bwd = sum(per_layer[:-1]) if len(per_layer) >= 2 else fl
+    w["cin_dw_gemm"] = ("tensor", gemm_bwd)
+    w["cin_da_gemm"] = ("tensor", gemm_bwd)
     return w
 
 
 # library kernel -> (op whose algorithmic work it carries, share of that op's work)
 KERNEL_WORK = {
     "cin_fwd_tc_kernel": ("cin_fwd", 1.0),
-    "cin_dw_tc_kernel": ("cin_bwd", 0.5),          # dW GEMM = 1x forward FLOPs
-    "cin_da_tc_kernel": ("cin_bwd", 0.5),          # dA GEMM = 1x forward FLOPs
+    "cin_dw_tc_kernel": ("cin_dw_gemm", 1.0),      # layers 0..L-2 (last layer: rank-1 shortcut)
+    "cin_da_tc_kernel": ("cin_da_gemm", 1.0),
     "embed_fwd_vec_kernel": ("embed_fwd", 1.0),
     "embed_reduce_kernel": ("embed_bwd", 1.0),
 }
