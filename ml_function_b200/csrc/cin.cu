@@ -18,12 +18,12 @@ namespace kon {
 // implemented in cin_tc.cu
 size_t cin_tc_saved_bytes(int64_t B, int m, int D, const int32_t* hs, int nl);
 size_t cin_tc_workspace_bytes(int64_t B, int m, int D, const int32_t* hs, int nl, int sms);
-int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias, int nl,
+int cin_tc_fwd(const float* x0, long long x0_sb, const float* const* w, const float* const* bias, int nl,
                const int32_t* hs, int64_t B, int m, int D, float* pooled, void* saved,
                void* workspace, int sms, cudaStream_t st);
-int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias, int nl,
+int cin_tc_bwd(const float* x0, long long x0_sb, const float* const* w, const float* const* bias, int nl,
                const int32_t* hs, int64_t B, int m, int D, const float* d_pooled,
-               const void* saved, float* dx0, float* const* dw, float* const* dbias,
+               const void* saved, float* dx0, long long dx0_sb, float* const* dw, float* const* dbias,
                void* workspace, int sms, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
@@ -242,12 +242,19 @@ struct CinShape {
   int32_t hs[KON_CIN_MAX_LAYERS];
 };
 
+// [B,m,D] float32 whose last two dims are compact; the batch stride is free in the bf16 path
+// (x0 / dx0 may be windows of the [B, W] concat buffer and of its gradient)
+bool rows_compact(const DLTensor* t) {
+  return t->ndim == 3 && (t->shape[2] == 1 || stride_of(t, 2) == 1) &&
+         (t->shape[1] == 1 || stride_of(t, 1) == t->shape[2]);
+}
+
 int cin_check(const DLTensor* x0, const DLTensor* const* w, const DLTensor* const* bias,
-              int32_t n_layers, CinShape* s) {
+              int32_t n_layers, int32_t precision, CinShape* s) {
   KON_TRY(check_cuda_tensor(x0, "x0"));
   const int dev = x0->device.device_id;
-  KON_REQUIRE(is_f32(x0) && x0->ndim == 3 && is_compact(x0), KON_EINVAL,
-              "x0 must be compact float32 [B,m,D]");
+  KON_REQUIRE(is_f32(x0) && x0->ndim == 3 && (precision == KON_CIN_BF16 ? rows_compact(x0) : is_compact(x0)),
+              KON_EINVAL, "x0 must be float32 [B,m,D] (compact; KON_CIN_BF16: free batch stride)");
   KON_REQUIRE(n_layers >= 1 && n_layers <= KON_CIN_MAX_LAYERS, KON_EUNSUPPORTED,
               "n_layers=%d outside [1,%d]", n_layers, KON_CIN_MAX_LAYERS);
   KON_REQUIRE(w != nullptr && bias != nullptr, KON_EINVAL, "w / bias arrays are NULL");
@@ -296,7 +303,7 @@ extern "C" int kon_cin_fwd(const DLTensor* x0, const DLTensor* const* w,
                            const DLTensor* const* bias, int32_t n_layers, DLTensor* pooled,
                            DLTensor* saved, DLTensor* workspace, int32_t precision, void* stream) {
   CinShape s;
-  KON_TRY(cin_check(x0, w, bias, n_layers, &s));
+  KON_TRY(cin_check(x0, w, bias, n_layers, precision, &s));
   const int dev = x0->device.device_id;
   KON_TRY(check_cuda_tensor(pooled, "pooled", dev));
   KON_TRY(check_cuda_tensor(saved, "saved", dev));
@@ -326,7 +333,7 @@ extern "C" int kon_cin_fwd(const DLTensor* x0, const DLTensor* const* w,
   KON_TRY(check_cuda_tensor(workspace, "workspace", dev));
   KON_REQUIRE(is_u8(workspace) && (size_t)numel(workspace) >= wneed, KON_EWORKSPACE,
               "workspace has %lld bytes, need %zu", (long long)numel(workspace), wneed);
-  return cin_tc_fwd(data_ptr<float>(x0), wp, bp, s.nl, s.hs, s.B, s.m, s.D,
+  return cin_tc_fwd(data_ptr<float>(x0), s.B > 1 ? stride_of(x0, 0) : (long long)s.m * s.D, wp, bp, s.nl, s.hs, s.B, s.m, s.D,
                     data_ptr<float>(pooled), data_ptr<char>(saved), data_ptr<char>(workspace), sms,
                     st);
 }
@@ -337,7 +344,7 @@ extern "C" int kon_cin_bwd(const DLTensor* x0, const DLTensor* const* w,
                            DLTensor* const* dw, DLTensor* const* dbias, DLTensor* workspace,
                            int32_t precision, void* stream) {
   CinShape s;
-  KON_TRY(cin_check(x0, w, bias, n_layers, &s));
+  KON_TRY(cin_check(x0, w, bias, n_layers, precision, &s));
   const int dev = x0->device.device_id;
   KON_TRY(check_cuda_tensor(d_pooled, "d_pooled", dev));
   KON_TRY(check_cuda_tensor(saved, "saved", dev));
@@ -347,8 +354,9 @@ extern "C" int kon_cin_bwd(const DLTensor* x0, const DLTensor* const* w,
   KON_REQUIRE(is_f32(d_pooled) && d_pooled->ndim == 2 && d_pooled->shape[0] == s.B &&
                   d_pooled->shape[1] == (int64_t)s.nl * s.D && is_compact(d_pooled),
               KON_EINVAL, "d_pooled must be compact float32 [B, n_layers*D]");
-  KON_REQUIRE(is_f32(dx0) && numel(dx0) == numel(x0) && is_compact(dx0), KON_EINVAL,
-              "dx0 must be compact float32 like x0");
+  KON_REQUIRE(is_f32(dx0) && numel(dx0) == numel(x0) && dx0->ndim == 3 &&
+                  (precision == KON_CIN_BF16 ? rows_compact(dx0) : is_compact(dx0)),
+              KON_EINVAL, "dx0 must be float32 [B,m,D] like x0 (compact; KON_CIN_BF16: free batch stride)");
   KON_REQUIRE(precision == KON_CIN_FP32 || precision == KON_CIN_BF16, KON_EINVAL,
               "unknown precision %d", precision);
   float* dwp[KON_CIN_MAX_LAYERS];
@@ -387,7 +395,9 @@ extern "C" int kon_cin_bwd(const DLTensor* x0, const DLTensor* const* w,
     return cin_simt_bwd(data_ptr<float>(x0), wp, s.nl, s.hs, s.B, s.m, s.D,
                         data_ptr<float>(d_pooled), data_ptr<float>(saved), data_ptr<float>(dx0),
                         dwp, dbp, data_ptr<float>(workspace), sms, st);
-  return cin_tc_bwd(data_ptr<float>(x0), wp, bp, s.nl, s.hs, s.B, s.m, s.D,
-                    data_ptr<float>(d_pooled), data_ptr<char>(saved), data_ptr<float>(dx0), dwp,
+  const long long cs = (long long)s.m * s.D;
+  return cin_tc_bwd(data_ptr<float>(x0), s.B > 1 ? stride_of(x0, 0) : cs, wp, bp, s.nl, s.hs, s.B, s.m, s.D,
+                    data_ptr<float>(d_pooled), data_ptr<char>(saved), data_ptr<float>(dx0),
+                    s.B > 1 ? stride_of(dx0, 0) : cs, dwp,
                     dbp, data_ptr<char>(workspace), sms, st);
 }

@@ -60,7 +60,8 @@ cin_pack_w_fwd_kernel(const float* __restrict__ W, int C, int N, int N8, int nk,
 // The stream kernel
 // ---------------------------------------------------------------------------------------------
 struct FwdArgs {
-  const float* x0;              // [B, m, D] fp32 compact
+  const float* x0;              // [B, m, D] fp32, batch stride x0_sb (elements), rows compact
+  long long x0_sb;
   const unsigned short* pre;    // [B, Hp, D] bf16 bits, or nullptr on layer 1 (pre == x0)
   const unsigned char* wpack;   // nk blocks of kblk bytes
   const float* bias;            // [N]
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
       const bool valid = r < a.rows;
       const long long b = valid ? r / a.D : 0;
       const int d = valid ? (int)(r - b * a.D) : 0;
-      const float* xrow = a.x0 + b * (long long)MF * a.D + d;          // x0[b,i,d] = xrow[i*D]
+      const float* xrow = a.x0 + b * a.x0_sb + d;                      // x0[b,i,d] = xrow[i*D]
       uint32_t x2[MF / 2];
 #pragma unroll
       for (int i = 0; i < MF / 2; ++i) {
@@ -221,7 +222,7 @@ size_t cin_tc_workspace_bytes(int64_t B, int m, int D, const int32_t* hs, int nl
   return L.work_total;
 }
 
-int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias, int nl,
+int cin_tc_fwd(const float* x0, long long x0_sb, const float* const* w, const float* const* bias, int nl,
                const int32_t* hs, int64_t B, int m, int D, float* pooled, void* saved,
                void* workspace, int sms, cudaStream_t st) {
   TcLayout L;
@@ -246,6 +247,7 @@ int cin_tc_fwd(const float* x0, const float* const* w, const float* const* bias,
   for (int l = 0; l < nl; ++l) {
     FwdArgs a;
     a.x0 = x0;
+    a.x0_sb = x0_sb;
     a.pre = l == 0 ? nullptr : reinterpret_cast<const unsigned short*>(sv + L.zt_off[l - 1]);
     a.wpack = ws + L.wpack_off[l];
     a.bias = bias[l];

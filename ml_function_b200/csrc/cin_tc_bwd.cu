@@ -31,30 +31,26 @@ static_assert(kSub == 2, "the backward kernels are written for two 128-lane sub-
 // ---------------------------------------------------------------------------------------------
 // small helper kernels
 // ---------------------------------------------------------------------------------------------
+// x0 fp32 [B,m,D] (batch stride sb) -> x0b bf16 [B,m,D] compact and, for D == 16, x0h bf16 [B][2][m][8]
+// (the two 16-byte halves of every field's 16 coordinates in separate planes: 32 lanes reading 32
+// different fields hit 32 different banks).  One thread per 8 consecutive coordinates.
 __global__ void __launch_bounds__(256)
-cin_x0_bf16_kernel(const float* __restrict__ x0, unsigned short* __restrict__ out, long long n) {
-  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < n;
-       i += (long long)gridDim.x * blockDim.x * 2) {
-    const float a = x0[i], b = (i + 1 < n) ? x0[i + 1] : 0.f;
-    const uint32_t pk = tc::pack_bf16(a, b);
-    if (i + 1 < n) *reinterpret_cast<uint32_t*>(out + i) = pk;
-    else out[i] = (unsigned short)(pk & 0xffffu);
-  }
-}
-
-// x0 fp32 [B,m,16] -> bf16 [B][2][m][8]: the two 16-byte halves of every field's 16 coordinates are
-// stored in separate planes, so that 32 lanes reading 32 different fields hit 32 different banks.
-__global__ void __launch_bounds__(256)
-cin_x0_halves_kernel(const float* __restrict__ x0, unsigned short* __restrict__ out, long long B, int m) {
-  const long long total = B * m * 16;
+cin_x0_convert_kernel(const float* __restrict__ x0, long long sb, unsigned short* __restrict__ x0b,
+                      unsigned short* __restrict__ x0h, long long B, int m, int D) {
+  const int d8 = D / 8;
+  const long long total = B * m * d8;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int d = (int)(idx & 15);
-    const long long t = idx >> 4;
+    const int q = (int)(idx % d8);
+    const long long t = idx / d8;
     const int i = (int)(t % m);
     const long long b = t / m;
-    const __nv_bfloat16 v = __float2bfloat16_rn(x0[idx]);
-    out[b * (m * 16) + (d >> 3) * (m * 8) + i * 8 + (d & 7)] = *reinterpret_cast<const unsigned short*>(&v);
+    const float4* src = reinterpret_cast<const float4*>(x0 + b * sb + (long long)i * D + q * 8);
+    const float4 lo = src[0], hi = src[1];
+    const uint4 pk = make_uint4(tc::pack_bf16(lo.x, lo.y), tc::pack_bf16(lo.z, lo.w), tc::pack_bf16(hi.x, hi.y),
+                                tc::pack_bf16(hi.z, hi.w));
+    *reinterpret_cast<uint4*>(x0b + (b * m + i) * (long long)D + q * 8) = pk;
+    if (x0h) *reinterpret_cast<uint4*>(x0h + b * (m * 16) + q * (m * 8) + i * 8) = pk;
   }
 }
 
@@ -159,7 +155,8 @@ struct LastDaArgs {
   const float* gpool;          // d_pooled [B, gstride]
   int gstride, gcol, gcol_prev;
   unsigned char* dz_prev;      // blocked, N8p column groups
-  float* dx0;                  // [B,m,D] accumulated
+  float* dx0;                  // [B,m,D] accumulated; batch stride dx_sb
+  long long dx_sb;
   long long rows;
   int D, Hp, Hp8, N8p;
 };
@@ -225,7 +222,7 @@ __global__ void __launch_bounds__(256) cin_last_da_kernel(const LastDaArgs a) {
         *reinterpret_cast<uint4*>(a.dz_prev + ((r >> 3) * a.N8p + (h0 >> 3)) * 128 + (r & 7) * 16) =
             make_uint4(outw[0], outw[1], outw[2], outw[3]);
     }
-    float* dxr = a.dx0 + b * (long long)MF * a.D + d;
+    float* dxr = a.dx0 + b * a.dx_sb + d;
     float old[MF];
 #pragma unroll
     for (int i = 0; i < MF; ++i) old[i] = dxr[(long long)i * a.D];
@@ -745,7 +742,8 @@ struct DaArgs {
   const unsigned char* wpack;    // n_chunks chunks
   const unsigned short* x0b;     // [B,m,D] bf16
   const unsigned short* pre;     // [B,Hp,D] bf16 (layer 0: == x0b)
-  float* dx0;                    // [B,m,D] fp32, accumulated
+  float* dx0;                    // [B,m,D] fp32, accumulated; batch stride dx_sb
+  long long dx_sb;
   float* dpre0;                  // [B,m,D] fp32 scratch: layer 0's dpre (pre == x0), folded into dx0 per tile
   unsigned char* dz_prev;        // blocked dZ_{l-1} (N8p column groups) or nullptr on layer 0
   const float* gpool;            // d_pooled [B, gstride]
@@ -915,7 +913,7 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
         }
       }
       if (valid) {
-        float* dxr = a.dx0 + b * (long long)MF * a.D + d;
+        float* dxr = a.dx0 + b * a.dx_sb + d;
         float old[MF];
 #pragma unroll
         for (int i = 0; i < MF; ++i) old[i] = dxr[(long long)i * a.D];          // all loads first
@@ -1000,9 +998,9 @@ int grid_of(long long total, int sms, int mult = 8) {
 
 }  // namespace
 
-int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias, int nl,
+int cin_tc_bwd(const float* x0, long long x0_sb, const float* const* w, const float* const* bias, int nl,
                const int32_t* hs, int64_t B, int m, int D, const float* d_pooled, const void* saved,
-               float* dx0, float* const* dw, float* const* dbias, void* workspace, int sms,
+               float* dx0, long long dx0_sb, float* const* dw, float* const* dbias, void* workspace, int sms,
                cudaStream_t st) {
   TcLayout L;
   KON_TRY(tc_check_layout(tc_layout(B, m, D, hs, nl, sms, &L), m, D));
@@ -1024,14 +1022,11 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
   }
   unsigned short* x0b = reinterpret_cast<unsigned short*>(ws + L.x0b_off);
   const long long nx = B * m * D;
-  cin_x0_bf16_kernel<<<grid_of(nx / 2 + 1, sms), 256, 0, st>>>(x0, x0b, nx);
-  KON_LAUNCH_CHECK("cin_x0_bf16_kernel");
   unsigned short* x0h = reinterpret_cast<unsigned short*>(ws + L.x0h_off);
-  if (D == 16) {
-    cin_x0_halves_kernel<<<grid_of(nx, sms), 256, 0, st>>>(x0, x0h, B, m);
-    KON_LAUNCH_CHECK("cin_x0_halves_kernel");
-  }
-  KON_CUDA(cudaMemsetAsync(dx0, 0, (size_t)nx * 4, st));
+  KON_REQUIRE(((uintptr_t)x0 & 15u) == 0 && x0_sb % 4 == 0, KON_EINVAL, "x0 rows must be 16-B aligned");
+  cin_x0_convert_kernel<<<grid_of(nx / 8, sms), 256, 0, st>>>(x0, x0_sb, x0b, D == 16 ? x0h : nullptr, B, m, D);
+  KON_LAUNCH_CHECK("cin_x0_convert_kernel");
+  KON_CUDA(cudaMemset2DAsync(dx0, (size_t)dx0_sb * 4, 0, (size_t)m * D * 4, (size_t)B, st));
   bool ragged = false;
   for (int l = 0; l < nl; ++l) {
     const long long tot = (long long)L.n_chunks[l] * L.nkA[l] * 2 * (kDaChunkH * m / 8) * 64;
@@ -1123,6 +1118,7 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
       z.gcol_prev = (l - 1) * D;
       z.dz_prev = ws + L.dz_off[cur ^ 1];
       z.dx0 = dx0;
+      z.dx_sb = dx0_sb;
       z.rows = rows;
       z.D = D;
       z.Hp = L.Hp[l];
@@ -1144,6 +1140,7 @@ int cin_tc_bwd(const float* x0, const float* const* w, const float* const* bias,
     p.x0b = x0b;
     p.pre = pre;
     p.dx0 = dx0;
+    p.dx_sb = dx0_sb;
     p.dpre0 = reinterpret_cast<float*>(ws + L.dpre0_off);
     p.dz_prev = l == 0 ? nullptr : ws + L.dz_off[cur ^ 1];
     p.gpool = d_pooled;

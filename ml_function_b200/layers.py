@@ -295,10 +295,14 @@ class CIN(nn.Module):
             self.logit_kernel = nn.Parameter(logit_kernel.clone())
             self.logit_bias = nn.Parameter(logit_bias.clone())
 
-    def forward(self, inputs, **kwargs):
+    def forward(self, inputs, fields=None, **kwargs):
+        """``inputs``: ``[B,m,D]``; or the concat buffer ``[B,W]`` with ``fields=(m,D)`` (its first
+        m*D columns are read in place and the gradient comes back as one ``[B,W]`` tensor)."""
+        m, D = fields if fields is not None else (inputs.shape[1], inputs.shape[2])
         if len(self.conv_kernels) == 0:
-            self.build(inputs.shape[1], inputs.shape[2], inputs.device)
-        pooled = ops.cin(inputs, [k[0] for k in self.conv_kernels], list(self.conv_biases), self.precision)
+            self.build(m, D, inputs.device)
+        pooled = ops.cin(inputs, [k[0] for k in self.conv_kernels], list(self.conv_biases), self.precision,
+                         fields=fields)
         if self.output_dim == 1:
             return torch.addmm(self.logit_bias, pooled, self.logit_kernel)      # IL:325
         return pooled
@@ -393,6 +397,28 @@ class StackLayer(nn.Module):
         return torch.cat(list(inputs), dim=self.axis if self.axis else -1)
 
 
+class _DenseFn(torch.autograd.Function):
+    """``x @ w + b`` whose bias gradient is a GEMV ``ones^T @ g`` on cuBLAS instead of torch's
+    column reduction (65,536 x 256 bf16: 65 us -> a few us)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(b, x, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        gw = x.t() @ g if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[2]:
+            ones = torch.ones((1, g.shape[0]), dtype=g.dtype, device=g.device)
+            gb = (ones @ g).reshape(-1)
+        return gx, gw, gb
+
+
 class DnnLayer(nn.Module):
     """CL:159-226 with the defaults the CTR builders use (``res_unit=1``, no BN/LN, ReLU):
     per hidden layer ``Dense`` -> ``Add([ori, x])`` when the shapes allow it (CL:206-214)
@@ -444,7 +470,7 @@ class DnnLayer(nn.Module):
             x = x.to(cd)
         for w, b in zip(self.kernels, self.biases):
             ori = x
-            x = torch.addmm(b.to(x.dtype), x, w.to(x.dtype))
+            x = _DenseFn.apply(x, w.to(x.dtype), b.to(x.dtype))
             if ori.shape == x.shape:
                 x = ori + x
             x = torch.relu(x)

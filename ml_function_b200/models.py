@@ -192,7 +192,7 @@ class XDeepFM(_CtrModel):
     def logit(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
         linear = self.linear_embed.lookup_sum(ids)         # [B,1] (useAddLinear, IL:233-234)
-        cin_out = self.cin(v)                              # [B,1]
+        cin_out = self.cin(xcat, fields=(self.F, self.k))  # [B,1]; reads xcat[:, :F*k] in place
         dnn_out = self.dnn(xcat)                           # [B,1]
         return ScoreLayer.summed([linear.unsqueeze(1), cin_out, dnn_out])   # [B,1,1]
 

@@ -233,11 +233,21 @@ def cross(x0, w, b):
 # --------------------------------------------------------------------------- #
 class _Cin(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x0, precision, n_layers, *wb):
+    def forward(ctx, x0, precision, n_layers, fields, *wb):
+        """x0: [B,m,D], or (fields=(m,D)) the concat buffer xcat [B,W] whose first m*D columns are
+        the field embeddings -- the bf16 path then reads them in place (batch stride W) and the
+        backward returns the gradient of the whole buffer, written in place too."""
         lib = L.lib()
         ws_ = [t.contiguous() for t in wb[:n_layers]]
         bs_ = [t.contiguous() for t in wb[n_layers:]]
-        x0 = x0.contiguous()
+        src = x0
+        if fields is not None:
+            m, D = fields
+            x0 = x0[:, :m * D].view(x0.shape[0], m, D)
+        strided_ok = precision == L.KON_CIN_BF16 and x0.stride(2) == 1 and x0.stride(1) == x0.shape[2] \
+            and x0.stride(0) % 4 == 0 and x0.data_ptr() % 16 == 0
+        if not strided_ok:
+            x0 = x0.contiguous()
         B, m, D = x0.shape
         dev = x0.device
         hs = L.i32_array([w.shape[1] for w in ws_])
@@ -253,6 +263,8 @@ class _Cin(torch.autograd.Function):
         ctx.save_for_backward(x0, saved, *ws_, *bs_)
         ctx.precision, ctx.n_layers = precision, n_layers
         ctx.work = work
+        ctx.fields = fields
+        ctx.src_shape = tuple(src.shape)
         return pooled
 
     @staticmethod
@@ -264,7 +276,17 @@ class _Cin(torch.autograd.Function):
         bs_ = list(ctx.saved_tensors[2 + nl:])
         dev = x0.device
         g = g.contiguous()
-        dx0 = torch.empty_like(x0)
+        B, m, D = x0.shape
+        if ctx.fields is not None and ctx.precision == L.KON_CIN_BF16:
+            gsrc = torch.empty(ctx.src_shape, dtype=x0.dtype, device=dev)     # gradient of xcat
+            if ctx.src_shape[1] > m * D:
+                gsrc[:, m * D:] = 0
+            dx0 = gsrc[:, :m * D].view(B, m, D)
+        else:
+            dx0 = torch.empty((B, m, D), dtype=x0.dtype, device=dev)
+            gsrc = dx0
+            if ctx.fields is not None:
+                gsrc = torch.zeros(ctx.src_shape, dtype=x0.dtype, device=dev)
         dws = [torch.empty_like(w) for w in ws_]
         dbs = [torch.empty_like(b) for b in bs_]
         wa, k1 = L.tensor_array(ws_)
@@ -275,12 +297,16 @@ class _Cin(torch.autograd.Function):
         with _prof("cin_bwd"):
             L.check(lib.kon_cin_bwd(a[0].ptr, wa, ba, nl, a[1].ptr, a[2].ptr, a[3].ptr, dwa, dba, a[4].ptr,
                                     ctx.precision, L.stream_ptr(dev)), "kon_cin_bwd")
-        return (dx0, None, None, *dws, *dbs)
+        if ctx.fields is not None and gsrc is not dx0 and gsrc.data_ptr() != dx0.data_ptr():
+            gsrc[:, :m * D] = dx0.reshape(B, m * D)
+        return (gsrc, None, None, None, *dws, *dbs)
 
 
-def cin(x0, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], precision: int = L.KON_CIN_FP32):
-    """x0 [B,m,D], weights[l] [H_{l-1}*m, H_l], biases[l] [H_l] -> pooled [B, L*D]."""
-    return _Cin.apply(x0, precision, len(weights), *weights, *biases)
+def cin(x0, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], precision: int = L.KON_CIN_FP32,
+        fields=None):
+    """x0 [B,m,D] (or, with ``fields=(m,D)``, the concat buffer [B,W] holding the fields in its first
+    m*D columns), weights[l] [H_{l-1}*m, H_l], biases[l] [H_l] -> pooled [B, L*D]."""
+    return _Cin.apply(x0, precision, len(weights), fields, *weights, *biases)
 
 
 # --------------------------------------------------------------------------- #
