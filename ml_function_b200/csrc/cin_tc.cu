@@ -74,8 +74,19 @@ struct FwdArgs {
   long long n_pairs;            // ceil(rows / (128*kSub))
 };
 
+// Row warps come in kFwdSets sets (cf. cin_dw2_tc_kernel): with kNS == 2 A slots per sub-tile, set s
+// fills slot s for the groups g = s, s+2, ..., so the wait -> HMUL2 -> tcgen05.st -> wait::st ->
+// arrive chain of one group overlaps with the other set's chain.
+#ifndef KON_FWD_SETS
+#define KON_FWD_SETS 1
+#endif
+constexpr int kFwdSets = KON_FWD_SETS;
+constexpr int kFwdProd = kProdWarps * kFwdSets;
+constexpr int kFwdThreads = 32 * (kFwdProd + 2);
+static_assert(kFwdSets == 1 || (kFwdSets == 2 && kNS == 2), "two sets <-> two A slots");
+
 template <int MF>
-__global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1) cin_fwd_tc_kernel(const FwdArgs a) {
   constexpr int LCM = lcm_(16, MF);
   constexpr int PK = LCM / 16;   // k-steps per period
   constexpr int PH = LCM / MF;   // feature maps (h) per period
@@ -85,22 +96,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   __shared__ float s_bias[kMaxN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < kMaxN; i += kTcThreads) s_bias[i] = i < a.N ? a.bias[i] : 0.f;
+  for (int i = tid; i < kMaxN; i += kFwdThreads) s_bias[i] = i < a.N ? a.bias[i] : 0.f;
 
-  stream_init(bars, tid, warp);
+  stream_init(bars, tid, warp, 1, kFwdProd);
   const uint32_t tmem = bars.tmem_base;
 
-  if (warp < kProdWarps) {
+  if (warp < kFwdProd) {
     // ================= producers + epilogue =================================================
-    const int sub = warp >> 2;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int set = warp / kProdWarps, w8 = warp % kProdWarps;
+    const int sub = w8 >> 2;
+    const uint32_t lane_base = (uint32_t)((w8 & 3) * 32) << 16;
     const uint32_t colD = sub ? kColD1 : kColD0;
     const uint32_t colA = sub ? kColA1 : kColA0;
     const int n_periods = (a.Hp + PH - 1) / PH;
-    SlotWriter sw;
+    SlotWriter sw;                 // kFwdSets == 1
+    uint32_t my_phase = 0;         // kFwdSets == 2: phase of this set's slot
+    int gcnt = 0, gpar = 0;        // k-steps into the current group / parity of the current group
     uint32_t tile_it = 0;
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x, ++tile_it) {
-      const long long r = pair * (128 * kSub) + sub * 128 + (warp & 3) * 32 + lane;
+      const long long r = pair * (128 * kSub) + sub * 128 + (w8 & 3) * 32 + lane;
       const bool valid = r < a.rows;
       const long long b = valid ? r / a.D : 0;
       const int d = valid ? (int)(r - b * a.D) : 0;
@@ -139,14 +153,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
 #pragma unroll
         for (int j = 0; j < PK; ++j) {
           if (ks_global < a.nk) {
-            uint32_t w[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int cl = 16 * j + 2 * q;            // compile-time after unrolling
-              w[q] = hmul2_bf16(cur[cl / MF], x2[(cl % MF) / 2]);
-            }
             ++ks_global;
-            sw.put(bars, sub, tmem + lane_base + colA, w, ks_global == a.nk, lane);
+            const bool last = ks_global == a.nk;
+            if (kFwdSets == 1 || gpar == set) {
+              uint32_t w[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int cl = 16 * j + 2 * q;            // compile-time after unrolling
+                w[q] = hmul2_bf16(cur[cl / MF], x2[(cl % MF) / 2]);
+              }
+              if (kFwdSets == 1) {
+                sw.put(bars, sub, tmem + lane_base + colA, w, last, lane);
+              } else {
+                if (gcnt == 0) {
+                  mbar_wait(&bars.a_empty[sub][set], my_phase ^ 1);
+                  tc::fence_after();
+                }
+                tc::st8(tmem + lane_base + colA + set * (8 * kG) + 8 * gcnt, w);
+                if (gcnt == kG - 1 || last) {
+                  tc::wait_st();
+                  tc::fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&bars.a_full[sub][set]);
+                  my_phase ^= 1;
+                }
+              }
+            }
+            if (kFwdSets == 2) {
+              if (++gcnt == kG || last) { gcnt = 0; gpar ^= 1; }
+            }
           }
         }
       }
@@ -156,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
       float rsum = 0.f;
       unsigned short* zrow = a.zt + b * (long long)a.N * a.D + d;       // zt[b,o,d] = zrow[o*D]
       const int n_full = a.N & ~15;
-      for (int o0 = 0; o0 < n_full; o0 += 16) {
+      for (int o0 = (kFwdSets == 2 ? set * 16 : 0); o0 < n_full; o0 += 16 * kFwdSets) {
         uint32_t v[16];
         tc::ld16(tmem + lane_base + colD + o0, v);
         tc::wait_ld();
@@ -173,7 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
           }
         }
       }
-      for (int o0 = n_full; o0 < a.N; o0 += 8) {     // tail: N % 16 in {8} or ragged
+      for (int o0 = n_full; o0 < a.N && (kFwdSets == 1 || set == 0); o0 += 8) {     // tail: N % 16 in {8} or ragged
         uint32_t v[8];
         tc::ld8(tmem + lane_base + colD + o0, v);
         tc::wait_ld();
@@ -186,10 +221,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
           }
         }
       }
-      if (valid) a.pooled[b * a.pooled_stride + a.pooled_col0 + d] = rsum;
+      if (valid) {
+        float* pp = a.pooled + b * a.pooled_stride + a.pooled_col0 + d;
+        if (kFwdSets == 1) *pp = rsum;
+        else atomicAdd(pp, rsum);     // two addends onto a zeroed cell: order-independent, deterministic
+      }
       tc::fence_before();   // our tcgen05.ld are complete (wait_ld) before the next tile's a_full arrive
+      // two sets: the set that owns slot 0 must not let the next tile's first MMA (which overwrites
+      // the accumulator) start before the OTHER set has finished reading its columns
+      if (kFwdSets == 2) tc::named_bar_sync(1 + sub, 32 * kProdWarps / kSub * kFwdSets);
     }
-  } else if (warp == kProdWarps) {
+  } else if (warp == kFwdProd) {
     // ================= MMA issuer ===========================================================
     {
       const long long n_items = a.n_pairs > blockIdx.x ? (a.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -205,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_fwd_tc_kernel(const FwdArgs
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == kProdWarps) tc::tmem_dealloc(tmem, 512);
+  if (warp == kFwdProd) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -244,6 +286,7 @@ int cin_tc_fwd(const float* x0, long long x0_sb, const float* const* w, const fl
         w[l], L.Hp[l] * m, L.N[l], L.N8[l], L.nk[l], reinterpret_cast<__nv_bfloat16*>(ws + L.wpack_off[l]));
     KON_LAUNCH_CHECK("cin_pack_w_fwd_kernel");
   }
+  if (kFwdSets == 2) KON_CUDA(cudaMemsetAsync(pooled, 0, (size_t)B * nl * D * 4, st));
   for (int l = 0; l < nl; ++l) {
     FwdArgs a;
     a.x0 = x0;
@@ -266,7 +309,7 @@ int cin_tc_fwd(const float* x0, long long x0_sb, const float* const* w, const fl
     const int grid = (int)std::min<long long>(a.n_pairs, sms);
     {
       ProfileScope ps("cin_fwd_tc_kernel", st);
-      cin_fwd_tc_kernel<26><<<grid, kTcThreads, smem, st>>>(a);
+      cin_fwd_tc_kernel<26><<<grid, kFwdThreads, smem, st>>>(a);
     }
     KON_LAUNCH_CHECK("cin_fwd_tc_kernel");
   }
