@@ -145,11 +145,53 @@ __global__ void __launch_bounds__(kFwdThreads, 1) cin_fwd_tc_kernel(const FwdArg
       for (int j = 0; j < PH; ++j) nraw[j] = load_raw(j);
 
       int ks_global = 0;     // k-step index within this tile
-      for (int per = 0; per < n_periods; ++per) {
+      int per = 0;
+      // one k-step: 8 packed products of this lane's row (j = k-step within the period: static)
+#define KON_FWD_KSTEP(J, W)                                                         \
+  _Pragma("unroll") for (int q = 0; q < 8; ++q) {                                   \
+    const int cl = 16 * (J) + 2 * q;                                                \
+    (W)[q] = hmul2_bf16(cur[cl / MF], x2[(cl % MF) / 2]);                           \
+  }
+      auto refresh = [&]() {
 #pragma unroll
         for (int j = 0; j < PH; ++j) cur[j] = to_bcast(nraw[j], per * PH + j);
 #pragma unroll
         for (int j = 0; j < PH; ++j) nraw[j] = load_raw((per + 1) * PH + j);
+        ++per;
+      };
+      if (kFwdSets == 1) {
+        // ---- fast path: kG periods = kG*PK k-steps = PK groups; every slot wait / hand-over sits at
+        // a compile-time position of the unrolled body (the generic loop below spends 3x the
+        // instructions of the 8 HMUL2 + STTM on per-k-step slot bookkeeping)
+        while (sw.cnt == 0 && ks_global + kG * PK <= a.nk) {
+#pragma unroll
+          for (int pp = 0; pp < kG; ++pp) {
+            refresh();
+#pragma unroll
+            for (int j = 0; j < PK; ++j) {
+              const int jj = pp * PK + j;                 // static
+              if (jj % kG == 0) {
+                mbar_wait(&bars.a_empty[sub][sw.slot], sw.phase ^ 1);
+                tc::fence_after();
+              }
+              uint32_t w[8];
+              KON_FWD_KSTEP(j, w)
+              tc::st8(tmem + lane_base + colA + sw.slot * (8 * kG) + 8 * (jj % kG), w);
+              if (jj % kG == kG - 1) {
+                tc::wait_st();
+                tc::fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.a_full[sub][sw.slot]);
+                if (++sw.slot == kNS) { sw.slot = 0; sw.phase ^= 1; }
+              }
+            }
+          }
+          ks_global += kG * PK;
+        }
+      }
+      // ---- generic path (tail of the K loop, partial periods, two-set mode) ---------------------
+      for (; per < n_periods;) {
+        refresh();
 #pragma unroll
         for (int j = 0; j < PK; ++j) {
           if (ks_global < a.nk) {
@@ -157,11 +199,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) cin_fwd_tc_kernel(const FwdArg
             const bool last = ks_global == a.nk;
             if (kFwdSets == 1 || gpar == set) {
               uint32_t w[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int cl = 16 * j + 2 * q;            // compile-time after unrolling
-                w[q] = hmul2_bf16(cur[cl / MF], x2[(cl % MF) / 2]);
-              }
+              KON_FWD_KSTEP(j, w)
               if (kFwdSets == 1) {
                 sw.put(bars, sub, tmem + lane_base + colA, w, last, lane);
               } else {
@@ -185,6 +223,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) cin_fwd_tc_kernel(const FwdArg
           }
         }
       }
+#undef KON_FWD_KSTEP
       // ---- epilogue: z = D + bias; pooled = sum_o z; z^T (bf16) -> zt ---------------------
       mbar_wait(&bars.d_full, tile_it & 1);
       tc::fence_after();
