@@ -361,26 +361,232 @@ __global__ void __launch_bounds__(416) cin_last_dw_kernel(const LastDwArgs a) {
   }
 }
 
-// dW[c,o] = sum_cta part[cta][h][i] for every o;  dbias[o] = sum_cta gsum[cta]
+// dW[c,o] = sum_cta part[cta][h][i] for every o;  dbias[o] = sum_cta gsum[cta].  One warp per weight
+// row c: the lanes split the CTA partials in a fixed pattern, warp-reduce, then write the row.
 __global__ void __launch_bounds__(256)
 cin_last_dw_reduce_kernel(const float* __restrict__ part, const float* __restrict__ gsum, int n_cta, int Hp16,
                           int m, int C, int N, float* __restrict__ dW, float* __restrict__ dbias) {
-  const long long total = (long long)(C + 1) * N;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long c = idx / N;
-    const int o = (int)(idx - c * N);
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = w0; c <= C; c += nw) {
     float acc = 0.f;
     if (c < C) {
       const int h = (int)(c / m), i = (int)(c % m);
       const float* p = part + (long long)h * 32 + i;
-      for (int s = 0; s < n_cta; ++s) acc += p[(long long)s * Hp16 * 32];
-      dW[idx] = acc;
+      for (int s = lane; s < n_cta; s += 32) acc += p[(long long)s * Hp16 * 32];
     } else {
-      for (int s = 0; s < n_cta; ++s) acc += gsum[s];
-      dbias[o] = acc;
+      for (int s = lane; s < n_cta; s += 32) acc += gsum[s];
+    }
+    acc = warp_sum(acc);
+    float* dst = c < C ? dW + c * N : dbias;
+    for (int o = lane; o < N; o += 32) dst[o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Last layer on tcgen05: both mat-vecs of cin_last_da_kernel as two tiny GEMMs per 128-row tile,
+//   D1[r,h] = sum_i x0[r,i] T[h,i]   (A = x0 row in TMEM, K = 32;  B = T   [Nh x 32]  in smem, constant)
+//   D2[r,i] = sum_h pre[r,h] T[h,i]  (A = pre row in TMEM, K = Hp16; B = T^T [32 x Hp16] in smem, constant)
+// then dZ_{L-1}[r,h] = g[r] D1 + g_prev[r]  and  dx0[r,i] += g[r] D2.  15 MMAs per tile: the kernel is
+// bound by moving the rows (419 MB of pre in, 419 MB of dZ out), not by math.
+// ---------------------------------------------------------------------------------------------
+// T[h,i] = sum_o W[(h*m+i),o] packed twice as bf16 core matrices:
+//   Th (K-major B[n=h][k=i]):  off = s*(2*Nh8*128) + kg*Nh8*128 + (h/8)*128 + (h%8)*16 + (i%8)*2,  i = 16s+8kg+i%8
+//   Ti (K-major B[n=i][k=h]):  off = s*1024        + kg*512      + (i/8)*128 + (i%8)*16 + (h%8)*2,  h = 16s+8kg+h%8
+__global__ void __launch_bounds__(256)
+cin_tpack_kernel(const float* __restrict__ T, int Hp, int m, int Nh8, int nkh, unsigned short* __restrict__ th,
+                 unsigned short* __restrict__ ti) {
+  const int n_th = 2 * 2 * Nh8 * 64, n_ti = nkh * 2 * 4 * 64;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_th + n_ti; idx += gridDim.x * blockDim.x) {
+    int h, i;
+    if (idx < n_th) {
+      const int i7 = idx & 7, h7 = (idx >> 3) & 7;
+      int t = idx >> 6;
+      const int h8 = t % Nh8;
+      t /= Nh8;
+      const int kg = t & 1, s = t >> 1;
+      h = h8 * 8 + h7;
+      i = 16 * s + 8 * kg + i7;
+    } else {
+      const int j = idx - n_th;
+      const int h7 = j & 7, i7 = (j >> 3) & 7;
+      int t = j >> 6;
+      const int i8 = t & 3;
+      t >>= 2;
+      const int kg = t & 1, s = t >> 1;
+      i = i8 * 8 + i7;
+      h = 16 * s + 8 * kg + h7;
+    }
+    const float v = (h < Hp && i < m) ? T[h * kTRow + i] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    const unsigned short u = *reinterpret_cast<const unsigned short*>(&b);
+    if (idx < n_th) th[idx] = u;
+    else ti[idx - n_th] = u;
+  }
+}
+
+struct LastDaTcArgs {
+  const unsigned short* x0b;   // [B,m,D] bf16
+  const unsigned short* pre;   // [B,Hp,D] bf16
+  const unsigned char* tpack;  // Th then Ti
+  const float* gpool;
+  int gstride, gcol, gcol_prev;
+  unsigned char* dz_prev;      // blocked, N8p column groups
+  float* dx0;
+  long long dx_sb, rows, n_tiles;
+  int D, Hp, N8p, Nh8, nkh;
+};
+
+constexpr uint32_t kLtD1 = 0, kLtD2 = 208, kLtAx = 240, kLtAp = 256;
+
+// Warps 0-3: rows (one TMEM lane each); warp 4: MMA issue; warp 5: bulk-copy loader that streams each
+// tile's `pre` rows (128*Hp*2 contiguous bytes) and x0 rows one tile ahead into a 2-stage smem ring, so
+// the row warps never wait on HBM.
+template <int MF>
+__global__ void __launch_bounds__(192, 1) cin_last_da_tc_kernel(const LastDaTcArgs a) {
+  static_assert(MF <= 32 && MF % 2 == 0, "field count");
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t a_full, d_full, s_full[2], s_empty[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t th_bytes = 2u * 2u * a.Nh8 * 128u, ti_bytes = (uint32_t)a.nkh * 1024u;
+  const uint32_t tab_bytes = (th_bytes + ti_bytes + 127u) & ~127u;
+  const uint32_t pre_tile = 128u * a.Hp * 2u, x_tile = 128u * MF * 2u;          // bytes per full tile
+  const uint32_t stage_bytes = (pre_tile + x_tile + 127u) & ~127u;
+  for (uint32_t i = tid; i < (th_bytes + ti_bytes) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(a.tpack) + i);
+  if (tid == 0) {
+    mbar_init(&a_full, 4);
+    mbar_init(&d_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 4) tc::tmem_alloc(&s_tmem, 512);
+  fence_proxy_async_smem();
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = s_tmem;
+  uint32_t it = 0;
+  if (warp < 4) {
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int rl = warp * 32 + lane;                 // row within the tile
+    const int bl = rl / a.D, d = rl - bl * a.D;      // sample within the tile, coordinate
+    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const long long r = tile * 128 + rl;
+      const bool valid = r < a.rows;
+      const long long b = valid ? r / a.D : 0;
+      const uint32_t stg = it & 1;
+      const unsigned char* sp = smem + tab_bytes + stg * stage_bytes;
+      const unsigned short* prow = reinterpret_cast<const unsigned short*>(sp) + (long long)bl * a.Hp * a.D + d;
+      const unsigned short* xrow = reinterpret_cast<const unsigned short*>(sp + pre_tile) + (long long)bl * MF * a.D + d;
+      mbar_wait(&s_full[stg], (it >> 1) & 1);
+      // ---- A operands: x0 row (K = 32) and pre row (K = 16*nkh), from shared memory ------------
+      {
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const uint32_t lo = (valid && 2 * q < MF) ? xrow[(2 * q) * a.D] : 0u;
+          const uint32_t hi = (valid && 2 * q + 1 < MF) ? xrow[(2 * q + 1) * a.D] : 0u;
+          w[q] = lo | (hi << 16);
+        }
+        tc::st8(tmem + lane_base + kLtAx, w);
+        tc::st8(tmem + lane_base + kLtAx + 8, w + 8);
+      }
+      for (int s0 = 0; s0 < a.nkh; ++s0) {
+        uint32_t w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int h = 16 * s0 + 2 * q;
+          const uint32_t lo = (valid && h < a.Hp) ? prow[h * a.D] : 0u;
+          const uint32_t hi = (valid && h + 1 < a.Hp) ? prow[(h + 1) * a.D] : 0u;
+          w[q] = lo | (hi << 16);
+        }
+        tc::st8(tmem + lane_base + kLtAp + 8 * s0, w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stg]);                  // our reads of this stage are done
+      tc::wait_st();
+      tc::fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full);
+      const float g = valid ? a.gpool[b * a.gstride + a.gcol + d] : 0.f;
+      const float gprev = valid ? a.gpool[b * a.gstride + a.gcol_prev + d] : 0.f;
+      float* dxr = a.dx0 + b * a.dx_sb + d;
+      float old[MF];
+#pragma unroll
+      for (int i = 0; i < MF; ++i) old[i] = valid ? dxr[(long long)i * a.D] : 0.f;
+      // ---- epilogue ------------------------------------------------------------------------
+      mbar_wait(&d_full, it & 1);
+      tc::fence_after();
+      for (int o0 = 0; o0 < a.N8p * 8; o0 += 16) {
+        uint32_t v[16];
+        tc::ld16(tmem + lane_base + kLtD1 + o0, v);
+        tc::wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float v0 = (o0 + 2 * q < a.Hp) ? fmaf(g, __uint_as_float(v[2 * q]), gprev) : 0.f;
+          const float v1 = (o0 + 2 * q + 1 < a.Hp) ? fmaf(g, __uint_as_float(v[2 * q + 1]), gprev) : 0.f;
+          pk[q] = tc::pack_bf16(v0, v1);
+        }
+        if (valid) {
+          unsigned char* dst = a.dz_prev + ((r >> 3) * a.N8p + (o0 >> 3)) * 128 + (r & 7) * 16;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if ((o0 >> 3) + 1 < a.N8p) *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      {
+        uint32_t v[32];
+        tc::ld32(tmem + lane_base + kLtD2, v);
+        tc::wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < MF; ++i) dxr[(long long)i * a.D] = fmaf(g, __uint_as_float(v[i]), old[i]);
+        }
+      }
+      tc::fence_before();
+    }
+  } else if (warp == 4) {
+    const bool leader = tc::elect_one();
+    const uint32_t idesc1 = tc::idesc_bf16(128, a.Nh8 * 8, 0, 0), idesc2 = tc::idesc_bf16(128, 32, 0, 0);
+    const uint64_t bd1 = tc::smem_desc(smem_u32(smem), (uint32_t)a.Nh8 * 128, 128);
+    const uint64_t bd2 = tc::smem_desc(smem_u32(smem + th_bytes), 512, 128);
+    const uint32_t adv1 = (2u * a.Nh8 * 128u) >> 4;
+    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(&a_full, it & 1);
+      tc::fence_after();
+      if (leader) {
+        tc::mma_ts(tmem + kLtD1, tmem + kLtAx, bd1, idesc1, 0u);
+        tc::mma_ts(tmem + kLtD1, tmem + kLtAx + 8, bd1 + (uint64_t)adv1, idesc1, 1u);
+#pragma unroll
+        for (int s = 0; s < 13; ++s)
+          if (s < a.nkh) tc::mma_ts(tmem + kLtD2, tmem + kLtAp + 8 * s, bd2 + (uint64_t)(s * 64), idesc2, s > 0 ? 1u : 0u);
+        tc::commit(&d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    if (lane == 0) {
+      const long long spt = 128 / a.D;                       // samples per tile
+      const long long n_samples = a.rows / a.D;
+      for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t stg = it & 1;
+        const long long b0 = tile * spt;
+        const long long nb = min(spt, n_samples - b0);
+        unsigned char* sp = smem + tab_bytes + stg * stage_bytes;
+        mbar_wait(&s_empty[stg], ((it >> 1) & 1) ^ 1);
+        const uint32_t pb = (uint32_t)(nb * a.Hp * a.D * 2), xb = (uint32_t)(nb * MF * a.D * 2);
+        mbar_expect_tx(&s_full[stg], pb + xb);
+        bulk_g2s(sp, a.pre + b0 * a.Hp * a.D, pb, &s_full[stg]);
+        bulk_g2s(sp + pre_tile, a.x0b + b0 * MF * a.D, xb, &s_full[stg]);
+      }
     }
   }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
 // dW[c,o] = sum_slices part[s][c][0] for every o (c < C);  dbias[o] = sum_slices part[s][C][0]
@@ -1017,6 +1223,7 @@ int cin_tc_bwd(const float* x0, long long x0_sb, const float* const* w, const fl
     KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
     KON_CUDA(cudaFuncSetAttribute(cin_dw_tc_kernel<26, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw));
     KON_CUDA(cudaFuncSetAttribute(cin_dw2_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw));
+    KON_CUDA(cudaFuncSetAttribute(cin_last_da_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     KON_CUDA(cudaFuncSetAttribute(cin_da_tc_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_da));
     attr_done = true;
   }
@@ -1068,7 +1275,7 @@ int cin_tc_bwd(const float* x0, long long x0_sb, const float* const* w, const fl
         cin_last_dw_kernel<<<n_cta, 416, 0, st>>>(z);
       }
       KON_LAUNCH_CHECK("cin_last_dw_kernel");
-      cin_last_dw_reduce_kernel<<<grid_of((long long)(L.Hp[l] * m + 1) * L.N[l], sms), 256, 0, st>>>(
+      cin_last_dw_reduce_kernel<<<grid_of((long long)(L.Hp[l] * m + 1) * 32, sms), 256, 0, st>>>(
           z.part, z.gsum, n_cta, Hp16, m, L.Hp[l] * m, L.N[l], dw[l], dbias[l]);
       KON_LAUNCH_CHECK("cin_last_dw_reduce_kernel");
     }
@@ -1105,13 +1312,18 @@ int cin_tc_bwd(const float* x0, long long x0_sb, const float* const* w, const fl
     }
     if (sc) {
       const int Hp8 = (L.Hp[l] + 7) / 8 * 8;
-      float* T = reinterpret_cast<float*>(ws + L.part_off + L.part_bytes - align256((size_t)(kMaxN + 8) * kTRow * 4));
+      float* T = reinterpret_cast<float*>(ws + L.tail_off);
       cin_wsum_kernel<<<grid_of((long long)Hp8 * kTRow * 32, sms), 256, 0, st>>>(w[l], q.C, L.N[l], m, Hp8, T);
       KON_LAUNCH_CHECK("cin_wsum_kernel");
-      LastDaArgs z;
+      const int Nh8 = (L.Hp[l] + 15) / 16 * 2, nkh = (L.Hp[l] + 15) / 16;
+      unsigned short* th = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(T) + align256((size_t)Hp8 * kTRow * 4));
+      unsigned short* ti = th + 2 * 2 * Nh8 * 64;
+      cin_tpack_kernel<<<32, 256, 0, st>>>(T, L.Hp[l], m, Nh8, nkh, th, ti);
+      KON_LAUNCH_CHECK("cin_tpack_kernel");
+      LastDaTcArgs z;
       z.x0b = x0b;
       z.pre = pre;
-      z.T = T;
+      z.tpack = reinterpret_cast<const unsigned char*>(th);
       z.gpool = d_pooled;
       z.gstride = nl * D;
       z.gcol = l * D;
@@ -1120,16 +1332,19 @@ int cin_tc_bwd(const float* x0, long long x0_sb, const float* const* w, const fl
       z.dx0 = dx0;
       z.dx_sb = dx0_sb;
       z.rows = rows;
+      z.n_tiles = (rows + 127) / 128;
       z.D = D;
       z.Hp = L.Hp[l];
-      z.Hp8 = Hp8;
       z.N8p = L.N8[l - 1];
+      z.Nh8 = Nh8;
+      z.nkh = nkh;
+      const size_t smem_lt = (((size_t)2 * 2 * Nh8 * 128 + (size_t)nkh * 1024 + 127) & ~(size_t)127) +
+                             2 * (((size_t)128 * L.Hp[l] * 2 + (size_t)128 * m * 2 + 127) & ~(size_t)127);
       {
         ProfileScope ps("cin_last_da_kernel", st);
-        cin_last_da_kernel<26><<<(int)std::min<long long>((rows + 255) / 256, (long long)sms * 4), 256,
-                                 (size_t)Hp8 * kTRow * 4, st>>>(z);
+        cin_last_da_tc_kernel<26><<<(int)std::min<long long>(z.n_tiles, sms), 192, smem_lt, st>>>(z);
       }
-      KON_LAUNCH_CHECK("cin_last_da_kernel");
+      KON_LAUNCH_CHECK("cin_last_da_tc_kernel");
       cur ^= 1;
       continue;
     }
