@@ -361,6 +361,10 @@ def run_gpu(args):
         d, ids, y = resident[i % len(resident)]
         return trainer.step(d, ids, y)
 
+    def step_resident_graph(i):
+        d, ids, y = resident[i % len(resident)]
+        return trainer.step_graph(d, ids, y)
+
     stage = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
@@ -369,7 +373,7 @@ def run_gpu(args):
         st = stage[i % 2]
         for dst, src in zip(st, hb):
             dst.copy_(src, non_blocking=True)
-        loss = trainer.step(*st)
+        loss = trainer.step_graph(*st)
         loss_host.copy_(loss.view(1), non_blocking=True)
 
     for i in range(max(args.warmup, 3)):
@@ -388,6 +392,18 @@ def run_gpu(args):
     prof = ops.profile_summary()
     ops.PROFILE = None
     kprof = {kn: _lib.profile_read(kn) for kn in KERNEL_WORK}
+    ms_eager = ms
+    # ---- the same step replayed from a CUDA graph (kernel stats above come from the eager pass:
+    # events cannot be recorded inside a capture) ------------------------------------------------
+    graphed = False
+    if args.graph and (world == 1 or args.graph_multi):
+        graphed = trainer.capture(*resident[0])
+        if graphed:
+            for i in range(3):
+                step_resident_graph(i)
+            ms = timed(step_resident_graph, args.steps)
+        elif rank == 0:
+            print("CUDA-graph capture failed, staying eager:", trainer.capture_error, file=sys.stderr)
     # ---- end-to-end timing (H2D + step + D2H) ---------------------------------------------
     for i in range(2):
         step_e2e(i)
@@ -477,6 +493,7 @@ def run_gpu(args):
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "cuda_graph": graphed, "ms_per_step_eager": ms_eager / args.steps,
         "clocks": clocks,
         "roofline": roof,
         "kernel_stats": kstats,
@@ -502,6 +519,8 @@ def main():
     ap.add_argument("--n-batches", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--graph-multi", action="store_true", help="also capture when world_size > 1 (NCCL in the graph)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at
     # stderr (NCCL / C libraries print banners straight to fd 1), and is restored for the result.

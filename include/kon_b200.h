@@ -118,6 +118,11 @@ int kon_embed_sgd(DLTensor* arena, const DLTensor* unique_rows, const DLTensor* 
 int kon_embed_adam(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTensor* unique_rows,
                    const DLTensor* grads, const DLTensor* n_unique, float lr, float beta1,
                    float beta2, float eps, float l2, int32_t step, void* stream);
+/* Same, with the step counter read from a device int32[1] (the bias correction is computed in the
+ * kernel), so that a captured CUDA graph of the training step can be replayed. */
+int kon_embed_adam_devstep(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTensor* unique_rows,
+                           const DLTensor* grads, const DLTensor* n_unique, float lr, float beta1,
+                           float beta2, float eps, float l2, const DLTensor* step, void* stream);
 
 /* ============================ a5-a6: FM ========================================== */
 /* Replaces InnerLayer's 325 tf.multiply + sequential Add (IL:59-66) and FmLayer's Add

@@ -485,7 +485,11 @@ __global__ void __launch_bounds__(256)
 embed_adam_kernel(float* __restrict__ arena, float* __restrict__ m, float* __restrict__ v,
                   const int* __restrict__ rows, const float* __restrict__ grads,
                   const int* __restrict__ n_unique, int dim, float lr_t, float b1, float b2,
-                  float eps, float l2) {
+                  float eps, float l2, const int* __restrict__ step_dev, float lr) {
+  if (step_dev) {   // step counter lives on the device (CUDA-graph replay): bias correction here
+    const float t = (float)(*step_dev);
+    lr_t = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+  }
   const long long total = (long long)(*n_unique) * dim;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -896,10 +900,32 @@ extern "C" int kon_embed_sgd(DLTensor* arena, const DLTensor* unique_rows, const
   return KON_OK;
 }
 
+static int embed_adam_impl(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTensor* unique_rows,
+                           const DLTensor* grads, const DLTensor* n_unique, float lr, float beta1,
+                           float beta2, float eps, float l2, int32_t step, const DLTensor* step_dev,
+                           void* stream);
+
 extern "C" int kon_embed_adam(DLTensor* arena, DLTensor* m, DLTensor* v,
                               const DLTensor* unique_rows, const DLTensor* grads,
                               const DLTensor* n_unique, float lr, float beta1, float beta2,
                               float eps, float l2, int32_t step, void* stream) {
+  return embed_adam_impl(arena, m, v, unique_rows, grads, n_unique, lr, beta1, beta2, eps, l2, step, nullptr,
+                         stream);
+}
+
+extern "C" int kon_embed_adam_devstep(DLTensor* arena, DLTensor* m, DLTensor* v,
+                                      const DLTensor* unique_rows, const DLTensor* grads,
+                                      const DLTensor* n_unique, float lr, float beta1, float beta2,
+                                      float eps, float l2, const DLTensor* step, void* stream) {
+  KON_TRY(check_cuda_tensor(step, "step"));
+  KON_REQUIRE(is_i32(step) && numel(step) >= 1, KON_EINVAL, "step must be a device int32[1]");
+  return embed_adam_impl(arena, m, v, unique_rows, grads, n_unique, lr, beta1, beta2, eps, l2, 1, step, stream);
+}
+
+static int embed_adam_impl(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTensor* unique_rows,
+                           const DLTensor* grads, const DLTensor* n_unique, float lr, float beta1,
+                           float beta2, float eps, float l2, int32_t step, const DLTensor* step_dev,
+                           void* stream) {
   KON_TRY(check_sparse_update(arena, unique_rows, grads, n_unique));
   const int dev = arena->device.device_id;
   KON_TRY(check_cuda_tensor(m, "m", dev));
@@ -916,7 +942,7 @@ extern "C" int kon_embed_adam(DLTensor* arena, DLTensor* m, DLTensor* v,
   embed_adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       data_ptr<float>(arena), data_ptr<float>(m), data_ptr<float>(v), data_ptr<int>(unique_rows),
       data_ptr<float>(grads), data_ptr<int>(n_unique), (int)arena->shape[1], lr_t, beta1, beta2,
-      eps, l2);
+      eps, l2, step_dev ? data_ptr<int>(step_dev) : nullptr, lr);
   KON_LAUNCH_CHECK("embed_adam_kernel");
   return KON_OK;
 }

@@ -146,6 +146,16 @@ def embed_sgd(arena, sg: SparseGrad, lr: float, l2: float = 0.0):
                 "kon_embed_sgd")
 
 
+def embed_adam_devstep(arena, m, v, sg: SparseGrad, lr, beta1, beta2, eps, l2, step_dev):
+    """Row-wise lazy Adam with the step counter on the device (CUDA-graph friendly)."""
+    lib = L.lib()
+    a = [L._arg(t) for t in (arena, m, v, sg.rows, sg.grads, sg.n, step_dev)]
+    with _prof("embed_adam"):
+        L.check(lib.kon_embed_adam_devstep(a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr, lr, beta1,
+                                           beta2, eps, l2, a[6].ptr, L.stream_ptr(arena.device)),
+                "kon_embed_adam_devstep")
+
+
 def embed_adam(arena, m, v, sg: SparseGrad, lr, beta1, beta2, eps, l2, step):
     lib = L.lib()
     a = [L._arg(t) for t in (arena, m, v, sg.rows, sg.grads, sg.n)]

@@ -21,14 +21,15 @@ from .models import XDeepFM, keras_binary_crossentropy
 
 
 class SparseAdam:
-    """Row-wise lazy Adam state for one arena."""
+    """Row-wise lazy Adam state for one arena.  The step counter lives on the device so that the
+    whole training step can be captured in a CUDA graph and replayed."""
 
     def __init__(self, arena: torch.nn.Parameter, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, l2=0.0):
         self.arena = arena
         self.m = torch.zeros_like(arena.data)
         self.v = torch.zeros_like(arena.data)
         self.lr, self.beta1, self.beta2, self.eps, self.l2 = lr, beta1, beta2, eps, l2
-        self.t = 0
+        self.t = torch.zeros(1, dtype=torch.int32, device=arena.device)
 
     def step(self):
         sgs = getattr(self.arena, "kon_sparse_grads", None)
@@ -36,8 +37,8 @@ class SparseAdam:
             return
         self.t += 1
         for sg in sgs:
-            ops.embed_adam(self.arena.data, self.m, self.v, sg, self.lr, self.beta1, self.beta2, self.eps,
-                           self.l2, self.t)
+            ops.embed_adam_devstep(self.arena.data, self.m, self.v, sg, self.lr, self.beta1, self.beta2,
+                                   self.eps, self.l2, self.t)
         self.arena.kon_sparse_grads = []
 
 
@@ -54,11 +55,14 @@ class Trainer:
             if emb is not None:
                 self.sparse_opts.append(SparseAdam(emb.arena, lr=lr, l2=emb.emb_reg))
         self.is_sigmoid = isinstance(model, XDeepFM)
+        self._g = None
+        self.capture_error = None
 
     def _ensure_dense_opt(self):
         if self.dense_opt is None:      # lazily: layers build their weights on first call
             self._dense_params = self.model.dense_parameters()
-            self.dense_opt = torch.optim.Adam(self._dense_params, lr=self.lr, eps=1e-7, fused=True)
+            self.dense_opt = torch.optim.Adam(self._dense_params, lr=self.lr, eps=1e-7, fused=True,
+                                              capturable=True)
 
     def loss(self, dense, ids, labels):
         out = self.model(dense, ids)
@@ -82,3 +86,39 @@ class Trainer:
         for so in self.sparse_opts:
             so.step()
         return loss.detach()
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole step (launch-bound tails: ~150 kernels per step)
+    # ------------------------------------------------------------------------------------------
+    def capture(self, dense, ids, labels, warmup: int = 3):
+        """Capture ``step`` for this batch shape; afterwards ``step_graph`` copies a batch into the
+        static buffers and replays.  Returns False (and stays eager) if the capture fails."""
+        self._g = None
+        self._static = tuple(t.clone() for t in (dense, ids, labels))
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self.step(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_loss = self.step(*self._static)
+            self._g = g
+            return True
+        except Exception as e:          # noqa: BLE001 -- report and fall back to eager steps
+            self._g = None
+            self.capture_error = repr(e)
+            torch.cuda.synchronize()
+            return False
+
+    def step_graph(self, dense, ids, labels) -> torch.Tensor:
+        if self._g is None:
+            return self.step(dense, ids, labels)
+        for dst, src in zip(self._static, (dense, ids, labels)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._g.replay()
+        return self._static_loss
