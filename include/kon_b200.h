@@ -110,6 +110,15 @@ int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids, const int64_t* fie
                   int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                   DLTensor* workspace, void* stream);
 
+/* Same as kon_embed_bwd, but skips the key build / radix sort / run-head scan and reuses the sorted
+ * (key, position, run id) arrays a previous kon_embed_bwd call left at the front of the SAME
+ * `workspace` for the SAME ids and field_row_offset (e.g. the first-order tables after the
+ * embedding tables of one step: identical routing, different payload width).  The workspace must be
+ * large enough for both calls (max of kon_embed_bwd_workspace_bytes over the two dims). */
+int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+                        int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                        DLTensor* workspace, void* stream);
+
 /* Sparse row-wise SGD on the arena: w[r] -= lr * (g + 2*l2*w[r]) for the n_unique rows
  * (the L2 term is the reference's embeddings_regularizer, IL:217, applied lazily). */
 int kon_embed_sgd(DLTensor* arena, const DLTensor* unique_rows, const DLTensor* grads,

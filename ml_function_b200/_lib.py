@@ -134,6 +134,7 @@ def lib():
         "kon_embed_fwd": (ctypes.c_int, [T, T, i64p, i32, T, T, i32, vp]),
         "kon_embed_bwd_workspace_bytes": (sz, [i64, i32]),
         "kon_embed_bwd": (ctypes.c_int, [T, T, i64p, i32, T, T, T, T, vp]),
+        "kon_embed_bwd_reuse": (ctypes.c_int, [T, T, i64p, i32, T, T, T, T, vp]),
         "kon_embed_sgd": (ctypes.c_int, [T, T, T, T, f32, f32, vp]),
         "kon_embed_adam": (ctypes.c_int, [T, T, T, T, T, T, f32, f32, f32, f32, f32, i32, vp]),
         "kon_embed_adam_devstep": (ctypes.c_int, [T, T, T, T, T, T, f32, f32, f32, f32, f32, T, vp]),
@@ -163,7 +164,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "kon_abi_version", "kon_last_error", "kon_launch_count", "kon_profile_enable", "kon_profile_reset",
     "kon_profile_read", "kon_device_info", "kon_embed_fwd",
-    "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_sgd", "kon_embed_adam",
+    "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_bwd_reuse", "kon_embed_sgd", "kon_embed_adam",
     "kon_embed_adam_devstep",
     "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",

@@ -24,6 +24,15 @@
 
 namespace kon {
 
+#ifndef KON_EMB_U
+#define KON_EMB_U 4
+#endif
+#ifndef KON_EMB_WIN
+#define KON_EMB_WIN 16
+#endif
+#ifndef KON_EMB_RED_MINB
+#define KON_EMB_RED_MINB 1
+#endif
 constexpr int kMaxFields = 256;
 constexpr int kFwdThreads = 256;
 constexpr int kTileIds = 2048;   // ids staged per CTA iteration (per buffer)
@@ -41,7 +50,7 @@ __global__ void __launch_bounds__(kFwdThreads)
 embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ ids,
                      const __grid_constant__ FieldTable ft, int F, int L, int vec_per_row,
                      long long n_bags, int bags_per_tile, float* __restrict__ out,
-                     long long out_sb, long long out_sf, int* __restrict__ oob) {
+                     long long out_sb, long long out_sf, int* __restrict__ oob, unsigned int f_magic) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ long long s_off[kMaxFields + 1];
@@ -102,18 +111,24 @@ embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ i
     const IdT* s = sid[buf];
 
     if (L == 1) {
-      constexpr int U = 4;
+      constexpr int U = KON_EMB_U;
+      // jj / F by multiplication: jj < tile + F < 65536, f_magic = ceil(2^24 / F) -> exact
+      auto divF = [&](int jj) { return (int)(((unsigned long long)(unsigned)jj * f_magic) >> 24); };
       for (int j0 = g; j0 < nb; j0 += G * U) {
         float4 r[U];
         bool ok[U];
+        int fs[U], qs[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * G;
           ok[u] = false;
           r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          fs[u] = qs[u] = 0;
           if (j < nb) {
             const int jj = f0 + j;
-            const int f = jj % F;
+            qs[u] = divF(jj);
+            const int f = jj - qs[u] * F;
+            fs[u] = f;
             const long long id = (long long)s[j];
             const long long rows = s_off[f + 1] - s_off[f];
             ok[u] = true;
@@ -128,10 +143,9 @@ embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ i
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * G;
           if (ok[u] && lane_on) {
-            const int jj = f0 + j;
-            const long long b = b0 + jj / F;
-            const int f = jj % F;
-            *reinterpret_cast<float4*>(out + b * out_sb + f * out_sf + lane * 4) = r[u];
+            (void)j;
+            const long long b = b0 + qs[u];
+            *reinterpret_cast<float4*>(out + b * out_sb + fs[u] * out_sf + lane * 4) = r[u];
           }
         }
       }
@@ -243,7 +257,7 @@ struct RunHead {
   }
 };
 
-constexpr int kWin = 16;           // sorted lookups per lane group
+constexpr int kWin = KON_EMB_WIN;  // sorted lookups per lane group
 constexpr int kRedThreads = 256;
 // per-window / per-CTA meta bits
 constexpr int kHasHead = 1;        // first run continues a run of the previous window
@@ -271,7 +285,7 @@ struct BwdArgs {
 // then stitches runs that cross window boundaries through shared memory, and leaves at
 // most one head and one tail partial per CTA for embed_fixup_kernel.
 template <int LPR>
-__global__ void __launch_bounds__(kRedThreads) embed_reduce_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kRedThreads, KON_EMB_RED_MINB) embed_reduce_kernel(const BwdArgs a) {
   constexpr int G = kRedThreads / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_head = reinterpret_cast<float4*>(smem_raw);          // [G][LPR]
@@ -554,7 +568,8 @@ static int launch_fwd_vec(int lpr, int grid, size_t smem, cudaStream_t st, const
 #define KON_FWD_CASE(N)                                                                         \
   case N:                                                                                       \
     embed_fwd_vec_kernel<IdT, N><<<grid, kFwdThreads, smem, st>>>(arena, ids, ft, F, L, vpr,    \
-                                                                  n_bags, bpt, out, sb, sf, oob); \
+                                                                  n_bags, bpt, out, sb, sf, oob, \
+                                                                  (unsigned)(((1u << 24) + F - 1) / F)); \
     break;
   ProfileScope ps("embed_fwd_vec_kernel", st);
   switch (lpr) {
@@ -724,10 +739,29 @@ __global__ void pad1_kernel(const float* __restrict__ src, long long sb, long lo
   }
 }
 
+static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+                          int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                          DLTensor* workspace, int reuse_sort, void* stream);
+
 extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
                              const int64_t* field_row_offset, int32_t n_fields,
                              DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                              DLTensor* workspace, void* stream) {
+  return embed_bwd_impl(d_out, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 0,
+                        stream);
+}
+
+extern "C" int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids,
+                                   const int64_t* field_row_offset, int32_t n_fields,
+                                   DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                                   DLTensor* workspace, void* stream) {
+  return embed_bwd_impl(d_out, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 1,
+                        stream);
+}
+
+static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+                          int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                          DLTensor* workspace, int reuse_sort, void* stream) {
   KON_TRY(check_cuda_tensor(d_out, "d_out"));
   const int dev = d_out->device.device_id;
   IdsView v;
@@ -785,6 +819,7 @@ extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
   while (end_bit < 32 && (total_rows >> end_bit) != 0) ++end_bit;
 
   const int kgrid = (int)std::min<long long>((n + 255) / 256, (long long)sms * 16);
+  if (!reuse_sort) {
   if (v.i64)
     embed_keys_kernel<long long><<<kgrid, 256, 0, st>>>(data_ptr<long long>(ids), ft, (int)v.F,
                                                         (int)v.L, n, sentinel, keys_in, vals_in);
@@ -802,6 +837,7 @@ extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
   cub_bytes = l.cub_bytes;
   auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), RunHead{keys_out});
   KON_CUDA(cub::DeviceScan::InclusiveSum(ws + l.cub, cub_bytes, it, segidx, (int)n, st));
+  }   // !reuse_sort
 
   BwdArgs a;
   a.d_out = data_ptr<float>(d_out);

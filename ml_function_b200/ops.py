@@ -86,7 +86,27 @@ def embed_fwd_raw(arena, ids, field_row_offset: Sequence[int], sum_fields=False,
     return out
 
 
-def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int]) -> SparseGrad:
+# Routing (sort) results of the current step, keyed by (ids storage, offsets): the embedding and the
+# first-order tables of a model are looked up with the same ids and the same per-field row counts, so
+# the second backward reuses the first one's sorted keys (kon_embed_bwd_reuse).  Cleared by new_step().
+_SORT_CACHE = {}
+_SHARE_SORT = False      # only inside new_step() ... end_step(): the ids tensors are alive (saved for the
+                         # backward), so a storage address identifies them
+
+
+def new_step():
+    global _SHARE_SORT
+    _SORT_CACHE.clear()
+    _SHARE_SORT = True
+
+
+def end_step():
+    global _SHARE_SORT
+    _SORT_CACHE.clear()
+    _SHARE_SORT = False
+
+
+def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None) -> SparseGrad:
     """d_out [B,F,dim] (any strides on dims 0/1, e.g. an expanded [B,1,dim])."""
     lib = L.lib()
     F = ids.shape[1]
@@ -96,12 +116,24 @@ def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int]) -> SparseGrad:
     rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
     nu = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = _ws(lib.kon_embed_bwd_workspace_bytes(n, dim), dev)
+    if share_sort is None:
+        share_sort = _SHARE_SORT
+    key = (ids.data_ptr(), ids._version, tuple(field_row_offset), n)
+    cached = _SORT_CACHE.get(key) if share_sort else None
+    need = lib.kon_embed_bwd_workspace_bytes(n, dim)
+    if cached is not None and cached.numel() >= need:
+        ws, fn, what = cached, lib.kon_embed_bwd_reuse, "kon_embed_bwd_reuse"
+    else:
+        # sized for the widest payload seen in practice plus the dim-1 path, so a later call can reuse it
+        ws = _ws(max(need, lib.kon_embed_bwd_workspace_bytes(n, 1), lib.kon_embed_bwd_workspace_bytes(n, 32)), dev)
+        fn, what = lib.kon_embed_bwd, "kon_embed_bwd"
+        if share_sort:
+            _SORT_CACHE[key] = ws
     offs = L.i64_array(list(field_row_offset))
     a = [L._arg(t) for t in (d_out, ids, rows, grads, nu, ws)]
     with _prof("embed_bwd" if dim > 1 else "embed_bwd_lin"):
-        L.check(lib.kon_embed_bwd(a[0].ptr, a[1].ptr, offs, F, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
-                                  L.stream_ptr(dev)), "kon_embed_bwd")
+        L.check(fn(a[0].ptr, a[1].ptr, offs, F, a[2].ptr, a[3].ptr, a[4].ptr, a[5].ptr,
+                   L.stream_ptr(dev)), what)
     return SparseGrad(rows, grads, nu)
 
 

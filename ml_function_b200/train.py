@@ -73,6 +73,7 @@ class Trainer:
         ``[B,1]`` for XDeepFM's sigmoid head.  Returns the (device) loss."""
         for so in self.sparse_opts:
             so.arena.kon_sparse_grads = []
+        ops.new_step()
         loss = self.loss(dense, ids, labels)
         self._ensure_dense_opt()
         self.dense_opt.zero_grad(set_to_none=True)
@@ -85,6 +86,7 @@ class Trainer:
         self.dense_opt.step()
         for so in self.sparse_opts:
             so.step()
+        ops.end_step()
         return loss.detach()
 
     # ------------------------------------------------------------------------------------------

@@ -325,3 +325,24 @@ def test_attention_fwd_bwd(B, F, kin, H, d, flags):
         if nm in ("dgamma", "dbeta") and not use_ln:
             continue
         assert_rel(tc[i].grad, g64[i], 2e-5 if relu else FP32_TOL, f"attn {nm}")
+
+
+def test_embed_bwd_shared_sort_matches_separate():
+    """kon_embed_bwd_reuse: the first-order tables reuse the routing (sorted keys) of the embedding
+    tables of the same step -- results must be identical to two independent calls."""
+    ops = _ops()
+    g = gen(21)
+    rows = [50, 3000, 7, 100000]
+    B = 5000
+    ids = make_ids(B, rows, g).to(DEV)
+    offs = offsets(rows)
+    g16 = torch.randn(B, 4, 16, generator=g).to(DEV)
+    g1 = torch.randn(B, 4, 1, generator=g).to(DEV)
+    a16, a1 = ops.embed_bwd_raw(g16, ids, offs, share_sort=False), ops.embed_bwd_raw(g1, ids, offs, share_sort=False)
+    ops.new_step()
+    b16, b1 = ops.embed_bwd_raw(g16, ids, offs), ops.embed_bwd_raw(g1, ids, offs)
+    ops.end_step()
+    for x, y in ((a16, b16), (a1, b1)):
+        n = int(x.n.item())
+        assert n == int(y.n.item())
+        assert torch.equal(x.rows[:n], y.rows[:n]) and torch.equal(x.grads[:n], y.grads[:n])
