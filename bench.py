@@ -328,7 +328,9 @@ def run_gpu(args):
     name = args.model
     B = args.batch
     k = MODEL_CFG[name]["k"]
-    mlp_dtype = {"bf16": torch.bfloat16, "f32": None}[args.mlp_dtype]
+    mlp_dtype = {"bf16": torch.bfloat16, "f32": None, "tf32": None}[args.mlp_dtype]
+    if args.mlp_dtype == "tf32":
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(2020)
     model = build_model(name, dev, cin_precision=args.cin_precision, mlp_dtype=mlp_dtype)
     if dctx is not None:
@@ -415,13 +417,25 @@ def run_gpu(args):
                 for i in range(3):
                     fn(i)
                 torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for i in range(reps):
-                    fn(i)
-                e1.record()
-                torch.cuda.synchronize()
-                iso[kn] = e0.elapsed_time(e1) / reps
+                # the launches are replayed from a CUDA graph: the Python/ctypes call (~50 us) is longer
+                # than the kernel, so eager back-to-back launches would time the host, not the GPU
+                try:
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        for i in range(reps):
+                            fn(i)
+                    gr.replay()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    gr.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    iso[kn] = e0.elapsed_time(e1) / reps
+                    del gr
+                except Exception as e:      # noqa: BLE001
+                    print("isolated timing of", kn, "failed:", repr(e), file=sys.stderr)
+                    torch.cuda.synchronize()
     # ---- the same step replayed from a CUDA graph (kernel stats above come from the eager pass:
     # events cannot be recorded inside a capture) ------------------------------------------------
     graphed = False
@@ -489,7 +503,7 @@ def run_gpu(args):
     for kn, ms_iso in iso.items():
         op = "embed_fwd" if kn == "embed_fwd_vec_kernel" else "embed_bwd"
         amount = work[op][1]
-        kstats[kn + " (back-to-back)"] = {
+        kstats[kn + " (graph replay, back-to-back)"] = {
             "bound": "hbm", "launches_per_step": 1.0, "ms_per_launch": ms_iso, "work_per_launch": amount,
             "achieved": amount / (ms_iso * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
             "frac": amount / (ms_iso * 1e-3) / 1e9 / pk["hbm"], "share_of_step": ms_iso / (ms_eager / args.steps),
@@ -552,7 +566,7 @@ def main():
     ap.add_argument("--model", default="xdeepfm", choices=list(MODEL_CFG))
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cin-precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "f32", "tf32"])
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--n-batches", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=3)

@@ -30,7 +30,25 @@ struct AttnDims {
   float ln_eps;
 };
 
-__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+// sigmoid with the fast exponential and reciprocal (relative error ~2e-7: two orders below the 1e-5 gate)
+__device__ __forceinline__ float sigmoidf_(float z) { return __frcp_rn(1.f + __expf(-z)); }
+
+__host__ __device__ inline int al4(int n) { return (n + 3) & ~3; }
+
+// DH contiguous floats from a 16-byte aligned shared-memory row (128-bit loads when DH % 4 == 0)
+template <int DH>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float* out) {
+  if constexpr (DH % 4 == 0) {
+#pragma unroll
+    for (int e = 0; e < DH; e += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p + e);
+      out[e] = v.x; out[e + 1] = v.y; out[e + 2] = v.z; out[e + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < DH; ++e) out[e] = p[e];
+  }
+}
 
 // Projection of this lane's row onto head h: q/k/r[e] = sum_c x[c] * W[c][h][e].
 template <int DH>
@@ -63,14 +81,14 @@ __device__ __forceinline__ void attend(const float* q, const float* __restrict__
                                        bool use_scale, float sqrt_d, float* o) {
 #pragma unroll
   for (int e = 0; e < DH; ++e) o[e] = 0.f;
+  const float inv_sd = use_scale ? 1.f / sqrt_d : 1.f;
   for (int j = 0; j < F; ++j) {
     float kj[DH];
-#pragma unroll
-    for (int e = 0; e < DH; ++e) kj[e] = ks[j * DH + e];
+    load_row<DH>(ks + j * DH, kj);
     float z = 0.f;
 #pragma unroll
     for (int e = 0; e < DH; ++e) z = fmaf(q[e], kj[e], z);
-    if (use_scale) z = __fdiv_rn(z, sqrt_d);
+    z *= inv_sd;
     const float sg = sigmoidf_(z);
 #pragma unroll
     for (int e = 0; e < DH; ++e) o[e] = fmaf(sg, kj[e], o[e]);
@@ -93,11 +111,11 @@ attn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
   float* bet = gam + DH;
   const int xstride = kin + 1;
   constexpr int kWarps = kAttnFwdThreads / 32;
-  float* warp_base = bet + DH;
-  const int per_warp = F * xstride + F * DH;
+  float* warp_base = smem + al4(3 * wsz + 2 * DH);
+  const int per_warp = al4(F * xstride) + al4(F * DH);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* xs = warp_base + wid * per_warp;
-  float* ks = xs + F * xstride;
+  float* ks = xs + al4(F * xstride);
   for (int i = threadIdx.x; i < wsz; i += kAttnFwdThreads) {
     Wq[i] = wq[i];
     Wk[i] = wk[i];
@@ -175,20 +193,22 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
   float* Wr = Wk + wsz;
   float* gam = Wr + wsz;
   float* bet = gam + DH;
-  float* warp_base = bet + DH;
+  float* warp_base = smem + al4(3 * wsz + 2 * DH);
   const int xstride = kin + 1;
-  // per warp: xs, dxs [F][xstride]; qs, ks, gos, gqs, gks, grs [F][DH]; dW [3][wsz]; dgb [2*DH]
-  const int per_warp = 2 * F * xstride + 6 * F * DH + 3 * wsz + 2 * DH;
+  // per warp (every array 16-byte aligned): xs, dxs [F][xstride]; qs, ks, gos, gqs, gks, grs [F][DH];
+  // dW [3][wsz] directly followed by dgb [2*DH]
+  const int axs = al4(F * xstride), afd = al4(F * DH);
+  const int per_warp = 2 * axs + 6 * afd + al4(3 * wsz + 2 * DH);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* xs = warp_base + wid * per_warp;
-  float* dxs = xs + F * xstride;
-  float* qs = dxs + F * xstride;
-  float* ks = qs + F * DH;
-  float* gos = ks + F * DH;
-  float* gqs = gos + F * DH;
-  float* gks = gqs + F * DH;
-  float* grs = gks + F * DH;
-  float* dWs = grs + F * DH;
+  float* dxs = xs + axs;
+  float* qs = dxs + axs;
+  float* ks = qs + afd;
+  float* gos = ks + afd;
+  float* gqs = gos + afd;
+  float* gks = gqs + afd;
+  float* grs = gks + afd;
+  float* dWs = grs + afd;
   float* dgb = dWs + 3 * wsz;
   for (int i = threadIdx.x; i < wsz; i += kAttnBwdThreads) {
     Wq[i] = wq[i];
@@ -291,15 +311,14 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
         const float inv_scale = p.use_scale ? 1.f / sqrt_d : 1.f;
         for (int j = 0; j < F; ++j) {
           float kj[DH];
-#pragma unroll
-          for (int e = 0; e < DH; ++e) kj[e] = ks[j * DH + e];
+          load_row<DH>(ks + j * DH, kj);
           float z = 0.f, gs = 0.f;
 #pragma unroll
           for (int e = 0; e < DH; ++e) {
             z = fmaf(q[e], kj[e], z);
             gs = fmaf(gO[e], kj[e], gs);
           }
-          if (p.use_scale) z = __fdiv_rn(z, sqrt_d);
+          z *= inv_scale;
           const float sg = sigmoidf_(z);
           const float gz = gs * sg * (1.f - sg) * inv_scale;
 #pragma unroll
@@ -307,18 +326,15 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
         }
         for (int i = 0; i < F; ++i) {
           float qi[DH], goi[DH];
-#pragma unroll
-          for (int e = 0; e < DH; ++e) {
-            qi[e] = qs[i * DH + e];
-            goi[e] = gos[i * DH + e];
-          }
+          load_row<DH>(qs + i * DH, qi);
+          load_row<DH>(gos + i * DH, goi);
           float z = 0.f, gs = 0.f;
 #pragma unroll
           for (int e = 0; e < DH; ++e) {
             z = fmaf(qi[e], k[e], z);
             gs = fmaf(goi[e], k[e], gs);
           }
-          if (p.use_scale) z = __fdiv_rn(z, sqrt_d);
+          z *= inv_scale;
           const float sg = sigmoidf_(z);
           const float gz = gs * sg * (1.f - sg) * inv_scale;
 #pragma unroll
@@ -384,7 +400,7 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
   for (int i = threadIdx.x; i < pf; i += kAttnBwdThreads) {
     float acc = 0.f;
     for (int w = 0; w < kWarps; ++w) {
-      const float* base = warp_base + w * per_warp + 2 * F * xstride + 6 * F * DH;
+      const float* base = warp_base + w * per_warp + 2 * axs + 6 * afd;
       acc += base[i];   // dWs (3*wsz) is directly followed by dgb (2*DH)
     }
     out[i] = acc;
@@ -412,12 +428,12 @@ static int attn_bwd_grid(long long B, int sms) {
 }
 
 static size_t attn_fwd_smem(int F, int kin, int H, int DH) {
-  return sizeof(float) * ((size_t)3 * kin * H * DH + 2 * DH +
-                          (size_t)(kAttnFwdThreads / 32) * (F * (kin + 1) + F * DH));
+  return sizeof(float) * ((size_t)al4(3 * kin * H * DH + 2 * DH) +
+                          (size_t)(kAttnFwdThreads / 32) * (al4(F * (kin + 1)) + al4(F * DH)));
 }
 static size_t attn_bwd_smem(int F, int kin, int H, int DH) {
-  const size_t per_warp = 2 * (size_t)F * (kin + 1) + 6 * (size_t)F * DH + 3 * (size_t)kin * H * DH + 2 * DH;
-  return sizeof(float) * ((size_t)3 * kin * H * DH + 2 * DH + (kAttnBwdThreads / 32) * per_warp);
+  const size_t per_warp = 2 * (size_t)al4(F * (kin + 1)) + 6 * (size_t)al4(F * DH) + al4(3 * kin * H * DH + 2 * DH);
+  return sizeof(float) * ((size_t)al4(3 * kin * H * DH + 2 * DH) + (kAttnBwdThreads / 32) * per_warp);
 }
 
 }  // namespace kon

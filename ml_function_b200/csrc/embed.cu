@@ -35,7 +35,14 @@ namespace kon {
 #endif
 constexpr int kMaxFields = 256;
 constexpr int kFwdThreads = 256;
-constexpr int kTileIds = 2048;   // ids staged per CTA iteration (per buffer)
+#ifndef KON_EMB_TILE
+#define KON_EMB_TILE 512
+#endif
+#ifndef KON_EMB_CTAS
+#define KON_EMB_CTAS 4
+#endif
+constexpr int kTileIds = KON_EMB_TILE;   // ids staged per CTA iteration (per buffer): small tiles keep the
+                                         // persistent CTAs balanced (832 tiles of 2048 over 592 resident CTAs = 2 uneven waves)
 constexpr int kMaxBagLen = 512;
 
 struct FieldTable {
@@ -647,7 +654,7 @@ extern "C" int kon_embed_fwd(const DLTensor* arena, const DLTensor* ids,
     const long long n_tiles = (n_bags + bpt - 1) / bpt;
     const size_t idsz = v.i64 ? 8 : 4;
     const size_t smem = 2 * (size_t)bpt * v.L * idsz;
-    int grid = (int)std::min<long long>(n_tiles, (long long)sms * 8);
+    int grid = (int)std::min<long long>(n_tiles, (long long)sms * KON_EMB_CTAS);   // = resident CTAs: one wave, tiles strided
     if (v.i64)
       return launch_fwd_vec<long long>(lpr, grid, smem, st, reinterpret_cast<const float4*>(ap),
                                        data_ptr<long long>(ids), ft, (int)v.F, (int)v.L, vpr,
