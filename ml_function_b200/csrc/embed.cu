@@ -31,7 +31,7 @@ namespace kon {
 #define KON_EMB_WIN 16
 #endif
 #ifndef KON_EMB_RED_MINB
-#define KON_EMB_RED_MINB 1
+#define KON_EMB_RED_MINB 3
 #endif
 constexpr int kMaxFields = 256;
 constexpr int kFwdThreads = 256;
