@@ -42,7 +42,7 @@ MODEL_CFG = {
     "deepfm": dict(k=16, desc="DeepFM, 26 sparse + 13 dense, emb 16, MLP 256-128-64"),
     "dcn": dict(k=32, desc="DCN-v1, 6 CrossLayers, emb 32, MLP 256-128-64"),
     "xdeepfm": dict(k=16, desc="xDeepFM, CIN [200,200,200] bf16 tcgen05, emb 16, MLP 256-128-64"),
-    "autoint": dict(k=16, desc="AutoInt, 3 layers x 2 heads x d=8, emb 16"),
+    "autoint": dict(k=16, desc="AutoInt, 3 layers x 2 heads x d=8 (bf16 tensor-core attention), emb 16"),
     "fm": dict(k=16, desc="FM, emb 16"),
 }
 
@@ -181,7 +181,7 @@ def build_model(name, device, cin_precision="bf16", rows=CRITEO_ROWS, mlp_dtype=
     elif name == "xdeepfm":
         m = KM.XDeepFM(fea, cin_precision=cin_precision)
     elif name == "autoint":
-        m = KM.AutoInt(fea, attention_dim=8, attention_head_dim=2, n_layers=3)
+        m = KM.AutoInt(fea, attention_dim=8, attention_head_dim=2, n_layers=3, precision="bf16")
     else:
         m = KM.FM(fea)
     if mlp_dtype is not None and hasattr(m, "dnn"):

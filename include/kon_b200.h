@@ -196,6 +196,9 @@ int kon_cin_bwd(const DLTensor* x0, const DLTensor* const* w, const DLTensor* co
 #define KON_ATTN_USE_LN    2   /* use_ln    (BL:368-369), eps = 1e-3  */
 #define KON_ATTN_USE_RES   4   /* use_res   (BL:365-366) + Add (CL:212) */
 #define KON_ATTN_RELU      8   /* DnnLayer's activation (CL:216)      */
+#define KON_ATTN_BF16      16  /* bf16 operands on tensor cores (warp-level MMA), fp32 accumulate, sigmoid /
+                                  LayerNorm in fp32; tolerance 2e-2.  Needs F <= 32, kin in {16,32,48,64},
+                                  d == 8.  Without it: fp32 CUDA-core arithmetic (parity mode, 1e-5). */
 int kon_attn_fwd(const DLTensor* x, const DLTensor* wq, const DLTensor* wk, const DLTensor* wr,
                  const DLTensor* gamma, const DLTensor* beta, DLTensor* y, float ln_eps,
                  int32_t flags, void* stream);

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("KON_B200_LIB") or os.path.join(_HERE, "libkon_b200.so
 
 KON_EMBED_SUM_FIELDS = 1
 KON_CIN_FP32, KON_CIN_BF16 = 0, 1
-KON_ATTN_USE_SCALE, KON_ATTN_USE_LN, KON_ATTN_USE_RES, KON_ATTN_RELU = 1, 2, 4, 8
+KON_ATTN_USE_SCALE, KON_ATTN_USE_LN, KON_ATTN_USE_RES, KON_ATTN_RELU, KON_ATTN_BF16 = 1, 2, 4, 8, 16
 
 
 class KonError(RuntimeError):

@@ -16,21 +16,13 @@
 // X, gY in, dX out (bwd; Q/K/S/O and the LayerNorm statistics are recomputed).
 // Weight gradients are accumulated per warp in shared memory, reduced per CTA in warp
 // order and finished by a second kernel in CTA order (deterministic).
-#include "common.cuh"
+#include "attn_common.cuh"
 
 namespace kon {
 
 constexpr int kAttnFwdThreads = 256;
 constexpr int kAttnBwdThreads = 128;
 
-struct AttnDims {
-  long long B;
-  int F, kin, H;
-  int use_scale, use_ln, use_res, relu;
-  float ln_eps;
-};
-
-// sigmoid with the fast exponential and reciprocal (relative error ~2e-7: two orders below the 1e-5 gate)
 __device__ __forceinline__ float sigmoidf_(float z) { return __frcp_rn(1.f + __expf(-z)); }
 
 __host__ __device__ inline int al4(int n) { return (n + 3) & ~3; }
@@ -504,6 +496,14 @@ extern "C" int kon_attn_fwd(const DLTensor* x, const DLTensor* wq, const DLTenso
   if (p.B == 0) return KON_OK;
   DeviceGuard guard(dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (flags & KON_ATTN_BF16) {
+    KON_REQUIRE(attn_tc_supported(p, DH), KON_EUNSUPPORTED,
+                "KON_ATTN_BF16 needs F <= 32, kin in {16,32,48,64}, d == 8, H <= 8 (got F=%d kin=%d d=%d H=%d)",
+                p.F, p.kin, DH, p.H);
+    return attn_tc_fwd(data_ptr<float>(x), data_ptr<float>(wq), data_ptr<float>(wk),
+                       p.use_res ? data_ptr<float>(wr) : nullptr, p.use_ln ? data_ptr<float>(gamma) : nullptr,
+                       p.use_ln ? data_ptr<float>(beta) : nullptr, data_ptr<float>(y), p, sm_count_of(dev), st);
+  }
   const size_t smem = attn_fwd_smem(p.F, p.kin, p.H, DH);
   KON_REQUIRE(smem <= 227 * 1024, KON_EUNSUPPORTED, "attention shape needs %zu B of shared memory",
               smem);
@@ -579,6 +579,18 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
   KON_REQUIRE(smem <= 227 * 1024, KON_EUNSUPPORTED, "attention shape needs %zu B of shared memory",
               smem);
   float* partial = data_ptr<float>(workspace);
+  if ((flags & KON_ATTN_BF16) && attn_tc_bwd_supported(p, DH)) {
+    int used = grid;
+    KON_TRY(attn_tc_bwd(data_ptr<float>(x), data_ptr<float>(wq), data_ptr<float>(wk),
+                        p.use_res ? data_ptr<float>(wr) : nullptr, p.use_ln ? data_ptr<float>(gamma) : nullptr,
+                        p.use_ln ? data_ptr<float>(beta) : nullptr, data_ptr<float>(gy), data_ptr<float>(dx),
+                        partial, grid, p, sm_count_of(dev), &used, st));
+    attn_bwd_finalize_kernel<<<(pf + 255) / 256, 256, 0, st>>>(partial, used, pf, p.kin * p.H * DH, DH,
+                                                              data_ptr<float>(dwq), data_ptr<float>(dwk), dwr_p,
+                                                              dg_p, db_p);
+    KON_LAUNCH_CHECK("attn_bwd_finalize_kernel");
+    return KON_OK;
+  }
 #define CALL(N)                                                                                  \
   KON_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)smem));                                                     \

@@ -1,0 +1,660 @@
+// a9-a10 on tensor cores (KON_ATTN_BF16): the AutoInt block with bf16 operands / fp32 accumulate.
+//
+// The per-sample matrices are tiny (F = 26 fields, k_in = 16, d = 8): far below one tcgen05 tile
+// (M = 128), and the op is HBM-bound on paper.  The fp32 kernel of attn.cu is instruction-bound on
+// the CUDA cores (62 % issue utilisation, ~4000 warp instructions per sample); here one warp owns one
+// sample and runs the whole block as 36 warp-level m16n8k16 MMAs, FlashAttention-2 style:
+//   * X [32(pad) x k_in] -> A fragments straight from global memory (fp32 -> bf16x2);
+//   * Q/K/R = X W: B fragments of W pre-packed once per call (attn_pack_w_kernel);
+//   * S = Q K^T: the accumulator fragments of K ARE the col-major B fragments of K^T;
+//   * P = sigmoid(S) (BL:286, fp32) -> the accumulator fragments of two adjacent n-tiles ARE the
+//     A fragment of the next k-step;  O = P K needs K transposed: K goes through 512 B of shared
+//     memory and comes back with ldmatrix.trans;
+//   * LayerNorm (eps 1e-3) / residual / ReLU on the accumulator fragments, 8-byte stores of y.
+// Legacy mma.sync on purpose: at 26x8 tiles tcgen05 would waste 75 % of every tile, and the goal is
+// only to get the math off the critical path of an HBM-bound kernel.
+#include <cuda_bf16.h>
+
+#include "attn_common.cuh"
+
+namespace kon {
+
+namespace {
+
+constexpr int kAtWarps = 8;
+constexpr int kAtThreads = 32 * kAtWarps;
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ float fast_sigmoid(float z) { return __frcp_rn(1.f + __expf(-z)); }
+
+// B fragments of W[kin][H][8] for m16n8k16 (k = c, n = e), built by every CTA in shared memory:
+//   word[((mat*H + h)*KS + ks)*64 + r*32 + lane],  r = 0: (W[16ks+2t][h][g], W[16ks+2t+1][h][g]),  r = 1: rows +8
+__device__ __forceinline__ void pack_w_frags(const float* __restrict__ wq, const float* __restrict__ wk,
+                                             const float* __restrict__ wr, int KS, int H, uint32_t* out,
+                                             int tid, int nthreads) {
+  const int total = 3 * H * KS * 64;
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int lane = idx & 31, r = (idx >> 5) & 1;
+    int t = idx >> 6;
+    const int ks = t % KS;
+    t /= KS;
+    const int h = t % H, mat = t / H;
+    const float* W = mat == 0 ? wq : (mat == 1 ? wk : wr);
+    const int g = lane >> 2, t4 = lane & 3;
+    const int c = 16 * ks + 2 * t4 + 8 * r;
+    const float lo = W ? W[((long long)c * H + h) * 8 + g] : 0.f;
+    const float hi = W ? W[((long long)(c + 1) * H + h) * 8 + g] : 0.f;
+    out[idx] = pack2(lo, hi);
+  }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(kAtThreads)
+attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, const float* __restrict__ wk,
+                   const float* __restrict__ wr, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                   const AttnDims p) {
+  extern __shared__ __align__(16) uint32_t smem_w[];                 // [3*H*KS*64] W fragments
+  __shared__ __align__(16) unsigned short s_k[kAtWarps][32 * 8];     // per warp: K (bf16) [j][e]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int H = p.H, F = p.F, kin = 16 * KS;
+  pack_w_frags(wq, wk, wr, KS, H, smem_w, tid, kAtThreads);
+  __syncthreads();
+  const float sc = p.use_scale ? rsqrtf(8.f) : 1.f;
+  float gam[2], bet[2];
+  gam[0] = p.use_ln ? gamma[2 * t] : 1.f;  gam[1] = p.use_ln ? gamma[2 * t + 1] : 1.f;
+  bet[0] = p.use_ln ? beta[2 * t] : 0.f;   bet[1] = p.use_ln ? beta[2 * t + 1] : 0.f;
+  unsigned short* ksm = s_k[warp];
+
+  for (long long b = (long long)blockIdx.x * kAtWarps + warp; b < p.B; b += (long long)gridDim.x * kAtWarps) {
+    // ---- A fragments of X: rows 16mt+g (+8), cols 16ks+2t (+8) ------------------------------
+    uint32_t ax[2][KS][4];
+    const float* xb = x + b * (long long)F * kin;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int c0 = 16 * ks + 2 * t;
+        float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+        if (r0 < F) {
+          v00 = __ldg(reinterpret_cast<const float2*>(xb + r0 * kin + c0));
+          v01 = __ldg(reinterpret_cast<const float2*>(xb + r0 * kin + c0 + 8));
+        }
+        if (r1 < F) {
+          v10 = __ldg(reinterpret_cast<const float2*>(xb + r1 * kin + c0));
+          v11 = __ldg(reinterpret_cast<const float2*>(xb + r1 * kin + c0 + 8));
+        }
+        ax[mt][ks][0] = pack2(v00.x, v00.y);
+        ax[mt][ks][1] = pack2(v10.x, v10.y);
+        ax[mt][ks][2] = pack2(v01.x, v01.y);
+        ax[mt][ks][3] = pack2(v11.x, v11.y);
+      }
+    }
+    for (int h = 0; h < H; ++h) {
+      // ---- projections ----------------------------------------------------------------------
+      float qc[2][4], kc[2][4], rc[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) qc[mt][q] = kc[mt][q] = rc[mt][q] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t* wq_ = smem_w + ((0 * H + h) * KS + ks) * 64;
+        const uint32_t* wk_ = smem_w + ((1 * H + h) * KS + ks) * 64;
+        const uint32_t* wr_ = smem_w + ((2 * H + h) * KS + ks) * 64;
+        const uint32_t bq0 = wq_[lane], bq1 = wq_[32 + lane], bk0 = wk_[lane], bk1 = wk_[32 + lane];
+        const uint32_t br0 = wr_[lane], br1 = wr_[32 + lane];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma16816(qc[mt], ax[mt][ks], bq0, bq1);
+          mma16816(kc[mt], ax[mt][ks], bk0, bk1);
+          if (p.use_res) mma16816(rc[mt], ax[mt][ks], br0, br1);
+        }
+      }
+      // ---- K (bf16) -> shared [j][e] for the transposed read; Q / K fragments for S = Q K^T ----
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        *reinterpret_cast<uint32_t*>(ksm + (16 * mt + g) * 8 + 2 * t) = pack2(kc[mt][0], kc[mt][1]);
+        *reinterpret_cast<uint32_t*>(ksm + (16 * mt + g + 8) * 8 + 2 * t) = pack2(kc[mt][2], kc[mt][3]);
+      }
+      __syncwarp();
+      uint32_t aq[2][4], bkf[4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        aq[mt][0] = pack2(qc[mt][0] * sc, qc[mt][1] * sc);
+        aq[mt][1] = pack2(qc[mt][2] * sc, qc[mt][3] * sc);
+        aq[mt][2] = aq[mt][3] = 0u;                       // k = 8..15: padding of d = 8
+        bkf[2 * mt] = pack2(kc[mt][0], kc[mt][1]);        // n-tile 2mt   : rows j = 16mt + g
+        bkf[2 * mt + 1] = pack2(kc[mt][2], kc[mt][3]);    // n-tile 2mt+1 : rows j = 16mt + 8 + g
+      }
+      float o[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s[nt][q] = 0.f;
+          mma16816(s[nt], aq[mt], bkf[nt], 0u);
+        }
+        // P = sigmoid(S), columns j >= F masked; two n-tiles -> one A fragment (k = 16 rows of K)
+        uint32_t ap[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int j0 = 8 * nt + 2 * t;
+          const float p0 = j0 < F ? fast_sigmoid(s[nt][0]) : 0.f, p1 = j0 + 1 < F ? fast_sigmoid(s[nt][1]) : 0.f;
+          const float p2 = j0 < F ? fast_sigmoid(s[nt][2]) : 0.f, p3 = j0 + 1 < F ? fast_sigmoid(s[nt][3]) : 0.f;
+          ap[nt >> 1][(nt & 1) * 2] = pack2(p0, p1);        // row g
+          ap[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);    // row g + 8
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[mt][q] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          uint32_t bt0, bt1;
+          ldmatrix_x2_trans(bt0, bt1, ksm + (16 * kk + (lane & 15)) * 8);
+          mma16816(o[mt], ap[kk], bt0, bt1);
+        }
+      }
+      // ---- LayerNorm over d = 8 (a row's 8 values live in the 4 lanes of a quad), residual, ReLU -----
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v0 = o[mt][2 * half], v1 = o[mt][2 * half + 1];
+          if (p.use_ln) {
+            float sum = v0 + v1;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float mean = sum * 0.125f;
+            float var = (v0 - mean) * (v0 - mean) + (v1 - mean) * (v1 - mean);
+            var += __shfl_xor_sync(0xffffffffu, var, 1);
+            var += __shfl_xor_sync(0xffffffffu, var, 2);
+            const float rstd = rsqrtf(var * 0.125f + p.ln_eps);
+            v0 = (v0 - mean) * rstd * gam[0] + bet[0];
+            v1 = (v1 - mean) * rstd * gam[1] + bet[1];
+          }
+          if (p.use_res) { v0 += rc[mt][2 * half]; v1 += rc[mt][2 * half + 1]; }
+          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          const int row = 16 * mt + g + 8 * half;
+          if (row < F)
+            *reinterpret_cast<float2*>(y + (((long long)h * p.B + b) * F + row) * 8 + 2 * t) = make_float2(v0, v1);
+        }
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+// Everything of the forward is recomputed per head in fragments; then (q' = q / sqrt(d)):
+//   gP = gy . relu'            LayerNorm backward -> gO            gR = gP
+//   gS = gO K^T,  gZ = gS . P . (1 - P)                           gQ' = gZ K
+//   transposed side (fresh MMAs instead of fragment transposes):
+//   S^T = K q'^T, P^T = sigmoid(S^T), gS^T = K gO^T, gZ^T = gS^T . P^T . (1 - P^T)
+//   gK = gZ^T q' + P^T gO
+//   dX += (gQ'/sqrt(d)) Wq^T + gK Wk^T + gR Wr^T
+//   dWq += X^T (gQ'/sqrt(d)),  dWk += X^T gK,  dWr += X^T gR       (accumulated per warp in registers)
+// Operands that must be read "the other way round" (K, q', gO, X, gQ, gK, gR) go through a few
+// hundred bytes of per-warp shared memory and come back with ldmatrix.trans.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+// C fragment [16 x 8] -> A fragment whose k = 0..7 are those 8 columns (k = 8..15 zero)
+__device__ __forceinline__ void c_to_a_k8(const float* c, uint32_t* a, float scale = 1.f) {
+  a[0] = pack2(c[0] * scale, c[1] * scale);
+  a[1] = pack2(c[2] * scale, c[3] * scale);
+  a[2] = a[3] = 0u;
+}
+// two C fragments of adjacent n-tiles -> one A fragment (k = 16)
+__device__ __forceinline__ void cc_to_a(const float* c0, const float* c1, uint32_t* a) {
+  a[0] = pack2(c0[0], c0[1]);
+  a[1] = pack2(c0[2], c0[3]);
+  a[2] = pack2(c1[0], c1[1]);
+  a[3] = pack2(c1[2], c1[3]);
+}
+// store a C fragment [16 x 8] as bf16 rows [row][8] (row = 16mt + g, +8)
+__device__ __forceinline__ void store_c_bf16(unsigned short* sm, int mt, int g, int t, const float* c, float scale = 1.f) {
+  *reinterpret_cast<uint32_t*>(sm + (16 * mt + g) * 8 + 2 * t) = pack2(c[0] * scale, c[1] * scale);
+  *reinterpret_cast<uint32_t*>(sm + (16 * mt + g + 8) * 8 + 2 * t) = pack2(c[2] * scale, c[3] * scale);
+}
+
+constexpr int kAtBwdWarps = 4;
+constexpr int kAtBwdThreads = 32 * kAtBwdWarps;
+
+template <int KS, int HT>
+__global__ void __launch_bounds__(kAtBwdThreads)
+attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, const float* __restrict__ wk,
+                   const float* __restrict__ wr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ gy, float* __restrict__ dx, float* __restrict__ partial,
+                   const AttnDims p) {
+  constexpr int KIN = 16 * KS;
+  extern __shared__ __align__(16) uint32_t smem_dyn[];
+  // dynamic smem: [W fragments 3*H*KS*64] [W^T fragments 3*H*(KIN/8)*32] [per-warp partial sums]
+  const int H = p.H, F = p.F;
+  uint32_t* w_frag = smem_dyn;
+  uint32_t* wt_frag = w_frag + 3 * H * KS * 64;
+  float* red = reinterpret_cast<float*>(wt_frag + 3 * H * (KIN / 8) * 32);
+  __shared__ __align__(16) unsigned short s_buf[kAtBwdWarps][6][32 * 8];     // K, q', gO, gQ, gK, gR  (bf16 [row][8])
+  __shared__ __align__(16) unsigned short s_x[kAtBwdWarps][32 * KIN];         // X (bf16) [i][c]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  pack_w_frags(wq, wk, wr, KS, H, w_frag, tid, kAtBwdThreads);
+  // W^T fragments (k = e, n = c): word[((mat*H + h)*(KIN/8) + ntc)*32 + lane] = (W[8ntc+g][h][2t], W[8ntc+g][h][2t+1])
+  for (int idx = tid; idx < 3 * H * (KIN / 8) * 32; idx += kAtBwdThreads) {
+    const int l = idx & 31;
+    int u = idx >> 5;
+    const int ntc = u % (KIN / 8);
+    u /= (KIN / 8);
+    const int h = u % H, mat = u / H;
+    const float* W = mat == 0 ? wq : (mat == 1 ? wk : wr);
+    const int c = 8 * ntc + (l >> 2), e = 2 * (l & 3);
+    wt_frag[idx] = W ? pack2(W[((long long)c * H + h) * 8 + e], W[((long long)c * H + h) * 8 + e + 1]) : 0u;
+  }
+  __syncthreads();
+  const float sc = p.use_scale ? rsqrtf(8.f) : 1.f;
+  float gam[2], bet[2];
+  gam[0] = p.use_ln ? gamma[2 * t] : 1.f;  gam[1] = p.use_ln ? gamma[2 * t + 1] : 1.f;
+  bet[0] = p.use_ln ? beta[2 * t] : 0.f;   bet[1] = p.use_ln ? beta[2 * t + 1] : 0.f;
+  unsigned short* ksm = s_buf[warp][0];
+  unsigned short* qsm = s_buf[warp][1];
+  unsigned short* gosm = s_buf[warp][2];
+  unsigned short* gqsm = s_buf[warp][3];
+  unsigned short* gksm = s_buf[warp][4];
+  unsigned short* grsm = s_buf[warp][5];
+  unsigned short* xsm = s_x[warp];
+
+  // per-warp accumulators: dW fragments (rows c = 16ks + g (+8), cols e = 2t, 2t+1) and dgamma/dbeta (cols 2t, 2t+1)
+  float dwq[HT][KS][4], dwk[HT][KS][4], dwr[HT][KS][4];      // H <= HT
+#pragma unroll
+  for (int h = 0; h < HT; ++h)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dwq[h][ks][q] = dwk[h][ks][q] = dwr[h][ks][q] = 0.f;
+  float dgam[2] = {0.f, 0.f}, dbet[2] = {0.f, 0.f};
+
+  for (long long b = (long long)blockIdx.x * kAtBwdWarps + warp; b < p.B; b += (long long)gridDim.x * kAtBwdWarps) {
+    uint32_t ax[2][KS][4];
+    const float* xb = x + b * (long long)F * KIN;
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int c0 = 16 * ks + 2 * t;
+        float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+        if (r0 < F) {
+          v00 = __ldg(reinterpret_cast<const float2*>(xb + r0 * KIN + c0));
+          v01 = __ldg(reinterpret_cast<const float2*>(xb + r0 * KIN + c0 + 8));
+        }
+        if (r1 < F) {
+          v10 = __ldg(reinterpret_cast<const float2*>(xb + r1 * KIN + c0));
+          v11 = __ldg(reinterpret_cast<const float2*>(xb + r1 * KIN + c0 + 8));
+        }
+        ax[mt][ks][0] = pack2(v00.x, v00.y);
+        ax[mt][ks][1] = pack2(v10.x, v10.y);
+        ax[mt][ks][2] = pack2(v01.x, v01.y);
+        ax[mt][ks][3] = pack2(v11.x, v11.y);
+        *reinterpret_cast<uint32_t*>(xsm + r0 * KIN + c0) = ax[mt][ks][0];
+        *reinterpret_cast<uint32_t*>(xsm + r1 * KIN + c0) = ax[mt][ks][1];
+        *reinterpret_cast<uint32_t*>(xsm + r0 * KIN + c0 + 8) = ax[mt][ks][2];
+        *reinterpret_cast<uint32_t*>(xsm + r1 * KIN + c0 + 8) = ax[mt][ks][3];
+      }
+    }
+    float dxc[2][KIN / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < KIN / 8; ++n)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dxc[mt][n][q] = 0.f;
+
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      if (h < H) {
+        // ---- forward recompute ----------------------------------------------------------------
+        float qc[2][4], kc[2][4], rc[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) qc[mt][q] = kc[mt][q] = rc[mt][q] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t* wq_ = w_frag + ((0 * H + h) * KS + ks) * 64;
+          const uint32_t* wk_ = w_frag + ((1 * H + h) * KS + ks) * 64;
+          const uint32_t* wr_ = w_frag + ((2 * H + h) * KS + ks) * 64;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma16816(qc[mt], ax[mt][ks], wq_[lane], wq_[32 + lane]);
+            mma16816(kc[mt], ax[mt][ks], wk_[lane], wk_[32 + lane]);
+            if (p.use_res) mma16816(rc[mt], ax[mt][ks], wr_[lane], wr_[32 + lane]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          store_c_bf16(ksm, mt, g, t, kc[mt]);
+          store_c_bf16(qsm, mt, g, t, qc[mt], sc);
+        }
+        __syncwarp();
+        uint32_t aq[2][4], ak[2][4], bkf[4], bqf[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          c_to_a_k8(qc[mt], aq[mt], sc);
+          c_to_a_k8(kc[mt], ak[mt]);
+          bkf[2 * mt] = pack2(kc[mt][0], kc[mt][1]);
+          bkf[2 * mt + 1] = pack2(kc[mt][2], kc[mt][3]);
+          bqf[2 * mt] = pack2(qc[mt][0] * sc, qc[mt][1] * sc);
+          bqf[2 * mt + 1] = pack2(qc[mt][2] * sc, qc[mt][3] * sc);
+        }
+        uint32_t kt[2][2], qt[2][2];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          ldmatrix_x2_trans(kt[kk][0], kt[kk][1], ksm + (16 * kk + (lane & 15)) * 8);
+          ldmatrix_x2_trans(qt[kk][0], qt[kk][1], qsm + (16 * kk + (lane & 15)) * 8);
+        }
+        float P[2][4][4];          // sigmoid(S), rows i, cols j
+        float o[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(s4, aq[mt], bkf[nt], 0u);
+            const int j0 = 8 * nt + 2 * t;
+            P[mt][nt][0] = j0 < F ? fast_sigmoid(s4[0]) : 0.f;
+            P[mt][nt][1] = j0 + 1 < F ? fast_sigmoid(s4[1]) : 0.f;
+            P[mt][nt][2] = j0 < F ? fast_sigmoid(s4[2]) : 0.f;
+            P[mt][nt][3] = j0 + 1 < F ? fast_sigmoid(s4[3]) : 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[mt][q] = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint32_t ap[4];
+            cc_to_a(P[mt][2 * kk], P[mt][2 * kk + 1], ap);
+            mma16816(o[mt], ap, kt[kk][0], kt[kk][1]);
+          }
+        }
+        // ---- output gradient through ReLU / residual / LayerNorm -> gO, gR -------------------
+        float gO[2][4], gR[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int row = 16 * mt + g + 8 * half;
+            float v0 = o[mt][2 * half], v1 = o[mt][2 * half + 1];
+            float mean = 0.f, rstd = 1.f;
+            if (p.use_ln) {
+              float sum = v0 + v1;
+              sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+              mean = sum * 0.125f;
+              float var = (v0 - mean) * (v0 - mean) + (v1 - mean) * (v1 - mean);
+              var += __shfl_xor_sync(0xffffffffu, var, 1);
+              var += __shfl_xor_sync(0xffffffffu, var, 2);
+              rstd = rsqrtf(var * 0.125f + p.ln_eps);
+            }
+            const float xh0 = (v0 - mean) * rstd, xh1 = (v1 - mean) * rstd;
+            float pre0 = p.use_ln ? xh0 * gam[0] + bet[0] : v0;
+            float pre1 = p.use_ln ? xh1 * gam[1] + bet[1] : v1;
+            if (p.use_res) { pre0 += rc[mt][2 * half]; pre1 += rc[mt][2 * half + 1]; }
+            float g0 = 0.f, g1 = 0.f;
+            if (row < F) {
+              const float2 gv = __ldg(reinterpret_cast<const float2*>(gy + (((long long)h * p.B + b) * F + row) * 8 + 2 * t));
+              g0 = (p.relu && !(pre0 > 0.f)) ? 0.f : gv.x;
+              g1 = (p.relu && !(pre1 > 0.f)) ? 0.f : gv.y;
+            }
+            gR[mt][2 * half] = p.use_res ? g0 : 0.f;
+            gR[mt][2 * half + 1] = p.use_res ? g1 : 0.f;
+            if (p.use_ln) {
+              dgam[0] = fmaf(g0, xh0, dgam[0]); dgam[1] = fmaf(g1, xh1, dgam[1]);
+              dbet[0] += g0; dbet[1] += g1;
+              const float gx0 = g0 * gam[0], gx1 = g1 * gam[1];
+              float m1 = gx0 + gx1, m2 = gx0 * xh0 + gx1 * xh1;
+              m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+              m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+              m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+              m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+              m1 *= 0.125f;
+              m2 *= 0.125f;
+              gO[mt][2 * half] = rstd * (gx0 - m1 - xh0 * m2);
+              gO[mt][2 * half + 1] = rstd * (gx1 - m1 - xh1 * m2);
+            } else {
+              gO[mt][2 * half] = g0;
+              gO[mt][2 * half + 1] = g1;
+            }
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          store_c_bf16(gosm, mt, g, t, gO[mt]);
+          store_c_bf16(grsm, mt, g, t, gR[mt]);
+        }
+        __syncwarp();
+        uint32_t got[2][2], bgo[4];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) ldmatrix_x2_trans(got[kk][0], got[kk][1], gosm + (16 * kk + (lane & 15)) * 8);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          bgo[2 * mt] = pack2(gO[mt][0], gO[mt][1]);
+          bgo[2 * mt + 1] = pack2(gO[mt][2], gO[mt][3]);
+        }
+        // ---- gQ' = (gS . P . (1-P)) K ------------------------------------------------------------
+        float gq[2][4], gk[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t ago[4];
+          c_to_a_k8(gO[mt], ago);
+          float gz[4][4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(s4, ago, bkf[nt], 0u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gz[nt][q] = s4[q] * P[mt][nt][q] * (1.f - P[mt][nt][q]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gq[mt][q] = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint32_t az[4];
+            cc_to_a(gz[2 * kk], gz[2 * kk + 1], az);
+            mma16816(gq[mt], az, kt[kk][0], kt[kk][1]);
+          }
+        }
+        // ---- transposed side: gK = gZ^T q' + P^T gO  (rows = j) ------------------------------------
+#pragma unroll
+        for (int mtj = 0; mtj < 2; ++mtj) {
+          float pt[4][4], gzt[4][4];
+#pragma unroll
+          for (int nti = 0; nti < 4; ++nti) {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(s4, ak[mtj], bqf[nti], 0u);        // S^T[j][i] = K[j] . q'[i]
+            mma16816(g4, ak[mtj], bgo[nti], 0u);        // gS^T[j][i] = K[j] . gO[i]
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = 16 * mtj + g + (q >= 2 ? 8 : 0);
+              const float pv = j < F ? fast_sigmoid(s4[q]) : 0.f;
+              pt[nti][q] = pv;
+              gzt[nti][q] = g4[q] * pv * (1.f - pv);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gk[mtj][q] = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint32_t a1[4], a2[4];
+            cc_to_a(gzt[2 * kk], gzt[2 * kk + 1], a1);
+            cc_to_a(pt[2 * kk], pt[2 * kk + 1], a2);
+            mma16816(gk[mtj], a1, qt[kk][0], qt[kk][1]);
+            mma16816(gk[mtj], a2, got[kk][0], got[kk][1]);
+          }
+        }
+        // ---- dX += gQ Wq^T + gK Wk^T + gR Wr^T ;  gQ = gQ' / sqrt(d) ---------------------------------
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t a1[4], a2[4], a3[4];
+          c_to_a_k8(gq[mt], a1, sc);
+          c_to_a_k8(gk[mt], a2);
+          c_to_a_k8(gR[mt], a3);
+#pragma unroll
+          for (int n = 0; n < KIN / 8; ++n) {
+            mma16816(dxc[mt][n], a1, wt_frag[((0 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
+            mma16816(dxc[mt][n], a2, wt_frag[((1 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
+            if (p.use_res) mma16816(dxc[mt][n], a3, wt_frag[((2 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
+          }
+          store_c_bf16(gqsm, mt, g, t, gq[mt], sc);
+          store_c_bf16(gksm, mt, g, t, gk[mt]);
+        }
+        __syncwarp();
+        // ---- dW += X^T g*  (M = c, K = i, N = e) ------------------------------------------------------
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          uint32_t bq[2], bk[2], br[2];
+          ldmatrix_x2_trans(bq[0], bq[1], gqsm + (16 * kk + (lane & 15)) * 8);
+          ldmatrix_x2_trans(bk[0], bk[1], gksm + (16 * kk + (lane & 15)) * 8);
+          ldmatrix_x2_trans(br[0], br[1], grsm + (16 * kk + (lane & 15)) * 8);
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t axt[4];     // X^T fragment: rows c = 16ks + .., k = i = 16kk + ..
+            const int m = lane >> 3;
+            ldmatrix_x4_trans(axt, xsm + (16 * kk + 8 * (m >> 1) + (lane & 7)) * KIN + 16 * ks + 8 * (m & 1));
+            mma16816(dwq[h][ks], axt, bq[0], bq[1]);
+            mma16816(dwk[h][ks], axt, bk[0], bk[1]);
+            if (p.use_res) mma16816(dwr[h][ks], axt, br[0], br[1]);
+          }
+        }
+      }
+    }
+    // ---- dX out -------------------------------------------------------------------------------------
+    float* dxb = dx + b * (long long)F * KIN;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < KIN / 8; ++n) {
+        const int r0 = 16 * mt + g, c0 = 8 * n + 2 * t;
+        if (r0 < F) *reinterpret_cast<float2*>(dxb + r0 * KIN + c0) = make_float2(dxc[mt][n][0], dxc[mt][n][1]);
+        if (r0 + 8 < F) *reinterpret_cast<float2*>(dxb + (r0 + 8) * KIN + c0) = make_float2(dxc[mt][n][2], dxc[mt][n][3]);
+      }
+  }
+  // ---- reduce the per-warp accumulators: warp -> CTA (warp order) -> partial[blockIdx] ---------------
+  const int wsz = KIN * H * 8;
+  const int pf = 3 * wsz + 16;
+  float* mine = red + warp * pf;
+  for (int i = lane; i < pf; i += 32) mine[i] = 0.f;
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < HT; ++h) {
+    if (h < H) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int c0 = 16 * ks + g;
+        float* a0 = mine + ((c0 * H + h) * 8 + 2 * t);
+        float* a1 = mine + (((c0 + 8) * H + h) * 8 + 2 * t);
+        a0[0] = dwq[h][ks][0]; a0[1] = dwq[h][ks][1]; a1[0] = dwq[h][ks][2]; a1[1] = dwq[h][ks][3];
+        a0[wsz] = dwk[h][ks][0]; a0[wsz + 1] = dwk[h][ks][1]; a1[wsz] = dwk[h][ks][2]; a1[wsz + 1] = dwk[h][ks][3];
+        a0[2 * wsz] = dwr[h][ks][0]; a0[2 * wsz + 1] = dwr[h][ks][1];
+        a1[2 * wsz] = dwr[h][ks][2]; a1[2 * wsz + 1] = dwr[h][ks][3];
+      }
+    }
+  }
+  // dgamma / dbeta: lanes with the same t hold the same columns -> sum over g
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float a = dgam[q], c = dbet[q];
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      c += __shfl_xor_sync(0xffffffffu, c, off);
+    }
+    if (g == 0) {
+      mine[3 * wsz + 2 * t + q] = a;
+      mine[3 * wsz + 8 + 2 * t + q] = c;
+    }
+  }
+  __syncthreads();
+  float* out = partial + (long long)blockIdx.x * pf;
+  for (int i = tid; i < pf; i += kAtBwdThreads) {
+    float acc = 0.f;
+    for (int w = 0; w < kAtBwdWarps; ++w) acc += red[w * pf + i];
+    out[i] = acc;
+  }
+}
+
+}  // namespace
+
+bool attn_tc_supported(const AttnDims& p, int DH) {
+  return DH == 8 && p.F <= 32 && p.kin % 16 == 0 && p.kin <= 64 && p.H <= 8;
+}
+
+int attn_tc_fwd(const float* x, const float* wq, const float* wk, const float* wr, const float* gamma,
+                const float* beta, float* y, const AttnDims& p, int sms, cudaStream_t st) {
+  const int KS = p.kin / 16;
+  const float* wr_ = p.use_res ? wr : nullptr;
+  const size_t smem = (size_t)3 * p.H * KS * 64 * 4;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((p.B + kAtWarps - 1) / kAtWarps, (long long)sms * 6));
+  switch (KS) {
+    case 1: attn_tc_fwd_kernel<1><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
+    case 2: attn_tc_fwd_kernel<2><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
+    case 3: attn_tc_fwd_kernel<3><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
+    default: attn_tc_fwd_kernel<4><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
+  }
+  KON_LAUNCH_CHECK("attn_tc_fwd_kernel");
+  return KON_OK;
+}
+
+bool attn_tc_bwd_supported(const AttnDims& p, int DH) {
+  return attn_tc_supported(p, DH) && p.kin <= 32 && p.H <= 4;
+}
+
+// partial: [grid][3*wsz + 2*8] floats (same layout as the fp32 path: dWq | dWk | dWr | dgamma | dbeta)
+int attn_tc_bwd(const float* x, const float* wq, const float* wk, const float* wr, const float* gamma,
+                const float* beta, const float* gy, float* dx, float* partial, int max_grid,
+                const AttnDims& p, int sms, int* grid_used, cudaStream_t st) {
+  const int KS = p.kin / 16;
+  const float* wr_ = p.use_res ? wr : nullptr;
+  const int wsz = p.kin * p.H * 8, pf = 3 * wsz + 16;
+  const size_t smem = (size_t)3 * p.H * KS * 64 * 4 + (size_t)3 * p.H * (p.kin / 8) * 32 * 4 +
+                      (size_t)kAtBwdWarps * pf * 4;
+  int grid = (int)std::max<long long>(1, std::min<long long>((p.B + kAtBwdWarps - 1) / kAtBwdWarps, (long long)sms * 4));
+  grid = std::min(grid, max_grid);
+  *grid_used = grid;
+#define KON_ATB(KS_, HT_)                                                                                   \
+  do {                                                                                                      \
+    KON_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KS_, HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                              \
+    attn_tc_bwd_kernel<KS_, HT_><<<grid, kAtBwdThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, gy, dx,     \
+                                                                   partial, p);                             \
+  } while (0)
+  if (KS == 1 && p.H <= 2) KON_ATB(1, 2);
+  else if (KS == 1) KON_ATB(1, 4);
+  else if (p.H <= 2) KON_ATB(2, 2);
+  else KON_ATB(2, 4);
+#undef KON_ATB
+  KON_LAUNCH_CHECK("attn_tc_bwd_kernel");
+  return KON_OK;
+}
+
+}  // namespace kon

@@ -321,8 +321,9 @@ class MultHeadAttentionLayer(nn.Module):
     ``DnnLayer`` makes of it, ``ReLU(res + atten_v)`` (CL:205-216), in ONE kernel."""
 
     def __init__(self, attention_dim, attention_head_dim, seed=2020, use_scale=True, use_res=True,
-                 use_ln=True, head_concat=False, supports_masking=True, atten_mask_mod=1):
+                 use_ln=True, head_concat=False, supports_masking=True, atten_mask_mod=1, precision="fp32"):
         super().__init__()
+        self.bf16 = {"fp32": False, "bf16": True}[precision]     # bf16: tensor-core path, tolerance 2e-2
         self.attention_dim, self.attention_head_dim = attention_dim, attention_head_dim
         self.seed, self.use_scale, self.use_res, self.use_ln = seed, use_scale, use_res, use_ln
         self.head_concat, self.atten_mask_mod = head_concat, atten_mask_mod
@@ -356,7 +357,8 @@ class MultHeadAttentionLayer(nn.Module):
         """``ReLU(LN(sigmoid(QK^T/sqrt d) K) + X res_w)`` -> ``[H,B,F,d]``."""
         self._ensure(x)
         return ops.attention(x, self.query_w, self.key_w, self.res_w, self.ln_gamma, self.ln_beta,
-                             use_scale=self.use_scale, use_ln=self.use_ln, use_res=self.use_res, relu=True)
+                             use_scale=self.use_scale, use_ln=self.use_ln, use_res=self.use_res, relu=True,
+                             bf16=self.bf16)
 
     def forward(self, inputs, mask=None, **kwargs):
         if mask is not None:

@@ -213,12 +213,13 @@ class AutoInt(_CtrModel):
     """MD:150-165.  ``n_layers > 1`` stacks blocks by re-packing ``[H,B,F,d] -> [B,F,H*d]``
     (standard AutoInt; an extension, the reference wires exactly one block)."""
 
-    def __init__(self, inputFea: InputFeature = None, attention_dim=8, attention_head_dim=3, n_layers=1):
+    def __init__(self, inputFea: InputFeature = None, attention_dim=8, attention_head_dim=3, n_layers=1,
+                 precision="fp32"):
         super().__init__(inputFea)
         self.blocks = nn.ModuleList([
             DnnLayer(res_unit=1, other_dense=[MultHeadAttentionLayer(
                 attention_dim=attention_dim, attention_head_dim=attention_head_dim, use_ln=True,
-                atten_mask_mod=1)]) for _ in range(n_layers)])
+                atten_mask_mod=1, precision=precision)]) for _ in range(n_layers)])
         self.head = MergeScoreLayer(use_merge=False)
 
     def forward(self, dense_inputs, sparse_inputs):

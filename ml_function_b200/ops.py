@@ -389,10 +389,11 @@ class _Attn(torch.autograd.Function):
 
 
 def attention(x, wq, wk, wr=None, gamma=None, beta=None, use_scale=True, use_ln=True, use_res=True,
-              relu=True, eps: float = 1e-3):
+              relu=True, eps: float = 1e-3, bf16: bool = False):
     """x [B,F,kin]; w* [kin,H,d] -> [H,B,F,d] = ReLU(LN(sigmoid(QK^T/sqrt d) K) + X Wr)."""
     flags = ((L.KON_ATTN_USE_SCALE if use_scale else 0) | (L.KON_ATTN_USE_LN if use_ln else 0) |
-             (L.KON_ATTN_USE_RES if use_res else 0) | (L.KON_ATTN_RELU if relu else 0))
+             (L.KON_ATTN_USE_RES if use_res else 0) | (L.KON_ATTN_RELU if relu else 0) |
+             (L.KON_ATTN_BF16 if bf16 else 0))
     return _Attn.apply(x, wq, wk, wr if use_res else None, gamma if use_ln else None,
                        beta if use_ln else None, flags, eps)
 
