@@ -133,6 +133,51 @@ int kon_embed_adam_devstep(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTe
                            const DLTensor* grads, const DLTensor* n_unique, float lr, float beta1,
                            float beta2, float eps, float l2, const DLTensor* step, void* stream);
 
+/* ================= 8e: sharded embeddings over NVLink peer memory =================== */
+/* The reference is single-process (no distributed code at all); this is the scale-out of
+ * SparseEmbed.call (IL:225-242) and of its implicit gradient for one process per GPU.  Tables are
+ * sharded table-wise / row-wise over the ranks (ml_function_b200/parallel.py); the pooled-embedding
+ * all-to-all of the forward and the dOut all-to-all of the backward are NOT separate collectives:
+ * the gather kernel stores each row straight into the concat buffer of the rank that owns the
+ * sample, and the segmented reduction loads each gradient row straight from the rank that
+ * produced it -- 16-byte accesses over NVLink 5 / NVSwitch through CUDA-IPC mappings.
+ *
+ * kon_peer_alloc   cudaMalloc + zero + cudaIpcGetMemHandle; `handle64` receives the 64 opaque
+ *                  bytes another process passes to kon_peer_open (cudaIpcOpenMemHandle, peer
+ *                  access enabled lazily).  kon_peer_close / kon_peer_free undo them.
+ * kon_peer_barrier one tiny kernel on `stream`: rank `rank` releases a flag into every peer's flag
+ *                  block and acquires every peer's flag in its own; peer_flags[q] = this process's
+ *                  mapping of rank q's flag block (>= 128 zero-initialised bytes).  Graph-capturable.
+ *                  A peer that does not arrive within timeout_ms (<= 0: 10 s) sets word 17 of the
+ *                  caller's own flag block instead of hanging the GPU.
+ */
+int kon_peer_alloc(int device_id, size_t bytes, void** ptr, void* handle64);
+int kon_peer_open(int device_id, const void* handle64, void** ptr);
+int kon_peer_close(int device_id, void* ptr);
+int kon_peer_free(int device_id, void* ptr);
+int kon_peer_barrier(void* const* peer_flags, int32_t n_peers, int32_t rank, int device_id,
+                     int64_t timeout_ms, void* stream);
+
+/* Forward: `ids` [B_global, F_local] are this rank's lookups for the GLOBAL batch (F_local = the
+ * fields whose tables this rank owns, `field_row_offset` into its local `arena`).  Sample b belongs
+ * to rank q = b / rows_per_peer; its row for local field f is stored at
+ *     peer_out[q] + (b - q*rows_per_peer)*out_stride_b + f*out_stride_f        (floats)
+ * so peer_out[q] already points at the column of this rank's first field inside rank q's buffer.
+ * flags: KON_EMBED_SKIP_INVALID leaves the destination untouched for out-of-range ids (row-wise
+ * shards mark the rows of other ranks with -1; their owner writes them). */
+#define KON_EMBED_SKIP_INVALID 2
+int kon_embed_fwd_peer(const DLTensor* arena, const DLTensor* ids, const int64_t* field_row_offset,
+                       int32_t n_fields, void* const* peer_out, int32_t n_peers,
+                       int64_t rows_per_peer, int64_t out_stride_b, int64_t out_stride_f,
+                       DLTensor* oob, int32_t flags, void* stream);
+/* Backward: kon_embed_bwd with the gradient row of (sample b, local field f) loaded from
+ *     peer_d_out[q] + (b - q*rows_per_peer)*stride_b + f*stride_f,   q = b / rows_per_peer.
+ * Out-of-range ids (rows owned by another rank) carry no gradient. */
+int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers, int64_t rows_per_peer,
+                       int64_t stride_b, int64_t stride_f, int32_t dim, const DLTensor* ids,
+                       const int64_t* field_row_offset, int32_t n_fields, DLTensor* unique_rows,
+                       DLTensor* grads, DLTensor* n_unique, DLTensor* workspace, void* stream);
+
 /* ============================ a5-a6: FM ========================================== */
 /* Replaces InnerLayer's 325 tf.multiply + sequential Add (IL:59-66) and FmLayer's Add
  * of the linear terms (IL:161-170) by one pass:

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KON_B200_LIB") or os.path.join(_HERE, "libkon_b200.so")
 
 KON_EMBED_SUM_FIELDS = 1
+KON_EMBED_SKIP_INVALID = 2
 KON_CIN_FP32, KON_CIN_BF16 = 0, 1
 KON_ATTN_USE_SCALE, KON_ATTN_USE_LN, KON_ATTN_USE_RES, KON_ATTN_RELU, KON_ATTN_BF16 = 1, 2, 4, 8, 16
 
@@ -138,6 +139,13 @@ def lib():
         "kon_embed_sgd": (ctypes.c_int, [T, T, T, T, f32, f32, vp]),
         "kon_embed_adam": (ctypes.c_int, [T, T, T, T, T, T, f32, f32, f32, f32, f32, i32, vp]),
         "kon_embed_adam_devstep": (ctypes.c_int, [T, T, T, T, T, T, f32, f32, f32, f32, f32, T, vp]),
+        "kon_peer_alloc": (ctypes.c_int, [ctypes.c_int, sz, ctypes.POINTER(vp), vp]),
+        "kon_peer_open": (ctypes.c_int, [ctypes.c_int, vp, ctypes.POINTER(vp)]),
+        "kon_peer_close": (ctypes.c_int, [ctypes.c_int, vp]),
+        "kon_peer_free": (ctypes.c_int, [ctypes.c_int, vp]),
+        "kon_peer_barrier": (ctypes.c_int, [ctypes.POINTER(vp), i32, i32, ctypes.c_int, i64, vp]),
+        "kon_embed_fwd_peer": (ctypes.c_int, [T, T, i64p, i32, ctypes.POINTER(vp), i32, i64, i64, i64, T, i32, vp]),
+        "kon_embed_bwd_peer": (ctypes.c_int, [ctypes.POINTER(vp), i32, i64, i64, i64, i32, T, i64p, i32, T, T, T, T, vp]),
         "kon_fm_fwd": (ctypes.c_int, [T, T, T, vp]),
         "kon_fm_bwd": (ctypes.c_int, [T, T, T, T, vp]),
         "kon_cross_fwd": (ctypes.c_int, [T, T, T, T, T, vp]),
@@ -166,6 +174,8 @@ EXPORTED_SYMBOLS = (
     "kon_profile_read", "kon_device_info", "kon_embed_fwd",
     "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_bwd_reuse", "kon_embed_sgd", "kon_embed_adam",
     "kon_embed_adam_devstep",
+    "kon_peer_alloc", "kon_peer_open", "kon_peer_close", "kon_peer_free", "kon_peer_barrier",
+    "kon_embed_fwd_peer", "kon_embed_bwd_peer",
     "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",

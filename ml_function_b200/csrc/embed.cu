@@ -49,15 +49,28 @@ struct FieldTable {
   int64_t off[kMaxFields + 1];
 };
 
+// Sharded embeddings over NVLink peer memory: the batch axis of `out` / `d_out` is
+// split in `rows`-sample slabs, slab q living in the memory of rank q (base[q], mapped into this
+// process with cudaIpcOpenMemHandle).  n == 0: the ordinary single-buffer call.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+  float* base[kMaxPeers];
+  long long rows;       // samples per peer slab
+  int n;                // peers (0 = off)
+  int skip_invalid;     // forward: leave the destination untouched for out-of-range ids (row-wise
+                        // shards: the id belongs to another rank, which writes the row itself)
+};
+
 // -------------------------------------------------------------------------------------
 // forward, vector path: dim % 4 == 0, 16-B aligned rows
 // -------------------------------------------------------------------------------------
-template <typename IdT, int LPR>
+template <typename IdT, int LPR, bool PEER>
 __global__ void __launch_bounds__(kFwdThreads)
 embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ ids,
                      const __grid_constant__ FieldTable ft, int F, int L, int vec_per_row,
                      long long n_bags, int bags_per_tile, float* __restrict__ out,
-                     long long out_sb, long long out_sf, int* __restrict__ oob, unsigned int f_magic) {
+                     long long out_sb, long long out_sf, int* __restrict__ oob, unsigned int f_magic,
+                     const __grid_constant__ PeerTable pt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ long long s_off[kMaxFields + 1];
@@ -141,8 +154,9 @@ embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ i
             ok[u] = true;
             if (id >= 0 && id < rows) {
               if (lane_on) r[u] = ldg_stream_f4(arena + (s_off[f] + id) * vec_per_row + lane);
-            } else if (lane == 0 && oob) {
-              atomicAdd(oob, 1);
+            } else {
+              if (PEER && pt.skip_invalid) ok[u] = false;
+              else if (lane == 0 && oob) atomicAdd(oob, 1);
             }
           }
         }
@@ -151,8 +165,14 @@ embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ i
           const int j = j0 + u * G;
           if (ok[u] && lane_on) {
             (void)j;
-            const long long b = b0 + qs[u];
-            *reinterpret_cast<float4*>(out + b * out_sb + fs[u] * out_sf + lane * 4) = r[u];
+            long long b = b0 + qs[u];
+            float* dst = out;
+            if (PEER) {   // slab q of the batch axis lives on rank q: 16-B stores straight over NVLink
+              const long long q = b / pt.rows;
+              dst = pt.base[q];
+              b -= q * pt.rows;
+            }
+            *reinterpret_cast<float4*>(dst + b * out_sb + fs[u] * out_sf + lane * 4) = r[u];
           }
         }
       }
@@ -286,6 +306,10 @@ struct BwdArgs {
   float* cta_head;  // [n_cta, dim]
   float* cta_tail;  // [n_cta, dim]
   int* cta_meta;    // [n_cta]
+  // peer mode (n_peers > 0): sample b's gradient row is read from rank b / peer_rows over NVLink
+  int n_peers;
+  long long peer_rows;
+  const float* peer[kMaxPeers];
 };
 
 // One lane group (LPR lanes x float4) reduces one window of kWin sorted lookups; the CTA
@@ -345,11 +369,17 @@ __global__ void __launch_bounds__(kRedThreads, KON_EMB_RED_MINB) embed_reduce_ke
           ky[u] = a.keys[i];
           const long long p = a.vals[i];
           const long long bag = p / a.L;
-          const long long b = bag / a.F;
+          long long b = bag / a.F;
           const int f = (int)(bag - b * a.F);
+          const float* src = a.d_out;
+          if (a.n_peers) {
+            const long long q = b / a.peer_rows;
+            src = a.peer[q];
+            b -= q * a.peer_rows;
+          }
           if (lane_on)
             r[u] = ldg_stream_f4(
-                reinterpret_cast<const float4*>(a.d_out + b * a.sb + f * a.sf) + lane);
+                reinterpret_cast<const float4*>(src + b * a.sb + f * a.sf) + lane);
         }
       }
 #pragma unroll
@@ -567,18 +597,18 @@ static int pow2_ge(int x) {
   return p;
 }
 
-template <typename IdT>
+template <typename IdT, bool PEER>
 static int launch_fwd_vec(int lpr, int grid, size_t smem, cudaStream_t st, const float4* arena,
                           const IdT* ids, const FieldTable& ft, int F, int L, int vpr,
                           long long n_bags, int bpt, float* out, long long sb, long long sf,
-                          int* oob) {
+                          int* oob, const PeerTable& pt) {
 #define KON_FWD_CASE(N)                                                                         \
   case N:                                                                                       \
-    embed_fwd_vec_kernel<IdT, N><<<grid, kFwdThreads, smem, st>>>(arena, ids, ft, F, L, vpr,    \
-                                                                  n_bags, bpt, out, sb, sf, oob, \
-                                                                  (unsigned)(((1u << 24) + F - 1) / F)); \
+    embed_fwd_vec_kernel<IdT, N, PEER><<<grid, kFwdThreads, smem, st>>>(                        \
+        arena, ids, ft, F, L, vpr, n_bags, bpt, out, sb, sf, oob,                               \
+        (unsigned)(((1u << 24) + F - 1) / F), pt);                                              \
     break;
-  ProfileScope ps("embed_fwd_vec_kernel", st);
+  ProfileScope ps(PEER ? "embed_fwd_peer_kernel" : "embed_fwd_vec_kernel", st);
   switch (lpr) {
     KON_FWD_CASE(1)
     KON_FWD_CASE(2)
@@ -655,13 +685,14 @@ extern "C" int kon_embed_fwd(const DLTensor* arena, const DLTensor* ids,
     const size_t idsz = v.i64 ? 8 : 4;
     const size_t smem = 2 * (size_t)bpt * v.L * idsz;
     int grid = (int)std::min<long long>(n_tiles, (long long)sms * KON_EMB_CTAS);   // = resident CTAs: one wave, tiles strided
+    PeerTable pt{};
     if (v.i64)
-      return launch_fwd_vec<long long>(lpr, grid, smem, st, reinterpret_cast<const float4*>(ap),
-                                       data_ptr<long long>(ids), ft, (int)v.F, (int)v.L, vpr,
-                                       n_bags, bpt, outp, sb, sf, oob_p);
-    return launch_fwd_vec<int>(lpr, grid, smem, st, reinterpret_cast<const float4*>(ap),
-                               data_ptr<int>(ids), ft, (int)v.F, (int)v.L, vpr, n_bags, bpt, outp,
-                               sb, sf, oob_p);
+      return launch_fwd_vec<long long, false>(lpr, grid, smem, st, reinterpret_cast<const float4*>(ap),
+                                              data_ptr<long long>(ids), ft, (int)v.F, (int)v.L, vpr,
+                                              n_bags, bpt, outp, sb, sf, oob_p, pt);
+    return launch_fwd_vec<int, false>(lpr, grid, smem, st, reinterpret_cast<const float4*>(ap),
+                                      data_ptr<int>(ids), ft, (int)v.F, (int)v.L, vpr, n_bags, bpt,
+                                      outp, sb, sf, oob_p, pt);
   }
   const long long n_out_rows = sum_fields ? v.B : v.B * v.F;
   const long long total = n_out_rows * dim;
@@ -676,6 +707,68 @@ extern "C" int kon_embed_fwd(const DLTensor* arena, const DLTensor* ids,
                                                        sf, sum_fields ? 1 : 0, oob_p);
   KON_LAUNCH_CHECK("embed_fwd_scalar_kernel");
   return KON_OK;
+}
+
+// Sharded forward over peer memory: this rank gathers the rows of ITS tables for the GLOBAL batch
+// and stores each row straight into the concat buffer of the rank that owns the sample.
+extern "C" int kon_embed_fwd_peer(const DLTensor* arena, const DLTensor* ids,
+                                  const int64_t* field_row_offset, int32_t n_fields,
+                                  void* const* peer_out, int32_t n_peers, int64_t rows_per_peer,
+                                  int64_t out_stride_b, int64_t out_stride_f, DLTensor* oob,
+                                  int32_t flags, void* stream) {
+  KON_TRY(check_cuda_tensor(arena, "arena"));
+  const int dev = arena->device.device_id;
+  IdsView v;
+  FieldTable ft;
+  KON_TRY(parse_common(ids, field_row_offset, n_fields, dev, &v, &ft));
+  KON_REQUIRE(is_f32(arena) && arena->ndim == 2 && is_compact(arena), KON_EINVAL,
+              "arena must be compact [R,dim] float32");
+  KON_REQUIRE(ft.off[n_fields] <= arena->shape[0], KON_EINVAL,
+              "field_row_offset[F]=%lld exceeds arena rows %lld", (long long)ft.off[n_fields],
+              (long long)arena->shape[0]);
+  KON_REQUIRE(peer_out != nullptr && n_peers >= 1 && n_peers <= kMaxPeers, KON_EINVAL,
+              "n_peers=%d outside [1,%d]", n_peers, kMaxPeers);
+  KON_REQUIRE(rows_per_peer >= 1 && v.B <= rows_per_peer * n_peers, KON_EINVAL,
+              "ids has %lld samples, peers hold %lld x %d", (long long)v.B, (long long)rows_per_peer,
+              n_peers);
+  KON_REQUIRE(v.L == 1, KON_EUNSUPPORTED, "the peer exchange takes [B,F] ids (one id per field)");
+  const int64_t dim = arena->shape[1];
+  KON_REQUIRE(dim % 4 == 0 && dim <= 128 && aligned16(data_ptr<float>(arena)) &&
+                  out_stride_b % 4 == 0 && out_stride_f % 4 == 0 && aligned16(data_ptr<char>(ids)),
+              KON_EUNSUPPORTED, "the peer exchange needs dim %% 4 == 0 and 16-B aligned rows");
+  PeerTable pt{};
+  pt.n = n_peers;
+  pt.rows = rows_per_peer;
+  pt.skip_invalid = (flags & KON_EMBED_SKIP_INVALID) ? 1 : 0;
+  for (int q = 0; q < n_peers; ++q) {
+    KON_REQUIRE(peer_out[q] != nullptr && aligned16(peer_out[q]), KON_EINVAL,
+                "peer_out[%d] is NULL or not 16-B aligned", q);
+    pt.base[q] = static_cast<float*>(peer_out[q]);
+  }
+  int* oob_p = nullptr;
+  if (oob) {
+    KON_TRY(check_cuda_tensor(oob, "oob", dev));
+    KON_REQUIRE(is_i32(oob) && numel(oob) >= 1, KON_EINVAL, "oob must be int32[1]");
+    oob_p = data_ptr<int>(oob);
+  }
+  if (v.B == 0) return KON_OK;
+  DeviceGuard guard(dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sms = sm_count_of(dev);
+  const int vpr = (int)(dim / 4);
+  const int lpr = pow2_ge(vpr);
+  const int bpt = (int)(kTileIds & ~3);
+  const long long n_bags = v.B * v.F;
+  const long long n_tiles = (n_bags + bpt - 1) / bpt;
+  const size_t smem = 2 * (size_t)bpt * (v.i64 ? 8 : 4);
+  const int grid = (int)std::min<long long>(n_tiles, (long long)sms * KON_EMB_CTAS);
+  const float4* ap = reinterpret_cast<const float4*>(data_ptr<float>(arena));
+  if (v.i64)
+    return launch_fwd_vec<long long, true>(lpr, grid, smem, st, ap, data_ptr<long long>(ids), ft,
+                                           (int)v.F, 1, vpr, n_bags, bpt, nullptr, out_stride_b,
+                                           out_stride_f, oob_p, pt);
+  return launch_fwd_vec<int, true>(lpr, grid, smem, st, ap, data_ptr<int>(ids), ft, (int)v.F, 1, vpr,
+                                   n_bags, bpt, nullptr, out_stride_b, out_stride_f, oob_p, pt);
 }
 
 // ---- backward workspace layout ----------------------------------------------------------
@@ -746,9 +839,41 @@ __global__ void pad1_kernel(const float* __restrict__ src, long long sb, long lo
   }
 }
 
-static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+namespace {
+// where the upstream gradient rows live: one local [B,F,dim] view, or per-rank slabs over NVLink
+struct GradSrc {
+  const float* p = nullptr;
+  long long sb = 0, sf = 0;
+  int64_t dim = 0;
+  int device = 0;
+  int n_peers = 0;
+  long long peer_rows = 0;
+  const float* peer[kMaxPeers] = {};
+};
+}  // namespace
+
+static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field_row_offset,
                           int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                           DLTensor* workspace, int reuse_sort, void* stream);
+
+static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+                          int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                          DLTensor* workspace, int reuse_sort, void* stream) {
+  KON_TRY(check_cuda_tensor(d_out, "d_out"));
+  KON_TRY(check_cuda_tensor(ids, "ids", d_out->device.device_id));
+  KON_REQUIRE(is_f32(d_out) && d_out->ndim == 3 && (ids->ndim == 2 || ids->ndim == 3) &&
+                  d_out->shape[0] == ids->shape[0] && d_out->shape[1] == ids->shape[1],
+              KON_EINVAL, "d_out must be float32 [B,F,dim]");
+  GradSrc src;
+  src.p = data_ptr<float>(d_out);
+  src.sb = stride_of(d_out, 0);
+  src.sf = stride_of(d_out, 1);
+  src.dim = d_out->shape[2];
+  src.device = d_out->device.device_id;
+  KON_REQUIRE(src.dim == 1 || stride_of(d_out, 2) == 1, KON_EINVAL, "d_out last dim must be compact");
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
+                        reuse_sort, stream);
+}
 
 extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
                              const int64_t* field_row_offset, int32_t n_fields,
@@ -766,11 +891,42 @@ extern "C" int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids,
                         stream);
 }
 
-static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+// Sharded backward over peer memory: the owner of the tables reads the gradient row of sample b
+// from the gradient buffer of rank b / rows_per_peer while it reduces the sorted segments.
+extern "C" int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers,
+                                  int64_t rows_per_peer, int64_t stride_b, int64_t stride_f,
+                                  int32_t dim, const DLTensor* ids, const int64_t* field_row_offset,
+                                  int32_t n_fields, DLTensor* unique_rows, DLTensor* grads,
+                                  DLTensor* n_unique, DLTensor* workspace, void* stream) {
+  KON_TRY(check_cuda_tensor(ids, "ids"));
+  KON_REQUIRE(peer_d_out != nullptr && n_peers >= 1 && n_peers <= kMaxPeers, KON_EINVAL,
+              "n_peers=%d outside [1,%d]", n_peers, kMaxPeers);
+  KON_REQUIRE(ids->ndim == 2, KON_EUNSUPPORTED, "the peer exchange takes [B,F] ids");
+  KON_REQUIRE(rows_per_peer >= 1 && ids->shape[0] <= rows_per_peer * n_peers, KON_EINVAL,
+              "ids has %lld samples, peers hold %lld x %d", (long long)ids->shape[0],
+              (long long)rows_per_peer, n_peers);
+  KON_REQUIRE(dim >= 4 && dim % 4 == 0, KON_EUNSUPPORTED, "the peer exchange needs dim %% 4 == 0");
+  GradSrc src;
+  src.sb = stride_b;
+  src.sf = stride_f;
+  src.dim = dim;
+  src.device = ids->device.device_id;
+  src.n_peers = n_peers;
+  src.peer_rows = rows_per_peer;
+  for (int q = 0; q < n_peers; ++q) {
+    KON_REQUIRE(peer_d_out[q] != nullptr && aligned16(peer_d_out[q]), KON_EINVAL,
+                "peer_d_out[%d] is NULL or not 16-B aligned", q);
+    src.peer[q] = static_cast<const float*>(peer_d_out[q]);
+  }
+  src.p = src.peer[0];
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 0,
+                        stream);
+}
+
+static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field_row_offset,
                           int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                           DLTensor* workspace, int reuse_sort, void* stream) {
-  KON_TRY(check_cuda_tensor(d_out, "d_out"));
-  const int dev = d_out->device.device_id;
+  const int dev = src.device;
   IdsView v;
   FieldTable ft;
   KON_TRY(parse_common(ids, field_row_offset, n_fields, dev, &v, &ft));
@@ -778,11 +934,7 @@ static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int6
   KON_TRY(check_cuda_tensor(grads, "grads", dev));
   KON_TRY(check_cuda_tensor(n_unique, "n_unique", dev));
   KON_TRY(check_cuda_tensor(workspace, "workspace", dev));
-  KON_REQUIRE(is_f32(d_out) && d_out->ndim == 3 && d_out->shape[0] == v.B &&
-                  d_out->shape[1] == v.F,
-              KON_EINVAL, "d_out must be float32 [B,F,dim]");
-  const int64_t dim = d_out->shape[2];
-  KON_REQUIRE(dim == 1 || stride_of(d_out, 2) == 1, KON_EINVAL, "d_out last dim must be compact");
+  const int64_t dim = src.dim;
   KON_REQUIRE(dim % 4 == 0 || dim == 1, KON_EUNSUPPORTED,
               "embedding dim must be 1 or a multiple of 4 (got %lld)", (long long)dim);
   const int64_t n = v.B * v.F * v.L;
@@ -847,9 +999,12 @@ static int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int6
   }   // !reuse_sort
 
   BwdArgs a;
-  a.d_out = data_ptr<float>(d_out);
-  a.sb = stride_of(d_out, 0);
-  a.sf = stride_of(d_out, 1);
+  a.d_out = src.p;
+  a.sb = src.sb;
+  a.sf = src.sf;
+  a.n_peers = src.n_peers;
+  a.peer_rows = src.peer_rows;
+  for (int q = 0; q < kMaxPeers; ++q) a.peer[q] = src.peer[q];
   a.F = (int)v.F;
   a.L = (int)v.L;
   a.dim = rdim;

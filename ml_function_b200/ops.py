@@ -137,6 +137,42 @@ def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optio
     return SparseGrad(rows, grads, nu)
 
 
+# ---- sharded embeddings over NVLink peer memory ----------------------------------
+def embed_fwd_peer(arena, ids, field_row_offset: Sequence[int], peer_out, n_peers: int, rows_per_peer: int,
+                   stride_b: int, stride_f: int, skip_invalid=False, oob=None):
+    """kon_embed_fwd_peer: gather this rank's tables for the GLOBAL batch ``ids`` [B_g, F_loc] and store
+    every row into the buffer of the rank that owns the sample.  ``peer_out``: ctypes ``c_void_p`` array
+    (this process's mappings of the ranks' buffers, already offset to this rank's first column)."""
+    lib = L.lib()
+    offs = L.i64_array(list(field_row_offset))
+    a, i, ob = L._arg(arena), L._arg(ids), L._arg(oob)
+    with _prof("embed_fwd_peer"):
+        L.check(lib.kon_embed_fwd_peer(a.ptr, i.ptr, offs, ids.shape[1], peer_out, n_peers, rows_per_peer,
+                                       stride_b, stride_f, L._p(ob),
+                                       L.KON_EMBED_SKIP_INVALID if skip_invalid else 0,
+                                       L.stream_ptr(arena.device)), "kon_embed_fwd_peer")
+
+
+def embed_bwd_peer(peer_d_out, n_peers: int, rows_per_peer: int, stride_b: int, stride_f: int, dim: int,
+                   ids, field_row_offset: Sequence[int]) -> SparseGrad:
+    """kon_embed_bwd_peer: sort-then-segment scatter-add whose gradient rows are loaded from the ranks
+    that produced them (``peer_d_out``: ctypes ``c_void_p`` array of mapped gradient buffers)."""
+    lib = L.lib()
+    n = ids.numel()
+    dev = ids.device
+    rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.kon_embed_bwd_workspace_bytes(n, dim), dev)
+    offs = L.i64_array(list(field_row_offset))
+    a = [L._arg(t) for t in (ids, rows, grads, nu, ws)]
+    with _prof("embed_bwd_peer"):
+        L.check(lib.kon_embed_bwd_peer(peer_d_out, n_peers, rows_per_peer, stride_b, stride_f, dim, a[0].ptr, offs,
+                                       ids.shape[1], a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, L.stream_ptr(dev)),
+                "kon_embed_bwd_peer")
+    return SparseGrad(rows, grads, nu)
+
+
 class _EmbedLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, arena, ids, field_row_offset, sum_fields):

@@ -18,9 +18,19 @@ of the same step:
   sort-then-segment ``kon_embed_bwd``; non-owned ids carry no gradient).
   The first-order (dim-1) tables only ever enter the models through their sum over fields, so
   each rank sums its own fields/rows and one tiny ``reduce_scatter`` finishes the job.
+
+On NCCL/CUDA the payload exchange is FUSED into the embedding kernels (``PeerRegion``,
+``_PeerLookup``; C-ABI ``kon_embed_fwd_peer`` / ``kon_embed_bwd_peer`` / ``kon_peer_barrier``): every
+rank owns one CUDA-IPC region ``[flags | xcat | dxcat]`` mapped by all the others; the gather kernel
+stores each row straight into the concat buffer of the sample's rank over NVLink, the segmented
+reduction of the backward loads each gradient row straight from the rank that produced it, and a
+one-CTA flag barrier replaces the collective.  Only the 4-byte ids (and the dim-1 sums) still go
+through NCCL.  ``KON_PEER_EXCHANGE=0`` selects the NCCL all-to-all path above (the baseline).
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -173,6 +183,160 @@ class _ShardedLookup(torch.autograd.Function):
         return None, None, None
 
 
+# ------------------------------------------------------------------------------------------
+# peer memory (CUDA IPC over NVLink / NVSwitch)
+# ------------------------------------------------------------------------------------------
+class _RawCuda:
+    """``__cuda_array_interface__`` holder so torch can view memory the library allocated."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerRegion:
+    """One exchange region per rank, mapped by every other rank.
+
+    Layout (bytes): ``[0,256)`` barrier flag block, then 256-B aligned sub-buffers handed out by
+    ``carve``.  ``ptrs[q]`` is THIS process's address of rank q's region."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, group, device: torch.device, nbytes: int):
+        from . import _lib as L
+        self.L, self.lib = L, L.lib()
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = int(nbytes)
+        self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        L.check(self.lib.kon_peer_alloc(self.dev_index, self.nbytes, ctypes.byref(ptr), handle), "kon_peer_alloc")
+        self.local_ptr = ptr.value
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, (bytes(handle), self.nbytes), group=group)
+        self.ptrs: List[int] = []
+        for q, (h, nb) in enumerate(handles):
+            if nb != self.nbytes:
+                raise RuntimeError(f"PeerRegion: rank {q} allocated {nb} bytes, this rank {self.nbytes}")
+            if q == self.rank:
+                self.ptrs.append(self.local_ptr)
+                continue
+            pp = ctypes.c_void_p()
+            hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            L.check(self.lib.kon_peer_open(self.dev_index, hb, ctypes.byref(pp)), "kon_peer_open")
+            self.ptrs.append(pp.value)
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*self.ptrs)
+        self._bytes = torch.as_tensor(_RawCuda(self.local_ptr, self.nbytes), device=device)
+        self._used = self.FLAG_BYTES
+        self.flags = self._bytes[:self.FLAG_BYTES].view(torch.int32)
+        dist.barrier(group=group)       # every mapping exists before anybody stores through one
+
+    def carve(self, shape, dtype=torch.float32):
+        """-> (local tensor view, byte offset inside the region)."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        off = self._used
+        if off + nb > self.nbytes:
+            raise RuntimeError("PeerRegion exhausted")
+        self._used = (off + nb + 255) // 256 * 256
+        return self._bytes[off:off + nb].view(dtype).view(*shape), off
+
+    def ptr_array(self, byte_offset: int):
+        return (ctypes.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
+
+    def barrier(self, timeout_ms: int = 10000):
+        self.L.check(self.lib.kon_peer_barrier(self._flag_ptrs, self.world, self.rank, self.dev_index, timeout_ms,
+                                               self.L.stream_ptr(self.device)), "kon_peer_barrier")
+
+    def timed_out(self) -> bool:
+        """True when a barrier gave up waiting for a peer (word 17 of the flag block); synchronises."""
+        return bool(self.flags[17].item() != 0)
+
+    def close(self):
+        if getattr(self, "local_ptr", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody unmaps while a peer may still touch the region
+        for q, p in enumerate(self.ptrs):
+            if q != self.rank:
+                self.lib.kon_peer_close(self.dev_index, ctypes.c_void_p(p))
+        dist.barrier(group=self.group)
+        self._bytes = self.flags = None
+        self.lib.kon_peer_free(self.dev_index, ctypes.c_void_p(self.local_ptr))
+        self.local_ptr = None
+
+
+class _PeerLookup(torch.autograd.Function):
+    """ids_local [B_l,F] (+ dense [B_l,nd]) -> xcat [B_l,width] = [emb (F*k, global field order) | dense | 0]
+    with the pooled-embedding exchange fused into the gather kernel (stores over NVLink) and the dOut
+    exchange fused into the backward's segmented reduction (loads over NVLink)."""
+
+    @staticmethod
+    def forward(ctx, arena, ids_local, dense, sh: "ShardedEmbed", width: int):
+        from . import ops
+        plan, N, rank = sh.plan, sh.world, sh.rank
+        B_l, F = ids_local.shape
+        k = arena.shape[1]
+        ids_tw, ids_rw = sh.exchange_ids(ids_local)      # NCCL, 4 B per lookup; also orders this step's
+        px = sh.peer_buffers(B_l, width)                 # peer stores after every rank's previous step
+        xcat, region = px["xcat"], px["region"]
+        n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
+        if n_tw:
+            col0 = sh.tw_slabs[rank][0]
+            ops.embed_fwd_peer(arena.detach(), ids_tw, sh.tw_offs, region.ptr_array(px["xcat_off"] + col0 * k * 4),
+                               N, B_l, width, k)
+        if n_rw:
+            ops.embed_fwd_peer(arena.detach(), ids_rw, sh.rw_offs, region.ptr_array(px["xcat_off"] + n_tw_all * k * 4),
+                               N, B_l, width, k, skip_invalid=True)
+        nd = 0
+        if dense is not None:
+            nd = dense.shape[1]
+            xcat[:, F * k:F * k + nd].copy_(dense)
+        if width > F * k + nd:
+            xcat[:, F * k + nd:].zero_()
+        region.barrier()
+        if not plan.identity_order:      # row-wise fields interleaved with table-wise ones: one permutation copy
+            emb = xcat[:, :F * k].view(B_l, F, k).index_select(1, sh.to_global)
+            out = torch.cat([emb.reshape(B_l, F * k), xcat[:, F * k:]], dim=1)
+        else:
+            out = xcat
+        ctx.sh, ctx.arena, ctx.px = sh, arena, px
+        ctx.save_for_backward(ids_tw, ids_rw)
+        ctx.dims = (B_l, F, k, nd, width)
+        # a fresh tensor object every call (autograd attaches this call's history to it); the storage is
+        # the persistent exchange buffer: ONE step in flight, like the static buffers of a CUDA graph
+        return out.view(B_l, width)
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import ops
+        sh, arena, px = ctx.sh, ctx.arena, ctx.px
+        ids_tw, ids_rw = ctx.saved_tensors
+        plan, N, rank = sh.plan, sh.world, sh.rank
+        B_l, F, k, nd, width = ctx.dims
+        region, dbuf = px["region"], px["dbuf"]
+        gemb = gout[:, :F * k].view(B_l, F, k)
+        if not plan.identity_order:
+            gemb = gemb.index_select(1, sh.to_exchange)
+        dbuf.copy_(gemb)
+        region.barrier()                 # every rank's dOut is in place
+        n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
+        if arena.requires_grad:
+            if not hasattr(arena, "kon_sparse_grads"):
+                arena.kon_sparse_grads = []
+            if n_tw:
+                col0 = sh.tw_slabs[rank][0]
+                arena.kon_sparse_grads.append(ops.embed_bwd_peer(
+                    region.ptr_array(px["dbuf_off"] + col0 * k * 4), N, B_l, F * k, k, k, ids_tw, sh.tw_offs))
+            if n_rw:
+                arena.kon_sparse_grads.append(ops.embed_bwd_peer(
+                    region.ptr_array(px["dbuf_off"] + n_tw_all * k * 4), N, B_l, F * k, k, k, ids_rw, sh.rw_offs))
+        gdense = gout[:, F * k:F * k + nd] if nd else None
+        return None, None, gdense, None, None
+
+
 class _ShardedSum(torch.autograd.Function):
     """ids_local [B_l,F] -> sum over fields of the dim-1 (first-order) tables, [B_l, dim]."""
 
@@ -254,6 +418,30 @@ class ShardedEmbed(nn.Module):
             o += len(plan.tw_of_rank[p])
         self.tw_slabs = slabs
         self.tw_idx_of = [torch.tensor(plan.tw_of_rank[p], dtype=torch.long, device=device) for p in range(self.world)]
+        # fused NVLink exchange: NCCL process group + CUDA + vector-width rows (KON_PEER_EXCHANGE=0: NCCL baseline)
+        self.use_peer = (not is_linear and self.world > 1 and torch.device(device).type == "cuda"
+                         and dist.get_backend(group) == "nccl" and self.dim % 4 == 0 and self.world <= 16
+                         and os.environ.get("KON_PEER_EXCHANGE", "1") != "0")
+        self._peer = {}
+
+    def peer_buffers(self, B_l: int, width: int):
+        """The rank's exchange region for one (local batch, row width); built collectively on first use
+        (every rank sees the same shapes in the same order)."""
+        F, k = len(self.plan.rows), self.dim
+        if (B_l, width) in self._peer:
+            return self._peer[(B_l, width)]
+        nbytes = PeerRegion.FLAG_BYTES + (B_l * width * 4 + 255) // 256 * 256 + (B_l * F * k * 4 + 255) // 256 * 256
+        region = PeerRegion(self.group, self.arena.device, nbytes)
+        xcat, xo = region.carve((B_l, width))
+        dbuf, do = region.carve((B_l, F, k))
+        self._peer[(B_l, width)] = dict(region=region, xcat=xcat, xcat_off=xo, dbuf=dbuf, dbuf_off=do)
+        return self._peer[(B_l, width)]
+
+    def close_peer(self):
+        """Unmap / free the exchange regions (collective; call before destroying the process group)."""
+        for px in self._peer.values():
+            px["region"].close()
+        self._peer = {}
 
     def exchange_ids(self, ids_local: torch.Tensor):
         """Local ids ``[B_l,F]`` -> this rank's lookups for the GLOBAL batch:
@@ -295,13 +483,18 @@ class ShardedEmbed(nn.Module):
                 self.arena[self.all_offs[j]:self.all_offs[j + 1]].copy_(t)
 
     def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.use_peer:
+            B, F = ids.shape
+            return _PeerLookup.apply(self.arena, ids, None, self, F * self.dim).view(B, F, self.dim)
         return _ShardedLookup.apply(self.arena, ids, self)
 
     def lookup_sum(self, ids: torch.Tensor) -> torch.Tensor:
         return _ShardedSum.apply(self.arena, ids, self)
 
     def lookup_concat(self, ids: torch.Tensor, dense: Optional[torch.Tensor], width: int) -> torch.Tensor:
-        emb = self.lookup(ids)
+        if self.use_peer:
+            return _PeerLookup.apply(self.arena, ids, dense, self, width)
+        emb = _ShardedLookup.apply(self.arena, ids, self)
         B, F, k = emb.shape
         parts = [emb.reshape(B, F * k)]
         if dense is not None:

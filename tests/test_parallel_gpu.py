@@ -21,7 +21,8 @@ def _build(name, rows, k, dev):
     return KM.DeepFM(fea, hidden_units=[32, 16])
 
 
-def _worker(rank, world, port, name, ret):
+def _worker(rank, world, port, name, peer, ret):
+    os.environ["KON_PEER_EXCHANGE"] = peer      # "1": fused NVLink exchange kernels, "0": NCCL all-to-all baseline
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -58,8 +59,9 @@ def _worker(rank, world, port, name, ret):
     err_fwd = (out - out_ref[sl]).abs().max().item()
     # one training step on both; compare a dense weight and the loss
     tr_ref, tr = Trainer(ref, lr=1e-2), Trainer(model, lr=1e-2, dist_ctx=dctx)
-    l_ref = tr_ref.step(dense_all.to(dev), ids_all.to(dev), labels_all.to(dev))
-    l_loc = tr.step(dense_all[sl].to(dev), ids_all[sl].to(dev), labels_all[sl].to(dev))
+    for _ in range(2):      # two steps: the exchange buffers are reused
+        l_ref = tr_ref.step(dense_all.to(dev), ids_all.to(dev), labels_all.to(dev))
+        l_loc = tr.step(dense_all[sl].to(dev), ids_all[sl].to(dev), labels_all[sl].to(dev))
     lt = l_loc.clone()
     dist.all_reduce(lt)
     err_loss = abs(lt.item() / world - l_ref.item())
@@ -75,18 +77,23 @@ def _worker(rank, world, port, name, ret):
             full = full[rank::world]
         mine = model.sparse_embed.arena.detach()[model.sparse_embed.all_offs[j]:model.sparse_embed.all_offs[j + 1]]
         err_e = max(err_e, (mine - full).abs().max().item())
+    assert model.sparse_embed.use_peer == (peer == "1")
+    if peer == "1":
+        assert not any(px["region"].timed_out() for px in model.sparse_embed._peer.values())
+        model.sparse_embed.close_peer()
     ret[rank] = (err_fwd, err_loss, err_w, err_e)
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peer", ["1", "0"])
 @pytest.mark.parametrize("name", ["deepfm", "xdeepfm"])
-def test_sharded_model_matches_single_gpu(name):
+def test_sharded_model_matches_single_gpu(name, peer):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29611 + (os.getpid() % 500), name, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29611 + (os.getpid() % 500) + (7 if peer == "1" else 0), name, peer, ret), nprocs=world, join=True)
     for r in range(world):
         err_fwd, err_loss, err_w, err_e = ret[r]
         assert err_fwd < 1e-5 and err_loss < 1e-5 and err_w < 1e-4 and err_e < 1e-4, (r, ret[r])
