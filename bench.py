@@ -452,6 +452,12 @@ def run_gpu(args):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sample_clocks_stop(proc, f, clk_path, local) if rank == 0 else None
+    exchange = "single GPU"
+    if world > 1:
+        exchange = ("fused: gather/scatter kernels store/load over NVLink peer memory (kon_embed_*_peer)"
+                    if getattr(model.sparse_embed, "use_peer", False) else "NCCL all_to_all")
+        if hasattr(model.sparse_embed, "close_peer"):
+            model.sparse_embed.close_peer()
 
     if rank != 0:
         if world > 1:
@@ -541,7 +547,8 @@ def run_gpu(args):
                    "optimizer": "Adam (dense, fused) + row-wise lazy Adam (embeddings)",
                    "mlp_dtype": args.mlp_dtype, "cache": "working set per step (>1 GB) exceeds the 126 MB L2; "
                    f"{args.n_batches} distinct batches rotate",
-                   "parallelism": "single GPU" if world == 1 else dctx.describe()},
+                   "parallelism": "single GPU" if world == 1 else dctx.describe(),
+                   "embedding_exchange": exchange},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

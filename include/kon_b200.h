@@ -172,11 +172,13 @@ int kon_embed_fwd_peer(const DLTensor* arena, const DLTensor* ids, const int64_t
                        DLTensor* oob, int32_t flags, void* stream);
 /* Backward: kon_embed_bwd with the gradient row of (sample b, local field f) loaded from
  *     peer_d_out[q] + (b - q*rows_per_peer)*stride_b + f*stride_f,   q = b / rows_per_peer.
- * Out-of-range ids (rows owned by another rank) carry no gradient. */
+ * Out-of-range ids (rows owned by another rank) carry no gradient.  reuse_sort != 0: as
+ * kon_embed_bwd_reuse (the sorted routing of the same ids is already at the front of `workspace`). */
 int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers, int64_t rows_per_peer,
                        int64_t stride_b, int64_t stride_f, int32_t dim, const DLTensor* ids,
                        const int64_t* field_row_offset, int32_t n_fields, DLTensor* unique_rows,
-                       DLTensor* grads, DLTensor* n_unique, DLTensor* workspace, void* stream);
+                       DLTensor* grads, DLTensor* n_unique, DLTensor* workspace, int32_t reuse_sort,
+                       void* stream);
 
 /* ============================ a5-a6: FM ========================================== */
 /* Replaces InnerLayer's 325 tf.multiply + sequential Add (IL:59-66) and FmLayer's Add

@@ -145,7 +145,7 @@ def lib():
         "kon_peer_free": (ctypes.c_int, [ctypes.c_int, vp]),
         "kon_peer_barrier": (ctypes.c_int, [ctypes.POINTER(vp), i32, i32, ctypes.c_int, i64, vp]),
         "kon_embed_fwd_peer": (ctypes.c_int, [T, T, i64p, i32, ctypes.POINTER(vp), i32, i64, i64, i64, T, i32, vp]),
-        "kon_embed_bwd_peer": (ctypes.c_int, [ctypes.POINTER(vp), i32, i64, i64, i64, i32, T, i64p, i32, T, T, T, T, vp]),
+        "kon_embed_bwd_peer": (ctypes.c_int, [ctypes.POINTER(vp), i32, i64, i64, i64, i32, T, i64p, i32, T, T, T, T, i32, vp]),
         "kon_fm_fwd": (ctypes.c_int, [T, T, T, vp]),
         "kon_fm_bwd": (ctypes.c_int, [T, T, T, T, vp]),
         "kon_cross_fwd": (ctypes.c_int, [T, T, T, T, T, vp]),

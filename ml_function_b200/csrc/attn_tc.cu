@@ -39,7 +39,14 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
                : "=r"(r0), "=r"(r1)
                : "r"(smem_u32(smem_row)));
 }
-__device__ __forceinline__ float fast_sigmoid(float z) { return __frcp_rn(1.f + __expf(-z)); }
+// sigmoid(z) = 0.5 + 0.5 tanh(z/2): ONE special-function op (MUFU.TANH, abs. error ~2.5e-4 on the
+// sigmoid, below the bf16 rounding of P) instead of ex2 + rcp -- the kernels below are bound by
+// instruction issue and by the 4-lane/clk special-function unit, not by memory.
+__device__ __forceinline__ float fast_sigmoid(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 // B fragments of W[kin][H][8] for m16n8k16 (k = c, n = e), built by every CTA in shared memory:
 //   word[((mat*H + h)*KS + ks)*64 + r*32 + lane],  r = 0: (W[16ks+2t][h][g], W[16ks+2t+1][h][g]),  r = 1: rows +8
@@ -153,15 +160,14 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
           for (int q = 0; q < 4; ++q) s[nt][q] = 0.f;
           mma16816(s[nt], aq[mt], bkf[nt], 0u);
         }
-        // P = sigmoid(S), columns j >= F masked; two n-tiles -> one A fragment (k = 16 rows of K)
+        // P = sigmoid(S); two n-tiles -> one A fragment (k = 16 rows of K).  No mask on the padded
+        // columns j >= F: the padded rows of X are exact zeros, so rows j >= F of K are zeros and
+        // those columns of P contribute nothing to O = P K.
         uint32_t ap[2][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          const int j0 = 8 * nt + 2 * t;
-          const float p0 = j0 < F ? fast_sigmoid(s[nt][0]) : 0.f, p1 = j0 + 1 < F ? fast_sigmoid(s[nt][1]) : 0.f;
-          const float p2 = j0 < F ? fast_sigmoid(s[nt][2]) : 0.f, p3 = j0 + 1 < F ? fast_sigmoid(s[nt][3]) : 0.f;
-          ap[nt >> 1][(nt & 1) * 2] = pack2(p0, p1);        // row g
-          ap[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);    // row g + 8
+          ap[nt >> 1][(nt & 1) * 2] = pack2(fast_sigmoid(s[nt][0]), fast_sigmoid(s[nt][1]));        // row g
+          ap[nt >> 1][(nt & 1) * 2 + 1] = pack2(fast_sigmoid(s[nt][2]), fast_sigmoid(s[nt][3]));    // row g + 8
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) o[mt][q] = 0.f;
@@ -207,8 +213,8 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
 // Everything of the forward is recomputed per head in fragments; then (q' = q / sqrt(d)):
 //   gP = gy . relu'            LayerNorm backward -> gO            gR = gP
 //   gS = gO K^T,  gZ = gS . P . (1 - P)                           gQ' = gZ K
-//   transposed side (fresh MMAs instead of fragment transposes):
-//   S^T = K q'^T, P^T = sigmoid(S^T), gS^T = K gO^T, gZ^T = gS^T . P^T . (1 - P^T)
+//   transposed side: P and gZ are parked in shared memory as bf16 [i][j] (the words of their A
+//   fragments) and P^T / gZ^T come back as A fragments through ldmatrix.trans:
 //   gK = gZ^T q' + P^T gO
 //   dX += (gQ'/sqrt(d)) Wq^T + gK Wk^T + gR Wr^T
 //   dWq += X^T (gQ'/sqrt(d)),  dWk += X^T gK,  dWr += X^T gR       (accumulated per warp in registers)
@@ -238,11 +244,16 @@ __device__ __forceinline__ void store_c_bf16(unsigned short* sm, int mt, int g, 
   *reinterpret_cast<uint32_t*>(sm + (16 * mt + g + 8) * 8 + 2 * t) = pack2(c[2] * scale, c[3] * scale);
 }
 
+#ifndef KON_ATB_MINB
+#define KON_ATB_MINB 4
+#endif
 constexpr int kAtBwdWarps = 4;
+constexpr int kPStride = 40;   // bf16 per row of the parked P / gZ tiles: 80 B rows keep both the 32-bit fragment
+                               // stores and the ldmatrix row reads free of bank conflicts
 constexpr int kAtBwdThreads = 32 * kAtBwdWarps;
 
 template <int KS, int HT>
-__global__ void __launch_bounds__(kAtBwdThreads)
+__global__ void __launch_bounds__(kAtBwdThreads, KON_ATB_MINB)
 attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, const float* __restrict__ wk,
                    const float* __restrict__ wr, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ gy, float* __restrict__ dx, float* __restrict__ partial,
@@ -256,6 +267,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
   float* red = reinterpret_cast<float*>(wt_frag + 3 * H * (KIN / 8) * 32);
   __shared__ __align__(16) unsigned short s_buf[kAtBwdWarps][6][32 * 8];     // K, q', gO, gQ, gK, gR  (bf16 [row][8])
   __shared__ __align__(16) unsigned short s_x[kAtBwdWarps][32 * KIN];         // X (bf16) [i][c]
+  __shared__ __align__(16) unsigned short s_pz[kAtBwdWarps][2][32 * kPStride]; // P, gZ (bf16) [i][j], rows padded to 80 B
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   pack_w_frags(wq, wk, wr, KS, H, w_frag, tid, kAtBwdThreads);
@@ -282,6 +294,8 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
   unsigned short* gksm = s_buf[warp][4];
   unsigned short* grsm = s_buf[warp][5];
   unsigned short* xsm = s_x[warp];
+  unsigned short* psm = s_pz[warp][0];
+  unsigned short* zsm = s_pz[warp][1];
 
   // per-warp accumulators: dW fragments (rows c = 16ks + g (+8), cols e = 2t, 2t+1) and dgamma/dbeta (cols 2t, 2t+1)
   float dwq[HT][KS][4], dwk[HT][KS][4], dwr[HT][KS][4];      // H <= HT
@@ -358,15 +372,12 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
           store_c_bf16(qsm, mt, g, t, qc[mt], sc);
         }
         __syncwarp();
-        uint32_t aq[2][4], ak[2][4], bkf[4], bqf[4];
+        uint32_t aq[2][4], bkf[4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           c_to_a_k8(qc[mt], aq[mt], sc);
-          c_to_a_k8(kc[mt], ak[mt]);
           bkf[2 * mt] = pack2(kc[mt][0], kc[mt][1]);
           bkf[2 * mt + 1] = pack2(kc[mt][2], kc[mt][3]);
-          bqf[2 * mt] = pack2(qc[mt][0] * sc, qc[mt][1] * sc);
-          bqf[2 * mt + 1] = pack2(qc[mt][2] * sc, qc[mt][3] * sc);
         }
         uint32_t kt[2][2], qt[2][2];
 #pragma unroll
@@ -374,37 +385,35 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
           ldmatrix_x2_trans(kt[kk][0], kt[kk][1], ksm + (16 * kk + (lane & 15)) * 8);
           ldmatrix_x2_trans(qt[kk][0], qt[kk][1], qsm + (16 * kk + (lane & 15)) * 8);
         }
-        float P[2][4][4];          // sigmoid(S), rows i, cols j
-        float o[2][4];
+        // Row block mt (16 rows i) at a time: S -> P -> O -> LayerNorm/ReLU backward -> gO -> gS -> gZ -> gQ'.
+        // No masks on the padded rows/columns (>= F): padded rows of X are exact zeros, so K, q', gy, gO
+        // vanish there and every product that could see a padded P or gZ entry multiplies a zero.
+        // P and gZ (bf16, the very words of their A fragments) are parked in shared memory [i][j] so
+        // that the transposed products below read P^T / gZ^T back with ldmatrix.trans.
+        float gq[2][4], gO[2][4], gR[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
+          float P[4][4];
+          uint32_t ap[2][4];
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
             mma16816(s4, aq[mt], bkf[nt], 0u);
-            const int j0 = 8 * nt + 2 * t;
-            P[mt][nt][0] = j0 < F ? fast_sigmoid(s4[0]) : 0.f;
-            P[mt][nt][1] = j0 + 1 < F ? fast_sigmoid(s4[1]) : 0.f;
-            P[mt][nt][2] = j0 < F ? fast_sigmoid(s4[2]) : 0.f;
-            P[mt][nt][3] = j0 + 1 < F ? fast_sigmoid(s4[3]) : 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) P[nt][q] = fast_sigmoid(s4[q]);
+            ap[nt >> 1][(nt & 1) * 2] = pack2(P[nt][0], P[nt][1]);
+            ap[nt >> 1][(nt & 1) * 2 + 1] = pack2(P[nt][2], P[nt][3]);
+            *reinterpret_cast<uint32_t*>(psm + (16 * mt + g) * kPStride + 8 * nt + 2 * t) = ap[nt >> 1][(nt & 1) * 2];
+            *reinterpret_cast<uint32_t*>(psm + (16 * mt + g + 8) * kPStride + 8 * nt + 2 * t) = ap[nt >> 1][(nt & 1) * 2 + 1];
           }
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o[mt][q] = 0.f;
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            uint32_t ap[4];
-            cc_to_a(P[mt][2 * kk], P[mt][2 * kk + 1], ap);
-            mma16816(o[mt], ap, kt[kk][0], kt[kk][1]);
-          }
-        }
-        // ---- output gradient through ReLU / residual / LayerNorm -> gO, gR -------------------
-        float gO[2][4], gR[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+          for (int kk = 0; kk < 2; ++kk) mma16816(o, ap[kk], kt[kk][0], kt[kk][1]);
+          // ---- output gradient through ReLU / residual / LayerNorm -> gO, gR ----------------------
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int row = 16 * mt + g + 8 * half;
-            float v0 = o[mt][2 * half], v1 = o[mt][2 * half + 1];
+            float v0 = o[2 * half], v1 = o[2 * half + 1];
             float mean = 0.f, rstd = 1.f;
             if (p.use_ln) {
               float sum = v0 + v1;
@@ -446,87 +455,70 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
               gO[mt][2 * half + 1] = g1;
             }
           }
-        }
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          store_c_bf16(gosm, mt, g, t, gO[mt]);
-          store_c_bf16(grsm, mt, g, t, gR[mt]);
-        }
-        __syncwarp();
-        uint32_t got[2][2], bgo[4];
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) ldmatrix_x2_trans(got[kk][0], got[kk][1], gosm + (16 * kk + (lane & 15)) * 8);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          bgo[2 * mt] = pack2(gO[mt][0], gO[mt][1]);
-          bgo[2 * mt + 1] = pack2(gO[mt][2], gO[mt][3]);
-        }
-        // ---- gQ' = (gS . P . (1-P)) K ------------------------------------------------------------
-        float gq[2][4], gk[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
           uint32_t ago[4];
           c_to_a_k8(gO[mt], ago);
-          float gz[4][4];
+          *reinterpret_cast<uint32_t*>(gosm + (16 * mt + g) * 8 + 2 * t) = ago[0];
+          *reinterpret_cast<uint32_t*>(gosm + (16 * mt + g + 8) * 8 + 2 * t) = ago[1];
+          store_c_bf16(grsm, mt, g, t, gR[mt]);
+          // ---- gZ = (gO K^T) . P . (1 - P);  gQ' = gZ K ------------------------------------------
+          uint32_t az[2][4];
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
             mma16816(s4, ago, bkf[nt], 0u);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) gz[nt][q] = s4[q] * P[mt][nt][q] * (1.f - P[mt][nt][q]);
+            for (int q = 0; q < 4; ++q) s4[q] *= P[nt][q] * (1.f - P[nt][q]);
+            az[nt >> 1][(nt & 1) * 2] = pack2(s4[0], s4[1]);
+            az[nt >> 1][(nt & 1) * 2 + 1] = pack2(s4[2], s4[3]);
+            *reinterpret_cast<uint32_t*>(zsm + (16 * mt + g) * kPStride + 8 * nt + 2 * t) = az[nt >> 1][(nt & 1) * 2];
+            *reinterpret_cast<uint32_t*>(zsm + (16 * mt + g + 8) * kPStride + 8 * nt + 2 * t) = az[nt >> 1][(nt & 1) * 2 + 1];
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) gq[mt][q] = 0.f;
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            uint32_t az[4];
-            cc_to_a(gz[2 * kk], gz[2 * kk + 1], az);
-            mma16816(gq[mt], az, kt[kk][0], kt[kk][1]);
-          }
+          for (int kk = 0; kk < 2; ++kk) mma16816(gq[mt], az[kk], kt[kk][0], kt[kk][1]);
         }
-        // ---- transposed side: gK = gZ^T q' + P^T gO  (rows = j) ------------------------------------
+        __syncwarp();
+        // ---- transposed side: gK = gZ^T q' + P^T gO  (rows = j); A fragments of the transposes come
+        // back from shared memory with ldmatrix.trans ------------------------------------------------
+        uint32_t got[2][2];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) ldmatrix_x2_trans(got[kk][0], got[kk][1], gosm + (16 * kk + (lane & 15)) * 8);
+        float gk[2][4];
 #pragma unroll
         for (int mtj = 0; mtj < 2; ++mtj) {
-          float pt[4][4], gzt[4][4];
-#pragma unroll
-          for (int nti = 0; nti < 4; ++nti) {
-            float s4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
-            mma16816(s4, ak[mtj], bqf[nti], 0u);        // S^T[j][i] = K[j] . q'[i]
-            mma16816(g4, ak[mtj], bgo[nti], 0u);        // gS^T[j][i] = K[j] . gO[i]
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int j = 16 * mtj + g + (q >= 2 ? 8 : 0);
-              const float pv = j < F ? fast_sigmoid(s4[q]) : 0.f;
-              pt[nti][q] = pv;
-              gzt[nti][q] = g4[q] * pv * (1.f - pv);
-            }
-          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) gk[mtj][q] = 0.f;
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             uint32_t a1[4], a2[4];
-            cc_to_a(gzt[2 * kk], gzt[2 * kk + 1], a1);
-            cc_to_a(pt[2 * kk], pt[2 * kk + 1], a2);
+            const int m = lane >> 3;
+            const int off = (16 * kk + 8 * (m >> 1) + (lane & 7)) * kPStride + 16 * mtj + 8 * (m & 1);
+            ldmatrix_x4_trans(a1, zsm + off);
+            ldmatrix_x4_trans(a2, psm + off);
             mma16816(gk[mtj], a1, qt[kk][0], qt[kk][1]);
             mma16816(gk[mtj], a2, got[kk][0], got[kk][1]);
           }
         }
-        // ---- dX += gQ Wq^T + gK Wk^T + gR Wr^T ;  gQ = gQ' / sqrt(d) ---------------------------------
+        // ---- dX += [gQ | gK] [Wq^T ; Wk^T] + gR Wr^T ;  gQ = gQ' / sqrt(d) ---------------------------
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          uint32_t a1[4], a2[4], a3[4];
-          c_to_a_k8(gq[mt], a1, sc);
-          c_to_a_k8(gk[mt], a2);
+          uint32_t a12[4], a3[4];
+          a12[0] = pack2(gq[mt][0] * sc, gq[mt][1] * sc);
+          a12[1] = pack2(gq[mt][2] * sc, gq[mt][3] * sc);
+          a12[2] = pack2(gk[mt][0], gk[mt][1]);
+          a12[3] = pack2(gk[mt][2], gk[mt][3]);
           c_to_a_k8(gR[mt], a3);
 #pragma unroll
           for (int n = 0; n < KIN / 8; ++n) {
-            mma16816(dxc[mt][n], a1, wt_frag[((0 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
-            mma16816(dxc[mt][n], a2, wt_frag[((1 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
+            mma16816(dxc[mt][n], a12, wt_frag[((0 * H + h) * (KIN / 8) + n) * 32 + lane],
+                     wt_frag[((1 * H + h) * (KIN / 8) + n) * 32 + lane]);
             if (p.use_res) mma16816(dxc[mt][n], a3, wt_frag[((2 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
           }
-          store_c_bf16(gqsm, mt, g, t, gq[mt], sc);
-          store_c_bf16(gksm, mt, g, t, gk[mt]);
+          *reinterpret_cast<uint32_t*>(gqsm + (16 * mt + g) * 8 + 2 * t) = a12[0];
+          *reinterpret_cast<uint32_t*>(gqsm + (16 * mt + g + 8) * 8 + 2 * t) = a12[1];
+          *reinterpret_cast<uint32_t*>(gksm + (16 * mt + g) * 8 + 2 * t) = a12[2];
+          *reinterpret_cast<uint32_t*>(gksm + (16 * mt + g + 8) * 8 + 2 * t) = a12[3];
         }
         __syncwarp();
         // ---- dW += X^T g*  (M = c, K = i, N = e) ------------------------------------------------------

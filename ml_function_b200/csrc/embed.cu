@@ -897,7 +897,8 @@ extern "C" int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers
                                   int64_t rows_per_peer, int64_t stride_b, int64_t stride_f,
                                   int32_t dim, const DLTensor* ids, const int64_t* field_row_offset,
                                   int32_t n_fields, DLTensor* unique_rows, DLTensor* grads,
-                                  DLTensor* n_unique, DLTensor* workspace, void* stream) {
+                                  DLTensor* n_unique, DLTensor* workspace, int32_t reuse_sort,
+                                  void* stream) {
   KON_TRY(check_cuda_tensor(ids, "ids"));
   KON_REQUIRE(peer_d_out != nullptr && n_peers >= 1 && n_peers <= kMaxPeers, KON_EINVAL,
               "n_peers=%d outside [1,%d]", n_peers, kMaxPeers);
@@ -919,8 +920,8 @@ extern "C" int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers
     src.peer[q] = static_cast<const float*>(peer_d_out[q]);
   }
   src.p = src.peer[0];
-  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 0,
-                        stream);
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
+                        reuse_sort ? 1 : 0, stream);
 }
 
 static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field_row_offset,

@@ -94,41 +94,29 @@ _SHARE_SORT = False      # only inside new_step() ... end_step(): the ids tensor
                          # backward), so a storage address identifies them
 
 
+_STEP_CACHE = {}         # other per-step results keyed the same way (parallel.py: the exchanged ids)
+
+
 def new_step():
     global _SHARE_SORT
     _SORT_CACHE.clear()
+    _STEP_CACHE.clear()
     _SHARE_SORT = True
 
 
 def end_step():
     global _SHARE_SORT
     _SORT_CACHE.clear()
+    _STEP_CACHE.clear()
     _SHARE_SORT = False
 
 
-def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None) -> SparseGrad:
-    """d_out [B,F,dim] (any strides on dims 0/1, e.g. an expanded [B,1,dim])."""
+def _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort):
+    """-> (workspace, reuse): ``reuse`` when an earlier backward of this step left the sorted routing of the
+    same ids / offsets at the front of the returned workspace."""
     lib = L.lib()
-    F = ids.shape[1]
-    dim = d_out.shape[2]
-    n = ids.numel()
-    dev = d_out.device
-    rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
-    nu = torch.zeros(1, dtype=torch.int32, device=dev)
-    if share_sort is None:
-        share_sort = _SHARE_SORT
-    key = (ids.data_ptr(), ids._version, tuple(field_row_offset), n)
-    cached = _SORT_CACHE.get(key) if share_sort else None
-    need = lib.kon_embed_bwd_workspace_bytes(n, dim)
-    if cached is not None and cached.numel() >= need:
-        ws, fn, what = cached, lib.kon_embed_bwd_reuse, "kon_embed_bwd_reuse"
-    else:
-        # sized for the widest payload seen in practice plus the dim-1 path, so a later call can reuse it
-        ws = _ws(max(need, lib.kon_embed_bwd_workspace_bytes(n, 1), lib.kon_embed_bwd_workspace_bytes(n, 32)), dev)
-        fn, what = lib.kon_embed_bwd, "kon_embed_bwd"
-        if share_sort:
-            _SORT_CACHE[key] = ws
+    ws, reuse = _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort)
+    fn, what = (lib.kon_embed_bwd_reuse, "kon_embed_bwd_reuse") if reuse else (lib.kon_embed_bwd, "kon_embed_bwd")
     offs = L.i64_array(list(field_row_offset))
     a = [L._arg(t) for t in (d_out, ids, rows, grads, nu, ws)]
     with _prof("embed_bwd" if dim > 1 else "embed_bwd_lin"):
@@ -154,7 +142,7 @@ def embed_fwd_peer(arena, ids, field_row_offset: Sequence[int], peer_out, n_peer
 
 
 def embed_bwd_peer(peer_d_out, n_peers: int, rows_per_peer: int, stride_b: int, stride_f: int, dim: int,
-                   ids, field_row_offset: Sequence[int]) -> SparseGrad:
+                   ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None) -> SparseGrad:
     """kon_embed_bwd_peer: sort-then-segment scatter-add whose gradient rows are loaded from the ranks
     that produced them (``peer_d_out``: ctypes ``c_void_p`` array of mapped gradient buffers)."""
     lib = L.lib()
@@ -163,13 +151,13 @@ def embed_bwd_peer(peer_d_out, n_peers: int, rows_per_peer: int, stride_b: int, 
     rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
     nu = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = _ws(lib.kon_embed_bwd_workspace_bytes(n, dim), dev)
+    ws, reuse = _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort)
     offs = L.i64_array(list(field_row_offset))
     a = [L._arg(t) for t in (ids, rows, grads, nu, ws)]
     with _prof("embed_bwd_peer"):
         L.check(lib.kon_embed_bwd_peer(peer_d_out, n_peers, rows_per_peer, stride_b, stride_f, dim, a[0].ptr, offs,
-                                       ids.shape[1], a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, L.stream_ptr(dev)),
-                "kon_embed_bwd_peer")
+                                       ids.shape[1], a[1].ptr, a[2].ptr, a[3].ptr, a[4].ptr, 1 if reuse else 0,
+                                       L.stream_ptr(dev)), "kon_embed_bwd_peer")
     return SparseGrad(rows, grads, nu)
 
 

@@ -317,7 +317,7 @@ class _PeerLookup(torch.autograd.Function):
         plan, N, rank = sh.plan, sh.world, sh.rank
         B_l, F, k, nd, width = ctx.dims
         region, dbuf = px["region"], px["dbuf"]
-        gemb = gout[:, :F * k].view(B_l, F, k)
+        gemb = gout[:, :F * k].reshape(B_l, F, k)
         if not plan.identity_order:
             gemb = gemb.index_select(1, sh.to_exchange)
         dbuf.copy_(gemb)
@@ -346,7 +346,9 @@ class _ShardedSum(torch.autograd.Function):
         B_l, F = ids_local.shape
         dev = arena.device
         ids_tw, ids_rw = sh.exchange_ids(ids_local)
-        ids_loc = torch.cat([ids_tw, ids_rw], dim=1).contiguous()
+        # no row-wise fields: the very tensor the embedding lookup routes with, so that the two backward
+        # passes of the step share one sort (ops._SORT_CACHE)
+        ids_loc = ids_tw if ids_rw.shape[1] == 0 else torch.cat([ids_tw, ids_rw], dim=1).contiguous()
         part = sh.lookup_fn(arena, ids_loc, sh.all_offs, True)                # [B_g, dim]
         mine = torch.empty((B_l, arena.shape[1]), dtype=arena.dtype, device=dev)
         _reduce_scatter(mine, part, g)
@@ -448,7 +450,13 @@ class ShardedEmbed(nn.Module):
         (table-wise ids ``[B_g, n_tw_loc]``, row-wise local row ids ``[B_g, n_rw]`` with -1 where the
         row lives on another rank).  Each owner only receives the columns it owns (all-to-all of
         4 B ids), the row-wise columns are all-gathered."""
+        from . import ops
         N, g, plan = self.world, self.group, self.plan
+        # the embedding and the first-order tables of a model are looked up with the same ids: inside a
+        # training step (ops.new_step() ... end_step()) the second layer reuses the first one's exchange
+        ckey = ("ids", id(plan), ids_local.data_ptr(), ids_local._version, tuple(ids_local.shape))
+        if ops._SHARE_SORT and ckey in ops._STEP_CACHE:
+            return ops._STEP_CACHE[ckey]
         B_l = ids_local.shape[0]
         dev = ids_local.device
         n_loc = len(plan.tw_of_rank[self.rank])
@@ -470,6 +478,8 @@ class ShardedEmbed(nn.Module):
             ids_rw = torch.where(own, torch.div(r, N, rounding_mode="floor"), torch.full_like(r, -1)).contiguous()
         else:
             ids_rw = torch.empty((N * B_l, 0), dtype=ids_local.dtype, device=dev)
+        if ops._SHARE_SORT:
+            ops._STEP_CACHE[ckey] = (ids_tw, ids_rw)
         return ids_tw, ids_rw
 
     def load_global_tables(self, tables: Sequence[torch.Tensor]):

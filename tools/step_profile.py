@@ -54,8 +54,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"step_profile_{args.model}_n{world}.txt"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"step_profile_{args.model}_n{world}" + ("_nccl" if os.environ.get("KON_PEER_EXCHANGE") == "0" else "") + ".txt"), "w") as f:
         f.write(f"eager wall ms/step (no profiler): {(t1 - t0) / args.steps * 1e3:.3f}\n")
         f.write(prof.key_averages().table(sort_by="device_time_total", row_limit=args.rows, max_name_column_width=70))
 if world > 1:
+    if hasattr(model.sparse_embed, "close_peer"):
+        model.sparse_embed.close_peer()
     dist.destroy_process_group()
