@@ -416,7 +416,9 @@ attn_bwd_finalize_kernel(const float* __restrict__ partial, int n_part, int pf, 
 
 static int attn_bwd_grid(long long B, int sms) {
   constexpr int kWarps = kAttnBwdThreads / 32;
-  return (int)std::max<long long>(1, std::min<long long>((B + kWarps - 1) / kWarps, (long long)sms * 4));
+  // also the size of the partial-sum workspace: the tensor-core backward (4 warps per CTA) runs up to
+  // 6 resident CTAs per SM
+  return (int)std::max<long long>(1, std::min<long long>((B + kWarps - 1) / kWarps, (long long)sms * 6));
 }
 
 static size_t attn_fwd_smem(int F, int kin, int H, int DH) {
@@ -579,6 +581,7 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
   KON_REQUIRE(smem <= 227 * 1024, KON_EUNSUPPORTED, "attention shape needs %zu B of shared memory",
               smem);
   float* partial = data_ptr<float>(workspace);
+  const int grid32 = std::min(grid, sm_count_of(dev) * 4);      // fp32 CUDA-core path: 4 CTAs per SM
   if ((flags & KON_ATTN_BF16) && attn_tc_bwd_supported(p, DH)) {
     int used = grid;
     KON_TRY(attn_tc_bwd(data_ptr<float>(x), data_ptr<float>(wq), data_ptr<float>(wk),
@@ -594,7 +597,7 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
 #define CALL(N)                                                                                  \
   KON_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)smem));                                                     \
-  attn_bwd_kernel<N><<<grid, kAttnBwdThreads, smem, st>>>(                                       \
+  attn_bwd_kernel<N><<<grid32, kAttnBwdThreads, smem, st>>>(                                     \
       data_ptr<float>(x), data_ptr<float>(wq), data_ptr<float>(wk),                              \
       p.use_res ? data_ptr<float>(wr) : nullptr, p.use_ln ? data_ptr<float>(gamma) : nullptr,    \
       p.use_ln ? data_ptr<float>(beta) : nullptr, data_ptr<float>(gy), data_ptr<float>(dx),      \
@@ -603,7 +606,7 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
 #undef CALL
   KON_LAUNCH_CHECK("attn_bwd_kernel");
   attn_bwd_finalize_kernel<<<(pf + 255) / 256, 256, 0, st>>>(
-      partial, grid, pf, p.kin * p.H * DH, DH, data_ptr<float>(dwq), data_ptr<float>(dwk), dwr_p,
+      partial, grid32, pf, p.kin * p.H * DH, DH, data_ptr<float>(dwq), data_ptr<float>(dwk), dwr_p,
       dg_p, db_p);
   KON_LAUNCH_CHECK("attn_bwd_finalize_kernel");
   return KON_OK;

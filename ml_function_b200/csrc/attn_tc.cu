@@ -260,11 +260,10 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
                    const AttnDims p) {
   constexpr int KIN = 16 * KS;
   extern __shared__ __align__(16) uint32_t smem_dyn[];
-  // dynamic smem: [W fragments 3*H*KS*64] [W^T fragments 3*H*(KIN/8)*32] [per-warp partial sums]
+  // dynamic smem: [W fragments 3*H*KS*64] [W^T fragments 3*H*(KIN/8)*32]
   const int H = p.H, F = p.F;
   uint32_t* w_frag = smem_dyn;
   uint32_t* wt_frag = w_frag + 3 * H * KS * 64;
-  float* red = reinterpret_cast<float*>(wt_frag + 3 * H * (KIN / 8) * 32);
   __shared__ __align__(16) unsigned short s_buf[kAtBwdWarps][6][32 * 8];     // K, q', gO, gQ, gK, gR  (bf16 [row][8])
   __shared__ __align__(16) unsigned short s_x[kAtBwdWarps][32 * KIN];         // X (bf16) [i][c]
   __shared__ __align__(16) unsigned short s_pz[kAtBwdWarps][2][32 * kPStride]; // P, gZ (bf16) [i][j], rows padded to 80 B
@@ -551,28 +550,14 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
         if (r0 + 8 < F) *reinterpret_cast<float2*>(dxb + (r0 + 8) * KIN + c0) = make_float2(dxc[mt][n][2], dxc[mt][n][3]);
       }
   }
-  // ---- reduce the per-warp accumulators: warp -> CTA (warp order) -> partial[blockIdx] ---------------
+  // ---- reduce the per-warp accumulators: warps add their fragments into ONE CTA-wide array in warp
+  // order (deterministic), which reuses the shared memory of the P / gZ tiles -> partial[blockIdx] ----
   const int wsz = KIN * H * 8;
   const int pf = 3 * wsz + 16;
-  float* mine = red + warp * pf;
-  for (int i = lane; i < pf; i += 32) mine[i] = 0.f;
-  __syncwarp();
-#pragma unroll
-  for (int h = 0; h < HT; ++h) {
-    if (h < H) {
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int c0 = 16 * ks + g;
-        float* a0 = mine + ((c0 * H + h) * 8 + 2 * t);
-        float* a1 = mine + (((c0 + 8) * H + h) * 8 + 2 * t);
-        a0[0] = dwq[h][ks][0]; a0[1] = dwq[h][ks][1]; a1[0] = dwq[h][ks][2]; a1[1] = dwq[h][ks][3];
-        a0[wsz] = dwk[h][ks][0]; a0[wsz + 1] = dwk[h][ks][1]; a1[wsz] = dwk[h][ks][2]; a1[wsz + 1] = dwk[h][ks][3];
-        a0[2 * wsz] = dwr[h][ks][0]; a0[2 * wsz + 1] = dwr[h][ks][1];
-        a1[2 * wsz] = dwr[h][ks][2]; a1[2 * wsz + 1] = dwr[h][ks][3];
-      }
-    }
-  }
+  static_assert(sizeof(s_pz) >= (3 * KIN * HT * 8 + 16) * sizeof(float), "CTA accumulator must fit in the P/gZ tiles");
+  float* acc = reinterpret_cast<float*>(&s_pz[0][0][0]);
   // dgamma / dbeta: lanes with the same t hold the same columns -> sum over g
+  float dg[2], db[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     float a = dgam[q], c = dbet[q];
@@ -581,18 +566,40 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
       a += __shfl_xor_sync(0xffffffffu, a, off);
       c += __shfl_xor_sync(0xffffffffu, c, off);
     }
+    dg[q] = a;
+    db[q] = c;
+  }
+  for (int w = 0; w < kAtBwdWarps; ++w) {
+    __syncthreads();
+    if (warp != w) continue;
+    auto put = [&](float* dst, float v) { *dst = (w == 0) ? v : *dst + v; };
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      if (h < H) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int c0 = 16 * ks + g;
+          float* a0 = acc + ((c0 * H + h) * 8 + 2 * t);
+          float* a1 = acc + (((c0 + 8) * H + h) * 8 + 2 * t);
+          put(a0, dwq[h][ks][0]); put(a0 + 1, dwq[h][ks][1]); put(a1, dwq[h][ks][2]); put(a1 + 1, dwq[h][ks][3]);
+          put(a0 + wsz, dwk[h][ks][0]); put(a0 + wsz + 1, dwk[h][ks][1]);
+          put(a1 + wsz, dwk[h][ks][2]); put(a1 + wsz + 1, dwk[h][ks][3]);
+          put(a0 + 2 * wsz, dwr[h][ks][0]); put(a0 + 2 * wsz + 1, dwr[h][ks][1]);
+          put(a1 + 2 * wsz, dwr[h][ks][2]); put(a1 + 2 * wsz + 1, dwr[h][ks][3]);
+        }
+      }
+    }
     if (g == 0) {
-      mine[3 * wsz + 2 * t + q] = a;
-      mine[3 * wsz + 8 + 2 * t + q] = c;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        put(acc + 3 * wsz + 2 * t + q, dg[q]);
+        put(acc + 3 * wsz + 8 + 2 * t + q, db[q]);
+      }
     }
   }
   __syncthreads();
   float* out = partial + (long long)blockIdx.x * pf;
-  for (int i = tid; i < pf; i += kAtBwdThreads) {
-    float acc = 0.f;
-    for (int w = 0; w < kAtBwdWarps; ++w) acc += red[w * pf + i];
-    out[i] = acc;
-  }
+  for (int i = tid; i < pf; i += kAtBwdThreads) out[i] = acc[i];
 }
 
 }  // namespace
@@ -628,9 +635,9 @@ int attn_tc_bwd(const float* x, const float* wq, const float* wk, const float* w
   const int KS = p.kin / 16;
   const float* wr_ = p.use_res ? wr : nullptr;
   const int wsz = p.kin * p.H * 8, pf = 3 * wsz + 16;
-  const size_t smem = (size_t)3 * p.H * KS * 64 * 4 + (size_t)3 * p.H * (p.kin / 8) * 32 * 4 +
-                      (size_t)kAtBwdWarps * pf * 4;
-  int grid = (int)std::max<long long>(1, std::min<long long>((p.B + kAtBwdWarps - 1) / kAtBwdWarps, (long long)sms * 4));
+  const size_t smem = (size_t)3 * p.H * KS * 64 * 4 + (size_t)3 * p.H * (p.kin / 8) * 32 * 4;
+  int grid = (int)std::max<long long>(1, std::min<long long>((p.B + kAtBwdWarps - 1) / kAtBwdWarps,
+                                                             (long long)sms * KON_ATB_MINB));   // one resident wave
   grid = std::min(grid, max_grid);
   *grid_used = grid;
 #define KON_ATB(KS_, HT_)                                                                                   \

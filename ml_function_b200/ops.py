@@ -115,6 +115,30 @@ def _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort):
     """-> (workspace, reuse): ``reuse`` when an earlier backward of this step left the sorted routing of the
     same ids / offsets at the front of the returned workspace."""
     lib = L.lib()
+    if share_sort is None:
+        share_sort = _SHARE_SORT
+    key = (ids.data_ptr(), ids._version, tuple(field_row_offset), n)
+    cached = _SORT_CACHE.get(key) if share_sort else None
+    need = lib.kon_embed_bwd_workspace_bytes(n, dim)
+    if cached is not None and cached.numel() >= need:
+        return cached, True
+    # sized for the widest payload seen in practice plus the dim-1 path, so a later call can reuse it
+    ws = _ws(max(need, lib.kon_embed_bwd_workspace_bytes(n, 1), lib.kon_embed_bwd_workspace_bytes(n, 32)), dev)
+    if share_sort:
+        _SORT_CACHE[key] = ws
+    return ws, False
+
+
+def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None) -> SparseGrad:
+    """d_out [B,F,dim] (any strides on dims 0/1, e.g. an expanded [B,1,dim])."""
+    lib = L.lib()
+    F = ids.shape[1]
+    dim = d_out.shape[2]
+    n = ids.numel()
+    dev = d_out.device
+    rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int32, device=dev)
     ws, reuse = _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort)
     fn, what = (lib.kon_embed_bwd_reuse, "kon_embed_bwd_reuse") if reuse else (lib.kon_embed_bwd, "kon_embed_bwd")
     offs = L.i64_array(list(field_row_offset))

@@ -29,6 +29,16 @@ def test_header_symbols_all_exported():
     assert lib.kon_abi_version() == 1
 
 
+def test_ops_surface_is_complete():
+    """Every op entry the layers / trainer / sharding code calls exists (a GPU-only code path must not be
+    the first place a missing name shows up)."""
+    from ml_function_b200 import ops
+    for name in ("embed_fwd_raw", "embed_bwd_raw", "embed_fwd_peer", "embed_bwd_peer", "embed_lookup",
+                 "embed_lookup_concat", "embed_sgd", "embed_adam", "embed_adam_devstep", "fm", "cross", "cin",
+                 "attention", "new_step", "end_step", "profile_summary", "SparseGrad"):
+        assert callable(getattr(ops, name)), name
+
+
 def test_cpu_tensors_are_rejected_not_computed():
     L = _lib()
     from ml_function_b200 import ops
