@@ -256,6 +256,19 @@ int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTensor* wk, cons
                  DLTensor* dwq, DLTensor* dwk, DLTensor* dwr, DLTensor* dgamma, DLTensor* dbeta,
                  DLTensor* workspace, float ln_eps, int32_t flags, void* stream);
 
+/* ============================ a12: skinny heads ================================== */
+/* Replaces MergeScoreLayer.call (CL:86-100: Flatten + Concatenate + Dense(2); the softmax stays
+ * with the caller) and Dense(1) logit layers (CL:190): y = [x1 | x2] W + b without the concat copy.
+ *   x1 [B,D1] f32, x2 [B,D2] f32 or NULL (free row strides; with x2: D1 % 4 == 0), D1+D2 <= 1024,
+ *   w [D1+D2, N] f32 with N in {1,2} (Keras Dense kernel layout), b [N] or NULL, y [B,N].
+ * Backward: dx1 / dx2 (either may be NULL: not needed), dw [D,N], db [N] or NULL; deterministic. */
+int kon_head_fwd(const DLTensor* x1, const DLTensor* x2, const DLTensor* w, const DLTensor* b,
+                 DLTensor* y, void* stream);
+size_t kon_head_bwd_workspace_bytes(int64_t batch, int32_t dim, int32_t units, int device_id);
+int kon_head_bwd(const DLTensor* x1, const DLTensor* x2, const DLTensor* w, const DLTensor* gy,
+                 DLTensor* dx1, DLTensor* dx2, DLTensor* dw, DLTensor* db, DLTensor* workspace,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,6 +158,9 @@ def lib():
         "kon_attn_fwd": (ctypes.c_int, [T] * 7 + [f32, i32, vp]),
         "kon_attn_bwd_workspace_bytes": (sz, [i64, i32, i32, i32, i32, ctypes.c_int]),
         "kon_attn_bwd": (ctypes.c_int, [T] * 14 + [f32, i32, vp]),
+        "kon_head_fwd": (ctypes.c_int, [T] * 5 + [vp]),
+        "kon_head_bwd_workspace_bytes": (sz, [i64, i32, i32, ctypes.c_int]),
+        "kon_head_bwd": (ctypes.c_int, [T] * 9 + [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)   # AttributeError here = header and library disagree
@@ -179,6 +182,7 @@ EXPORTED_SYMBOLS = (
     "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",
+    "kon_head_fwd", "kon_head_bwd_workspace_bytes", "kon_head_bwd",
 )
 
 

@@ -3,18 +3,24 @@
 // Replaces CrossLayer.call (IL:275-282): per layer Transpose + MatMul ([B,1,D]x[D,1]) +
 // BatchMatMul ([B,D,1]x[B,1,1]) + 2 AddV2, i.e. 5*L passes over [B,D].
 //
-//   fwd: one warp per sample keeps x0 and x_l in registers for all L layers;
-//        x_{l+1} = (x0 * s_l + x_l) + b_l with s_l = x_l . w_l (warp reduction).
-//        HBM traffic: read x0, write x_L (+ L scalars s_l) = 2*D*4 + 4L bytes/sample.
-//   bwd: with G_l = dL/dx_{l+1}:  t_l = x0 . G_l,  dx0 += G_l * s_l,  G_{l-1} = G_l + t_l w_l,
-//        finally dx0 += G_{-1}.  x_l is never stored: x_l = x0 * c_l + beta_l with
-//        c_l = 1 + sum_{j<l} s_j and beta_l = sum_{j<l} b_j, which turns the weight
-//        gradients into batch reductions of x0 and g only:
-//            dw_l[d] = sum_b x0[b,d] * (c_l t_l)[b] + beta_l[d] * T_l,   T_l = sum_b t_l[b]
-//            db_l[d] = sum_b g[b,d] + sum_{j>l} w_j[d] * T_j
-//        Each CTA accumulates its share in registers in a fixed order, writes one partial,
-//        and a finalize kernel adds the partials in CTA order (deterministic).
-//        HBM traffic: read x0, g, write dx0 = 3*D*4 bytes/sample.
+// HBM-bound fp32 work; everything rests on one identity: x_l is never needed as a vector,
+//     x_l = c_l x0 + beta_l,   c_0 = 1, c_{l+1} = c_l + s_l,   beta_l = sum_{j<l} b_j  (batch-independent)
+// so with the L INDEPENDENT dot products p_l = x0 . w_l of a sample and the per-layer constants
+// q_l = beta_l . w_l the whole recurrence is scalar:  s_l = x_l . w_l = c_l p_l + q_l.
+//
+//   fwd : one pass: read x0, L dots against w (shared memory, 128-bit reads), scalar recurrence,
+//         write x_L = c_L x0 + beta_L and the L scalars s_l.         2*D*4 + 4L bytes / sample
+//   bwd : with G_l = dL/dx_{l+1} = g + sum_{j>l} t_j w_j and t_l = x0 . G_l:
+//             t_l = a + sum_{j>l} t_j p_j,  a = x0 . g        (scalar recurrence again)
+//             dx0 = c_L g + sum_l u_l w_l,  u_l = c_l t_l
+//             dw_l[d] = sum_b x0[b,d] u_l[b] + beta_l[d] T_l,   T_l = sum_b t_l[b]
+//             db_l[d] = sum_b g[b,d] + sum_{j>l} w_j[d] T_j
+//         kernel 1 (per sample): x0, g -> dx0, u; column sums of g and T_l in registers.  3*D*4 B / sample
+//         kernel 2: the skinny GEMM  M = X0^T U  ([D x B] x [B x L]) per CTA slab, in registers
+//         kernel 3/4: fixed-order reduction of the per-CTA partials and the dw / db formulas
+//         (deterministic: every sum has a fixed association order).
+// A lane owns 4 consecutive columns per 128-column group, so rows move as 128-bit accesses when the
+// row stride allows it (the model's concat buffer: W % 4 == 0); any other layout takes scalar accesses.
 #include "common.cuh"
 
 namespace kon {
@@ -22,203 +28,365 @@ namespace kon {
 constexpr int kCrossThreads = 256;
 constexpr int kCrossWarps = kCrossThreads / 32;
 constexpr int kCrossMaxL = 8;
+constexpr int kCrossSlab = 32;      // samples per staging step of the dw kernel
 
-template <int NPER>
-__global__ void __launch_bounds__(kCrossThreads)
-cross_fwd_kernel(const float* __restrict__ x0, long long xs, const float* __restrict__ w,
-                 const float* __restrict__ b, float* __restrict__ out, float* __restrict__ s,
-                 long long B, int D, int L) {
-  extern __shared__ __align__(16) float smem[];
-  float* w_s = smem;            // [L][D]
-  float* b_s = smem + L * D;    // [L][D]
-  for (int i = threadIdx.x; i < L * D; i += kCrossThreads) {
-    w_s[i] = w[i];
-    b_s[i] = b[i];
+template <int NJ>
+__device__ __forceinline__ void cross_load_row(const float* __restrict__ p, bool vec, int D, int lane,
+                                               float4 (&x)[NJ]) {
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int d0 = 128 * j + 4 * lane;
+    if (vec && d0 + 3 < D) {
+      x[j] = __ldg(reinterpret_cast<const float4*>(p + d0));
+    } else {
+      x[j].x = d0 < D ? __ldg(p + d0) : 0.f;
+      x[j].y = d0 + 1 < D ? __ldg(p + d0 + 1) : 0.f;
+      x[j].z = d0 + 2 < D ? __ldg(p + d0 + 2) : 0.f;
+      x[j].w = d0 + 3 < D ? __ldg(p + d0 + 3) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void cross_store4(float* __restrict__ p, bool vec, int D, int d0, float4 v) {
+  if (vec && d0 + 3 < D) {
+    *reinterpret_cast<float4*>(p + d0) = v;
+  } else {
+    if (d0 < D) p[d0] = v.x;
+    if (d0 + 1 < D) p[d0 + 1] = v.y;
+    if (d0 + 2 < D) p[d0 + 2] = v.z;
+    if (d0 + 3 < D) p[d0 + 3] = v.w;
+  }
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+
+// w -> shared [L][Dp] (zero padded), beta_L -> bl_s[Dp], q_l = beta_l . w_l -> q_s[kCrossMaxL].
+// Fixed association order (column-strided per thread, shuffle tree, warps in order): every CTA gets
+// bit-identical constants.
+__device__ void cross_stage_constants(const float* __restrict__ w, const float* __restrict__ b, int D, int Dp,
+                                      int L, float* w_s, float* bl_s, float* q_s, float* red_s) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < L * Dp; i += kCrossThreads) {
+    const int l = i / Dp, d = i - l * Dp;
+    w_s[i] = d < D ? w[l * D + d] : 0.f;
+  }
+  float qp[kCrossMaxL];
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) qp[l] = 0.f;
+  for (int d = tid; d < Dp; d += kCrossThreads) {
+    float beta = 0.f;
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      if (l < L && d < D) {
+        qp[l] = fmaf(beta, w[l * D + d], qp[l]);
+        if (b) beta += b[l * D + d];
+      }
+    }
+    if (bl_s) bl_s[d] = beta;
+  }
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) {
+    const float v = warp_sum(qp[l]);
+    if (lane == 0) red_s[wid * kCrossMaxL + l] = v;
   }
   __syncthreads();
+  if (tid < kCrossMaxL) {
+    float v = 0.f;
+    for (int ws = 0; ws < kCrossWarps; ++ws) v += red_s[ws * kCrossMaxL + tid];
+    q_s[tid] = v;
+  }
+  __syncthreads();
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(kCrossThreads, 2)
+cross_fwd_kernel(const float* __restrict__ x0, long long xs, const float* __restrict__ w,
+                 const float* __restrict__ b, float* __restrict__ out, float* __restrict__ s,
+                 long long B, int D, int L, int vec_in, int vec_out) {
+  constexpr int Dp = NJ * 128;
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;                    // [L][Dp]
+  float* bl_s = w_s + L * Dp;           // [Dp]  beta_L
+  float* q_s = bl_s + Dp;               // [kCrossMaxL]
+  float* red_s = q_s + kCrossMaxL;      // [kCrossWarps][kCrossMaxL]
+  cross_stage_constants(w, b, D, Dp, L, w_s, bl_s, q_s, red_s);
+
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kCrossWarps + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kCrossWarps;
-  for (long long r = warp0; r < B; r += nwarps) {
-    float x0r[NPER], xl[NPER];
-    const float* xp = x0 + r * xs;
+  // two samples per warp iteration: every 128-bit read of w serves both
+  for (long long r = 2 * warp0; r < B; r += 2 * nwarps) {
+    const bool two = r + 1 < B;
+    float4 xa[NJ], xb[NJ];
+    cross_load_row<NJ>(x0 + r * xs, vec_in != 0, D, lane, xa);
+    cross_load_row<NJ>(x0 + (two ? r + 1 : r) * xs, vec_in != 0, D, lane, xb);
+    float pa[kCrossMaxL], pb[kCrossMaxL];
 #pragma unroll
-    for (int j = 0; j < NPER; ++j) {
-      const int d = lane + 32 * j;
-      x0r[j] = d < D ? __ldg(xp + d) : 0.f;
-      xl[j] = x0r[j];
-    }
-    for (int l = 0; l < L; ++l) {
-      float dot = 0.f;
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      pa[l] = pb[l] = 0.f;
+      if (l < L) {
 #pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-        const int d = lane + 32 * j;
-        if (d < D) dot = fmaf(xl[j], w_s[l * D + d], dot);
-      }
-      dot = warp_sum(dot);
-      if (lane == 0) s[r * L + l] = dot;
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-        const int d = lane + 32 * j;
-        if (d < D) xl[j] = __fadd_rn(__fadd_rn(__fmul_rn(x0r[j], dot), xl[j]), b_s[l * D + d]);
+        for (int j = 0; j < NJ; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(w_s + l * Dp + 128 * j + 4 * lane);
+          pa[l] = dot4(xa[j], wv, pa[l]);
+          pb[l] = dot4(xb[j], wv, pb[l]);
+        }
+        pa[l] = warp_sum(pa[l]);
+        pb[l] = warp_sum(pb[l]);
       }
     }
-    float* op = out + r * (long long)D;
+    float ca = 1.f, cb = 1.f;
 #pragma unroll
-    for (int j = 0; j < NPER; ++j) {
-      const int d = lane + 32 * j;
-      if (d < D) op[d] = xl[j];
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      if (l < L) {
+        const float sa = fmaf(ca, pa[l], q_s[l]), sb = fmaf(cb, pb[l], q_s[l]);
+        if (lane == 0) {
+          s[r * L + l] = sa;
+          if (two) s[(r + 1) * L + l] = sb;
+        }
+        ca += sa;
+        cb += sb;
+      }
+    }
+    float* oa = out + r * (long long)D;
+    float* ob = oa + D;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int d0 = 128 * j + 4 * lane;
+      const float4 bl = *reinterpret_cast<const float4*>(bl_s + d0);
+      cross_store4(oa, vec_out != 0, D, d0,
+                   make_float4(fmaf(ca, xa[j].x, bl.x), fmaf(ca, xa[j].y, bl.y), fmaf(ca, xa[j].z, bl.z),
+                               fmaf(ca, xa[j].w, bl.w)));
+      if (two)
+        cross_store4(ob, vec_out != 0, D, d0,
+                     make_float4(fmaf(cb, xb[j].x, bl.x), fmaf(cb, xb[j].y, bl.y), fmaf(cb, xb[j].z, bl.z),
+                                 fmaf(cb, xb[j].w, bl.w)));
     }
   }
 }
 
-// Partial layout per CTA: [D] colsum(g) | [L][D] M | [kCrossMaxL] T
-__host__ __device__ inline long long cross_partial_floats(int D, int L) {
-  return (long long)D + (long long)L * D + kCrossMaxL;
-}
-
-template <int NPER>
-__global__ void __launch_bounds__(kCrossThreads)
+// ---- backward, kernel 1: per sample -------------------------------------------------------------
+// partial_cg [grid][D], partial_T [grid][kCrossMaxL], u [B][kCrossMaxL]
+template <int NJ>
+__global__ void __launch_bounds__(kCrossThreads, 2)
 cross_bwd_kernel(const float* __restrict__ x0, long long xs, const float* __restrict__ w,
                  const float* __restrict__ s, const float* __restrict__ g, long long gs,
-                 float* __restrict__ dx0, float* __restrict__ partial, long long B, int D, int L) {
+                 float* __restrict__ dx0, float* __restrict__ u, float* __restrict__ partial_cg,
+                 float* __restrict__ partial_T, long long B, int D, int L, int vec_x, int vec_g, int vec_dx) {
+  constexpr int Dp = NJ * 128;
   extern __shared__ __align__(16) float smem[];
-  float* w_s = smem;                               // [L][D]
-  float* x_s = w_s + L * D;                        // [kCrossWarps][D]
-  float* g_s = x_s + kCrossWarps * D;              // [kCrossWarps][D]
-  float* u_s = g_s + kCrossWarps * D;              // [kCrossWarps][kCrossMaxL]  c_l * t_l
-  float* t_s = u_s + kCrossWarps * kCrossMaxL;     // [kCrossWarps][kCrossMaxL]
-  for (int i = threadIdx.x; i < L * D; i += kCrossThreads) w_s[i] = w[i];
+  float* w_s = smem;                    // [L][Dp]
+  float* q_s = w_s + L * Dp;            // unused constants slot (keeps the helper shared)
+  float* red_s = q_s + kCrossMaxL;      // [kCrossWarps][kCrossMaxL]
+  float* cg_s = red_s + kCrossWarps * kCrossMaxL;   // [kCrossWarps][Dp] (epilogue)
+  cross_stage_constants(w, nullptr, D, Dp, L, w_s, nullptr, q_s, red_s);
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  constexpr int CPT = (NPER * 32 + kCrossThreads - 1) / kCrossThreads;   // columns per thread
-  float cg[CPT], M[CPT][kCrossMaxL], T = 0.f;
+  float4 cg[NJ];
+  float Tacc[kCrossMaxL];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    cg[c] = 0.f;
+  for (int j = 0; j < NJ; ++j) cg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int l = 0; l < kCrossMaxL; ++l) M[c][l] = 0.f;
-  }
-  __syncthreads();
+  for (int l = 0; l < kCrossMaxL; ++l) Tacc[l] = 0.f;
 
-  const long long n_batches = (B + kCrossWarps - 1) / kCrossWarps;
-  for (long long bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
-    const long long r = bt * kCrossWarps + wid;
-    float* xr_s = x_s + wid * D;
-    float* gr_s = g_s + wid * D;
-    if (r < B) {
-      float x0r[NPER], G[NPER], dx[NPER];
-      const float* xp = x0 + r * xs;
-      const float* gp = g + r * gs;
+  for (long long r = (long long)blockIdx.x * kCrossWarps + wid; r < B; r += (long long)gridDim.x * kCrossWarps) {
+    float4 x[NJ], G[NJ];
+    cross_load_row<NJ>(x0 + r * xs, vec_x != 0, D, lane, x);
+    cross_load_row<NJ>(g + r * gs, vec_g != 0, D, lane, G);
+    float a = 0.f, pl[kCrossMaxL];
 #pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-        const int d = lane + 32 * j;
-        x0r[j] = d < D ? __ldg(xp + d) : 0.f;
-        G[j] = d < D ? __ldg(gp + d) : 0.f;
-        dx[j] = 0.f;
-        if (d < D) {
-          xr_s[d] = x0r[j];
-          gr_s[d] = G[j];
-        }
+    for (int j = 0; j < NJ; ++j) {
+      a = dot4(x[j], G[j], a);
+      cg[j].x += G[j].x; cg[j].y += G[j].y; cg[j].z += G[j].z; cg[j].w += G[j].w;
+    }
+    a = warp_sum(a);
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      pl[l] = 0.f;
+      if (l < L) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          pl[l] = dot4(x[j], *reinterpret_cast<const float4*>(w_s + l * Dp + 128 * j + 4 * lane), pl[l]);
+        pl[l] = warp_sum(pl[l]);
       }
-      float sl[kCrossMaxL], cl[kCrossMaxL];
-      float c = 1.f;
+    }
+    // scalars: c_l from the saved s_l; t_l backwards; u_l = c_l t_l
+    float cl[kCrossMaxL + 1], tl[kCrossMaxL], ul[kCrossMaxL];
+    cl[0] = 1.f;
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) cl[l + 1] = cl[l] + (l < L ? __ldg(s + r * L + l) : 0.f);
+#pragma unroll
+    for (int l = kCrossMaxL - 1; l >= 0; --l) {
+      float t = 0.f;
+      if (l < L) {
+        t = a;
+#pragma unroll
+        for (int j = kCrossMaxL - 1; j > l; --j)
+          if (j < L) t = fmaf(tl[j], pl[j], t);
+      }
+      tl[l] = t;
+      ul[l] = cl[l] * t;
+      Tacc[l] += t;
+    }
+    if (lane < kCrossMaxL) {
+      float v = 0.f;
+#pragma unroll
+      for (int l = 0; l < kCrossMaxL; ++l) v = lane == l ? ul[l] : v;
+      u[r * kCrossMaxL + lane] = v;
+    }
+    // dx0 = c_L g + sum_l u_l w_l
+    const float cL = cl[kCrossMaxL];
+    float* dp = dx0 + r * (long long)D;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int d0 = 128 * j + 4 * lane;
+      float4 o = make_float4(cL * G[j].x, cL * G[j].y, cL * G[j].z, cL * G[j].w);
 #pragma unroll
       for (int l = 0; l < kCrossMaxL; ++l) {
-        sl[l] = l < L ? __ldg(s + r * L + l) : 0.f;
-        cl[l] = c;
-        c += sl[l];
-      }
-#pragma unroll
-      for (int l = kCrossMaxL - 1; l >= 0; --l) {
         if (l < L) {
-          float t = 0.f;
-#pragma unroll
-          for (int j = 0; j < NPER; ++j) t = fmaf(x0r[j], G[j], t);
-          t = warp_sum(t);
-#pragma unroll
-          for (int j = 0; j < NPER; ++j) {
-            const int d = lane + 32 * j;
-            dx[j] = fmaf(G[j], sl[l], dx[j]);
-            if (d < D) G[j] = fmaf(t, w_s[l * D + d], G[j]);
-          }
-          if (lane == 0) {
-            u_s[wid * kCrossMaxL + l] = cl[l] * t;
-            t_s[wid * kCrossMaxL + l] = t;
-          }
+          const float4 wv = *reinterpret_cast<const float4*>(w_s + l * Dp + d0);
+          o.x = fmaf(ul[l], wv.x, o.x); o.y = fmaf(ul[l], wv.y, o.y);
+          o.z = fmaf(ul[l], wv.z, o.z); o.w = fmaf(ul[l], wv.w, o.w);
         }
       }
-      float* dp = dx0 + r * (long long)D;
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-        const int d = lane + 32 * j;
-        if (d < D) dp[d] = dx[j] + G[j];
-      }
-    } else {
-      for (int d = lane; d < D; d += 32) {
-        xr_s[d] = 0.f;
-        gr_s[d] = 0.f;
-      }
-      if (lane < kCrossMaxL) {
-        u_s[wid * kCrossMaxL + lane] = 0.f;
-        t_s[wid * kCrossMaxL + lane] = 0.f;
-      }
-    }
-    __syncthreads();
-    // CTA phase: thread owns columns d = tid + 256*c; samples are added in warp order.
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int d = threadIdx.x + kCrossThreads * c;
-      if (d < D) {
-#pragma unroll
-        for (int ws = 0; ws < kCrossWarps; ++ws) {
-          const float xv = x_s[ws * D + d];
-          cg[c] += g_s[ws * D + d];
-#pragma unroll
-          for (int l = 0; l < kCrossMaxL; ++l) M[c][l] = fmaf(xv, u_s[ws * kCrossMaxL + l], M[c][l]);
-        }
-      }
-    }
-    if (threadIdx.x < kCrossMaxL) {
-#pragma unroll
-      for (int ws = 0; ws < kCrossWarps; ++ws) T += t_s[ws * kCrossMaxL + threadIdx.x];
-    }
-    __syncthreads();
-  }
-  float* p = partial + blockIdx.x * cross_partial_floats(D, L);
-#pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int d = threadIdx.x + kCrossThreads * c;
-    if (d < D) {
-      p[d] = cg[c];
-#pragma unroll
-      for (int l = 0; l < kCrossMaxL; ++l)
-        if (l < L) p[D + l * D + d] = M[c][l];
+      cross_store4(dp, vec_dx != 0, D, d0, o);
     }
   }
-  if (threadIdx.x < kCrossMaxL) p[D + L * D + threadIdx.x] = T;
-}
-
-__global__ void __launch_bounds__(256)
-cross_bwd_finalize_kernel(const float* __restrict__ partial, int n_part,
-                          const float* __restrict__ w, const float* __restrict__ b,
-                          float* __restrict__ dw, float* __restrict__ db, int D, int L) {
-  __shared__ float T[kCrossMaxL];
-  const long long pf = cross_partial_floats(D, L);
-  if (threadIdx.x < kCrossMaxL) {
-    float t = 0.f;
-    for (int p = 0; p < n_part; ++p) t += partial[p * pf + D + L * D + threadIdx.x];
-    T[threadIdx.x] = t;
+  // epilogue: per-warp column sums / T -> CTA partial, warps in order
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+    *reinterpret_cast<float4*>(cg_s + wid * Dp + 128 * j + 4 * lane) = cg[j];
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) red_s[wid * kCrossMaxL + l] = Tacc[l];
   }
   __syncthreads();
+  for (int d = threadIdx.x; d < D; d += kCrossThreads) {
+    float v = 0.f;
+#pragma unroll
+    for (int ws = 0; ws < kCrossWarps; ++ws) v += cg_s[ws * Dp + d];
+    partial_cg[(long long)blockIdx.x * D + d] = v;
+  }
+  if (threadIdx.x < kCrossMaxL) {
+    float v = 0.f;
+#pragma unroll
+    for (int ws = 0; ws < kCrossWarps; ++ws) v += red_s[ws * kCrossMaxL + threadIdx.x];
+    partial_T[blockIdx.x * kCrossMaxL + threadIdx.x] = v;
+  }
+}
+
+// ---- backward, kernel 2: M = X0^T U per CTA; thread = 4 columns, slabs of kCrossSlab samples ----
+__global__ void __launch_bounds__(kCrossThreads)
+cross_dw_kernel(const float* __restrict__ x0, long long xs, const float* __restrict__ u,
+                float* __restrict__ partial_M, long long B, int D, int L, int vec_x) {
+  __shared__ __align__(16) float u_s[kCrossSlab * kCrossMaxL];
+  const int tid = threadIdx.x;
+  const int d0 = 4 * tid;
+  float4 M[kCrossMaxL];
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) M[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long n_slabs = (B + kCrossSlab - 1) / kCrossSlab;
+  for (long long sl = blockIdx.x; sl < n_slabs; sl += gridDim.x) {
+    const long long b0 = sl * kCrossSlab;
+    const int nb = (int)min((long long)kCrossSlab, B - b0);
+    __syncthreads();
+    u_s[tid] = (tid < nb * kCrossMaxL) ? __ldg(u + b0 * kCrossMaxL + tid) : 0.f;
+    __syncthreads();
+    if (d0 < D) {
+#pragma unroll 8
+      for (int i = 0; i < kCrossSlab; ++i) {
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nb) {
+          const float* xp = x0 + (b0 + i) * xs;
+          if (vec_x && d0 + 3 < D) {
+            xv = __ldg(reinterpret_cast<const float4*>(xp + d0));
+          } else {
+            xv.x = __ldg(xp + d0);
+            if (d0 + 1 < D) xv.y = __ldg(xp + d0 + 1);
+            if (d0 + 2 < D) xv.z = __ldg(xp + d0 + 2);
+            if (d0 + 3 < D) xv.w = __ldg(xp + d0 + 3);
+          }
+        }
+        const float4 ua = *reinterpret_cast<const float4*>(u_s + i * kCrossMaxL);
+        const float4 ub = *reinterpret_cast<const float4*>(u_s + i * kCrossMaxL + 4);
+        const float uu[kCrossMaxL] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+        for (int l = 0; l < kCrossMaxL; ++l) {
+          M[l].x = fmaf(xv.x, uu[l], M[l].x); M[l].y = fmaf(xv.y, uu[l], M[l].y);
+          M[l].z = fmaf(xv.z, uu[l], M[l].z); M[l].w = fmaf(xv.w, uu[l], M[l].w);
+        }
+      }
+    }
+  }
+  if (d0 < D) {
+    float* p = partial_M + (long long)blockIdx.x * L * D;
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      if (l < L) {
+        p[l * D + d0] = M[l].x;
+        if (d0 + 1 < D) p[l * D + d0 + 1] = M[l].y;
+        if (d0 + 2 < D) p[l * D + d0 + 2] = M[l].z;
+        if (d0 + 3 < D) p[l * D + d0 + 3] = M[l].w;
+      }
+    }
+  }
+}
+
+// ---- backward, kernel 3: fixed-order sums of the per-CTA partials --------------------------------
+// grid (ceil(D/32), L + 2): rows y < L: M_y (n2 partials), y == L: colsum(g) (n1), y == L+1: T (n1, 8 wide)
+// red layout: [L][D] M | [D] cg | [kCrossMaxL] T
+__global__ void __launch_bounds__(256)
+cross_reduce_kernel(const float* __restrict__ partial_M, int n2, const float* __restrict__ partial_cg,
+                    const float* __restrict__ partial_T, int n1, float* __restrict__ red, int D, int L) {
+  __shared__ float sm[8][32];
+  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int y = blockIdx.y;
+  const int d = blockIdx.x * 32 + col;
+  const float* base;
+  long long stride;
+  int n, width;
+  if (y < L) { base = partial_M + (long long)y * D; stride = (long long)L * D; n = n2; width = D; }
+  else if (y == L) { base = partial_cg; stride = D; n = n1; width = D; }
+  else { base = partial_T; stride = kCrossMaxL; n = n1; width = kCrossMaxL; }
+  const int per = (n + 7) / 8;
+  const int lo = slice * per, hi = min(n, lo + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (d < width) {
+    int p = lo;
+    for (; p + 3 < hi; p += 4) {
+      a0 += base[(long long)p * stride + d];
+      a1 += base[(long long)(p + 1) * stride + d];
+      a2 += base[(long long)(p + 2) * stride + d];
+      a3 += base[(long long)(p + 3) * stride + d];
+    }
+    for (; p < hi; ++p) a0 += base[(long long)p * stride + d];
+  }
+  sm[slice][col] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (slice == 0 && d < width) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sm[k][col];
+    red[(y < L ? (long long)y * D : (y == L ? (long long)L * D : (long long)L * D + D)) + d] = v;
+  }
+}
+
+// ---- backward, kernel 4: dw / db from the reduced sums ---------------------------------------------
+__global__ void __launch_bounds__(256)
+cross_bwd_finalize_kernel(const float* __restrict__ red, const float* __restrict__ w,
+                          const float* __restrict__ b, float* __restrict__ dw, float* __restrict__ db,
+                          int D, int L) {
+  const float* T = red + (long long)L * D + D;
   for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
-    float cg = 0.f;
-    for (int p = 0; p < n_part; ++p) cg += partial[p * pf + d];
+    const float cg = red[(long long)L * D + d];
     float beta = 0.f;   // beta_l[d] = sum_{j<l} b_j[d]
     for (int l = 0; l < L; ++l) {
-      float m = 0.f;
-      for (int p = 0; p < n_part; ++p) m += partial[p * pf + D + l * D + d];
-      dw[l * D + d] = m + beta * T[l];
+      dw[l * D + d] = red[(long long)l * D + d] + beta * T[l];
       beta += b[l * D + d];
     }
     float tail = 0.f;   // sum_{j>l} w_j[d] T_j
@@ -229,9 +397,29 @@ cross_bwd_finalize_kernel(const float* __restrict__ partial, int n_part,
   }
 }
 
-static int cross_bwd_grid(long long B, int sms) {
-  const long long n_batches = (B + kCrossWarps - 1) / kCrossWarps;
-  return (int)std::max<long long>(1, std::min<long long>(n_batches, (long long)sms * 2));
+static int cross_grid1(long long B, int sms) {
+  return (int)std::max<long long>(1, std::min<long long>((B + kCrossWarps - 1) / kCrossWarps, (long long)sms * 2));   // = resident CTAs
+}
+static int cross_grid2(long long B, int sms) {
+  return (int)std::max<long long>(1, std::min<long long>((B + kCrossSlab - 1) / kCrossSlab, (long long)sms * 4));
+}
+static size_t cross_align(size_t x) { return (x + 255) / 256 * 256; }
+
+struct CrossWs {
+  size_t u, pm, pcg, pt, red, total;
+};
+static CrossWs cross_ws_layout(long long B, int D, int L, int sms) {
+  CrossWs l;
+  const int g1 = cross_grid1(B, sms), g2 = cross_grid2(B, sms);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = cross_align(o + bytes); return r; };
+  l.u = take((size_t)std::max<long long>(B, 1) * kCrossMaxL * 4);
+  l.pm = take((size_t)g2 * L * D * 4);
+  l.pcg = take((size_t)g1 * D * 4);
+  l.pt = take((size_t)g1 * kCrossMaxL * 4);
+  l.red = take(((size_t)L * D + D + kCrossMaxL) * 4);
+  l.total = o;
+  return l;
 }
 
 }  // namespace kon
@@ -262,14 +450,22 @@ static int cross_check(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
 
 #define KON_CROSS_DISPATCH(D, CALL)            \
   do {                                         \
-    const int nper = (int)(((D) + 31) / 32);   \
-    if (nper <= 4) { CALL(4); }                \
-    else if (nper <= 8) { CALL(8); }           \
-    else if (nper <= 14) { CALL(14); }         \
-    else if (nper <= 20) { CALL(20); }         \
-    else if (nper <= 27) { CALL(27); }         \
-    else { CALL(32); }                         \
+    const int nj = (int)(((D) + 127) / 128);   \
+    if (nj <= 1) { CALL(1); }                  \
+    else if (nj <= 2) { CALL(2); }             \
+    else if (nj <= 4) { CALL(4); }             \
+    else if (nj <= 7) { CALL(7); }             \
+    else { CALL(8); }                          \
   } while (0)
+
+static int cross_nj(int64_t D) {
+  const int nj = (int)((D + 127) / 128);
+  return nj <= 1 ? 1 : nj <= 2 ? 2 : nj <= 4 ? 4 : nj <= 7 ? 7 : 8;
+}
+// rows can move as 128-bit accesses when every row start is 16-B aligned
+static int cross_vec(const float* p, int64_t row_stride) {
+  return (aligned16(p) && row_stride % 4 == 0) ? 1 : 0;
+}
 
 extern "C" int kon_cross_fwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
                              DLTensor* out, DLTensor* s, void* stream) {
@@ -286,15 +482,18 @@ extern "C" int kon_cross_fwd(const DLTensor* x0, const DLTensor* w, const DLTens
   if (B == 0) return KON_OK;
   DeviceGuard guard(dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = 2 * (size_t)L * D * sizeof(float);
-  const int grid = (int)std::min<long long>((B + kCrossWarps - 1) / kCrossWarps,
-                                            (long long)sm_count_of(dev) * 8);
+  const int Dp = cross_nj(D) * 128;
+  const size_t smem = ((size_t)L * Dp + Dp + kCrossMaxL + kCrossWarps * kCrossMaxL) * sizeof(float);
+  const int grid = (int)std::min<long long>((B + 2 * kCrossWarps - 1) / (2 * kCrossWarps),
+                                            (long long)sm_count_of(dev) * 2);   // = resident CTAs
+  const int vin = cross_vec(data_ptr<float>(x0), stride_of(x0, 0));
+  const int vout = cross_vec(data_ptr<float>(out), D);
 #define CALL(N)                                                                                  \
   KON_CUDA(cudaFuncSetAttribute(cross_fwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)smem));                                                     \
   cross_fwd_kernel<N><<<grid, kCrossThreads, smem, st>>>(                                        \
       data_ptr<float>(x0), stride_of(x0, 0), data_ptr<float>(w), data_ptr<float>(b),             \
-      data_ptr<float>(out), data_ptr<float>(s), B, (int)D, (int)L)
+      data_ptr<float>(out), data_ptr<float>(s), B, (int)D, (int)L, vin, vout)
   KON_CROSS_DISPATCH(D, CALL);
 #undef CALL
   KON_LAUNCH_CHECK("cross_fwd_kernel");
@@ -303,8 +502,7 @@ extern "C" int kon_cross_fwd(const DLTensor* x0, const DLTensor* w, const DLTens
 
 extern "C" size_t kon_cross_bwd_workspace_bytes(int64_t batch, int32_t dim, int32_t layers,
                                                 int device_id) {
-  const int grid = cross_bwd_grid(batch, sm_count_of(device_id));
-  return (size_t)grid * cross_partial_floats(dim, layers) * sizeof(float);
+  return cross_ws_layout(batch, dim, layers, sm_count_of(device_id)).total;
 }
 
 extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
@@ -332,25 +530,43 @@ extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTens
               KON_EINVAL, "dw and db must be compact float32 [L,D]");
   DeviceGuard guard(dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = cross_bwd_grid(B, sm_count_of(dev));
-  const size_t need = (size_t)grid * cross_partial_floats((int)D, (int)L) * sizeof(float);
-  KON_REQUIRE(is_u8(workspace) && (size_t)numel(workspace) >= need, KON_EWORKSPACE,
-              "workspace has %lld bytes, need %zu", (long long)numel(workspace), need);
-  float* partial = data_ptr<float>(workspace);
-  const size_t smem = ((size_t)L * D + 2 * (size_t)kCrossWarps * D + 2 * kCrossWarps * kCrossMaxL) *
+  const int sms = sm_count_of(dev);
+  const CrossWs l = cross_ws_layout(B, (int)D, (int)L, sms);
+  KON_REQUIRE(is_u8(workspace) && (size_t)numel(workspace) >= l.total, KON_EWORKSPACE,
+              "workspace has %lld bytes, need %zu", (long long)numel(workspace), l.total);
+  char* ws = data_ptr<char>(workspace);
+  KON_REQUIRE(((uintptr_t)ws & 15u) == 0, KON_EINVAL, "workspace must be 16-B aligned");
+  float* u = (float*)(ws + l.u);
+  float* pm = (float*)(ws + l.pm);
+  float* pcg = (float*)(ws + l.pcg);
+  float* pt = (float*)(ws + l.pt);
+  float* red = (float*)(ws + l.red);
+  const int g1 = cross_grid1(B, sms), g2 = cross_grid2(B, sms);
+  const int Dp = cross_nj(D) * 128;
+  const size_t smem = ((size_t)L * Dp + kCrossMaxL + kCrossWarps * kCrossMaxL + (size_t)kCrossWarps * Dp) *
                       sizeof(float);
+  const int vx = cross_vec(data_ptr<float>(x0), stride_of(x0, 0));
+  const int vg = cross_vec(data_ptr<float>(g), stride_of(g, 0));
+  const int vdx = cross_vec(data_ptr<float>(dx0), D);
 #define CALL(N)                                                                                  \
   KON_CUDA(cudaFuncSetAttribute(cross_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)smem));                                                     \
-  cross_bwd_kernel<N><<<grid, kCrossThreads, smem, st>>>(                                        \
+  cross_bwd_kernel<N><<<g1, kCrossThreads, smem, st>>>(                                          \
       data_ptr<float>(x0), stride_of(x0, 0), data_ptr<float>(w), data_ptr<float>(s),             \
-      data_ptr<float>(g), stride_of(g, 0), data_ptr<float>(dx0), partial, B, (int)D, (int)L)
+      data_ptr<float>(g), stride_of(g, 0), data_ptr<float>(dx0), u, pcg, pt, B, (int)D, (int)L,  \
+      vx, vg, vdx)
   KON_CROSS_DISPATCH(D, CALL);
 #undef CALL
   KON_LAUNCH_CHECK("cross_bwd_kernel");
-  cross_bwd_finalize_kernel<<<(int)((D + 255) / 256), 256, 0, st>>>(
-      partial, grid, data_ptr<float>(w), data_ptr<float>(b), data_ptr<float>(dw),
-      data_ptr<float>(db), (int)D, (int)L);
+  cross_dw_kernel<<<g2, kCrossThreads, 0, st>>>(data_ptr<float>(x0), stride_of(x0, 0), u, pm, B, (int)D,
+                                                (int)L, vx);
+  KON_LAUNCH_CHECK("cross_dw_kernel");
+  cross_reduce_kernel<<<dim3((unsigned)((D + 31) / 32), (unsigned)(L + 2)), 256, 0, st>>>(pm, g2, pcg, pt, g1,
+                                                                                       red, (int)D, (int)L);
+  KON_LAUNCH_CHECK("cross_reduce_kernel");
+  cross_bwd_finalize_kernel<<<(int)((D + 255) / 256), 256, 0, st>>>(red, data_ptr<float>(w), data_ptr<float>(b),
+                                                                    data_ptr<float>(dw), data_ptr<float>(db),
+                                                                    (int)D, (int)L);
   KON_LAUNCH_CHECK("cross_bwd_finalize_kernel");
   return KON_OK;
 }

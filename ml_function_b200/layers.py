@@ -220,6 +220,12 @@ class FmLayer(nn.Module):
         lin = lin.reshape(lin.shape[0], -1)                # only the sum over fields enters the result
         return ops.fm(v, lin).unsqueeze(1)
 
+    def on_concat(self, xcat, lin, F: int, k: int):
+        """Same result for ``cross_embed = xcat[:, :F*k]`` (the model's concat buffer, a11), with the
+        gradient of ``xcat`` produced in one piece."""
+        lin = None if lin is None else lin.reshape(lin.shape[0], -1)
+        return ops.fm_xcat(xcat, lin, F, k).unsqueeze(1)
+
 
 # --------------------------------------------------------------------------------------
 # a7  CrossLayer (IL:250-282)
@@ -500,11 +506,14 @@ class MergeScoreLayer(nn.Module):
         self.kernel, self.bias = nn.Parameter(kernel.clone()), nn.Parameter(bias.clone())
 
     def logits(self, inputs):
-        if self.use_merge:
-            inputs = torch.cat([t.reshape(t.shape[0], -1) for t in inputs], dim=-1)
+        parts = [t.reshape(t.shape[0], -1) for t in inputs] if self.use_merge else [inputs.reshape(inputs.shape[0], -1)]
+        d = sum(t.shape[1] for t in parts)
         if isinstance(self.kernel, nn.UninitializedParameter):
-            self.build(inputs.shape[-1], inputs.device)
-        return torch.addmm(self.bias, inputs, self.kernel)
+            self.build(d, parts[0].device)
+        x1, x2 = parts[0], (parts[1] if len(parts) == 2 else None)
+        if len(parts) <= 2 and x1.is_cuda and ops.head_supported(x1, x2, self.kernel):
+            return ops.head(x1, x2, self.kernel, self.bias)        # both inputs read in place: no Concatenate copy
+        return torch.addmm(self.bias, torch.cat(parts, dim=-1) if len(parts) > 1 else x1, self.kernel)
 
     def forward(self, inputs, **kwargs):
         return torch.softmax(self.logits(inputs), dim=-1)

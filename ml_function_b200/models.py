@@ -134,7 +134,7 @@ class DeepFM(_CtrModel):
     def forward(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
         lin = self.linear_embed.lookup_sum(ids)
-        fm_ = self.fm([v, lin])
+        fm_ = self.fm.on_concat(xcat, lin, self.F, self.k)     # = self.fm([v, lin]) on the window of xcat
         dnn_ = self.dnn(xcat)
         return self.head([fm_, dnn_])
 

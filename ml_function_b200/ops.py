@@ -273,6 +273,48 @@ class _Fm(torch.autograd.Function):
         return dv, dlin
 
 
+class _FmXcat(torch.autograd.Function):
+    """FM on the fields window of the concat buffer ``xcat [B,W]`` (columns ``[0,F*k)``): the backward
+    writes ``dv`` straight into a ``[B,W]`` gradient of ``xcat`` (strided output of kon_fm_bwd) instead of
+    autograd's slice_backward (a zero fill plus a copy of the same 109 MB)."""
+
+    @staticmethod
+    def forward(ctx, xcat, lin, F, k):
+        lib = L.lib()
+        v = xcat[:, :F * k].view(xcat.shape[0], F, k)
+        out = torch.empty((xcat.shape[0], k), dtype=xcat.dtype, device=xcat.device)
+        a, b, o = L._arg(v), L._arg(lin), L._arg(out)
+        with _prof("fm_fwd"):
+            L.check(lib.kon_fm_fwd(a.ptr, L._p(b), o.ptr, L.stream_ptr(xcat.device)), "kon_fm_fwd")
+        ctx.save_for_backward(xcat)
+        ctx.F, ctx.k = F, k
+        ctx.lin_shape = None if lin is None else lin.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        (xcat,) = ctx.saved_tensors
+        F, k = ctx.F, ctx.k
+        B, W = xcat.shape
+        g = g.contiguous()
+        gx = torch.empty((B, W), dtype=xcat.dtype, device=xcat.device)
+        if W > F * k:
+            gx[:, F * k:].zero_()
+        v = xcat[:, :F * k].view(B, F, k)
+        dv = gx[:, :F * k].view(B, F, k)
+        dlin = torch.empty(ctx.lin_shape, dtype=xcat.dtype, device=xcat.device) if ctx.lin_shape is not None else None
+        a, b, c, d = L._arg(v), L._arg(g), L._arg(dv), L._arg(dlin)
+        with _prof("fm_bwd"):
+            L.check(lib.kon_fm_bwd(a.ptr, b.ptr, c.ptr, L._p(d), L.stream_ptr(xcat.device)), "kon_fm_bwd")
+        return gx, dlin, None, None
+
+
+def fm_xcat(xcat: torch.Tensor, lin: Optional[torch.Tensor], F: int, k: int) -> torch.Tensor:
+    """FM over ``xcat[:, :F*k]`` viewed as ``[B,F,k]``; gradient delivered as a full ``[B,W]`` tensor."""
+    return _FmXcat.apply(xcat, lin, F, k)
+
+
 def fm(v: torch.Tensor, lin: Optional[torch.Tensor] = None) -> torch.Tensor:
     """v [B,F,k], lin [B,F] or None -> [B,k]  (FmLayer / InnerLayer(use_add=True))."""
     return _Fm.apply(v, lin)
@@ -449,6 +491,51 @@ def attention(x, wq, wk, wr=None, gamma=None, beta=None, use_scale=True, use_ln=
 # --------------------------------------------------------------------------- #
 # a11: the concat buffer (StackLayer without the copy)
 # --------------------------------------------------------------------------- #
+# --------------------------------------------------------------------------- #
+# skinny heads (a12): y = [x1 | x2] W + b, N in {1,2}
+# --------------------------------------------------------------------------- #
+class _Head(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, w, b):
+        lib = L.lib()
+        y = torch.empty((x1.shape[0], w.shape[1]), dtype=torch.float32, device=x1.device)
+        a = [L._arg(t) for t in (x1, x2, w, b, y)]
+        with _prof("head_fwd"):
+            L.check(lib.kon_head_fwd(*[L._p(t) for t in a], L.stream_ptr(x1.device)), "kon_head_fwd")
+        ctx.save_for_backward(x1, x2, w)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.lib()
+        x1, x2, w = ctx.saved_tensors
+        dev = x1.device
+        gy = gy.contiguous()
+        dx1 = torch.empty_like(x1, memory_format=torch.contiguous_format) if ctx.needs_input_grad[0] else None
+        dx2 = (torch.empty_like(x2, memory_format=torch.contiguous_format)
+               if (x2 is not None and ctx.needs_input_grad[1]) else None)
+        dw = torch.empty_like(w)
+        db = torch.empty(w.shape[1], dtype=torch.float32, device=dev) if ctx.has_b else None
+        ws = _ws(lib.kon_head_bwd_workspace_bytes(x1.shape[0], w.shape[0], w.shape[1], dev.index or 0), dev)
+        a = [L._arg(t) for t in (x1, x2, w, gy, dx1, dx2, dw, db, ws)]
+        with _prof("head_bwd"):
+            L.check(lib.kon_head_bwd(*[L._p(t) for t in a], L.stream_ptr(dev)), "kon_head_bwd")
+        return dx1, dx2, dw, db
+
+
+def head_supported(x1, x2, w) -> bool:
+    d = x1.shape[1] + (0 if x2 is None else x2.shape[1])
+    return (x1.dim() == 2 and x1.dtype == torch.float32 and w.dtype == torch.float32 and w.shape[1] in (1, 2)
+            and d <= 1024 and x1.stride(1) == 1
+            and (x2 is None or (x2.dim() == 2 and x2.dtype == torch.float32 and x1.shape[1] % 4 == 0 and x2.stride(1) == 1)))
+
+
+def head(x1, x2, w, b=None):
+    """``[x1 | x2] @ w + b`` for the 1- and 2-unit heads, both inputs read in place (no concat)."""
+    return _Head.apply(x1, x2, w, b)
+
+
 class _EmbedConcat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, arena, ids, field_row_offset, dense, width):

@@ -389,3 +389,60 @@ def test_attention_bf16_tensor_core(B, F, kin, H, flags):
     assert_rel(xg.grad, xd.grad, gtol, "attention bf16 dx")
     assert_rel(wg[0].grad, wd[0].grad, gtol, "attention bf16 dwq")
     assert_rel(wg[1].grad, wd[1].grad, gtol, "attention bf16 dwk")
+
+
+# ------------------------------------------------------------------ skinny heads (a12)
+@pytest.mark.parametrize("B,D1,D2,N", [(1000, 848, 64, 2), (77, 16, 64, 2), (33, 80, None, 2), (129, 48, None, 1),
+                                        (5, 7, None, 1), (64, 416, None, 2), (9, 1000, 24, 1), (300, 12, 5, 2)])
+def test_head_fwd_bwd(B, D1, D2, N):
+    """MergeScoreLayer's Dense(N) on [x1 | x2] (CL:86-100) against the fp64 oracle (keras_dense of the concat)."""
+    ops = _ops()
+    g = gen(B + D1)
+    wide = torch.randn(B, D1 + 8, generator=g)                      # x1 is a window of a wider buffer
+    x1 = wide[:, :D1]
+    x2 = torch.randn(B, D2, generator=g) if D2 else None
+    D = D1 + (D2 or 0)
+    w = torch.randn(D, N, generator=g) / D ** 0.5
+    b = torch.randn(N, generator=g)
+    gy = torch.randn(B, N, generator=g)
+    xd = [t.double().requires_grad_(True) for t in ([x1, x2] if D2 else [x1])]
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = ko.keras_dense(torch.cat(xd, 1), wd, bd)
+    (ref * gy.double()).sum().backward()
+    wide_c = wide.to(DEV)
+    x1c = wide_c[:, :D1].detach().requires_grad_(True)
+    x2c = x2.to(DEV).requires_grad_(True) if D2 else None
+    wc, bc = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    assert ops.head_supported(x1c, x2c, wc)
+    y = ops.head(x1c, x2c, wc, bc)
+    (y * gy.to(DEV)).sum().backward()
+    assert_rel(y, ref, FP32_TOL, "head fwd")
+    assert_rel(x1c.grad, xd[0].grad, FP32_TOL, "head dx1")
+    if D2:
+        assert_rel(x2c.grad, xd[1].grad, FP32_TOL, "head dx2")
+    assert_rel(wc.grad, wd.grad, FP32_TOL, "head dw")
+    assert_rel(bc.grad, bd.grad, FP32_TOL, "head db")
+    # deterministic: a second backward gives the same bits
+    wc.grad = None
+    y2 = ops.head(x1c, x2c, wc, bc)
+    g1 = torch.autograd.grad((y2 * gy.to(DEV)).sum(), wc)[0]
+    g2 = torch.autograd.grad((ops.head(x1c, x2c, wc, bc) * gy.to(DEV)).sum(), wc)[0]
+    assert torch.equal(g1, g2)
+
+
+def test_fm_on_concat_buffer_matches_fm_on_view():
+    ops = _ops()
+    g = gen(11)
+    B, F, k, W = 257, 26, 16, 432
+    xcat = torch.randn(B, W, generator=g).to(DEV)
+    lin = torch.randn(B, 1, generator=g).to(DEV)
+    gy = torch.randn(B, k, generator=g).to(DEV)
+    xa = xcat.clone().requires_grad_(True)
+    la = lin.clone().requires_grad_(True)
+    ya = ops.fm(xa[:, :F * k].view(B, F, k), la)
+    (ya * gy).sum().backward()
+    xb = xcat.clone().requires_grad_(True)
+    lb = lin.clone().requires_grad_(True)
+    yb = ops.fm_xcat(xb, lb, F, k)
+    (yb * gy).sum().backward()
+    assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad) and torch.equal(la.grad, lb.grad)
