@@ -314,6 +314,9 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("KON_BENCH_WATCHDOG"):       # debugging aid: dump every thread's stack and exit after N s
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["KON_BENCH_WATCHDOG"]), exit=True, file=sys.stderr)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")

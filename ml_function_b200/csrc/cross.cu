@@ -284,19 +284,28 @@ cross_bwd_kernel(const float* __restrict__ x0, long long xs, const float* __rest
 __global__ void __launch_bounds__(kCrossThreads)
 cross_dw_kernel(const float* __restrict__ x0, long long xs, const float* __restrict__ u,
                 float* __restrict__ partial_M, long long B, int D, int L, int vec_x) {
-  __shared__ __align__(16) float u_s[kCrossSlab * kCrossMaxL];
+  __shared__ __align__(16) float u_s[2][kCrossSlab * kCrossMaxL];
   const int tid = threadIdx.x;
   const int d0 = 4 * tid;
   float4 M[kCrossMaxL];
 #pragma unroll
   for (int l = 0; l < kCrossMaxL; ++l) M[l] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long n_slabs = (B + kCrossSlab - 1) / kCrossSlab;
-  for (long long sl = blockIdx.x; sl < n_slabs; sl += gridDim.x) {
-    const long long b0 = sl * kCrossSlab;
-    const int nb = (int)min((long long)kCrossSlab, B - b0);
-    __syncthreads();
-    u_s[tid] = (tid < nb * kCrossMaxL) ? __ldg(u + b0 * kCrossMaxL + tid) : 0.f;
-    __syncthreads();
+  // every CTA owns one contiguous, evenly sized range of samples (balanced to within one sample);
+  // the u rows of slab i+1 are staged while slab i is consumed (one barrier per slab)
+  const long long lo = B * blockIdx.x / gridDim.x, hi = B * (blockIdx.x + 1) / gridDim.x;
+  const int n_slabs = (int)((hi - lo + kCrossSlab - 1) / kCrossSlab);
+  auto stage = [&](int sl, int buf) {
+    const long long b0 = lo + (long long)sl * kCrossSlab;
+    const int nb = (int)min((long long)kCrossSlab, hi - b0);
+    u_s[buf][tid] = (tid < nb * kCrossMaxL) ? __ldg(u + b0 * kCrossMaxL + tid) : 0.f;
+  };
+  if (n_slabs > 0) stage(0, 0);
+  for (int sl = 0; sl < n_slabs; ++sl) {
+    const int buf = sl & 1;
+    __syncthreads();                     // u_s[buf] staged; everyone is done reading u_s[buf ^ 1]
+    if (sl + 1 < n_slabs) stage(sl + 1, buf ^ 1);
+    const long long b0 = lo + (long long)sl * kCrossSlab;
+    const int nb = (int)min((long long)kCrossSlab, hi - b0);
     if (d0 < D) {
 #pragma unroll 8
       for (int i = 0; i < kCrossSlab; ++i) {
@@ -312,8 +321,8 @@ cross_dw_kernel(const float* __restrict__ x0, long long xs, const float* __restr
             if (d0 + 3 < D) xv.w = __ldg(xp + d0 + 3);
           }
         }
-        const float4 ua = *reinterpret_cast<const float4*>(u_s + i * kCrossMaxL);
-        const float4 ub = *reinterpret_cast<const float4*>(u_s + i * kCrossMaxL + 4);
+        const float4 ua = *reinterpret_cast<const float4*>(&u_s[buf][i * kCrossMaxL]);
+        const float4 ub = *reinterpret_cast<const float4*>(&u_s[buf][i * kCrossMaxL + 4]);
         const float uu[kCrossMaxL] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
 #pragma unroll
         for (int l = 0; l < kCrossMaxL; ++l) {

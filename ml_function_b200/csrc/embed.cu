@@ -839,6 +839,16 @@ __global__ void pad1_kernel(const float* __restrict__ src, long long sb, long lo
   }
 }
 
+// grads [N,4] (column 0 valid) -> [N,1]; only the n_unique leading rows carry data
+__global__ void __launch_bounds__(256)
+unpad1_kernel(const float4* __restrict__ src, const int* __restrict__ n_unique, long long n,
+              float* __restrict__ dst) {
+  const long long nu = min((long long)*n_unique, n);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nu;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i].x;
+}
+
 namespace {
 // where the upstream gradient rows live: one local [B,F,dim] view, or per-rank slabs over NVLink
 struct GradSrc {
@@ -1058,9 +1068,10 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
       return fail(KON_EUNSUPPORTED, "embedding dim too large");
   }
 #undef KON_RED_CASE
-  if (dim == 1) {   // compact [N,4] -> [N,1]
-    KON_CUDA(cudaMemcpy2DAsync(data_ptr<float>(grads), 4, padded_grads, 16, 4, (size_t)n,
-                               cudaMemcpyDeviceToDevice, st));
+  if (dim == 1) {   // compact [N,4] -> [N,1]  (a 2-D memcpy with 4-byte rows takes 160 us for 1.7 M rows)
+    unpad1_kernel<<<(int)std::min<long long>((n + 255) / 256, (long long)sms * 16), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(padded_grads), a.n_unique, n, data_ptr<float>(grads));
+    KON_LAUNCH_CHECK("unpad1_kernel");
   }
   return KON_OK;
 }

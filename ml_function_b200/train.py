@@ -106,7 +106,10 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # multi-GPU: the process group's watchdog thread issues CUDA calls of its own; only THIS
+            # thread's calls may invalidate the capture
+            mode = "thread_local" if self.dist is not None else "global"
+            with torch.cuda.graph(g, capture_error_mode=mode):
                 self._static_loss = self.step(*self._static)
             self._g = g
             return True
