@@ -442,7 +442,7 @@ def run_gpu(args):
     # ---- the same step replayed from a CUDA graph (kernel stats above come from the eager pass:
     # events cannot be recorded inside a capture) ------------------------------------------------
     graphed = False
-    if args.graph and (world == 1 or args.graph_multi):
+    if args.graph and (world == 1 or args.graph_multi):      # --no-graph-multi: eager steps when world_size > 1
         graphed = trainer.capture(*resident[0])
         if graphed:
             for i in range(3):
@@ -462,9 +462,9 @@ def run_gpu(args):
         if hasattr(model.sparse_embed, "close_peer"):
             model.sparse_embed.close_peer()
 
+    trainer.release_graph()
+    torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     pk = peaks()
     work = algo_work(name, B, k)
@@ -563,8 +563,23 @@ def run_gpu(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
+
+
+def shutdown_process_group():
+    """After the result line is out: tear the process group down, but never let a stuck NCCL teardown
+    turn a finished measurement into a hung job."""
+    try:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        import threading
+        t = threading.Timer(45.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         dist.destroy_process_group()
+        t.cancel()
+    except Exception as e:      # noqa: BLE001
+        print("process-group teardown:", repr(e), file=sys.stderr)
 
 
 def main():
@@ -582,7 +597,10 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="do not replay the step from a CUDA graph")
-    ap.add_argument("--graph-multi", action="store_true", help="also capture when world_size > 1 (NCCL in the graph)")
+    ap.add_argument("--no-graph-multi", dest="graph_multi", action="store_false",
+                    help="world_size > 1: do not capture the step (NCCL + peer kernels) in a CUDA graph")
+    ap.add_argument("--graph-multi", dest="graph_multi", action="store_true", help=argparse.SUPPRESS)
+    ap.set_defaults(graph_multi=True)
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at
     # stderr (NCCL / C libraries print banners straight to fd 1), and is restored for the result.
@@ -607,6 +625,7 @@ def main():
             print(l, file=sys.stderr)
     if out:
         print(out[-1], flush=True)
+    shutdown_process_group()
 
 
 if __name__ == "__main__":

@@ -119,6 +119,13 @@ class Trainer:
             torch.cuda.synchronize()
             return False
 
+    def release_graph(self):
+        """Drop the captured graph (and its private memory pool).  Call before
+        ``dist.destroy_process_group()``: a live graph that holds NCCL kernels keeps the communicator busy."""
+        self._g = None
+        self._static = None
+        self._static_loss = None
+
     def step_graph(self, dense, ids, labels) -> torch.Tensor:
         if self._g is None:
             return self.step(dense, ids, labels)
