@@ -532,6 +532,10 @@ embed_sgd_kernel(float* __restrict__ arena, const int* __restrict__ rows,
   }
 }
 
+// VEC = 4: dim % 4 == 0, one thread per 128-bit group (rows are 16-B aligned); VEC = 1: any dim.
+// 32-bit index math (n_unique * dim < 2^31 is checked by the host), shift instead of a division when
+// the groups-per-row count is a power of two.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 embed_adam_kernel(float* __restrict__ arena, float* __restrict__ m, float* __restrict__ v,
                   const int* __restrict__ rows, const float* __restrict__ grads,
@@ -541,19 +545,39 @@ embed_adam_kernel(float* __restrict__ arena, float* __restrict__ m, float* __res
     const float t = (float)(*step_dev);
     lr_t = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
   }
-  const long long total = (long long)(*n_unique) * dim;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long u = i / dim;
-    const int c = (int)(i - u * dim);
-    const long long o = (long long)rows[u] * dim + c;
-    const float wv = arena[o];
-    const float gq = grads[i] + 2.f * l2 * wv;
-    const float mn = b1 * m[o] + (1.f - b1) * gq;
-    const float vn = b2 * v[o] + (1.f - b2) * gq * gq;
-    m[o] = mn;
-    v[o] = vn;
-    arena[o] = wv - lr_t * mn / (sqrtf(vn) + eps);
+  const unsigned gpr = (unsigned)(dim / VEC);                 // groups per row
+  const int shift = (gpr & (gpr - 1)) == 0 ? __ffs(gpr) - 1 : -1;
+  const unsigned total = (unsigned)(*n_unique) * gpr;
+  const float c1 = 1.f - b1, c2 = 1.f - b2, tl2 = 2.f * l2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned u = shift >= 0 ? (i >> shift) : i / gpr;
+    const unsigned c = i - u * gpr;
+    const size_t o = (size_t)rows[u] * gpr + c;
+    if (VEC == 4) {
+      float4 wv = reinterpret_cast<float4*>(arena)[o];
+      float4 mv = reinterpret_cast<float4*>(m)[o];
+      float4 vv = reinterpret_cast<float4*>(v)[o];
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(grads) + i);
+      float* w_ = &wv.x; float* m_ = &mv.x; float* v_ = &vv.x; const float* g_ = &g4.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gq = g_[e] + tl2 * w_[e];
+        m_[e] = b1 * m_[e] + c1 * gq;
+        v_[e] = b2 * v_[e] + c2 * gq * gq;
+        w_[e] = w_[e] - lr_t * m_[e] / (sqrtf(v_[e]) + eps);
+      }
+      reinterpret_cast<float4*>(m)[o] = mv;
+      reinterpret_cast<float4*>(v)[o] = vv;
+      reinterpret_cast<float4*>(arena)[o] = wv;
+    } else {
+      const float wv = arena[o];
+      const float gq = grads[i] + tl2 * wv;
+      const float mn = b1 * m[o] + c1 * gq;
+      const float vn = b2 * v[o] + c2 * gq * gq;
+      m[o] = mn;
+      v[o] = vn;
+      arena[o] = wv - lr_t * mn / (sqrtf(vn) + eps);
+    }
   }
 }
 
@@ -1148,11 +1172,21 @@ static int embed_adam_impl(DLTensor* arena, DLTensor* m, DLTensor* v, const DLTe
   const long long total = grads->shape[0] * grads->shape[1];
   if (total == 0) return KON_OK;
   const float lr_t = lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
-  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count_of(dev) * 16);
-  embed_adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      data_ptr<float>(arena), data_ptr<float>(m), data_ptr<float>(v), data_ptr<int>(unique_rows),
-      data_ptr<float>(grads), data_ptr<int>(n_unique), (int)arena->shape[1], lr_t, beta1, beta2,
-      eps, l2, step_dev ? data_ptr<int>(step_dev) : nullptr, lr);
+  KON_REQUIRE(total < 0x7fffffffLL, KON_EUNSUPPORTED, "more than 2^31-1 elements in one sparse update");
+  const int dim_i = (int)arena->shape[1];
+  const bool vec = dim_i % 4 == 0 && aligned16(data_ptr<float>(arena)) && aligned16(data_ptr<float>(m)) &&
+                   aligned16(data_ptr<float>(v)) && aligned16(data_ptr<float>(grads));
+  const long long work = vec ? total / 4 : total;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((work + 255) / 256, (long long)sm_count_of(dev) * 16));
+#define KON_ADAM_ARGS                                                                               \
+  data_ptr<float>(arena), data_ptr<float>(m), data_ptr<float>(v), data_ptr<int>(unique_rows),       \
+      data_ptr<float>(grads), data_ptr<int>(n_unique), dim_i, lr_t, beta1, beta2, eps, l2,          \
+      step_dev ? data_ptr<int>(step_dev) : nullptr, lr
+  if (vec)
+    embed_adam_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(KON_ADAM_ARGS);
+  else
+    embed_adam_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(KON_ADAM_ARGS);
+#undef KON_ADAM_ARGS
   KON_LAUNCH_CHECK("embed_adam_kernel");
   return KON_OK;
 }

@@ -1,0 +1,170 @@
+"""-m gpu: the hot path at BASELINE.json's FULL sizes (B = 65,536, 26 Criteo-cardinality tables = 33.76 M
+rows, emb 16, CIN [200,200,200], cross width 848 x 6 layers) through properties that do not need the CPU
+oracle to finish a 65,536-sample batch:
+
+* rows are independent: any subset of rows of a full-size launch must equal the oracle on that subset;
+* the oracle's own torch code evaluated in fp64 ON THE GPU where its temporaries fit (FM, cross);
+* gather == plain indexing (bit-exact); scatter-add: sorted / unique rows, checksum of checksums, fp64
+  index_add, bit-reproducible;
+* batch additivity of weight gradients: dW(batch) == dW(first half) + dW(second half).
+"""
+import pytest
+import torch
+
+from helpers import CRITEO_ROWS, assert_rel, gen, offsets
+from oracle import kon_oracle as ko
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+B, F, K = 65536, 26, 16
+
+
+def _dgen(seed):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+@pytest.fixture(scope="module")
+def criteo():
+    g = _dgen(2020)
+    offs = offsets(CRITEO_ROWS)
+    arena = torch.randn(int(offs[-1]), K, device=DEV, generator=g)
+    ids = torch.stack([torch.randint(0, r, (B,), device=DEV, generator=g) for r in CRITEO_ROWS], 1).to(torch.int32)
+    offs_t = torch.tensor(offs[:-1], device=DEV, dtype=torch.long)
+    yield arena, ids, [int(o) for o in offs], offs_t
+    del arena
+    torch.cuda.empty_cache()
+
+
+def test_fullsize_gather_is_plain_indexing(criteo):
+    from ml_function_b200 import ops
+    arena, ids, offs, offs_t = criteo
+    out = ops.embed_fwd_raw(arena, ids, offs)
+    ref = arena[ids.long() + offs_t]                     # [B,F,K]
+    assert torch.equal(out, ref)
+    # the same rows written into the window of a concat buffer (a11)
+    xcat = torch.zeros(B, 432, device=DEV)
+    ops.embed_fwd_raw(arena, ids, offs, out=xcat[:, :F * K].view(B, F, K))
+    assert torch.equal(xcat[:, :F * K].view(B, F, K), ref) and float(xcat[:, F * K:].abs().sum()) == 0.0
+
+
+def test_fullsize_scatter_add_properties(criteo):
+    from ml_function_b200 import ops
+    arena, ids, offs, offs_t = criteo
+    g = torch.randn(B, F, K, device=DEV, generator=_dgen(7))
+    sg = ops.embed_bwd_raw(g, ids, offs, share_sort=False)
+    n = int(sg.n.item())
+    rows = sg.rows[:n].long()
+    assert bool((rows[1:] > rows[:-1]).all()), "unique rows must be strictly ascending"
+    keys = (ids.long() + offs_t).reshape(-1)
+    uniq, inv = torch.unique(keys, return_inverse=True)
+    assert n == uniq.numel() and torch.equal(rows, uniq)                                   # routing: bit-exact
+    dense = torch.zeros(n, K, device=DEV, dtype=torch.float64).index_add_(0, inv, g.reshape(-1, K).double())
+    assert_rel(sg.grads[:n], dense, 1e-6, "segment sums vs fp64 index_add")
+    assert_rel(sg.grads[:n].double().sum(0), g.double().sum((0, 1)), 1e-9, "checksum of checksums")
+    sg2 = ops.embed_bwd_raw(g, ids, offs, share_sort=False)
+    assert torch.equal(sg.grads[:n], sg2.grads[:n]) and torch.equal(sg.rows[:n], sg2.rows[:n])   # deterministic
+
+
+def test_fullsize_fm_against_fp64_oracle_on_device():
+    from ml_function_b200 import ops
+    g = _dgen(3)
+    v = torch.randn(B, F, K, device=DEV, generator=g)
+    lin = torch.randn(B, F, device=DEV, generator=g)
+    gy = torch.randn(B, K, device=DEV, generator=g)
+    vd, ld = v.double().requires_grad_(True), lin.double().requires_grad_(True)
+    ref = ko.fm_closed_form(vd, ld)
+    (ref * gy.double()).sum().backward()
+    vg, lg = v.clone().requires_grad_(True), lin.clone().requires_grad_(True)
+    y = ops.fm(vg, lg)
+    (y * gy).sum().backward()
+    assert_rel(y, ref, 1e-5, "fm fwd")
+    assert_rel(vg.grad, vd.grad, 1e-5, "fm dv")
+    assert_rel(lg.grad, ld.grad, 1e-5, "fm dlin")
+
+
+def test_fullsize_cross_against_fp64_oracle_on_device():
+    """DCN config: width 848 (= 26*32 + 13 + pad), 6 layers; x0 is the window of a wider buffer."""
+    from ml_function_b200 import ops
+    D, L = 848, 6
+    g = _dgen(4)
+    x = torch.randn(B, D, device=DEV, generator=g)
+    w = torch.randn(L, D, device=DEV, generator=g) / D ** 0.5
+    b = torch.randn(L, D, device=DEV, generator=g) * 0.1
+    gy = torch.randn(B, D, device=DEV, generator=g)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = ko.cross_layer(xd, [wd[i][:, None] for i in range(L)], [bd[i][:, None] for i in range(L)])[..., 0]
+    (ref * gy.double()).sum().backward()
+    xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y = ops.cross(xg, wg, bg)
+    (y * gy).sum().backward()
+    assert_rel(y, ref, 1e-5, "cross fwd")
+    assert_rel(xg.grad, xd.grad, 1e-5, "cross dx0")
+    assert_rel(wg.grad, wd.grad, 1e-5, "cross dw")
+    assert_rel(bg.grad, bd.grad, 1e-5, "cross db")
+
+
+def _cin_weights(seed):
+    g = gen(seed)
+    ws, bs, hp = [], [], F
+    for n in (200, 200, 200):
+        ws.append(ko.glorot_uniform((1, hp * F, n), g))
+        bs.append(torch.randn(n, generator=g) * 0.05)
+        hp = n
+    return ws, bs
+
+
+def test_fullsize_cin_bf16_sampled_rows_and_batch_additivity():
+    from ml_function_b200 import _lib as L, ops
+    ws, bs = _cin_weights(5)
+    g = _dgen(5)
+    x0 = torch.randn(B, F, K, device=DEV, generator=g) * 0.5
+    gout = torch.randn(B, 3 * K, device=DEV, generator=g)
+
+    def run(xs, gs):
+        xg = xs.clone().requires_grad_(True)
+        wg = [w[0].to(DEV).requires_grad_(True) for w in ws]
+        bg = [b.to(DEV).requires_grad_(True) for b in bs]
+        out = ops.cin(xg, wg, bg, L.KON_CIN_BF16)
+        (out * gs).sum().backward()
+        return out.detach(), xg.grad, [w.grad for w in wg], [b.grad for b in bg]
+
+    out, dx, dws, dbs = run(x0, gout)
+    idx = torch.randperm(B, generator=gen(9))[:96].to(DEV)
+    xd = x0[idx].double().cpu().requires_grad_(True)
+    ref, _ = ko.cin_closed_form(xd, [w.double() for w in ws], [b.double() for b in bs])
+    (ref * gout[idx].double().cpu()).sum().backward()
+    for l in range(3):
+        assert_rel(out[idx][:, l * K:(l + 1) * K], ref[:, l * K:(l + 1) * K], 2e-2, f"cin bf16 rows, layer {l}")
+    assert_rel(dx[idx], xd.grad, 2e-2, "cin bf16 dx0 rows")
+    h = B // 2
+    _, _, dwa, dba = run(x0[:h], gout[:h])
+    _, _, dwb, dbb = run(x0[h:], gout[h:])
+    for l in range(3):
+        assert_rel(dws[l], dwa[l].double() + dwb[l].double(), 1e-4, f"cin dW{l} batch additivity")
+        assert_rel(dbs[l], dba[l].double() + dbb[l].double(), 1e-4, f"cin dbias{l} batch additivity")
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_fullsize_attention_sampled_rows(bf16):
+    from ml_function_b200 import ops
+    H, d = 2, 8
+    g = _dgen(6)
+    x = torch.randn(B, F, K, device=DEV, generator=g)
+    wq, wk, wr = (torch.randn(K, H, d, device=DEV, generator=g) * 0.25 for _ in range(3))
+    gam = torch.rand(d, device=DEV, generator=g) + 0.5
+    bet = torch.randn(d, device=DEV, generator=g) * 0.1
+    gy = torch.randn(H, B, F, d, device=DEV, generator=g)
+    xg = x.clone().requires_grad_(True)
+    y = ops.attention(xg, wq, wk, wr, gam, bet, bf16=bf16)
+    (y * gy).sum().backward()
+    idx = torch.randperm(B, generator=gen(10))[:128].to(DEV)
+    xd = x[idx].double().requires_grad_(True)
+    atten_v, res = ko.mult_head_attention(xd, wq.double(), wk.double(), wr.double(), gam.double(), bet.double())
+    pre = ko.keras_add([res, atten_v])                   # CL:212; ReLU follows (CL:216)
+    tol = 2e-2 if bf16 else 1e-5
+    assert_rel(y[:, idx], torch.relu(pre), tol, "attention rows")
+    # gradients: a bf16 pre-activation within rounding distance of 0 flips the ReLU mask (a property of the
+    # kink, not of the kernel), so the bf16 reference gradient uses the mask the kernel's forward produced
+    ref = pre * (y[:, idx] > 0).double() if bf16 else torch.relu(pre)
+    (ref * gy[:, idx].double()).sum().backward()
+    assert_rel(xg.grad[idx], xd.grad, tol, "attention dx rows")

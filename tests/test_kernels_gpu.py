@@ -446,3 +446,45 @@ def test_fm_on_concat_buffer_matches_fm_on_view():
     yb = ops.fm_xcat(xb, lb, F, k)
     (yb * gy).sum().backward()
     assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad) and torch.equal(la.grad, lb.grad)
+
+
+# ------------------------------------------------------------------ sparse row-wise Adam (Keras 'adam' on touched rows)
+@pytest.mark.parametrize("dim", [16, 32, 1, 12, 6])
+def test_embed_adam_matches_keras_formulas(dim):
+    """kon_embed_adam / kon_embed_adam_devstep against the fp64 Keras-Adam update
+    (lr_t = lr sqrt(1-b2^t)/(1-b1^t);  w -= lr_t m / (sqrt(v) + eps);  L2 term 2*l2*w added to the gradient,
+    IL:217), applied lazily to the touched rows only; untouched rows keep their bits."""
+    ops = _ops()
+    g = gen(40 + dim)
+    R, n_buf, lr, b1, b2, eps, l2 = 5000, 900, 1e-2, 0.9, 0.999, 1e-7, 1e-3
+    w0 = torch.randn(R, dim, generator=g)
+    ref_w, ref_m, ref_v = w0.double().clone(), torch.zeros(R, dim, dtype=torch.float64), torch.zeros(R, dim, dtype=torch.float64)
+    for variant in ("host", "dev"):
+        w = w0.clone().to(DEV)
+        m, v = torch.zeros_like(w), torch.zeros_like(w)
+        rw, rm, rv = ref_w.clone(), ref_m.clone(), ref_v.clone()
+        tdev = torch.zeros(1, dtype=torch.int32, device=DEV)
+        for step in (1, 2, 3):
+            n = 700 - 100 * step
+            rows = torch.randperm(R, generator=gen(step))[:n].sort().values.to(torch.int32)
+            grads = torch.randn(n_buf, dim, generator=gen(100 + step))
+            sg = ops.SparseGrad(torch.cat([rows, torch.zeros(n_buf - n, dtype=torch.int32)]).to(DEV), grads.to(DEV),
+                                torch.tensor([n], dtype=torch.int32, device=DEV))
+            if variant == "host":
+                ops.embed_adam(w, m, v, sg, lr, b1, b2, eps, l2, step)
+            else:
+                tdev += 1
+                ops.embed_adam_devstep(w, m, v, sg, lr, b1, b2, eps, l2, tdev)
+            r = rows.long()
+            gq = grads[:n].double() + 2 * l2 * rw[r]
+            rm[r] = b1 * rm[r] + (1 - b1) * gq
+            rv[r] = b2 * rv[r] + (1 - b2) * gq * gq
+            lr_t = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+            rw[r] = rw[r] - lr_t * rm[r] / (rv[r].sqrt() + eps)
+        assert_rel(w, rw, 2e-6, f"adam w ({variant})")
+        assert_rel(m, rm, 2e-6, f"adam m ({variant})")
+        assert_rel(v, rv, 2e-6, f"adam v ({variant})")
+        touched = torch.zeros(R, dtype=torch.bool)
+        for step in (1, 2, 3):
+            touched[torch.randperm(R, generator=gen(step))[:700 - 100 * step]] = True
+        assert torch.equal(w.cpu()[~touched], w0[~touched])
