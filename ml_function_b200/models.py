@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .layers import (CIN, CrossLayer, DnnLayer, FieldList, FmLayer, MergeScoreLayer, MultHeadAttentionLayer,
+from .layers import (CIN, CrossLayer, DnnLayer, FieldList, FmLayer, InnerLayer, MergeScoreLayer, MultHeadAttentionLayer,
                      ScoreLayer, SparseEmbed, StackLayer, denseFea, pack_ids, sparseFea)
 
 
@@ -207,6 +207,38 @@ class XDeepFM(_CtrModel):
         self.dnn.load_reference_weights(ks, [p[f"dnn_b{i}"] for i in range(n)], p["dnn_logit_w"], p["dnn_logit_b"])
         self.cin.load_reference_weights([p[f"cin_w{i}"] for i in range(nc)], [p[f"cin_b{i}"] for i in range(nc)],
                                         p["cin_logit_w"], p["cin_logit_b"])
+
+
+class NFM(_CtrModel):
+    """MD:108-119 (a sibling that reuses the FM kernel).  The bi-interaction
+    ``InnerLayer(use_inner=True, use_add=True)`` is ``kon_fm_fwd/bwd`` without the linear term; the MLP
+    sees ``[dense | bi-interaction]`` (reference order, MD:113); output ``sigmoid`` ``[B,1,1]``."""
+
+    def __init__(self, inputFea: InputFeature = None, hidden_units=None):
+        super().__init__(inputFea)
+        self.hidden_units = hidden_units if hidden_units is not None else [256, 128, 64]
+        self.inner = InnerLayer(use_inner=True, use_add=True)
+        self.dnn = DnnLayer(hidden_units=self.hidden_units, output_dim=1)
+
+    def logit(self, dense_inputs, sparse_inputs):
+        ids = pack_ids(sparse_inputs)
+        v = self.sparse_embed.lookup(ids)                  # [B,F,k]
+        cross = self.inner(v)                              # [B,1,k]
+        linear = self.linear_embed.lookup_sum(ids)         # [B,1] = Add over the F first-order terms
+        parts = [cross.reshape(cross.shape[0], -1)]
+        if self.n_dense:
+            parts.insert(0, _pack_dense(dense_inputs))
+        dnn_out = self.dnn(torch.cat(parts, dim=1))        # [B,1]
+        return ScoreLayer.summed([linear.unsqueeze(1), dnn_out])      # [B,1,1]
+
+    def forward(self, dense_inputs, sparse_inputs):
+        return torch.sigmoid(self.logit(dense_inputs, sparse_inputs))
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        n = len(self.hidden_units)
+        self.dnn.load_reference_weights([p[f"dnn_w{i}"] for i in range(n)], [p[f"dnn_b{i}"] for i in range(n)],
+                                        p["dnn_logit_w"], p["dnn_logit_b"])
 
 
 class AutoInt(_CtrModel):

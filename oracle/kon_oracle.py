@@ -411,6 +411,18 @@ def model_xdeepfm(p, dense, sparse_ids, n_cin=3, n_hidden=3):
     return score_layer([linear, cin_out, dnn_out], use_add=True)  # MD:136
 
 
+def model_nfm(p, dense, sparse_ids, n_hidden=3):
+    """``NFM`` (MD:108-119): bi-interaction ``InnerLayer(use_inner=True, use_add=True)`` (MD:112) ->
+    ``StackLayer(dense + [cross])`` (MD:113) -> ``DnnLayer(output_dim=1)`` (MD:115) ->
+    ``Add(linear_embed + [dnn_fea])`` (MD:116) -> ``ScoreLayer()`` = sigmoid (MD:117).  ``[B,1,1]``."""
+    sparse, linear = _embed_lists(p, sparse_ids)
+    cross = inner_layer(sparse, use_add=True)                     # [B,1,k]
+    dnn_in = stack_layer(_dense_list(dense) + [cross])            # [B, 13 + k]
+    dnn_out = dnn_layer(dnn_in, [p[f"dnn_w{i}"] for i in range(n_hidden)],
+                        [p[f"dnn_b{i}"] for i in range(n_hidden)], p["dnn_logit_w"], p["dnn_logit_b"])
+    return score_layer(keras_add(linear + [dnn_out]))
+
+
 def model_autoint(p, dense, sparse_ids):
     """``AutoInt`` (MD:150-165): one attention block, heads flattened and
     concatenated, ``Dense(2, softmax)``."""

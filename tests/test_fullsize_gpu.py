@@ -60,7 +60,7 @@ def test_fullsize_scatter_add_properties(criteo):
     assert n == uniq.numel() and torch.equal(rows, uniq)                                   # routing: bit-exact
     dense = torch.zeros(n, K, device=DEV, dtype=torch.float64).index_add_(0, inv, g.reshape(-1, K).double())
     assert_rel(sg.grads[:n], dense, 1e-6, "segment sums vs fp64 index_add")
-    assert_rel(sg.grads[:n].double().sum(0), g.double().sum((0, 1)), 1e-9, "checksum of checksums")
+    assert_rel(sg.grads[:n].double().sum(0), g.double().sum((0, 1)), 1e-6, "checksum of checksums")   # fp32 segment sums
     sg2 = ops.embed_bwd_raw(g, ids, offs, share_sort=False)
     assert torch.equal(sg.grads[:n], sg2.grads[:n]) and torch.equal(sg.rows[:n], sg2.rows[:n])   # deterministic
 

@@ -67,6 +67,11 @@ def _params(name, rows, k, g, hidden=(24, 16, 8), conv=(10, 9, 8), heads=2, d=4,
             hp = n
         p["cin_logit_w"], p["cin_logit_b"] = ko.glorot_uniform((len(conv) * k, 1), g), torch.zeros(1)
         p["dnn_logit_w"], p["dnn_logit_b"] = ko.glorot_uniform((hidden[-1], 1), g), torch.zeros(1)
+    if name == "nfm":
+        dims = [13 + k] + list(hidden)
+        for i in range(3):
+            p[f"dnn_w{i}"] = ko.glorot_uniform((dims[i], dims[i + 1]), g)
+        p["dnn_logit_w"], p["dnn_logit_b"] = ko.glorot_uniform((hidden[-1], 1), g), torch.zeros(1)
     if name == "autoint":
         for w in ("query_w", "key_w", "res_w"):
             p[w] = ko.glorot_uniform((k, heads, d), g)
@@ -83,16 +88,17 @@ def _build(name, rows, k, p, cin_precision="fp32", hidden=(24, 16, 8), conv=(10,
     m = {"fm": lambda: KM.FM(fea), "deepfm": lambda: KM.DeepFM(fea, hidden_units=list(hidden)),
          "dcn": lambda: KM.DCN(fea, hidden_units=list(hidden), cross_hidden=3),
          "xdeepfm": lambda: KM.XDeepFM(fea, conv_size=list(conv), hidden_units=list(hidden), cin_precision=cin_precision),
+         "nfm": lambda: KM.NFM(fea, hidden_units=list(hidden)),
          "autoint": lambda: KM.AutoInt(fea, attention_dim=4, attention_head_dim=2)}[name]()
     m.load_reference_params({k_: v.to(DEV) for k_, v in p.items()})
     return m
 
 
 ORACLE = {"fm": ko.model_fm, "deepfm": ko.model_deepfm, "dcn": ko.model_dcn, "xdeepfm": ko.model_xdeepfm,
-          "autoint": ko.model_autoint}
+          "autoint": ko.model_autoint, "nfm": ko.model_nfm}
 
 
-@pytest.mark.parametrize("name", ["fm", "deepfm", "dcn", "xdeepfm", "autoint"])
+@pytest.mark.parametrize("name", ["fm", "deepfm", "dcn", "xdeepfm", "autoint", "nfm"])
 def test_model_forward_backward_matches_oracle(name):
     from ml_function_b200.models import keras_binary_crossentropy
     g = gen(11)
@@ -102,7 +108,7 @@ def test_model_forward_backward_matches_oracle(name):
     ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32)
     dense = torch.rand(B, 13, generator=g)
     y = (torch.rand(B, generator=g) < 0.3).float()
-    labels = y.view(B, 1, 1) if name == "xdeepfm" else torch.stack([1 - y, y], 1)
+    labels = y.view(B, 1, 1) if name in ("xdeepfm", "nfm") else torch.stack([1 - y, y], 1)
     # oracle in fp64 = truth; in fp32 = the reference's own arithmetic (its error sets the scale)
     p64 = {k_: v.double().requires_grad_(True) for k_, v in p.items()}
     out64 = ORACLE[name](p64, dense.double(), ids)
@@ -127,7 +133,7 @@ def test_model_forward_backward_matches_oracle(name):
     n = int(sgs[0].n.item())
     touched = torch.unique((ids.long() + torch.tensor(offs[:-1])).reshape(-1))
     assert torch.equal(sgs[0].rows[:n].cpu().long(), touched)                       # bit-exact routing
-    if name in ("fm", "deepfm", "xdeepfm"):
+    if name in ("fm", "deepfm", "xdeepfm", "nfm"):
         lg = model.linear_embed.arena.kon_sparse_grads[0].to_dense(offs[-1]).cpu()
         assert_rel(lg, torch.cat([p64[f"lin_{f}"].grad for f in range(len(rows))]), 2e-5, f"{name} linear grad")
     # a few dense weights
