@@ -456,7 +456,9 @@ def test_embed_adam_matches_keras_formulas(dim):
     IL:217), applied lazily to the touched rows only; untouched rows keep their bits."""
     ops = _ops()
     g = gen(40 + dim)
-    R, n_buf, lr, b1, b2, eps, l2 = 5000, 900, 1e-2, 0.9, 0.999, 1e-7, 1e-3
+    # the hyper-parameters reach the kernel as fp32 (as they do in Keras): 1 - fp32(0.999) differs from 1e-3 by 1.3e-5
+    R, n_buf = 5000, 900
+    lr, b1, b2, eps, l2 = (float(torch.tensor(x, dtype=torch.float32)) for x in (1e-2, 0.9, 0.999, 1e-7, 1e-3))
     w0 = torch.randn(R, dim, generator=g)
     ref_w, ref_m, ref_v = w0.double().clone(), torch.zeros(R, dim, dtype=torch.float64), torch.zeros(R, dim, dtype=torch.float64)
     for variant in ("host", "dev"):
