@@ -71,6 +71,10 @@ def algo_work(model, B, k, conv=(200, 200, 200), cross_layers=6, heads=2, d=8, k
         "attn_fwd": ("hbm", B * (F * kin * p + heads * F * d * p)),
         "attn_bwd": ("hbm", B * (2 * F * kin * p + heads * F * d * p)),
     }
+    hd = {"deepfm": k + 64, "fm": k, "dcn": W + 64, "autoint": heads * F * d}.get(model)
+    if hd:                                                     # MergeScoreLayer's Dense(2) over hd columns
+        w["head_fwd"] = ("hbm", B * (hd * p + 2 * p))
+        w["head_bwd"] = ("hbm", B * (2 * hd * p + 2 * p))
     hp, fl, per_layer = F, 0, []
     for n in conv:
         per_layer.append(2 * B * k * hp * F * n)
@@ -87,13 +91,22 @@ def algo_work(model, B, k, conv=(200, 200, 200), cross_layers=6, heads=2, d=8, k
     return w
 
 
-# library kernel -> (op whose algorithmic work it carries, share of that op's work)
+# library kernel (or kernel family bracketed by one event pair in the library) ->
+# (op whose algorithmic work it carries, share of that op's work, work is per LAUNCH rather than per step)
 KERNEL_WORK = {
-    "cin_fwd_tc_kernel": ("cin_fwd", 1.0),
-    "cin_dw_tc_kernel": ("cin_dw_gemm", 1.0),      # layers 0..L-2 (last layer: rank-1 shortcut)
-    "cin_da_tc_kernel": ("cin_da_gemm", 1.0),
-    "embed_fwd_vec_kernel": ("embed_fwd", 1.0),
-    "embed_reduce_kernel": ("embed_bwd", 1.0),
+    "cin_fwd_tc_kernel": ("cin_fwd", 1.0, False),
+    "cin_dw_tc_kernel": ("cin_dw_gemm", 1.0, False),      # layers 0..L-2 (last layer: rank-1 shortcut)
+    "cin_da_tc_kernel": ("cin_da_gemm", 1.0, False),
+    "embed_fwd_vec_kernel": ("embed_fwd", 1.0, False),
+    "embed_reduce_kernel": ("embed_bwd", 1.0, False),
+    "fm_fwd_kernel": ("fm_fwd", 1.0, True),
+    "fm_bwd_kernel": ("fm_bwd", 1.0, True),
+    "cross_fwd_kernel": ("cross_fwd", 1.0, True),
+    "cross_bwd_kernels": ("cross_bwd", 1.0, True),        # per-sample kernel + dw kernel + reduce + finalize
+    "attn_tc_fwd_kernel": ("attn_fwd", 1.0, True),        # one launch per attention layer
+    "attn_tc_bwd_kernel": ("attn_bwd", 1.0, True),
+    "head_fwd_kernel": ("head_fwd", 1.0, True),
+    "head_bwd_kernels": ("head_bwd", 1.0, True),
 }
 
 
@@ -495,20 +508,20 @@ def run_gpu(args):
     for kn, (tot_ms, n) in kprof.items():
         if n == 0:
             continue
-        op, share = KERNEL_WORK[kn]
+        op, share, per_launch = KERNEL_WORK[kn]
         if op not in work:
             continue
         bound, amount = work[op]
-        amount = amount * share                     # algorithmic work of this kernel family per step
+        lps = n / args.steps
+        amount = amount * share * (lps if per_launch else 1.0)   # algorithmic work of this kernel family per step
         per_step_ms = tot_ms / args.steps
         rate = amount / (per_step_ms * 1e-3)
         peak = pk["hbm"] if bound == "hbm" else pk["tc_sust"]
         scale = 1e9 if bound == "hbm" else 1e12
-        lps = n / args.steps
         kstats[kn] = {"bound": bound, "launches_per_step": lps, "ms_per_launch": per_step_ms / lps,
                       "work_per_launch": amount / lps, "achieved": rate / scale, "peak": peak,
                       "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": rate / scale / peak,
-                      "share_of_step": per_step_ms / (ms / args.steps)}
+                      "share_of_step": per_step_ms / (ms_eager / args.steps)}
     for kn, ms_iso in iso.items():
         op = "embed_fwd" if kn == "embed_fwd_vec_kernel" else "embed_bwd"
         amount = work[op][1]

@@ -614,6 +614,7 @@ int attn_tc_fwd(const float* x, const float* wq, const float* wk, const float* w
   const float* wr_ = p.use_res ? wr : nullptr;
   const size_t smem = (size_t)3 * p.H * KS * 64 * 4;
   const int grid = (int)std::max<long long>(1, std::min<long long>((p.B + kAtWarps - 1) / kAtWarps, (long long)sms * 6));
+  ProfileScope ps("attn_tc_fwd_kernel", st);
   switch (KS) {
     case 1: attn_tc_fwd_kernel<1><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
     case 2: attn_tc_fwd_kernel<2><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
@@ -640,6 +641,7 @@ int attn_tc_bwd(const float* x, const float* wq, const float* wk, const float* w
                                                              (long long)sms * KON_ATB_MINB));   // one resident wave
   grid = std::min(grid, max_grid);
   *grid_used = grid;
+  ProfileScope ps("attn_tc_bwd_kernel", st);
 #define KON_ATB(KS_, HT_)                                                                                   \
   do {                                                                                                      \
     KON_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KS_, HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

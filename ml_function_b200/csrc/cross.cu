@@ -307,27 +307,35 @@ cross_dw_kernel(const float* __restrict__ x0, long long xs, const float* __restr
     const long long b0 = lo + (long long)sl * kCrossSlab;
     const int nb = (int)min((long long)kCrossSlab, hi - b0);
     if (d0 < D) {
-#pragma unroll 8
-      for (int i = 0; i < kCrossSlab; ++i) {
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nb) {
-          const float* xp = x0 + (b0 + i) * xs;
-          if (vec_x && d0 + 3 < D) {
-            xv = __ldg(reinterpret_cast<const float4*>(xp + d0));
-          } else {
-            xv.x = __ldg(xp + d0);
-            if (d0 + 1 < D) xv.y = __ldg(xp + d0 + 1);
-            if (d0 + 2 < D) xv.z = __ldg(xp + d0 + 2);
-            if (d0 + 3 < D) xv.w = __ldg(xp + d0 + 3);
+      for (int i0 = 0; i0 < kCrossSlab; i0 += 8) {
+        float4 xv[8];     // 8 independent 128-bit loads in flight per thread before any of them is consumed
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = i0 + q;
+          xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nb) {
+            const float* xp = x0 + (b0 + i) * xs;
+            if (vec_x && d0 + 3 < D) {
+              xv[q] = __ldg(reinterpret_cast<const float4*>(xp + d0));
+            } else {
+              xv[q].x = __ldg(xp + d0);
+              if (d0 + 1 < D) xv[q].y = __ldg(xp + d0 + 1);
+              if (d0 + 2 < D) xv[q].z = __ldg(xp + d0 + 2);
+              if (d0 + 3 < D) xv[q].w = __ldg(xp + d0 + 3);
+            }
           }
         }
-        const float4 ua = *reinterpret_cast<const float4*>(&u_s[buf][i * kCrossMaxL]);
-        const float4 ub = *reinterpret_cast<const float4*>(&u_s[buf][i * kCrossMaxL + 4]);
-        const float uu[kCrossMaxL] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
 #pragma unroll
-        for (int l = 0; l < kCrossMaxL; ++l) {
-          M[l].x = fmaf(xv.x, uu[l], M[l].x); M[l].y = fmaf(xv.y, uu[l], M[l].y);
-          M[l].z = fmaf(xv.z, uu[l], M[l].z); M[l].w = fmaf(xv.w, uu[l], M[l].w);
+        for (int q = 0; q < 8; ++q) {
+          const int i = i0 + q;
+          const float4 ua = *reinterpret_cast<const float4*>(&u_s[buf][i * kCrossMaxL]);
+          const float4 ub = *reinterpret_cast<const float4*>(&u_s[buf][i * kCrossMaxL + 4]);
+          const float uu[kCrossMaxL] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+          for (int l = 0; l < kCrossMaxL; ++l) {
+            M[l].x = fmaf(xv[q].x, uu[l], M[l].x); M[l].y = fmaf(xv[q].y, uu[l], M[l].y);
+            M[l].z = fmaf(xv[q].z, uu[l], M[l].z); M[l].w = fmaf(xv[q].w, uu[l], M[l].w);
+          }
         }
       }
     }
@@ -497,6 +505,7 @@ extern "C" int kon_cross_fwd(const DLTensor* x0, const DLTensor* w, const DLTens
                                             (long long)sm_count_of(dev) * 2);   // = resident CTAs
   const int vin = cross_vec(data_ptr<float>(x0), stride_of(x0, 0));
   const int vout = cross_vec(data_ptr<float>(out), D);
+  ProfileScope ps("cross_fwd_kernel", st);
 #define CALL(N)                                                                                  \
   KON_CUDA(cudaFuncSetAttribute(cross_fwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)smem));                                                     \
@@ -557,6 +566,7 @@ extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTens
   const int vx = cross_vec(data_ptr<float>(x0), stride_of(x0, 0));
   const int vg = cross_vec(data_ptr<float>(g), stride_of(g, 0));
   const int vdx = cross_vec(data_ptr<float>(dx0), D);
+  ProfileScope ps("cross_bwd_kernels", st);     // per-sample kernel + dw kernel + partial reduction + finalize
 #define CALL(N)                                                                                  \
   KON_CUDA(cudaFuncSetAttribute(cross_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)smem));                                                     \

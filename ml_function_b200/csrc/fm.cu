@@ -173,6 +173,7 @@ extern "C" int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out,
   float* op = data_ptr<float>(out);
   const int sms = sm_count_of(dev);
   const bool vec = k % 4 == 0 && aligned16(vp) && aligned16(op) && sb % 4 == 0 && sf % 4 == 0;
+  ProfileScope ps("fm_fwd_kernel", st);
   if (vec) {
     const int cpr = (int)(k / 4);
     const long long total = B * cpr;
@@ -221,6 +222,7 @@ extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DL
   const int sms = sm_count_of(dev);
   const bool vec = k % 4 == 0 && k <= 128 && aligned16(vp) && aligned16(gp) && aligned16(dvp) &&
                    sb % 4 == 0 && sf % 4 == 0 && dsb % 4 == 0 && dsf % 4 == 0;
+  ProfileScope ps("fm_bwd_kernel", st);
   if (vec) {
     const int cpr = (int)(k / 4), cpr_pad = pow2_ge_i(cpr);
     const long long total = B * cpr_pad;

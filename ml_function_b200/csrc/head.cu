@@ -291,6 +291,7 @@ extern "C" int kon_head_fwd(const DLTensor* x1, const DLTensor* x2, const DLTens
   const int nj = head_nj(in.D);
   const size_t smem = (size_t)N * nj * 128 * sizeof(float);
   const int grid = head_grid(B, sm_count_of(dev));
+  ProfileScope ps("head_fwd_kernel", st);
 #define CALL(NJ, NN) \
   head_fwd_kernel<NJ, NN><<<grid, kHeadThreads, smem, st>>>(in, data_ptr<float>(w), bp, data_ptr<float>(y), B)
   KON_HEAD_DISPATCH(nj, N, CALL);
@@ -358,6 +359,7 @@ extern "C" int kon_head_bwd(const DLTensor* x1, const DLTensor* x2, const DLTens
   float* partial = data_ptr<float>(workspace);
   KON_REQUIRE(((uintptr_t)partial & 15u) == 0, KON_EINVAL, "workspace must be 16-B aligned");
   const size_t smem = ((size_t)2 * N * Dp + N) * sizeof(float);
+  ProfileScope ps("head_bwd_kernels", st);
 #define CALL(NJ, NN)                                                                                        \
   head_bwd_kernel<NJ, NN><<<grid, kHeadThreads, smem, st>>>(in, out, data_ptr<float>(w), data_ptr<float>(gy), \
                                                             partial, B)
