@@ -473,6 +473,8 @@ def run_gpu(args):
         exchange = ("fused: gather/scatter kernels store/load over NVLink peer memory (kon_embed_*_peer)"
                     if getattr(model.sparse_embed, "use_peer", False) else "NCCL all_to_all")
         if hasattr(model.sparse_embed, "close_peer"):
+            if any(px["region"].timed_out() for px in model.sparse_embed._peer.values()):
+                raise SystemExit(f"bench.py: rank {rank}: a peer barrier timed out; the measurement is void")
             model.sparse_embed.close_peer()
 
     trainer.release_graph()

@@ -108,3 +108,47 @@ def test_shard_plan_covers_every_row_once():
                 assert p.rw_fields == [] and p.identity_order
             elif world == 8:
                 assert len(p.rw_fields) == 5
+
+
+def _worker_step_cache(rank, world, port, ret):
+    """Inside a training step (ops.new_step() ... end_step()) the embedding and the first-order tables share
+    ONE ids exchange; outside a step nothing is cached (a recycled address must never hit)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ml_function_b200 import layers as KL, ops
+    from ml_function_b200 import parallel as P
+    rows = [7, 30, 5, 41]
+    info = [KL.make_sparse_fea(str(i), r, cross_unit=4) for i, r in enumerate(rows)]
+    plan = P.ShardPlan(rows, world)
+    emb = P.ShardedEmbed(info, plan, dist.group.WORLD, torch.device("cpu"), lookup_fn=None, scatter_fn=None)
+    lin = P.ShardedEmbed(info, plan, dist.group.WORLD, torch.device("cpu"), is_linear=True, lookup_fn=None, scatter_fn=None)
+    calls = {"n": 0}
+    real = P._all_to_all
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    P._all_to_all = counting
+    ids = torch.stack([torch.randint(0, r, (6,)) for r in rows], 1).to(torch.int32)
+    a = emb.exchange_ids(ids)
+    b = lin.exchange_ids(ids)
+    outside = calls["n"]
+    ops.new_step()
+    c = emb.exchange_ids(ids)
+    d = lin.exchange_ids(ids)
+    inside = calls["n"] - outside
+    ops.end_step()
+    e = emb.exchange_ids(ids)
+    after = calls["n"] - outside - inside
+    ret[rank] = (outside, inside, after, c[0] is d[0], torch.equal(a[0], c[0]) and torch.equal(a[0], e[0]), emb.use_peer)
+    dist.destroy_process_group()
+
+
+def test_ids_exchange_is_shared_within_a_step_only():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_step_cache, args=(2, 29931 + (os.getpid() % 300), ret), nprocs=2, join=True)
+    for r in range(2):
+        outside, inside, after, same_obj, same_val, use_peer = ret[r]
+        assert outside == 2 and inside == 1 and after == 1 and same_obj and same_val and not use_peer
