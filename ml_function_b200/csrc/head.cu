@@ -92,17 +92,19 @@ head_fwd_kernel(const HeadIn in, const float* __restrict__ w, const float* __res
     float acc[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[n] = 0.f;
+    float4 x[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) x[j] = head_load(in, r, 128 * j + 4 * lane);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int d0 = 128 * j + 4 * lane;
-      const float4 x = head_load(in, r, d0);
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         const float4 wv = *reinterpret_cast<const float4*>(w_s + n * Dp + d0);
-        acc[n] = fmaf(x.x, wv.x, acc[n]);
-        acc[n] = fmaf(x.y, wv.y, acc[n]);
-        acc[n] = fmaf(x.z, wv.z, acc[n]);
-        acc[n] = fmaf(x.w, wv.w, acc[n]);
+        acc[n] = fmaf(x[j].x, wv.x, acc[n]);
+        acc[n] = fmaf(x[j].y, wv.y, acc[n]);
+        acc[n] = fmaf(x[j].z, wv.z, acc[n]);
+        acc[n] = fmaf(x[j].w, wv.w, acc[n]);
       }
     }
 #pragma unroll
@@ -116,7 +118,7 @@ head_fwd_kernel(const HeadIn in, const float* __restrict__ w, const float* __res
 
 // partial layout per CTA: [N][Dp] dW (transposed) | [N] db
 template <int NJ, int N>
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kHeadThreads, 2)
 head_bwd_kernel(const HeadIn in, const HeadOut out, const float* __restrict__ w,
                 const float* __restrict__ gy, float* __restrict__ partial, long long B) {
   constexpr int Dp = NJ * 128;
@@ -140,18 +142,22 @@ head_bwd_kernel(const HeadIn in, const HeadOut out, const float* __restrict__ w,
       g[n] = __ldg(gy + r * N + n);
       db[n] += g[n];
     }
+    // all the row's loads are issued before the first store: dx may alias x as far as the compiler
+    // knows, so a store in between would serialise the remaining loads behind it
+    float4 x[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) x[j] = head_load(in, r, 128 * j + 4 * lane);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int d0 = 128 * j + 4 * lane;
-      const float4 x = head_load(in, r, d0);
       float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         const float4 wv = *reinterpret_cast<const float4*>(w_s + n * Dp + d0);
         dx.x = fmaf(g[n], wv.x, dx.x); dx.y = fmaf(g[n], wv.y, dx.y);
         dx.z = fmaf(g[n], wv.z, dx.z); dx.w = fmaf(g[n], wv.w, dx.w);
-        dw[j][n].x = fmaf(x.x, g[n], dw[j][n].x); dw[j][n].y = fmaf(x.y, g[n], dw[j][n].y);
-        dw[j][n].z = fmaf(x.z, g[n], dw[j][n].z); dw[j][n].w = fmaf(x.w, g[n], dw[j][n].w);
+        dw[j][n].x = fmaf(x[j].x, g[n], dw[j][n].x); dw[j][n].y = fmaf(x[j].y, g[n], dw[j][n].y);
+        dw[j][n].z = fmaf(x[j].z, g[n], dw[j][n].z); dw[j][n].w = fmaf(x[j].w, g[n], dw[j][n].w);
       }
       head_store(out, r, d0, dx);
     }
