@@ -107,3 +107,22 @@ def test_bench_reference_arm_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+def test_shard_plan_criteo_8_ranks():
+    """8xB200 plan for the Criteo cardinalities: contiguous table-wise blocks (3-4 fields per rank), no
+    permutation after the exchange, 100 M-row tables go row-wise (config 5)."""
+    from ml_function_b200.parallel import ShardPlan
+    from bench import CRITEO_ROWS
+    plan = ShardPlan(CRITEO_ROWS, 8)
+    assert plan.rw_fields == [] and plan.identity_order
+    sizes = [len(fs) for fs in plan.tw_of_rank]
+    assert sum(sizes) == 26 and max(sizes) - min(sizes) <= 1
+    flat = [f for fs in plan.tw_of_rank for f in fs]
+    assert flat == list(range(26))                       # contiguous blocks in field order
+    big = ShardPlan(CRITEO_ROWS + [100_000_000, 100_000_000], 8)
+    assert big.rw_fields == [26, 27] and big.identity_order
+    assert sum(big.local_rows(r, 26) for r in range(8)) == 100_000_000
+    mixed = ShardPlan([10, 60_000_000, 20], 4)
+    assert mixed.rw_fields == [1] and not mixed.identity_order and mixed.exchange_order == [0, 2, 1]
+    assert [mixed.to_global[f] for f in range(3)] == [0, 2, 1]
