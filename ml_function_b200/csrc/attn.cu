@@ -443,6 +443,7 @@ static int attn_check(const DLTensor* x, const DLTensor* wq, const DLTensor* wk,
   KON_TRY(check_cuda_tensor(wk, "wk", dev));
   KON_REQUIRE(is_f32(x) && x->ndim == 3 && is_compact(x), KON_EINVAL,
               "x must be compact float32 [B,F,kin]");
+  p->ysh = p->ysb = p->ysf = p->gsh = p->gsb = p->gsf = 0;
   p->B = x->shape[0];
   p->F = (int)x->shape[1];
   p->kin = (int)x->shape[2];
@@ -493,8 +494,14 @@ extern "C" int kon_attn_fwd(const DLTensor* x, const DLTensor* wq, const DLTenso
   const int dev = x->device.device_id;
   KON_TRY(check_cuda_tensor(y, "y", dev));
   KON_REQUIRE(is_f32(y) && y->ndim == 4 && y->shape[0] == p.H && y->shape[1] == p.B &&
-                  y->shape[2] == p.F && y->shape[3] == DH && is_compact(y),
-              KON_EINVAL, "y must be compact float32 [H,B,F,d]");
+                  y->shape[2] == p.F && y->shape[3] == DH && (DH == 1 || stride_of(y, 3) == 1),
+              KON_EINVAL, "y must be float32 [H,B,F,d] with a compact last dim");
+  KON_REQUIRE(is_compact(y) || ((flags & KON_ATTN_BF16) && stride_of(y, 0) % 2 == 0 && stride_of(y, 1) % 2 == 0 &&
+                                stride_of(y, 2) % 2 == 0 && ((uintptr_t)data_ptr<float>(y) & 7u) == 0),
+              KON_EINVAL, "a strided y (permuted window) is only taken by the KON_ATTN_BF16 path, 8-B aligned rows");
+  p.ysh = stride_of(y, 0);
+  p.ysb = stride_of(y, 1);
+  p.ysf = stride_of(y, 2);
   if (p.B == 0) return KON_OK;
   DeviceGuard guard(dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -548,8 +555,15 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
   KON_TRY(check_cuda_tensor(dwk, "dwk", dev));
   KON_TRY(check_cuda_tensor(workspace, "workspace", dev));
   KON_REQUIRE(is_f32(gy) && gy->ndim == 4 && gy->shape[0] == p.H && gy->shape[1] == p.B &&
-                  gy->shape[2] == p.F && gy->shape[3] == DH && is_compact(gy),
-              KON_EINVAL, "gy must be compact float32 [H,B,F,d]");
+                  gy->shape[2] == p.F && gy->shape[3] == DH && (DH == 1 || stride_of(gy, 3) == 1),
+              KON_EINVAL, "gy must be float32 [H,B,F,d] with a compact last dim");
+  KON_REQUIRE(is_compact(gy) || ((flags & KON_ATTN_BF16) && attn_tc_bwd_supported(p, DH) &&
+                                 stride_of(gy, 0) % 2 == 0 && stride_of(gy, 1) % 2 == 0 && stride_of(gy, 2) % 2 == 0 &&
+                                 ((uintptr_t)data_ptr<float>(gy) & 7u) == 0),
+              KON_EINVAL, "a strided gy (permuted window) is only taken by the KON_ATTN_BF16 backward, 8-B aligned rows");
+  p.gsh = stride_of(gy, 0);
+  p.gsb = stride_of(gy, 1);
+  p.gsf = stride_of(gy, 2);
   KON_REQUIRE(is_f32(dx) && numel(dx) == numel(x) && is_compact(dx), KON_EINVAL,
               "dx must be compact float32 like x");
   KON_REQUIRE(is_f32(dwq) && numel(dwq) == numel(wq) && is_compact(dwq) && is_f32(dwk) &&

@@ -9,6 +9,10 @@ struct AttnDims {
   int F, kin, H;
   int use_scale, use_ln, use_res, relu;
   float ln_eps;
+  // element strides of y / gy over (head, sample, field); the last dim (d) is compact.  Compact [H,B,F,d]
+  // unless the caller hands in a permuted window (bf16 path only): e.g. [B,F,H,d] so that the next
+  // attention layer reads [B,F,H*d] in place, or [B,H,F,d] = the flattened heads MergeScoreLayer reads.
+  long long ysh, ysb, ysf, gsh, gsb, gsf;
 };
 
 // sigmoid with the fast exponential and reciprocal (relative error ~2e-7: two orders below the 1e-5 gate)

@@ -200,7 +200,7 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
           if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
           const int row = 16 * mt + g + 8 * half;
           if (row < F)
-            *reinterpret_cast<float2*>(y + (((long long)h * p.B + b) * F + row) * 8 + 2 * t) = make_float2(v0, v1);
+            *reinterpret_cast<float2*>(y + h * p.ysh + b * p.ysb + row * p.ysf + 2 * t) = make_float2(v0, v1);
         }
       }
     }
@@ -430,7 +430,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
             if (p.use_res) { pre0 += rc[mt][2 * half]; pre1 += rc[mt][2 * half + 1]; }
             float g0 = 0.f, g1 = 0.f;
             if (row < F) {
-              const float2 gv = __ldg(reinterpret_cast<const float2*>(gy + (((long long)h * p.B + b) * F + row) * 8 + 2 * t));
+              const float2 gv = __ldg(reinterpret_cast<const float2*>(gy + h * p.gsh + b * p.gsb + row * p.gsf + 2 * t));
               g0 = (p.relu && !(pre0 > 0.f)) ? 0.f : gv.x;
               g1 = (p.relu && !(pre1 > 0.f)) ? 0.f : gv.y;
             }

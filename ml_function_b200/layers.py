@@ -359,12 +359,13 @@ class MultHeadAttentionLayer(nn.Module):
         if isinstance(self.query_w, nn.UninitializedParameter):
             self.build(x.shape[-1], x.device)
 
-    def fused_block(self, x) -> torch.Tensor:
-        """``ReLU(LN(sigmoid(QK^T/sqrt d) K) + X res_w)`` -> ``[H,B,F,d]``."""
+    def fused_block(self, x, layout: str = "hbfd") -> torch.Tensor:
+        """``ReLU(LN(sigmoid(QK^T/sqrt d) K) + X res_w)`` -> ``[H,B,F,d]`` (``layout``: memory order of the
+        result on the bf16 path, ``ops._ATTN_LAYOUTS``)."""
         self._ensure(x)
         return ops.attention(x, self.query_w, self.key_w, self.res_w, self.ln_gamma, self.ln_beta,
                              use_scale=self.use_scale, use_ln=self.use_ln, use_res=self.use_res, relu=True,
-                             bf16=self.bf16)
+                             bf16=self.bf16, layout=layout)
 
     def forward(self, inputs, mask=None, **kwargs):
         if mask is not None:
@@ -469,7 +470,7 @@ class DnnLayer(nn.Module):
     def forward(self, x, **kwargs):
         if self.other_dense is not None:                   # AutoInt wiring
             for layer in self.other_dense:
-                x = layer.fused_block(x)
+                x = layer.fused_block(x, **({"layout": kwargs["layout"]} if "layout" in kwargs else {}))
             return x
         if len(self.kernels) == 0 and self.hidden_units:
             self.build(x.shape[-1], x.device)

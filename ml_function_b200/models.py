@@ -258,9 +258,13 @@ class AutoInt(_CtrModel):
         ids = pack_ids(sparse_inputs)
         x = self.sparse_embed.lookup(ids)                  # StackLayer(use_flat=False, axis=1)
         for i, blk in enumerate(self.blocks):
-            a = blk(x)                                     # [H,B,F,d]
-            if i + 1 < len(self.blocks):
-                x = a.permute(1, 2, 0, 3).reshape(a.shape[1], a.shape[2], -1).contiguous()
+            last = i + 1 == len(self.blocks)
+            # [H,B,F,d]; on the bf16 path the kernel writes it in the order its consumer reads, so the
+            # re-packing below is a view (no permute copy, forward or backward)
+            a = blk(x, layout="bhfd" if last else "bfhd")
+            if not last:
+                x = a.permute(1, 2, 0, 3).reshape(a.shape[1], a.shape[2], -1)
+                x = x if x.is_contiguous() else x.contiguous()
         final = a.permute(1, 0, 2, 3).reshape(a.shape[1], -1)   # MD:162: heads side by side
         return self.head(final)
 

@@ -444,14 +444,27 @@ def cin(x0, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], pre
 # --------------------------------------------------------------------------- #
 # AutoInt attention (a9-a10)
 # --------------------------------------------------------------------------- #
+# Memory layouts of the attention output.  The result is always the [H,B,F,d] tensor of BL:377; with
+# "bfhd" / "bhfd" it is a permuted window of a buffer laid out [B,F,H,d] / [B,H,F,d], so that the consumer's
+# re-packing (the next attention layer reads [B,F,H*d]; MergeScoreLayer reads the heads side by side as
+# [B,H*F*d], MD:162) is a free view instead of a permute copy, forward and backward (bf16 path only).
+_ATTN_LAYOUTS = {"hbfd": None, "bfhd": (2, 0, 1, 3), "bhfd": (1, 0, 2, 3)}
+
+
 class _Attn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wq, wk, wr, gamma, beta, flags, eps):
+    def forward(ctx, x, wq, wk, wr, gamma, beta, flags, eps, layout):
         lib = L.lib()
         x, wq, wk = x.contiguous(), wq.contiguous(), wk.contiguous()
         wr = None if wr is None else wr.contiguous()
         H, d = wq.shape[1], wq.shape[2]
-        y = torch.empty((H, x.shape[0], x.shape[1], d), dtype=x.dtype, device=x.device)
+        B, F = x.shape[0], x.shape[1]
+        if layout == "bfhd":
+            y = torch.empty((B, F, H, d), dtype=x.dtype, device=x.device).permute(2, 0, 1, 3)
+        elif layout == "bhfd":
+            y = torch.empty((B, H, F, d), dtype=x.dtype, device=x.device).permute(1, 0, 2, 3)
+        else:
+            y = torch.empty((H, B, F, d), dtype=x.dtype, device=x.device)
         a = [L._arg(t) for t in (x, wq, wk, wr, gamma, beta, y)]
         with _prof("attn_fwd"):
             L.check(lib.kon_attn_fwd(*[L._p(t) for t in a], eps, flags, L.stream_ptr(x.device)), "kon_attn_fwd")
@@ -464,7 +477,11 @@ class _Attn(torch.autograd.Function):
         lib = L.lib()
         x, wq, wk, wr, gamma, beta = ctx.saved_tensors
         dev = x.device
-        gy = gy.contiguous()
+        # the bf16 backward reads gy through its strides (a permuted window of the consumer's gradient)
+        strided_ok = (ctx.flags & L.KON_ATTN_BF16) and gy.stride(-1) == 1 and x.shape[2] <= 32 and wq.shape[1] <= 4 \
+            and all(s % 2 == 0 for s in gy.stride()[:3]) and gy.data_ptr() % 8 == 0
+        if not strided_ok:
+            gy = gy.contiguous()
         dx = torch.empty_like(x)
         dwq, dwk = torch.empty_like(wq), torch.empty_like(wk)
         dwr = None if wr is None else torch.empty_like(wr)
@@ -475,17 +492,22 @@ class _Attn(torch.autograd.Function):
         a = [L._arg(t) for t in (x, wq, wk, wr, gamma, beta, gy, dx, dwq, dwk, dwr, dg, db, ws)]
         with _prof("attn_bwd"):
             L.check(lib.kon_attn_bwd(*[L._p(t) for t in a], ctx.eps, ctx.flags, L.stream_ptr(dev)), "kon_attn_bwd")
-        return dx, dwq, dwk, dwr, dg, db, None, None
+        return dx, dwq, dwk, dwr, dg, db, None, None, None
 
 
 def attention(x, wq, wk, wr=None, gamma=None, beta=None, use_scale=True, use_ln=True, use_res=True,
-              relu=True, eps: float = 1e-3, bf16: bool = False):
-    """x [B,F,kin]; w* [kin,H,d] -> [H,B,F,d] = ReLU(LN(sigmoid(QK^T/sqrt d) K) + X Wr)."""
+              relu=True, eps: float = 1e-3, bf16: bool = False, layout: str = "hbfd"):
+    """x [B,F,kin]; w* [kin,H,d] -> [H,B,F,d] = ReLU(LN(sigmoid(QK^T/sqrt d) K) + X Wr).
+    ``layout`` (bf16 path): memory order of the result, see ``_ATTN_LAYOUTS``."""
     flags = ((L.KON_ATTN_USE_SCALE if use_scale else 0) | (L.KON_ATTN_USE_LN if use_ln else 0) |
              (L.KON_ATTN_USE_RES if use_res else 0) | (L.KON_ATTN_RELU if relu else 0) |
              (L.KON_ATTN_BF16 if bf16 else 0))
+    if layout not in _ATTN_LAYOUTS:
+        raise L.KonError(f"attention layout {layout!r} not in {sorted(_ATTN_LAYOUTS)}")
+    if not bf16:
+        layout = "hbfd"
     return _Attn.apply(x, wq, wk, wr if use_res else None, gamma if use_ln else None,
-                       beta if use_ln else None, flags, eps)
+                       beta if use_ln else None, flags, eps, layout)
 
 
 # --------------------------------------------------------------------------- #

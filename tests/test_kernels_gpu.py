@@ -490,3 +490,45 @@ def test_embed_adam_matches_keras_formulas(dim):
         for step in (1, 2, 3):
             touched[torch.randperm(R, generator=gen(step))[:700 - 100 * step]] = True
         assert torch.equal(w.cpu()[~touched], w0[~touched])
+
+
+@pytest.mark.parametrize("layout", ["bfhd", "bhfd"])
+def test_attention_bf16_output_layouts_are_views_of_the_same_result(layout):
+    """The bf16 attention kernel writes [H,B,F,d] through strides: a permuted window ([B,F,H,d] for the next
+    attention layer, [B,H,F,d] for MergeScoreLayer's flattened heads) holds the same bits as the compact
+    result, and the backward reads the strided gradient in place."""
+    ops = _ops()
+    g = gen(77)
+    B, F, kin, H, d = 130, 26, 16, 2, 8
+    x = torch.randn(B, F, kin, generator=g).to(DEV)
+    wq, wk, wr = (torch.randn(kin, H, d, generator=g).mul_(0.3).to(DEV) for _ in range(3))
+    gam, bet = (torch.rand(d, generator=g) + 0.5).to(DEV), (torch.randn(d, generator=g) * 0.1).to(DEV)
+    gy = torch.randn(H, B, F, d, generator=g).to(DEV)
+
+    def run(lay):
+        xs = x.clone().requires_grad_(True)
+        ws = [w.clone().requires_grad_(True) for w in (wq, wk, wr)]
+        y = ops.attention(xs, ws[0], ws[1], ws[2], gam, bet, bf16=True, layout=lay)
+        # consume it the way the models do, so that autograd produces the strided gradient
+        if lay == "bfhd":
+            z = y.permute(1, 2, 0, 3).reshape(B, F, H * d)
+            assert z.data_ptr() == y.data_ptr() and z.is_contiguous()          # free view
+            (z * gy.permute(1, 2, 0, 3).reshape(B, F, H * d)).sum().backward()
+        elif lay == "bhfd":
+            z = y.permute(1, 0, 2, 3).reshape(B, -1)
+            assert z.data_ptr() == y.data_ptr() and z.is_contiguous()
+            (z * gy.permute(1, 0, 2, 3).reshape(B, -1)).sum().backward()
+        else:
+            (y * gy).sum().backward()
+        return y.detach().contiguous(), xs.grad, [w.grad for w in ws]
+
+    y0, dx0, dw0 = run("hbfd")
+    y1, dx1, dw1 = run(layout)
+    assert torch.equal(y0, y1) and torch.equal(dx0, dx1)
+    for a, b in zip(dw0, dw1):
+        assert torch.equal(a, b)
+    with pytest.raises(Exception):                                               # fp32 path: compact output only
+        from ml_function_b200 import _lib as L
+        ybad = torch.empty(B, F, H, d, device=DEV).permute(2, 0, 1, 3)
+        a = [L._arg(t) for t in (x, wq, wk, wr, gam, bet, ybad)]
+        L.check(L.lib().kon_attn_fwd(*[L._p(t) for t in a], 1e-3, 15, L.stream_ptr(x.device)), "kon_attn_fwd")
