@@ -399,13 +399,35 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
   }
 }
 
+// Fixed-order sum of the per-CTA partials: a CTA takes 32 outputs x 8 slices of the partial list (each
+// thread adds its slice front to back, the 8 slice sums are added in slice order) -> deterministic, and
+// pf/32 CTAs instead of the former 4 CTAs each walking all ~600 partials serially (27 us -> a few us).
 __global__ void __launch_bounds__(256)
 attn_bwd_finalize_kernel(const float* __restrict__ partial, int n_part, int pf, int wsz, int DH,
                          float* __restrict__ dwq, float* __restrict__ dwk, float* __restrict__ dwr,
                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pf; i += gridDim.x * blockDim.x) {
+  __shared__ float sm[8][32];
+  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
+  const int per = (n_part + 7) / 8;
+  const int lo = slice * per, hi = min(n_part, lo + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (i < pf) {
+    int p = lo;
+    for (; p + 3 < hi; p += 4) {
+      a0 += partial[(long long)p * pf + i];
+      a1 += partial[(long long)(p + 1) * pf + i];
+      a2 += partial[(long long)(p + 2) * pf + i];
+      a3 += partial[(long long)(p + 3) * pf + i];
+    }
+    for (; p < hi; ++p) a0 += partial[(long long)p * pf + i];
+  }
+  sm[slice][col] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (slice == 0 && i < pf) {
     float acc = 0.f;
-    for (int p = 0; p < n_part; ++p) acc += partial[(long long)p * pf + i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += sm[k][col];
     if (i < wsz) dwq[i] = acc;
     else if (i < 2 * wsz) dwk[i - wsz] = acc;
     else if (i < 3 * wsz) { if (dwr) dwr[i - 2 * wsz] = acc; }
@@ -602,7 +624,7 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
                         p.use_res ? data_ptr<float>(wr) : nullptr, p.use_ln ? data_ptr<float>(gamma) : nullptr,
                         p.use_ln ? data_ptr<float>(beta) : nullptr, data_ptr<float>(gy), data_ptr<float>(dx),
                         partial, grid, p, sm_count_of(dev), &used, st));
-    attn_bwd_finalize_kernel<<<(pf + 255) / 256, 256, 0, st>>>(partial, used, pf, p.kin * p.H * DH, DH,
+    attn_bwd_finalize_kernel<<<(pf + 31) / 32, 256, 0, st>>>(partial, used, pf, p.kin * p.H * DH, DH,
                                                               data_ptr<float>(dwq), data_ptr<float>(dwk), dwr_p,
                                                               dg_p, db_p);
     KON_LAUNCH_CHECK("attn_bwd_finalize_kernel");
@@ -619,7 +641,7 @@ extern "C" int kon_attn_bwd(const DLTensor* x, const DLTensor* wq, const DLTenso
   KON_ATTN_DISPATCH(DH, CALL)
 #undef CALL
   KON_LAUNCH_CHECK("attn_bwd_kernel");
-  attn_bwd_finalize_kernel<<<(pf + 255) / 256, 256, 0, st>>>(
+  attn_bwd_finalize_kernel<<<(pf + 31) / 32, 256, 0, st>>>(
       partial, grid32, pf, p.kin * p.H * DH, DH, data_ptr<float>(dwq), data_ptr<float>(dwk), dwr_p,
       dg_p, db_p);
   KON_LAUNCH_CHECK("attn_bwd_finalize_kernel");
