@@ -119,6 +119,12 @@ int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids, const int64_
                         int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                         DLTensor* workspace, void* stream);
 
+/* Routing only (key build, radix sort, run-head scan) into the front of `workspace`; the routing depends on
+ * the ids alone, so a trainer can run it on a side stream at the start of the step and call
+ * kon_embed_bwd_reuse (or kon_embed_bwd_peer with reuse_sort = 1) with the same workspace in the backward. */
+int kon_embed_sort(const DLTensor* ids, const int64_t* field_row_offset, int32_t n_fields,
+                   DLTensor* workspace, void* stream);
+
 /* Sparse row-wise SGD on the arena: w[r] -= lr * (g + 2*l2*w[r]) for the n_unique rows
  * (the L2 term is the reference's embeddings_regularizer, IL:217, applied lazily). */
 int kon_embed_sgd(DLTensor* arena, const DLTensor* unique_rows, const DLTensor* grads,

@@ -925,6 +925,19 @@ extern "C" int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids,
                         stream);
 }
 
+// Routing only: builds the (arena row, position) keys, sorts them and scans the run heads into the front
+// of `workspace`, where kon_embed_bwd_reuse / kon_embed_bwd_peer(reuse_sort = 1) pick them up.  The routing
+// depends on the ids alone, so a trainer runs it on a side stream at the START of the step, off the
+// critical path of the backward.
+extern "C" int kon_embed_sort(const DLTensor* ids, const int64_t* field_row_offset, int32_t n_fields,
+                              DLTensor* workspace, void* stream) {
+  KON_TRY(check_cuda_tensor(ids, "ids"));
+  GradSrc src;
+  src.dim = 4;
+  src.device = ids->device.device_id;
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, nullptr, nullptr, nullptr, workspace, 2, stream);
+}
+
 // Sharded backward over peer memory: the owner of the tables reads the gradient row of sample b
 // from the gradient buffer of rank b / rows_per_peer while it reduces the sorted segments.
 extern "C" int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers,
@@ -965,9 +978,12 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   IdsView v;
   FieldTable ft;
   KON_TRY(parse_common(ids, field_row_offset, n_fields, dev, &v, &ft));
-  KON_TRY(check_cuda_tensor(unique_rows, "unique_rows", dev));
-  KON_TRY(check_cuda_tensor(grads, "grads", dev));
-  KON_TRY(check_cuda_tensor(n_unique, "n_unique", dev));
+  const bool sort_only = reuse_sort == 2;     // kon_embed_sort: routing only (keys, radix sort, run-head scan)
+  if (!sort_only) {
+    KON_TRY(check_cuda_tensor(unique_rows, "unique_rows", dev));
+    KON_TRY(check_cuda_tensor(grads, "grads", dev));
+    KON_TRY(check_cuda_tensor(n_unique, "n_unique", dev));
+  }
   KON_TRY(check_cuda_tensor(workspace, "workspace", dev));
   const int64_t dim = src.dim;
   KON_REQUIRE(dim % 4 == 0 || dim == 1, KON_EUNSUPPORTED,
@@ -976,16 +992,18 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   KON_REQUIRE(n <= 0x7fffffffLL, KON_EUNSUPPORTED, "more than 2^31-1 lookups per call");
   const int64_t total_rows = ft.off[n_fields];
   KON_REQUIRE(total_rows < 0xffffffffLL, KON_EUNSUPPORTED, "arena with >= 2^32-1 rows");
-  KON_REQUIRE(is_i32(unique_rows) && numel(unique_rows) >= n && is_compact(unique_rows),
-              KON_EINVAL, "unique_rows must be compact int32 [>=N]");
-  KON_REQUIRE(is_f32(grads) && grads->ndim == 2 && grads->shape[0] >= n && grads->shape[1] == dim &&
-                  is_compact(grads),
-              KON_EINVAL, "grads must be compact float32 [>=N,dim]");
-  KON_REQUIRE(is_i32(n_unique) && numel(n_unique) >= 1, KON_EINVAL, "n_unique must be int32[1]");
+  if (!sort_only) {
+    KON_REQUIRE(is_i32(unique_rows) && numel(unique_rows) >= n && is_compact(unique_rows),
+                KON_EINVAL, "unique_rows must be compact int32 [>=N]");
+    KON_REQUIRE(is_f32(grads) && grads->ndim == 2 && grads->shape[0] >= n && grads->shape[1] == dim &&
+                    is_compact(grads),
+                KON_EINVAL, "grads must be compact float32 [>=N,dim]");
+    KON_REQUIRE(is_i32(n_unique) && numel(n_unique) >= 1, KON_EINVAL, "n_unique must be int32[1]");
+  }
   DeviceGuard guard(dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n == 0) {
-    KON_CUDA(cudaMemsetAsync(data_ptr<int>(n_unique), 0, 4, st));
+    if (!sort_only) KON_CUDA(cudaMemsetAsync(data_ptr<int>(n_unique), 0, 4, st));
     return KON_OK;
   }
   const int rdim = dim == 1 ? 4 : (int)dim;   // row width seen by the reduce kernels
@@ -1013,7 +1031,7 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   while (end_bit < 32 && (total_rows >> end_bit) != 0) ++end_bit;
 
   const int kgrid = (int)std::min<long long>((n + 255) / 256, (long long)sms * 16);
-  if (!reuse_sort) {
+  if (reuse_sort != 1) {
   if (v.i64)
     embed_keys_kernel<long long><<<kgrid, 256, 0, st>>>(data_ptr<long long>(ids), ft, (int)v.F,
                                                         (int)v.L, n, sentinel, keys_in, vals_in);
@@ -1031,7 +1049,8 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   cub_bytes = l.cub_bytes;
   auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), RunHead{keys_out});
   KON_CUDA(cub::DeviceScan::InclusiveSum(ws + l.cub, cub_bytes, it, segidx, (int)n, st));
-  }   // !reuse_sort
+  }   // reuse_sort != 1
+  if (sort_only) return KON_OK;
 
   BwdArgs a;
   a.d_out = src.p;

@@ -97,8 +97,16 @@ _SHARE_SORT = False      # only inside new_step() ... end_step(): the ids tensor
 _STEP_CACHE = {}         # other per-step results keyed the same way (parallel.py: the exchanged ids)
 
 
+def _join_side_streams():
+    # a routing sort nobody consumed (forward-only step): rejoin, so that no side-stream work outlives the step
+    for key, ev in list(_SORT_EVENTS.items()):
+        torch.cuda.current_stream().wait_event(ev)
+    _SORT_EVENTS.clear()
+
+
 def new_step():
     global _SHARE_SORT
+    _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
     _SHARE_SORT = True
@@ -106,6 +114,7 @@ def new_step():
 
 def end_step():
     global _SHARE_SORT
+    _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
     _SHARE_SORT = False
@@ -121,12 +130,57 @@ def _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort):
     cached = _SORT_CACHE.get(key) if share_sort else None
     need = lib.kon_embed_bwd_workspace_bytes(n, dim)
     if cached is not None and cached.numel() >= need:
+        ev = _SORT_EVENTS.pop(key, None)
+        if ev is not None:               # routed on the side stream: join it once
+            torch.cuda.current_stream(dev).wait_event(ev)
         return cached, True
     # sized for the widest payload seen in practice plus the dim-1 path, so a later call can reuse it
     ws = _ws(max(need, lib.kon_embed_bwd_workspace_bytes(n, 1), lib.kon_embed_bwd_workspace_bytes(n, 32)), dev)
     if share_sort:
         _SORT_CACHE[key] = ws
     return ws, False
+
+
+# The routing of the backward (keys, radix sort, run-head scan: ~0.14 ms of latency-bound launches for 1.7 M
+# lookups) depends on the ids alone.  Inside a training step it is therefore issued at the START of the step on
+# a side stream (kon_embed_sort), overlapped with the forward / interaction kernels; the backward waits on its
+# event and runs only the segmented reduction (kon_embed_bwd_reuse).  KON_PRESORT=0 keeps it in the backward.
+_SIDE_STREAMS = {}
+_SORT_EVENTS = {}
+PRESORT = __import__("os").environ.get("KON_PRESORT", "1") != "0"
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
+def embed_presort(ids, field_row_offset: Sequence[int]):
+    """Start the routing sort for ``ids`` on the side stream (no-op outside new_step() ... end_step(), or when
+    the same ids / offsets were already routed in this step)."""
+    if not (_SHARE_SORT and PRESORT) or not ids.is_cuda or ids.numel() == 0:
+        return
+    lib = L.lib()
+    n = ids.numel()
+    key = (ids.data_ptr(), ids._version, tuple(field_row_offset), n)
+    if key in _SORT_CACHE:
+        return
+    dev = ids.device
+    ws = _ws(max(lib.kon_embed_bwd_workspace_bytes(n, 1), lib.kon_embed_bwd_workspace_bytes(n, 32)), dev)
+    cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    side.wait_stream(cur)                    # the ids (H2D copy, exchange) are produced on the current stream
+    offs = L.i64_array(list(field_row_offset))
+    a, w = L._arg(ids), L._arg(ws)
+    with torch.cuda.stream(side):
+        L.check(lib.kon_embed_sort(a.ptr, offs, ids.shape[1], w.ptr, side.cuda_stream), "kon_embed_sort")
+        ev = torch.cuda.Event()
+        ev.record(side)
+    # no record_stream needed: `ws` (held by _SORT_CACHE) and `ids` (saved for the backward) stay alive until
+    # the side stream has been joined back into the current stream (wait_event in the backward / end_step)
+    _SORT_CACHE[key] = ws
+    _SORT_EVENTS[key] = ev
 
 
 def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None) -> SparseGrad:
@@ -188,6 +242,8 @@ def embed_bwd_peer(peer_d_out, n_peers: int, rows_per_peer: int, stride_b: int, 
 class _EmbedLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, arena, ids, field_row_offset, sum_fields):
+        if arena.requires_grad:
+            embed_presort(ids, field_row_offset)
         out = embed_fwd_raw(arena.detach(), ids, field_row_offset, sum_fields)
         ctx.save_for_backward(ids)
         ctx.arena = arena
@@ -566,6 +622,8 @@ class _EmbedConcat(torch.autograd.Function):
         Fk = F * dim
         nd = 0 if dense is None else dense.shape[1]
         assert width % 4 == 0 and width >= Fk + nd
+        if arena.requires_grad:
+            embed_presort(ids, field_row_offset)
         xcat = torch.empty((B, width), dtype=arena.dtype, device=arena.device)
         embed_fwd_raw(arena.detach(), ids, field_row_offset, False, out=xcat[:, :Fk].view(B, F, dim))
         if nd:

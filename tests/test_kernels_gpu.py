@@ -532,3 +532,41 @@ def test_attention_bf16_output_layouts_are_views_of_the_same_result(layout):
         ybad = torch.empty(B, F, H, d, device=DEV).permute(2, 0, 1, 3)
         a = [L._arg(t) for t in (x, wq, wk, wr, gam, bet, ybad)]
         L.check(L.lib().kon_attn_fwd(*[L._p(t) for t in a], 1e-3, 15, L.stream_ptr(x.device)), "kon_attn_fwd")
+
+
+def test_embed_presort_on_side_stream_matches_inline_sort():
+    """Inside a step the routing sort runs on a side stream at lookup time (kon_embed_sort) and the backward
+    reuses it: same unique rows, same bits, for the embedding and the first-order tables."""
+    ops = _ops()
+    g = gen(21)
+    rows = [3, 900, 17, 1, 50000]
+    B, dim = 777, 16
+    offs = offsets(rows)
+    ids = make_ids(B, rows, g).to(DEV)
+    arena = torch.nn.Parameter(torch.cat(make_tables(rows, dim, g)).to(DEV))
+    larena = torch.nn.Parameter(torch.cat(make_tables(rows, 1, g)).to(DEV))
+    gy = torch.randn(B, len(rows), dim, generator=g).to(DEV)
+    gl = torch.randn(B, 1, generator=g).to(DEV)
+
+    def run(in_step):
+        for p in (arena, larena):
+            p.kon_sparse_grads = []
+        if in_step:
+            ops.new_step()
+        v = ops.embed_lookup(arena, ids, offs)
+        lin = ops.embed_lookup(larena, ids, offs, True)
+        if in_step:
+            assert len(ops._SORT_EVENTS) == 1 and len(ops._SORT_CACHE) == 1     # one routing sort, on the side stream
+        ((v * gy).sum() + (lin * gl).sum()).backward()
+        if in_step:
+            assert len(ops._SORT_EVENTS) == 0                                     # joined by the first backward
+            ops.end_step()
+        torch.cuda.synchronize()
+        return arena.kon_sparse_grads[0], larena.kon_sparse_grads[0]
+
+    a16, a1 = run(False)
+    b16, b1 = run(True)
+    for x, y in ((a16, b16), (a1, b1)):
+        n = int(x.n.item())
+        assert n == int(y.n.item())
+        assert torch.equal(x.rows[:n], y.rows[:n]) and torch.equal(x.grads[:n], y.grads[:n])
