@@ -104,12 +104,18 @@ def _join_side_streams():
     _SORT_EVENTS.clear()
 
 
-def new_step():
-    global _SHARE_SORT
+_STEP_PRESORT = True
+
+
+def new_step(presort: bool = True):
+    """``presort=False``: keep the routing sort in the backward (steps dominated by the persistent tcgen05 CIN
+    kernels: sort kernels co-scheduled with them cost more than they hide, 9.95 -> 10.11 ms measured)."""
+    global _SHARE_SORT, _STEP_PRESORT
     _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
     _SHARE_SORT = True
+    _STEP_PRESORT = presort
 
 
 def end_step():
@@ -160,7 +166,7 @@ def _side_stream(dev):
 def embed_presort(ids, field_row_offset: Sequence[int]):
     """Start the routing sort for ``ids`` on the side stream (no-op outside new_step() ... end_step(), or when
     the same ids / offsets were already routed in this step)."""
-    if not (_SHARE_SORT and PRESORT) or not ids.is_cuda or ids.numel() == 0:
+    if not (_SHARE_SORT and PRESORT and _STEP_PRESORT) or not ids.is_cuda or ids.numel() == 0:
         return
     lib = L.lib()
     n = ids.numel()

@@ -55,6 +55,9 @@ class Trainer:
             if emb is not None:
                 self.sparse_opts.append(SparseAdam(emb.arena, lr=lr, l2=emb.emb_reg))
         self.is_sigmoid = isinstance(model, XDeepFM)
+        # routing sort of the embedding backward on a side stream at lookup time -- except next to the
+        # persistent tcgen05 CIN kernels, which lose more to the co-scheduled sort kernels than the overlap hides
+        self.presort = not isinstance(model, XDeepFM)
         self._g = None
         self.capture_error = None
 
@@ -73,7 +76,7 @@ class Trainer:
         ``[B,1]`` for XDeepFM's sigmoid head.  Returns the (device) loss."""
         for so in self.sparse_opts:
             so.arena.kon_sparse_grads = []
-        ops.new_step()
+        ops.new_step(presort=self.presort)
         loss = self.loss(dense, ids, labels)
         self._ensure_dense_opt()
         self.dense_opt.zero_grad(set_to_none=True)
