@@ -281,11 +281,8 @@ class _PeerLookup(torch.autograd.Function):
         k = arena.shape[1]
         ids_tw, ids_rw = sh.exchange_ids(ids_local)      # NCCL, 4 B per lookup; also orders this step's
         px = sh.peer_buffers(B_l, width)                 # peer stores after every rank's previous step
-        if arena.requires_grad:                          # routing sorts of the backward: side stream, off the critical path
-            if ids_tw.shape[1]:
-                ops.embed_presort(ids_tw, sh.tw_offs)
-            if ids_rw.shape[1]:
-                ops.embed_presort(ids_rw, sh.rw_offs)
+        # (the side-stream routing sort of ops.embed_presort is a single-GPU optimisation for now: it has not
+        # been measured next to the NCCL / peer traffic of the sharded step)
         xcat, region = px["xcat"], px["region"]
         n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
         if n_tw:
