@@ -138,3 +138,33 @@ def test_oracle_models_run_and_shapes():
     p["dnn_logit_w"], p["dnn_logit_b"] = torch.randn(5, 1, generator=g), torch.zeros(1)
     out = ko.model_xdeepfm(p, dense, ids)
     assert out.shape == (B, 1, 1) and float(out.min()) > 0 and float(out.max()) < 1
+
+
+def test_nfm_op_mirror_equals_closed_form():
+    """NFM (MD:108-119): the 325-product bi-interaction ``InnerLayer(use_add=True)`` equals
+    ``0.5((sum v)^2 - sum v^2)``; the rest is Dense/ReLU and a Keras Add with rank expansion."""
+    g = gen(31)
+    rows, k, B = [7, 30, 5, 11], 6, 19
+    p = {}
+    for f, r in enumerate(rows):
+        p[f"emb_{f}"] = torch.randn(r, k, generator=g, dtype=torch.float64)
+        p[f"lin_{f}"] = torch.randn(r, 1, generator=g, dtype=torch.float64)
+    dims = [13 + k, 9, 7, 5]
+    for i in range(3):
+        p[f"dnn_w{i}"] = torch.randn(dims[i], dims[i + 1], generator=g, dtype=torch.float64) * 0.3
+        p[f"dnn_b{i}"] = torch.randn(dims[i + 1], generator=g, dtype=torch.float64) * 0.1
+    p["dnn_logit_w"] = torch.randn(5, 1, generator=g, dtype=torch.float64)
+    p["dnn_logit_b"] = torch.randn(1, generator=g, dtype=torch.float64)
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1)
+    dense = torch.rand(B, 13, generator=g, dtype=torch.float64)
+    out = ko.model_nfm(p, dense, ids)
+    assert out.shape == (B, 1, 1)
+    v = torch.stack([p[f"emb_{f}"][ids[:, f]] for f in range(len(rows))], 1)           # [B,F,k]
+    bi = 0.5 * (v.sum(1) ** 2 - (v * v).sum(1))
+    x = torch.cat([dense, bi], 1)
+    for i in range(3):
+        x = torch.relu(x @ p[f"dnn_w{i}"] + p[f"dnn_b{i}"])
+    logit = x @ p["dnn_logit_w"] + p["dnn_logit_b"]
+    lin = sum(p[f"lin_{f}"][ids[:, f]] for f in range(len(rows)))                       # [B,1]
+    ref = torch.sigmoid(lin + logit).view(B, 1, 1)
+    assert rel_err(out, ref) < 1e-12
