@@ -16,6 +16,7 @@ namespace kon {
 // ----------------------------------------------------------------------------------
 char* tls_error_buf();                       // defined in abi.cu
 constexpr int kErrLen = 512;
+constexpr int kMaxPeers = 16;                 // ranks of one NVLink domain a peer table can address (8e)
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;

@@ -52,7 +52,6 @@ struct FieldTable {
 // Sharded embeddings over NVLink peer memory: the batch axis of `out` / `d_out` is
 // split in `rows`-sample slabs, slab q living in the memory of rank q (base[q], mapped into this
 // process with cudaIpcOpenMemHandle).  n == 0: the ordinary single-buffer call.
-constexpr int kMaxPeers = 16;
 struct PeerTable {
   float* base[kMaxPeers];
   long long rows;       // samples per peer slab

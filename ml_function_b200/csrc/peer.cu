@@ -19,7 +19,6 @@
 namespace kon {
 namespace {
 
-constexpr int kMaxPeers = 16;
 // flag block layout (uint32 words): [0,16) arrival slots, 16 epoch, 17 error
 constexpr int kEpochWord = 16;
 constexpr int kErrorWord = 17;

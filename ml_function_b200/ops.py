@@ -6,6 +6,7 @@ inputs that are not CUDA tensors raise ``KonError`` from the library's own check
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -153,7 +154,7 @@ def _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort):
 # event and runs only the segmented reduction (kon_embed_bwd_reuse).  KON_PRESORT=0 keeps it in the backward.
 _SIDE_STREAMS = {}
 _SORT_EVENTS = {}
-PRESORT = __import__("os").environ.get("KON_PRESORT", "1") != "0"
+PRESORT = os.environ.get("KON_PRESORT", "1") != "0"
 
 
 def _side_stream(dev):
