@@ -548,7 +548,7 @@ def run_gpu(args):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     # CPU baseline on rank 0, bounded sample
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N=1 only
         sb = CPU_SAMPLE_B[name]
         v, s_step, cores = cpu_arm(name, sb, args.cpu_steps, 1)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
