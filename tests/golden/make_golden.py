@@ -75,6 +75,27 @@ def main():
     out["attn_x"], out["attn_wq"], out["attn_wk"], out["attn_wr"] = xa.numpy(), wq.numpy(), wk.numpy(), wr.numpy()
     out["attn_gamma"], out["attn_beta"] = gam.numpy(), bet.numpy()
     out["attn_out"] = ko.autoint_block(xa, wq, wk, wr, gam, bet).numpy()
+    # 2-unit head over two inputs (MergeScoreLayer, CL:86-100) and NFM end to end (MD:108-119); appended after
+    # the original draws, so every earlier array keeps its bits
+    x1, x2 = torch.randn(B, 12, generator=g), torch.randn(B, 5, generator=g)
+    hw, hb = torch.randn(17, 2, generator=g) * 0.3, torch.randn(2, generator=g) * 0.1
+    out["head_x1"], out["head_x2"], out["head_w"], out["head_b"] = x1.numpy(), x2.numpy(), hw.numpy(), hb.numpy()
+    out["head_logits"] = ko.keras_dense(torch.cat([x1, x2], 1), hw, hb).numpy()
+    out["head_softmax"] = ko.merge_score_layer([x1, x2], hw, hb).numpy()
+    p = {}
+    for f in range(3):
+        p[f"emb_{f}"], p[f"lin_{f}"] = tables[f], lins[f]
+    dims = [13 + k, 10, 6, 4]
+    for i in range(3):
+        p[f"dnn_w{i}"] = torch.randn(dims[i], dims[i + 1], generator=g) * 0.3
+        p[f"dnn_b{i}"] = torch.randn(dims[i + 1], generator=g) * 0.1
+    p["dnn_logit_w"], p["dnn_logit_b"] = torch.randn(4, 1, generator=g) * 0.5, torch.zeros(1)
+    dense = torch.rand(B, 13, generator=g)
+    out["nfm_dense"] = dense.numpy()
+    for i in range(3):
+        out[f"nfm_dnn_w{i}"], out[f"nfm_dnn_b{i}"] = p[f"dnn_w{i}"].numpy(), p[f"dnn_b{i}"].numpy()
+    out["nfm_logit_w"] = p["dnn_logit_w"].numpy()
+    out["nfm_out"] = ko.model_nfm(p, dense, ids).numpy()
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kon_golden.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -168,3 +168,23 @@ def test_nfm_op_mirror_equals_closed_form():
     lin = sum(p[f"lin_{f}"][ids[:, f]] for f in range(len(rows)))                       # [B,1]
     ref = torch.sigmoid(lin + logit).view(B, 1, 1)
     assert rel_err(out, ref) < 1e-12
+
+
+def test_golden_head_and_nfm():
+    """Frozen vectors of the 2-unit head (MergeScoreLayer, CL:86-100) and of NFM end to end (MD:108-119)."""
+    x1, x2, w, b = _t("head_x1"), _t("head_x2"), _t("head_w"), _t("head_b")
+    logits = ko.keras_dense(torch.cat([x1, x2], 1), w, b)
+    assert torch.equal(logits, _t("head_logits"))
+    assert torch.equal(ko.merge_score_layer([x1, x2], w, b), _t("head_softmax"))
+    assert rel_err(torch.softmax(logits.double(), -1), _t("head_softmax").double()) < 1e-6
+    rows = GOLD["emb_rows"].tolist()
+    offs = np.concatenate([[0], np.cumsum(rows)])
+    p = {}
+    for f in range(3):
+        p[f"emb_{f}"] = _t("emb_tables")[offs[f]:offs[f + 1]]
+        p[f"lin_{f}"] = _t("emb_lins")[offs[f]:offs[f + 1]]
+    for i in range(3):
+        p[f"dnn_w{i}"], p[f"dnn_b{i}"] = _t(f"nfm_dnn_w{i}"), _t(f"nfm_dnn_b{i}")
+    p["dnn_logit_w"], p["dnn_logit_b"] = _t("nfm_logit_w"), torch.zeros(1)
+    out = ko.model_nfm(p, _t("nfm_dense"), _t("emb_ids"))
+    assert torch.equal(out, _t("nfm_out"))
