@@ -188,3 +188,41 @@ def test_golden_head_and_nfm():
     p["dnn_logit_w"], p["dnn_logit_b"] = _t("nfm_logit_w"), torch.zeros(1)
     out = ko.model_nfm(p, _t("nfm_dense"), _t("emb_ids"))
     assert torch.equal(out, _t("nfm_out"))
+
+
+# ------------------------------------------------------------------ plain-C restatement (oracle/kon_oracle_c.c)
+def test_c_oracle_agrees_with_torch_oracle_and_golden():
+    """An independent plain-C restatement of the byte-exact parts (gather, gradient routing + segment sums in
+    sample order) and of the fp32 op order of FmLayer / CrossLayer must reproduce the torch oracle's bits
+    (gather, routing, FM) resp. its values to fp32 rounding (cross: the MatMul's summation order is a BLAS detail),
+    and the committed golden vectors."""
+    from oracle import c_oracle as co
+    rows = GOLD["emb_rows"].tolist()
+    offs = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    assert np.array_equal(co.embed_gather(GOLD["emb_tables"], offs, GOLD["emb_ids"]), GOLD["emb_out"])
+    ur, ug = co.embed_grad(offs, GOLD["emb_ids"], GOLD["emb_dout"])
+    assert np.array_equal(ur, GOLD["emb_unique_rows"]) and np.array_equal(ug, GOLD["emb_grads"])
+    lin = np.stack([GOLD["emb_lins"][offs[f] + GOLD["emb_ids"][:, f], 0] for f in range(3)], 1)
+    assert np.array_equal(co.fm(GOLD["emb_out"], lin), GOLD["fm_out"])              # reference op order, bit for bit
+    got = co.cross(GOLD["cross_x"], GOLD["cross_w"][..., 0], GOLD["cross_b"][..., 0])
+    assert rel_err(torch.from_numpy(got), _t("cross_out")[..., 0]) < 2e-6
+    # a larger random case incl. heavy duplicates and the 26-field / 325-pair FM
+    g = gen(5)
+    rows = [3, 40, 1, 1000, 7] + [11] * 21
+    offs = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    B, k = 301, 16
+    tabs = [torch.randn(r, k, generator=g) for r in rows]
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32)
+    emb = ko.sparse_embed([ids[:, f:f + 1] for f in range(26)], tabs, use_flatten=False)
+    v = torch.cat(emb, 1)
+    assert np.array_equal(co.embed_gather(torch.cat(tabs).numpy(), offs, ids.numpy()), v.numpy())
+    lins = [torch.randn(B, 1, 1, generator=g) for _ in range(26)]
+    ref = ko.fm_layer(emb, lins)[:, 0]
+    assert np.array_equal(co.fm(v.numpy(), torch.cat(lins, 1)[..., 0].numpy()), ref.numpy())
+    d_out = torch.randn(B, 26, k, generator=g)
+    ur, ug = co.embed_grad(offs, ids.numpy(), d_out.numpy())
+    eu, eg = [], []
+    for f in range(26):
+        u, gr = ko.embedding_grad(ids[:, f].numpy(), d_out[:, f].numpy(), rows[f])
+        eu.append(u + offs[f]); eg.append(gr)
+    assert np.array_equal(ur, np.concatenate(eu)) and np.array_equal(ug, np.concatenate(eg))
