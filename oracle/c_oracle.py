@@ -33,6 +33,10 @@ def lib():
         L.kon_c_fm.restype = None
         L.kon_c_cross.argtypes = [f32p, f32p, f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, f32p]
         L.kon_c_cross.restype = None
+        L.kon_c_cin.argtypes = [f32p, f32p, f32p, i32p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, f32p]
+        L.kon_c_cin.restype = None
+        L.kon_c_autoint_block.argtypes = [f32p] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 4 + [f32p]
+        L.kon_c_autoint_block.restype = None
         _lib = L
     return _lib
 
@@ -87,3 +91,28 @@ def cross(x0, w, b):
     lib().kon_c_cross(_p(x0, ctypes.c_float), _p(w, ctypes.c_float), _p(b, ctypes.c_float), B, D, w.shape[0],
                       _p(out, ctypes.c_float))
     return out
+
+
+def cin(x0, weights, biases):
+    """x0 [B,m,D]; weights[l] [H_{l-1}*m, H_l]; biases[l] [H_l] -> pooled [B, L*D]."""
+    x0 = _f32(x0)
+    B, m, D = x0.shape
+    hs = np.array([w.shape[1] for w in weights], dtype=np.int32)
+    w = _f32(np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights]))
+    b = _f32(np.concatenate([np.asarray(x, dtype=np.float32).reshape(-1) for x in biases]))
+    out = np.empty((B, len(weights) * D), dtype=np.float32)
+    lib().kon_c_cin(_p(x0, ctypes.c_float), _p(w, ctypes.c_float), _p(b, ctypes.c_float), _p(hs, ctypes.c_int32),
+                    len(weights), B, m, D, _p(out, ctypes.c_float))
+    return out
+
+
+def autoint_block(x, wq, wk, wr, gamma, beta):
+    """x [B,F,kin]; w* [kin,H,d] -> [H,B,F,d] (scaled scores, LayerNorm eps 1e-3, residual, ReLU)."""
+    x, wq, wk, wr, gamma, beta = (_f32(a) for a in (x, wq, wk, wr, gamma, beta))
+    B, F, kin = x.shape
+    H, d = wq.shape[1], wq.shape[2]
+    assert d <= 64
+    y = np.empty((H, B, F, d), dtype=np.float32)
+    lib().kon_c_autoint_block(*[_p(a, ctypes.c_float) for a in (x, wq, wk, wr, gamma, beta)], B, F, kin, H, d,
+                              _p(y, ctypes.c_float))
+    return y

@@ -88,3 +88,94 @@ void kon_c_cross(const float* x0, const float* w, const float* b, int64_t B, int
   }
   free(xl);
 }
+
+/* CIN.call (IL:310-327), per layer l:  z[b,d,o] = sum_{h,i} W_l[h*m + i, o] * pre[b,h,d] * x0[b,i,d] + bias_l[o]
+ * (outer product over the field axes per embedding coordinate d, IL:316; channel index h*m + i from the transpose
+ * + reshape at IL:317-318; Conv1D(kernel 1) = per-position Dense, IL:308), pre' = z^T (IL:320), pooled over the
+ * feature maps o (IL:322).  x0 [B,m,D]; w[l] [H_{l-1}*m, H_l] concatenated in `w`; bias concatenated in `bias`;
+ * hs[L] layer sizes; pooled [B, L*D].  Accumulation in double (the BatchMatMul / Conv1D orders are BLAS details). */
+void kon_c_cin(const float* x0, const float* w, const float* bias, const int32_t* hs, int L, int64_t B, int m, int D,
+               float* pooled) {
+  int hmax = m;
+  for (int l = 0; l < L; ++l)
+    if (hs[l] > hmax) hmax = hs[l];
+  float* pre = (float*)malloc(sizeof(float) * (size_t)hmax * D);
+  float* nxt = (float*)malloc(sizeof(float) * (size_t)hmax * D);
+  for (int64_t b = 0; b < B; ++b) {
+    const float* xb = x0 + b * m * D;
+    int H = m;
+    memcpy(pre, xb, sizeof(float) * (size_t)m * D);
+    const float* wl = w;
+    const float* bl = bias;
+    for (int l = 0; l < L; ++l) {
+      const int N = hs[l];
+      for (int d = 0; d < D; ++d) {
+        double pool = 0.0;
+        for (int o = 0; o < N; ++o) {
+          double z = 0.0;
+          for (int h = 0; h < H; ++h)
+            for (int i = 0; i < m; ++i)
+              z += (double)wl[(size_t)(h * m + i) * N + o] * (double)pre[h * D + d] * (double)xb[i * D + d];
+          const float zf = (float)(z + (double)bl[o]);
+          nxt[o * D + d] = zf;
+          pool += (double)zf;
+        }
+        pooled[b * (int64_t)L * D + (int64_t)l * D + d] = (float)pool;
+      }
+      wl += (size_t)H * m * N;
+      bl += N;
+      H = N;
+      memcpy(pre, nxt, sizeof(float) * (size_t)N * D);
+    }
+  }
+  free(pre);
+  free(nxt);
+}
+
+/* The AutoInt block: MultHeadAttentionLayer.call (BL:356-377) + ProductAttentionLayer.call (BL:292-311) wrapped by
+ * DnnLayer.call (CL:201-226):  q = X Wq, k = X Wk, v = X Wk (BL:360: key_w, value_w is never read),
+ * score = sigmoid(q k^T / sqrt(d)) (BL:296-297, 286), a = score v, LayerNorm over d (eps 1e-3, biased variance,
+ * BL:331), y = ReLU(X Wr + a) (CL:212, 216).  x [B,F,kin]; w* [kin,H,d]; y [H,B,F,d]. */
+#include <math.h>
+void kon_c_autoint_block(const float* x, const float* wq, const float* wk, const float* wr, const float* gamma,
+                         const float* beta, int64_t B, int F, int kin, int H, int d, float* y) {
+  double* q = (double*)malloc(sizeof(double) * (size_t)F * d * 3);
+  double* k = q + (size_t)F * d;
+  double* r = k + (size_t)F * d;
+  const double scale = 1.0 / sqrt((double)d);
+  for (int64_t b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h) {
+      for (int f = 0; f < F; ++f)
+        for (int e = 0; e < d; ++e) {
+          double sq = 0, sk = 0, sr = 0;
+          for (int c = 0; c < kin; ++c) {
+            const double xv = x[(b * F + f) * kin + c];
+            sq += xv * wq[(c * H + h) * d + e];
+            sk += xv * wk[(c * H + h) * d + e];
+            sr += xv * wr[(c * H + h) * d + e];
+          }
+          q[f * d + e] = sq; k[f * d + e] = sk; r[f * d + e] = sr;
+        }
+      for (int i = 0; i < F; ++i) {
+        double a[64];
+        for (int e = 0; e < d; ++e) a[e] = 0;
+        for (int j = 0; j < F; ++j) {
+          double s = 0;
+          for (int e = 0; e < d; ++e) s += q[i * d + e] * k[j * d + e];
+          const double p = 1.0 / (1.0 + exp(-s * scale));
+          for (int e = 0; e < d; ++e) a[e] += p * k[j * d + e];
+        }
+        double mean = 0, var = 0;
+        for (int e = 0; e < d; ++e) mean += a[e];
+        mean /= d;
+        for (int e = 0; e < d; ++e) var += (a[e] - mean) * (a[e] - mean);
+        var /= d;
+        const double rstd = 1.0 / sqrt(var + 1e-3);
+        for (int e = 0; e < d; ++e) {
+          const double v = (a[e] - mean) * rstd * gamma[e] + beta[e] + r[i * d + e];
+          y[(((int64_t)h * B + b) * F + i) * d + e] = (float)(v > 0 ? v : 0);
+        }
+      }
+    }
+  free(q);
+}

@@ -226,3 +226,18 @@ def test_c_oracle_agrees_with_torch_oracle_and_golden():
         u, gr = ko.embedding_grad(ids[:, f].numpy(), d_out[:, f].numpy(), rows[f])
         eu.append(u + offs[f]); eg.append(gr)
     assert np.array_equal(ur, np.concatenate(eu)) and np.array_equal(ug, np.concatenate(eg))
+
+
+def test_c_oracle_cin_and_attention_against_golden():
+    """The C restatement of CIN.call (IL:310-327) and of the AutoInt block (BL:292-311, 356-377, CL:201-226)
+    against the committed vectors (fp32 op-mirror and fp64 closed form of the torch oracle)."""
+    from oracle import c_oracle as co
+    ws = [GOLD[f"cin_w{i}"][0] for i in range(2)]
+    bs = [GOLD[f"cin_b{i}"] for i in range(2)]
+    pooled = co.cin(GOLD["cin_x0"], ws, bs)
+    assert rel_err(torch.from_numpy(pooled), _t("cin_pooled_f64")) < 2e-6
+    assert rel_err(torch.from_numpy(pooled), _t("cin_pooled")) < 1e-5
+    y = co.autoint_block(GOLD["attn_x"], GOLD["attn_wq"], GOLD["attn_wk"], GOLD["attn_wr"], GOLD["attn_gamma"],
+                         GOLD["attn_beta"])
+    assert y.shape == GOLD["attn_out"].shape
+    assert rel_err(torch.from_numpy(y), _t("attn_out")) < 1e-5
