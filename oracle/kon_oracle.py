@@ -5,14 +5,21 @@ module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs use it, and only as the checker or
 the CPU baseline -- never as the thing shipped.
 
-PARITY UNPINNED.  The reference holds no tests, golden vectors or fixtures for
-this path, its arithmetic lives in TensorFlow 2.1 (README.md:4 badge, no
-lockfile) which is not installed here nor on the GPU box, and the hot-path
-modules import lightgbm/matplotlib/gensim at import time.  The functions below
-therefore restate the reference layer code op-for-op in torch-CPU, in the
-reference's op order, one function per reference ``call``; the Keras semantics
-they assume (listed in DESIGN.md) come from the published TF-2.1 behaviour and
-cannot be checked against a running reference in this environment.
+PARITY PINNED TO THE REFERENCE'S OWN SOURCE (round 2).  The reference holds no tests,
+golden vectors or fixtures, and its arithmetic lives in TensorFlow 2.1, which is not
+installable here.  But its layer files are plain Python: ``oracle/run_reference.py``
+imports the UNMODIFIED classes from /root/reference over a minimal eager ``tensorflow``
+shim (``oracle/_ref_shim``, torch-CPU) and ``tests/golden/make_ref_golden.py`` executes
+them -- every layer of the hot path and the builders FM / DeepFM / DCN / XDeepFM /
+AutoInt / NFM / AFM end to end, forward, loss and all gradients -- into the committed
+fixtures ``tests/golden/ref_layers.npz`` / ``ref_models.npz``.
+``tests/test_ref_pinned_cpu.py`` asserts that the functions below reproduce those
+fixtures BIT FOR BIT in fp32, and (where /root/reference exists) that the fixtures are
+what the reference produces today.  What remains assumed is only what the shim itself
+supplies -- the Keras primitives listed in ``oracle/_ref_shim/README.md`` (Embedding =
+cast + gather, Add = left-to-right sum with rank expansion at axis 1, Dense / Conv1D(1)
+= matmul + bias, LayerNormalization eps 1e-3, K.dot / K.batch_dot) -- written from the
+published TF-2.1 behaviour; a running TensorFlow is still not available to check those.
 
 Short names for citations (paths under the reference repo):
   IL = kon/model/ctr_model/layer/interactive_layer/interactive_layer.py
@@ -192,17 +199,18 @@ def cin(inputs: torch.Tensor, conv_kernels: Sequence[torch.Tensor],
     from the transpose ``[1,0,3,2]`` + reshape at IL:317-318), bias ``[H_l]``.
     No activation; pooling is over the feature-map axis (IL:322) so each layer
     contributes ``[B,D]``; ``output_dim==1`` applies ``Dense(1)`` (IL:304,325)."""
-    D = inputs.shape[-1]
-    x0 = torch.stack(torch.split(inputs, 1, dim=-1), dim=0)       # IL:311  [D,B,m,1]
+    x0 = list(torch.split(inputs, 1, dim=-1))                     # IL:311  D x [B,m,1]
     pre = x0
     pooled = []
     for kern, bias in zip(conv_kernels, conv_biases):
-        z = torch.matmul(x0, pre.transpose(-1, -2))               # IL:316  [D,B,m,H]
+        # tf.matmul packs its python-list operands afresh on every iteration (IL:316), so x0's
+        # gradient reaches `inputs` as one contribution per layer, summed in layer order
+        z = torch.matmul(torch.stack(x0, dim=0), torch.stack(pre, dim=0).transpose(-1, -2))   # [D,B,m,H]
         z = z.permute(1, 0, 3, 2)                                 # IL:317  [B,D,H,m]
         z = z.reshape(-1, z.shape[1], z.shape[2] * z.shape[3])    # IL:318  [B,D,H*m]
         z = keras_conv1d_k1(z, kern, bias)                        # IL:319  [B,D,N]
         pre = z.transpose(1, 2)                                   # IL:320  [B,N,D]
-        pre = torch.stack(torch.split(pre, 1, dim=-1), dim=0)     # IL:321  [D,B,N,1]
+        pre = list(torch.split(pre, 1, dim=-1))                   # IL:321  D x [B,N,1]
         pooled.append(torch.sum(z, dim=-1))                       # IL:322  [B,D]
     output = torch.cat(pooled, dim=-1)                            # IL:323
     if return_pooled:
@@ -277,15 +285,28 @@ def mult_head_attention(x, query_w, key_w, res_w=None, ln_gamma=None, ln_beta=No
     return [atten_v, res]
 
 
-def autoint_block(x, query_w, key_w, res_w, ln_gamma, ln_beta, use_scale=True):
+def autoint_block(x, query_w, key_w, res_w, ln_gamma, ln_beta, use_scale=True, mask=None, atten_mask_mod=1):
     """What ``DnnLayer(res_unit=1, other_dense=[MultHeadAttentionLayer])`` does to
     ``x`` (CL:201-226 around BL:356-377): ``ReLU(Add([res, atten_v]))`` ->
     ``[H,B,F,d]``.  (``hidden_layer(x)`` returns ``[atten_v, res]`` which the
     loop unpacks as ``[x, ori]``; idx 0: ``res=[ori,x]``; ``Add`` fires since the
     shapes match; ``use_bn/use_ln`` of ResActivateLayer default False.)"""
     atten_v, res = mult_head_attention(x, query_w, key_w, res_w, ln_gamma, ln_beta,
-                                       use_scale=use_scale)
+                                       use_scale=use_scale, mask=mask, atten_mask_mod=atten_mask_mod)
     return torch.relu(keras_add([res, atten_v]))
+
+
+def attention_base_layer(pairs: Sequence[torch.Tensor], score_w, score_b, mlp_w, out_w, out_b):
+    """``AttentionBaseLayer.call`` (IL:359-366), AFM's pooling: ``concat(pairs, 1)`` ``[B,P,k]``;
+    ``score = relu((x @ score_w + score_b) @ mlp_w)`` ``[B,P,1]`` (``Dense(1,'relu',use_bias=False)``,
+    IL:340); ``Activation('softmax')`` normalises over the LAST axis, which has size 1, so every
+    attention weight is exactly 1 (IL:341,363) and the scoring weights receive zero gradient;
+    ``Dense(output_dim)(sum_p weight * x)``."""
+    x = torch.cat(list(pairs), dim=1)
+    score = torch.relu(torch.matmul(torch.matmul(x, score_w) + score_b, mlp_w))
+    weight = torch.softmax(score, dim=-1)
+    pooled = torch.sum(weight * x, dim=1)
+    return keras_dense(pooled, out_w, out_b)
 
 
 # --------------------------------------------------------------------------- #
@@ -421,6 +442,16 @@ def model_nfm(p, dense, sparse_ids, n_hidden=3):
     dnn_out = dnn_layer(dnn_in, [p[f"dnn_w{i}"] for i in range(n_hidden)],
                         [p[f"dnn_b{i}"] for i in range(n_hidden)], p["dnn_logit_w"], p["dnn_logit_b"])
     return score_layer(keras_add(linear + [dnn_out]))
+
+
+def model_afm(p, dense, sparse_ids):
+    """``AFM`` (MD:141-147): ``InnerLayer()`` list of pairwise products -> ``AttentionBaseLayer()`` ->
+    ``ScoreLayer(use_add=True)(linear_embed + [atten_output])`` = sigmoid ``[B,1,1]``."""
+    sparse, linear = _embed_lists(p, sparse_ids)
+    cross = inner_layer(sparse)                                   # MD:143
+    atten = attention_base_layer(cross, p["afm_score_w"], p["afm_score_b"], p["afm_mlp_w"],
+                                 p["afm_out_w"], p["afm_out_b"])  # MD:144  [B,1]
+    return score_layer(linear + [atten], use_add=True)            # MD:145
 
 
 def model_autoint(p, dense, sparse_ids):

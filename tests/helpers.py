@@ -38,3 +38,52 @@ def make_ids(B, rows, g, L=None, dtype=torch.int32):
         shape = (B,) if L is None else (B, L)
         cols.append(torch.randint(0, r, shape, generator=g))
     return torch.stack(cols, dim=1).to(dtype)   # [B,F] or [B,F,L]
+
+
+# ---- reference-pinned fixtures (tests/golden/ref_*.npz, written by tests/golden/make_ref_golden.py
+# ---- from the unmodified reference classes) -------------------------------------------------------
+import os as _os
+
+_GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+_REF_CACHE = {}
+
+
+class RefCase(dict):
+    """One case of a ref_*.npz file: ``c["in/x"]``, ``c["out/y"]``, ``c["out64/y"]``,
+    ``c["grad/..."]`` as torch tensors; ``c.w`` = {oracle weight name: tensor}."""
+
+    @property
+    def w(self):
+        return {k[2:]: v for k, v in self.items() if k.startswith("w/")}
+
+    def grads(self):
+        return {k[5:]: v for k, v in self.items() if k.startswith("grad/")}
+
+
+def ref_case(which: str, name: str) -> RefCase:
+    """which: 'layers' | 'models'."""
+    if which not in _REF_CACHE:
+        _REF_CACHE[which] = np.load(_os.path.join(_GOLDEN, "ref_%s.npz" % which))
+    z = _REF_CACHE[which]
+    pre = name + "/"
+    c = RefCase()
+    for k in z.files:
+        if k.startswith(pre):
+            c[k[len(pre):]] = torch.from_numpy(z[k])
+    assert c, "no fixture case %r in ref_%s.npz" % (name, which)
+    return c
+
+
+def cin26_weights(seed: int, m=26, hs=(200, 200, 200), D=16):
+    """The big CIN case stores only its seed: re-draw the weights exactly as
+    make_ref_golden.cin_weights does (numpy RandomState is a frozen stream)."""
+    r = np.random.RandomState(seed)
+    ws, bs, hp = [], [], m
+    for n in hs:
+        lim = (6.0 / (hp * m + n)) ** 0.5
+        ws.append(torch.from_numpy(r.uniform(-lim, lim, (1, hp * m, n)).astype(np.float32)))
+        bs.append(torch.from_numpy((r.randn(n) * 0.05).astype(np.float32)))
+        hp = n
+    lw = torch.from_numpy((r.randn(len(hs) * D, 1) * 0.2).astype(np.float32))
+    lb = torch.from_numpy((r.randn(1) * 0.1).astype(np.float32))
+    return ws, bs, lw, lb
