@@ -275,6 +275,31 @@ int kon_head_bwd(const DLTensor* x1, const DLTensor* x2, const DLTensor* w, cons
                  DLTensor* dx1, DLTensor* dx2, DLTensor* dw, DLTensor* db, DLTensor* workspace,
                  void* stream);
 
+/* ===================== 8f: callers / siblings wired from the same layer classes ================ */
+/* SeqBaseLayer.call on a materialised sequence embedding (BL:45-46: reduce_sum(input_, axis=1)) and the
+ * reduce_sum over the pair axis in AFM's AttentionBaseLayer (IL:364):
+ *   x [B,L,k] f32 (free strides on dims 0/1) -> out [B,k] = sum_l x[b,l,:], l = 0..L-1 in order.
+ * (The fused gather + pool of a sequence feature is kon_embed_fwd with [B,F,L] ids.) */
+int kon_pool_sum_fwd(const DLTensor* x, DLTensor* out, void* stream);
+
+/* InnerLayer.call with use_inner=True, use_add=False (IL:61): the un-summed list of Hadamard products
+ * [v_i * v_j for i<j] in itertools.combinations order, packed as out [B, F(F-1)/2, k]
+ * (AFM, MD:143; IPNN, IL:68-80).  v [B,F,k] f32 (free strides on dims 0/1), 2 <= F <= 64.
+ * Backward: dv[b,f,:] = sum_{j != f} g[b,pair(f,j),:] * v[b,j,:]. */
+int kon_pairs_fwd(const DLTensor* v, DLTensor* out, void* stream);
+int kon_pairs_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, void* stream);
+
+/* ProductAttentionLayer.call (BL:292-311) on explicit [q, k, v] (each [..., F, d] f32 compact, identical
+ * shapes; leading dims are batch): out = sigmoid(mask(q k^T [/ sqrt(d)])) v.
+ *   mask_mode 0: no mask;  1: score = score @ mask (BL:300-302);  2: score += mask * (-100000) (BL:303-306);
+ *   mask [F,F] f32 (the reference casts its boolean mask to float the same way).
+ * Backward recomputes the scores: dq, dk, dv like q. */
+int kon_pattn_fwd(const DLTensor* q, const DLTensor* k, const DLTensor* v, const DLTensor* mask,
+                  DLTensor* out, int32_t use_scale, int32_t mask_mode, void* stream);
+int kon_pattn_bwd(const DLTensor* q, const DLTensor* k, const DLTensor* v, const DLTensor* mask,
+                  const DLTensor* g_out, DLTensor* dq, DLTensor* dk, DLTensor* dv, int32_t use_scale,
+                  int32_t mask_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,6 +162,11 @@ def lib():
         "kon_head_fwd": (ctypes.c_int, [T] * 5 + [vp]),
         "kon_head_bwd_workspace_bytes": (sz, [i64, i32, i32, ctypes.c_int]),
         "kon_head_bwd": (ctypes.c_int, [T] * 9 + [vp]),
+        "kon_pool_sum_fwd": (ctypes.c_int, [T, T, vp]),
+        "kon_pairs_fwd": (ctypes.c_int, [T, T, vp]),
+        "kon_pairs_bwd": (ctypes.c_int, [T, T, T, vp]),
+        "kon_pattn_fwd": (ctypes.c_int, [T] * 5 + [i32, i32, vp]),
+        "kon_pattn_bwd": (ctypes.c_int, [T] * 8 + [i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)   # AttributeError here = header and library disagree
@@ -184,6 +189,7 @@ EXPORTED_SYMBOLS = (
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",
     "kon_head_fwd", "kon_head_bwd_workspace_bytes", "kon_head_bwd",
+    "kon_pool_sum_fwd", "kon_pairs_fwd", "kon_pairs_bwd", "kon_pattn_fwd", "kon_pattn_bwd",
 )
 
 

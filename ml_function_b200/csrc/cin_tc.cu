@@ -289,6 +289,139 @@ __global__ void __launch_bounds__(kFwdThreads, 1) cin_fwd_tc_kernel(const FwdArg
   if (warp == kFwdProd) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Last layer, forward.  z_L feeds nothing but reduce_sum(z, -1) (IL:322) -- there is no next layer
+// to consume it as `pre` -- so the pooled output needs no GEMM at all:
+//     pool_L[r] = sum_o (sum_c A[r,c] W[c,o] + bias[o]) = sum_h pre[r,h] * (sum_i x0[r,i] wsum[h,i]) + sum_o bias[o]
+// with wsum[h,i] = sum_o W[h*m+i, o]: a 200x26 mat-vec per row (the backward already uses the same
+// identity, cin_last_da_kernel).  HBM-bound on the 419 MB of `pre` instead of a 2.18-TFLOP GEMM, in
+// fp32 (x0 is not even rounded to bf16), and z_L^T -- 419 MB nobody reads -- is never written.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPoolTRow = 28;   // wsum rows padded to 28 floats: 16-byte aligned rows, 2 zero columns
+
+// T[h*28 + i] = sum_o W[(h*m+i)*N + o] (one warp per entry); warp 0 of block 0 also leaves sum_o bias[o]
+__global__ void __launch_bounds__(256)
+cin_fwd_wsum_kernel(const float* __restrict__ W, const float* __restrict__ bias, int C, int N, int m, int Hp8,
+                    float* __restrict__ T, float* __restrict__ bsum) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)Hp8 * kPoolTRow;
+  for (long long t = w0; t < total; t += nw) {
+    const int h = (int)(t / kPoolTRow), i = (int)(t - (long long)h * kPoolTRow);
+    const long long c = (long long)h * m + i;
+    float acc = 0.f;
+    if (i < m && c < C)
+      for (int o = lane; o < N; o += 32) acc += W[c * N + o];
+    acc = warp_sum(acc);
+    if (lane == 0) T[t] = acc;
+  }
+  if (w0 == 0) {
+    float acc = 0.f;
+    for (int o = lane; o < N; o += 32) acc += bias[o];
+    acc = warp_sum(acc);
+    if (lane == 0) *bsum = acc;
+  }
+}
+
+struct LastPoolArgs {
+  const float* x0;              // [B, m, D] fp32, batch stride x0_sb
+  long long x0_sb;
+  const unsigned short* pre;    // [B, Hp, D] bf16 bits (z^T of the layer before)
+  const float* T;               // [Hp8, 28]
+  const float* bsum;            // [1]
+  float* pooled;
+  int pooled_stride, pooled_col0;
+  long long rows;               // B*D
+  int D, Hp, Hp8;
+};
+
+__device__ __forceinline__ void pool_ffma2(float2& acc, const float2 a, const float2 b) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(rc));
+}
+
+constexpr int kPoolThreads = 256;
+constexpr int kPoolRows = 2;    // rows per thread: every shared-memory read of wsum serves two rows
+
+template <int MF>
+__global__ void __launch_bounds__(kPoolThreads, 2) cin_last_pool_kernel(const LastPoolArgs a) {
+  static_assert(MF <= kPoolTRow && MF % 2 == 0, "field count");
+  extern __shared__ __align__(16) float sT[];                  // [Hp8][28]
+  for (int i = threadIdx.x; i < a.Hp8 * kPoolTRow; i += kPoolThreads) sT[i] = a.T[i];
+  __syncthreads();
+  const float bs = *a.bsum;
+  constexpr int TILE = kPoolThreads * kPoolRows;
+  for (long long base = (long long)blockIdx.x * TILE; base < a.rows; base += (long long)gridDim.x * TILE) {
+    float2 x[kPoolRows][kPoolTRow / 2];
+    const unsigned short* prow[kPoolRows];
+    bool valid[kPoolRows];
+    long long bb[kPoolRows];
+    int dd[kPoolRows];
+#pragma unroll
+    for (int u = 0; u < kPoolRows; ++u) {
+      const long long r = base + u * kPoolThreads + threadIdx.x;
+      valid[u] = r < a.rows;
+      const long long b = valid[u] ? r / a.D : 0;
+      const int d = valid[u] ? (int)(r - b * a.D) : 0;
+      bb[u] = b;
+      dd[u] = d;
+      const float* xrow = a.x0 + b * a.x0_sb + d;              // x0[b,i,d] = xrow[i*D]
+      prow[u] = a.pre + b * (long long)a.Hp * a.D + d;         // pre[b,h,d] = prow[h*D]
+#pragma unroll
+      for (int i = 0; i < kPoolTRow / 2; ++i) {
+        x[u][i].x = (2 * i < MF && valid[u]) ? __ldg(xrow + (long long)(2 * i) * a.D) : 0.f;
+        x[u][i].y = (2 * i + 1 < MF && valid[u]) ? __ldg(xrow + (long long)(2 * i + 1) * a.D) : 0.f;
+      }
+    }
+    float acc[kPoolRows];
+    unsigned short praw[kPoolRows][8];
+#pragma unroll
+    for (int u = 0; u < kPoolRows; ++u) {
+      acc[u] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) praw[u][q] = __ldg(prow[u] + (long long)min(q, a.Hp - 1) * a.D);
+    }
+    for (int h0 = 0; h0 < a.Hp8; h0 += 8) {
+      float pv[kPoolRows][8];
+#pragma unroll
+      for (int u = 0; u < kPoolRows; ++u) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pv[u][q] = (h0 + q < a.Hp) ? bf16_to_f32(praw[u][q]) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)      // next 8 feature maps, one iteration ahead (clamped address)
+          praw[u][q] = __ldg(prow[u] + (long long)min(h0 + 8 + q, a.Hp - 1) * a.D);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4* trow = reinterpret_cast<const float4*>(sT + (h0 + q) * kPoolTRow);
+        float2 s2[kPoolRows];
+#pragma unroll
+        for (int u = 0; u < kPoolRows; ++u) s2[u] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int z = 0; z < kPoolTRow / 4; ++z) {
+          const float4 t = trow[z];                            // warp-uniform address: one broadcast read
+#pragma unroll
+          for (int u = 0; u < kPoolRows; ++u) {
+            pool_ffma2(s2[u], make_float2(t.x, t.y), x[u][2 * z]);
+            pool_ffma2(s2[u], make_float2(t.z, t.w), x[u][2 * z + 1]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kPoolRows; ++u) acc[u] = fmaf(pv[u][q], s2[u].x + s2[u].y, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPoolRows; ++u)
+      if (valid[u]) a.pooled[bb[u] * a.pooled_stride + a.pooled_col0 + dd[u]] = acc[u] + bs;
+  }
+}
+
 }  // namespace
 
 size_t cin_tc_saved_bytes(int64_t B, int m, int D, const int32_t* hs, int nl) {
@@ -326,7 +459,38 @@ int cin_tc_fwd(const float* x0, long long x0_sb, const float* const* w, const fl
     KON_LAUNCH_CHECK("cin_pack_w_fwd_kernel");
   }
   if (kFwdSets == 2) KON_CUDA(cudaMemsetAsync(pooled, 0, (size_t)B * nl * D * 4, st));
+  // last layer (nl >= 2): pooled output straight from pre and the column sums of W (cin_last_pool_kernel)
+  const bool pool_shortcut = tc_last_layer_pooled_only(nl);
   for (int l = 0; l < nl; ++l) {
+    if (pool_shortcut && l == nl - 1) {
+      const int Hp8 = (L.Hp[l] + 7) / 8 * 8;
+      float* T = reinterpret_cast<float*>(ws + L.tail_off);
+      float* bsum = T + (size_t)Hp8 * kPoolTRow;
+      cin_fwd_wsum_kernel<<<(int)std::min<long long>(((long long)Hp8 * kPoolTRow * 32 + 255) / 256, (long long)sms * 8),
+                            256, 0, st>>>(w[l], bias[l], L.Hp[l] * m, L.N[l], m, Hp8, T, bsum);
+      KON_LAUNCH_CHECK("cin_fwd_wsum_kernel");
+      LastPoolArgs z;
+      z.x0 = x0;
+      z.x0_sb = x0_sb;
+      z.pre = reinterpret_cast<const unsigned short*>(sv + L.zt_off[l - 1]);
+      z.T = T;
+      z.bsum = bsum;
+      z.pooled = pooled;
+      z.pooled_stride = nl * D;
+      z.pooled_col0 = l * D;
+      z.rows = rows;
+      z.D = D;
+      z.Hp = L.Hp[l];
+      z.Hp8 = Hp8;
+      const long long tiles = (rows + kPoolThreads * kPoolRows - 1) / (kPoolThreads * kPoolRows);
+      const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);
+      {
+        ProfileScope ps("cin_last_pool_kernel", st);
+        cin_last_pool_kernel<26><<<grid, kPoolThreads, (size_t)Hp8 * kPoolTRow * 4, st>>>(z);
+      }
+      KON_LAUNCH_CHECK("cin_last_pool_kernel");
+      continue;
+    }
     FwdArgs a;
     a.x0 = x0;
     a.x0_sb = x0_sb;

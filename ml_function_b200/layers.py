@@ -149,13 +149,24 @@ class SparseEmbed(nn.Module):
     def forward(self, inputs, **kwargs):
         ids = pack_ids(inputs)
         if self.use_add:                                   # IL:233-234 (input_length 1)
+            if ids.dim() == 3 and ids.shape[2] > 1:
+                raise L.KonError("SparseEmbed(use_add=True) with input_length > 1 is not provided")
             out = ops.embed_lookup(self.arena, ids, self.field_row_offset, True)   # [B,dim]
             return out if self.use_flatten else out.unsqueeze(1)
         if ids.dim() == 3 and ids.shape[2] > 1:
-            # sequence features: the reference returns [B,L,dim] per field and pools later
-            # (SeqBaseLayer); the fused gather+pool is SeqBaseLayer.fused / lookup().
-            raise L.KonError("SparseEmbed.forward with input_length>1: use lookup() (fused bag-sum, "
-                             "BL:46) -- the un-pooled [B,L,dim] tensor is never materialised")
+            # sequence features (DP:74): the reference returns the un-pooled [B,L,dim] per field (and the
+            # Embedding masks) and pools later in SeqBaseLayer.  Same gather kernel, one row per (b,l,f):
+            # the ids are re-laid as [B*L, F] so that the output is one [B,L,F,dim] buffer whose per-field
+            # slices are the reference's tensors.  (Gather + pool in ONE pass: SeqBaseLayer.fused / lookup().)
+            B, F, L_ = ids.shape
+            ids_blf = ids.permute(0, 2, 1).reshape(B * L_, F).contiguous()
+            seq = ops.embed_lookup(self.arena, ids_blf, self.field_row_offset, False).view(B, L_, F, self.dim)
+            fl = FieldList(seq[:, :, f].reshape(B, L_ * self.dim) if self.use_flatten else seq[:, :, f]
+                           for f in range(F))
+            fl.packed_seq = seq
+            if self.mask_zero:                             # IL:238-242: Embedding.compute_mask = (ids != 0)
+                return fl, [ids[:, f] != 0 for f in range(F)]
+            return fl
         packed = self.lookup(ids)
         fl = FieldList.of(packed, flatten=self.use_flatten)
         if self.mask_zero:                                 # IL:238-242: (embeds, masks)
@@ -179,8 +190,21 @@ class SeqBaseLayer(nn.Module):
         return FieldList.of(embed.lookup(pack_ids(ids)))
 
     def forward(self, inputs, mask=None):
-        raise L.KonError("SeqBaseLayer.forward on materialised [B,L,k] tensors is not provided: "
-                         "call SeqBaseLayer.fused(embed_layer, ids) (gather+sum in one pass)")
+        """BL:45-46 on materialised tensors: ``[expand_dims(reduce_sum(x, 1), 1) for x in inputs]``, summed in
+        order l = 0..L-1 by ``kon_pool_sum_fwd``.  A list that came out of ``SparseEmbed`` is pooled in one
+        launch over its packed ``[B,L,F,k]`` buffer.  Padding id 0 still contributes row 0, as in the
+        reference (the mask is only forwarded, BL:48-51)."""
+        seq = getattr(inputs, "packed_seq", None)
+        if seq is not None:
+            B, L_, F, k = seq.shape
+            pooled = ops.pool_sum(seq.view(B, L_, F * k)).view(B, F, k)
+            return FieldList.of(pooled)
+        if isinstance(inputs, torch.Tensor):
+            inputs = [inputs]
+        return [ops.pool_sum(x).unsqueeze(1) for x in inputs]
+
+    def compute_mask(self, pre_mask, mask=None):
+        return pre_mask if self.mask_zero else None
 
 
 # --------------------------------------------------------------------------------------
@@ -197,10 +221,17 @@ class InnerLayer(nn.Module):
         self.use_inner, self.mod, self.seed, self.perm, self.use_add = use_inner, mod, seed, perm, use_add
 
     def forward(self, inputs, **kwargs):
-        if not (self.use_inner and self.use_add):
-            raise L.KonError("InnerLayer: only use_inner=True, use_add=True is on the B200 hot path")
+        if not self.use_inner:
+            raise L.KonError("InnerLayer(use_inner=False) is broken in the reference itself (self.dot is "
+                             "commented out at IL:56 but used at IL:63) and is not provided")
         v = pack_fields(inputs)
-        return ops.fm(v, None).unsqueeze(1)                # [B,1,k]
+        if self.use_add:
+            return ops.fm(v, None).unsqueeze(1)            # [B,1,k] = Add(pairwise products)
+        # IL:61: the list of F(F-1)/2 products [B,1,k] (AFM / IPNN input), views of one packed [B,P,k] buffer
+        P = ops.pairs(v)
+        fl = FieldList.of(P)
+        fl.source_fields = v
+        return fl
 
 
 class FmLayer(nn.Module):
@@ -268,11 +299,18 @@ class CIN(nn.Module):
     per-layer pools) or ``[B, n_layers*D]``.  ``precision``: ``"fp32"`` (CUDA-core parity
     mode, 1e-5) or ``"bf16"`` (tcgen05 tensor cores, fp32 accumulate, 2e-2)."""
 
-    def __init__(self, conv_size=None, output_dim=1, precision="bf16", seed=2020):
+    def __init__(self, conv_size=None, output_dim=1, precision="auto", seed=2020):
         super().__init__()
         self.conv_size = list(conv_size) if conv_size is not None else [200, 200, 200]
         self.output_dim = output_dim
-        self.precision = {"fp32": L.KON_CIN_FP32, "bf16": L.KON_CIN_BF16}[precision]
+        # "auto" (default): the bf16 tcgen05 path where its kernels cover the shape (26 fields, embedding
+        # dim a multiple of 16, layer sizes <= 208), else the fp32 kernels -- so a default-constructed layer
+        # works for every feature spec the reference accepts (e.g. sparse_fea_deal's cross_unit=8).
+        # "bf16" / "fp32" force one path (bf16 raises KonError on shapes it does not cover).
+        if precision not in ("auto", "fp32", "bf16"):
+            raise ValueError("CIN precision must be 'auto', 'fp32' or 'bf16'")
+        self.precision_mode = precision
+        self.precision = {"fp32": L.KON_CIN_FP32, "bf16": L.KON_CIN_BF16, "auto": None}[precision]
         self.seed = seed
         self.conv_kernels = nn.ParameterList()             # Keras Conv1D kernels [1,C,N]
         self.conv_biases = nn.ParameterList()
@@ -307,6 +345,10 @@ class CIN(nn.Module):
         m, D = fields if fields is not None else (inputs.shape[1], inputs.shape[2])
         if len(self.conv_kernels) == 0:
             self.build(m, D, inputs.device)
+        if self.precision is None:
+            sizes = [int(k.shape[-1]) for k in self.conv_kernels]
+            ok = m == 26 and D % 16 == 0 and all(1 <= n <= 208 for n in sizes)
+            self.precision = L.KON_CIN_BF16 if ok else L.KON_CIN_FP32
         pooled = ops.cin(inputs, [k[0] for k in self.conv_kernels], list(self.conv_biases), self.precision,
                          fields=fields)
         if self.output_dim == 1:
@@ -317,6 +359,21 @@ class CIN(nn.Module):
 # --------------------------------------------------------------------------------------
 # a9-a10  ProductAttentionLayer (BL:272-311), MultHeadAttentionLayer (BL:313-380)
 # --------------------------------------------------------------------------------------
+class ProductAttentionLayer(nn.Module):
+    """BL:278.  ``[q, k, v]`` (each ``[..., F, d]``) -> ``sigmoid(mask(q k^T [/ sqrt d])) v`` (the attribute the
+    reference calls ``softmax`` is a sigmoid, BL:286).  ``mask_mod`` 1: ``score @ float(mask)``; 2:
+    ``score + float(mask) * -1e5`` (BL:299-306); ``mask`` is a ``[F,F]`` tensor shared by all samples (what
+    SeqFM builds, MD:282-289)."""
+
+    def __init__(self, use_scale=False, supports_masking=True, mask_mod=1):
+        super().__init__()
+        self.use_scale, self.supports_masking, self.mask_mod = use_scale, supports_masking, mask_mod
+
+    def forward(self, inputs, mask=None, **kwargs):
+        q, k, v = inputs
+        return ops.product_attention(q, k, v, mask=mask, use_scale=self.use_scale, mask_mode=self.mask_mod)
+
+
 class MultHeadAttentionLayer(nn.Module):
     """BL:318.  ``x [B,F,k_in]`` -> ``[atten_v, res]``, both ``[H,B,F,d]`` (BL:377).
     ``attention_head_dim`` is the number of heads H, ``attention_dim`` the per-head width d
@@ -333,6 +390,7 @@ class MultHeadAttentionLayer(nn.Module):
         self.attention_dim, self.attention_head_dim = attention_dim, attention_head_dim
         self.seed, self.use_scale, self.use_res, self.use_ln = seed, use_scale, use_res, use_ln
         self.head_concat, self.atten_mask_mod = head_concat, atten_mask_mod
+        self.attention_cal = ProductAttentionLayer(use_scale=use_scale, mask_mod=atten_mask_mod)   # BL:327
         self.query_w = nn.UninitializedParameter()
 
     def build(self, k_in: int, device):
@@ -367,10 +425,27 @@ class MultHeadAttentionLayer(nn.Module):
                              use_scale=self.use_scale, use_ln=self.use_ln, use_res=self.use_res, relu=True,
                              bf16=self.bf16, layout=layout)
 
+    def _forward_masked(self, inputs, mask):
+        """BL:358-377 step by step for a masked call (SeqFM / BST reuse, MD:292-301): the three projections are
+        cuBLAS GEMMs (``tensordot``), the masked product attention is ``kon_pattn_fwd/bwd``."""
+        q = torch.tensordot(inputs, self.query_w, dims=1).permute(2, 0, 1, 3).contiguous()
+        k = torch.tensordot(inputs, self.key_w, dims=1).permute(2, 0, 1, 3).contiguous()
+        atten_v = self.attention_cal([q, k, k], mask=mask)          # v = X key_w (BL:360)
+        if self.use_ln:
+            atten_v = torch.nn.functional.layer_norm(atten_v, (self.attention_dim,), self.ln_gamma, self.ln_beta, 1e-3)
+        if self.head_concat:
+            atten_v = atten_v.permute(1, 0, 2, 3)
+        if self.attention_head_dim == 1:
+            return atten_v.squeeze(0)
+        res = []
+        if self.use_res:
+            res = torch.tensordot(inputs, self.res_w, dims=1).permute(2, 0, 1, 3)
+        return [atten_v, res]
+
     def forward(self, inputs, mask=None, **kwargs):
-        if mask is not None:
-            raise L.KonError("attention masks (BL:299-306) are not on the AutoInt hot path")
         self._ensure(inputs)
+        if mask is not None:
+            return self._forward_masked(inputs, mask)
         atten_v = ops.attention(inputs, self.query_w, self.key_w, None, self.ln_gamma, self.ln_beta,
                                 use_scale=self.use_scale, use_ln=self.use_ln, use_res=False, relu=False)
         if self.head_concat:
@@ -381,6 +456,53 @@ class MultHeadAttentionLayer(nn.Module):
         if self.use_res:
             res = torch.tensordot(inputs, self.res_w, dims=1).permute(2, 0, 1, 3)   # BL:366
         return [atten_v, res]
+
+
+class AttentionBaseLayer(nn.Module):
+    """IL:335-366, AFM's pooling over the pairwise products.  In the reference the attention weight is
+    ``Activation('softmax')`` of a ``[B,P,1]`` score (IL:340-341, 362-363): the softmax runs over the LAST
+    axis, whose size is 1, so every weight is exactly 1 and the layer computes
+    ``Dense(output_dim)(sum_p pair_p)``; the scoring weights (``single_score_w/b``, the ``Dense(1,relu)``
+    kernel) exist, keep their reference shapes for weight files, and receive no gradient -- the fixture from
+    the reference's own source (tests/golden/ref_models.npz, afm) shows exactly zeros there.
+    ``forward`` takes the reference's list of products; ``fused(v)`` takes the field embeddings and uses
+    ``sum_{i<j} v_i v_j`` from the FM kernel without materialising the ``[B, F(F-1)/2, k]`` tensor."""
+
+    def __init__(self, attention_dim=4, seed=2020, output_dim=1):
+        super().__init__()
+        self.atten_dim, self.seed, self.output_dim = attention_dim, seed, output_dim
+        self.kernel_w = nn.UninitializedParameter()
+
+    def build(self, k: int, device):
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+
+        def glorot(*shape):
+            fi, fo = (shape[0], shape[0]) if len(shape) == 1 else shape
+            lim = (6.0 / (fi + fo)) ** 0.5
+            return nn.Parameter(((torch.rand(*shape, generator=g) * 2 - 1) * lim).to(device))
+        self.kernel_w, self.kernel_b = glorot(k, self.atten_dim), glorot(self.atten_dim)
+        self.mlp_kernel = glorot(self.atten_dim, 1)
+        self.out_kernel = glorot(k, self.output_dim)
+        self.out_bias = nn.Parameter(torch.zeros(self.output_dim, device=device))
+
+    def load_reference_weights(self, score_w, score_b, mlp_w, out_w, out_b):
+        self.kernel_w, self.kernel_b = nn.Parameter(score_w.clone()), nn.Parameter(score_b.clone())
+        self.mlp_kernel = nn.Parameter(mlp_w.clone())
+        self.out_kernel, self.out_bias = nn.Parameter(out_w.clone()), nn.Parameter(out_b.clone())
+
+    def _dense(self, pooled):
+        if isinstance(self.kernel_w, nn.UninitializedParameter):
+            self.build(pooled.shape[-1], pooled.device)
+        if ops.head_supported(pooled, None, self.out_kernel):
+            return ops.head(pooled, None, self.out_kernel, self.out_bias)
+        return torch.addmm(self.out_bias, pooled, self.out_kernel)
+
+    def fused(self, v: torch.Tensor) -> torch.Tensor:
+        return self._dense(ops.fm(v, None))
+
+    def forward(self, inputs, **kwargs):
+        x = pack_fields(inputs)                            # tf.concat(inputs, axis=1)  [B,P,k]
+        return self._dense(ops.pool_sum(x))                # reduce_sum(1 * inputs, axis=1) -> Dense
 
 
 # --------------------------------------------------------------------------------------

@@ -23,8 +23,9 @@ import torch
 from torch import nn
 
 from . import ops
-from .layers import (CIN, CrossLayer, DnnLayer, FieldList, FmLayer, InnerLayer, MergeScoreLayer, MultHeadAttentionLayer,
-                     ScoreLayer, SparseEmbed, StackLayer, denseFea, pack_ids, sparseFea)
+from .layers import (CIN, AttentionBaseLayer, CrossLayer, DnnLayer, FieldList, FmLayer, InnerLayer, MergeScoreLayer,
+                     MultHeadAttentionLayer, ProductAttentionLayer, ScoreLayer, SeqBaseLayer, SparseEmbed, StackLayer,
+                     denseFea, pack_ids, sparseFea)
 
 
 class InputFeature(object):
@@ -83,6 +84,26 @@ class _CtrModel(nn.Module):
         pad = torch.zeros((self.W - self.Fk - nd,) + tuple(w_ref.shape[1:]), dtype=w_ref.dtype, device=w_ref.device)
         return torch.cat([w_ref[nd:], w_ref[:nd], pad], dim=0).contiguous()
 
+    def phys_to_ref_rows(self, w_phys: torch.Tensor) -> torch.Tensor:
+        """Inverse of ``ref_to_phys_rows`` (drops the pad rows)."""
+        nd = self.n_dense
+        return torch.cat([w_phys[self.Fk:self.Fk + nd], w_phys[:self.Fk]], dim=0)
+
+    # ---- gradients under the reference's weight names / layouts (parity tests, checkpoints) ----
+    def _dnn_grads(self, out: Dict[str, torch.Tensor], dnn: "DnnLayer", first_is_xcat: bool):
+        for i, (w, b) in enumerate(zip(dnn.kernels, dnn.biases)):
+            if w.grad is not None:
+                out[f"dnn_w{i}"] = self.phys_to_ref_rows(w.grad) if (i == 0 and first_is_xcat) else w.grad
+            if b.grad is not None:
+                out[f"dnn_b{i}"] = b.grad
+        if dnn.logit_kernel is not None and dnn.logit_kernel.grad is not None:
+            out["dnn_logit_w"], out["dnn_logit_b"] = dnn.logit_kernel.grad, dnn.logit_bias.grad
+
+    def reference_grads(self) -> Dict[str, torch.Tensor]:
+        """Dense-parameter gradients keyed by the names ``load_reference_params`` takes, in the reference's
+        layouts (rows of first-layer kernels back in dense-first order, ``[D,1]`` cross kernels, ...)."""
+        raise NotImplementedError
+
     def front(self, dense_inputs, sparse_inputs):
         ids = pack_ids(sparse_inputs)
         dense = _pack_dense(dense_inputs) if self.n_dense else None
@@ -120,6 +141,9 @@ class FM(_CtrModel):
         _load_embeds(self, p)
         self.head.load_reference_weights(p["head_w"], p["head_b"])
 
+    def reference_grads(self):
+        return {"head_w": self.head.kernel.grad, "head_b": self.head.bias.grad}
+
 
 class DeepFM(_CtrModel):
     """MD:80-90."""
@@ -145,6 +169,11 @@ class DeepFM(_CtrModel):
         ks[0] = self.ref_to_phys_rows(ks[0])
         self.dnn.load_reference_weights(ks, [p[f"dnn_b{i}"] for i in range(n)])
         self.head.load_reference_weights(p["head_w"], p["head_b"])
+
+    def reference_grads(self):
+        out = {"head_w": self.head.kernel.grad, "head_b": self.head.bias.grad}
+        self._dnn_grads(out, self.dnn, True)
+        return out
 
 
 class DCN(_CtrModel):
@@ -174,6 +203,15 @@ class DCN(_CtrModel):
         D = self.n_dense + self.Fk
         hw = p["head_w"]
         self.head.load_reference_weights(torch.cat([self.ref_to_phys_rows(hw[:D]), hw[D:]], 0), p["head_b"])
+
+    def reference_grads(self):
+        hg = self.head.kernel.grad
+        out = {"head_w": torch.cat([self.phys_to_ref_rows(hg[:self.W]), hg[self.W:]], 0), "head_b": self.head.bias.grad}
+        for i in range(self.cross.cross_hidden):
+            out[f"outer_weight_{i}"] = self.phys_to_ref_rows(self.cross.kernel.grad[i].unsqueeze(1))
+            out[f"outer_bias_{i}"] = self.phys_to_ref_rows(self.cross.bias.grad[i].unsqueeze(1))
+        self._dnn_grads(out, self.dnn, True)
+        return out
 
 
 class XDeepFM(_CtrModel):
@@ -208,6 +246,13 @@ class XDeepFM(_CtrModel):
         self.cin.load_reference_weights([p[f"cin_w{i}"] for i in range(nc)], [p[f"cin_b{i}"] for i in range(nc)],
                                         p["cin_logit_w"], p["cin_logit_b"])
 
+    def reference_grads(self):
+        out = {"cin_logit_w": self.cin.logit_kernel.grad, "cin_logit_b": self.cin.logit_bias.grad}
+        for i, (w, b) in enumerate(zip(self.cin.conv_kernels, self.cin.conv_biases)):
+            out[f"cin_w{i}"], out[f"cin_b{i}"] = w.grad, b.grad
+        self._dnn_grads(out, self.dnn, True)
+        return out
+
 
 class NFM(_CtrModel):
     """MD:108-119 (a sibling that reuses the FM kernel).  The bi-interaction
@@ -240,6 +285,43 @@ class NFM(_CtrModel):
         self.dnn.load_reference_weights([p[f"dnn_w{i}"] for i in range(n)], [p[f"dnn_b{i}"] for i in range(n)],
                                         p["dnn_logit_w"], p["dnn_logit_b"])
 
+    def reference_grads(self):
+        out = {}
+        self._dnn_grads(out, self.dnn, False)
+        return out
+
+
+class AFM(_CtrModel):
+    """MD:141-147: ``InnerLayer()`` pairwise products -> ``AttentionBaseLayer()`` ->
+    ``ScoreLayer(use_add=True)(linear_embed + [atten_output])`` = sigmoid ``[B,1,1]``.  The products are
+    never materialised here: the pooling weights of the reference are identically 1 (see
+    ``AttentionBaseLayer``), so the pooled vector is the FM kernel's ``sum_{i<j} v_i v_j``."""
+
+    def __init__(self, inputFea: InputFeature = None):
+        super().__init__(inputFea)
+        self.inner = InnerLayer()
+        self.atten = AttentionBaseLayer()
+
+    def logit(self, dense_inputs, sparse_inputs):
+        ids = pack_ids(sparse_inputs)
+        v = self.sparse_embed.lookup(ids)                  # [B,F,k]
+        atten_out = self.atten.fused(v)                    # [B,1]
+        linear = self.linear_embed.lookup_sum(ids)         # Add over the F first-order [B,1,1] terms
+        return ScoreLayer.summed([linear.unsqueeze(1), atten_out])      # [B,1,1]
+
+    def forward(self, dense_inputs, sparse_inputs):
+        return torch.sigmoid(self.logit(dense_inputs, sparse_inputs))
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        self.atten.load_reference_weights(p["afm_score_w"], p["afm_score_b"], p["afm_mlp_w"], p["afm_out_w"], p["afm_out_b"])
+
+    def reference_grads(self):
+        a = self.atten
+        z = lambda w: torch.zeros_like(w) if w.grad is None else w.grad     # never-read scoring weights
+        return {"afm_score_w": z(a.kernel_w), "afm_score_b": z(a.kernel_b), "afm_mlp_w": z(a.mlp_kernel),
+                "afm_out_w": a.out_kernel.grad, "afm_out_b": a.out_bias.grad}
+
 
 class AutoInt(_CtrModel):
     """MD:150-165.  ``n_layers > 1`` stacks blocks by re-packing ``[H,B,F,d] -> [B,F,H*d]``
@@ -269,10 +351,28 @@ class AutoInt(_CtrModel):
         return self.head(final)
 
     def load_reference_params(self, p):
+        """Block 0 takes the reference's names (``query_w`` ...); stacked blocks l >= 1 (the extension) take the
+        same names with an ``_l`` suffix (``query_w_1`` ...)."""
         _load_embeds(self, p)
-        self.blocks[0].other_dense[0].load_reference_weights(p["query_w"], p["key_w"], p["res_w"],
-                                                             p["ln_gamma"], p["ln_beta"])
+        for l, blk in enumerate(self.blocks):
+            sfx = "" if l == 0 else f"_{l}"
+            if ("query_w" + sfx) not in p:
+                if l == 0:
+                    raise KeyError("query_w")
+                continue
+            blk.other_dense[0].load_reference_weights(p["query_w" + sfx], p["key_w" + sfx], p["res_w" + sfx],
+                                                      p["ln_gamma" + sfx], p["ln_beta" + sfx],
+                                                      value_w=p.get("value_w" + sfx))
         self.head.load_reference_weights(p["head_w"], p["head_b"])
+
+    def reference_grads(self):
+        out = {"head_w": self.head.kernel.grad, "head_b": self.head.bias.grad}
+        for l, blk in enumerate(self.blocks):
+            sfx = "" if l == 0 else f"_{l}"
+            att = blk.other_dense[0]
+            for n in ("query_w", "key_w", "res_w", "ln_gamma", "ln_beta"):
+                out[n + sfx] = getattr(att, n).grad
+        return out
 
 
 def _load_embeds(model: _CtrModel, p):

@@ -661,3 +661,103 @@ class _EmbedConcat(torch.autograd.Function):
 def embed_lookup_concat(arena, ids, field_row_offset, dense, width):
     """-> xcat [B,width] = [F*dim embedding columns | dense | zero pad] (see models.py)."""
     return _EmbedConcat.apply(arena, ids, tuple(field_row_offset), dense, width)
+
+
+# --------------------------------------------------------------------------- #
+# callers / siblings wired from the same layer classes (SURVEY 8f): sum pooling of a materialised
+# sequence, the un-summed pairwise products, product attention on explicit q, k, v with masks
+# --------------------------------------------------------------------------- #
+class _PoolSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = L.lib()
+        if x.stride(2) != 1 and x.shape[2] != 1:
+            x = x.contiguous()
+        out = torch.empty((x.shape[0], x.shape[2]), dtype=x.dtype, device=x.device)
+        a, o = L._arg(x), L._arg(out)
+        with _prof("pool_sum"):
+            L.check(lib.kon_pool_sum_fwd(a.ptr, o.ptr, L.stream_ptr(x.device)), "kon_pool_sum_fwd")
+        ctx.L = x.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(1).expand(g.shape[0], ctx.L, g.shape[1])     # d(sum)/dx: a broadcast, no kernel
+
+
+def pool_sum(x: torch.Tensor) -> torch.Tensor:
+    """x [B,L,k] -> [B,k] = sum over axis 1 in order l = 0..L-1 (BL:46, IL:364)."""
+    return _PoolSum.apply(x)
+
+
+class _Pairs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v):
+        lib = L.lib()
+        if v.stride(2) != 1 and v.shape[2] != 1:
+            v = v.contiguous()
+        F = v.shape[1]
+        out = torch.empty((v.shape[0], F * (F - 1) // 2, v.shape[2]), dtype=v.dtype, device=v.device)
+        a, o = L._arg(v), L._arg(out)
+        with _prof("pairs_fwd"):
+            L.check(lib.kon_pairs_fwd(a.ptr, o.ptr, L.stream_ptr(v.device)), "kon_pairs_fwd")
+        ctx.save_for_backward(v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        (v,) = ctx.saved_tensors
+        g = g.contiguous()
+        dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+        a, b, c = L._arg(v), L._arg(g), L._arg(dv)
+        with _prof("pairs_bwd"):
+            L.check(lib.kon_pairs_bwd(a.ptr, b.ptr, c.ptr, L.stream_ptr(v.device)), "kon_pairs_bwd")
+        return dv
+
+
+def pairs(v: torch.Tensor) -> torch.Tensor:
+    """v [B,F,k] -> [B, F(F-1)/2, k]: v_i * v_j for i<j in itertools.combinations order (IL:61)."""
+    return _Pairs.apply(v)
+
+
+class _Pattn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, use_scale, mask_mode):
+        lib = L.lib()
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out = torch.empty_like(q)
+        a = [L._arg(t) for t in (q, k, v, mask, out)]
+        with _prof("pattn_fwd"):
+            L.check(lib.kon_pattn_fwd(*[L._p(t) for t in a], 1 if use_scale else 0, mask_mode,
+                                      L.stream_ptr(q.device)), "kon_pattn_fwd")
+        ctx.save_for_backward(q, k, v, mask)
+        ctx.use_scale, ctx.mask_mode = use_scale, mask_mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        q, k, v, mask = ctx.saved_tensors
+        g = g.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        a = [L._arg(t) for t in (q, k, v, mask, g, dq, dk, dv)]
+        with _prof("pattn_bwd"):
+            L.check(lib.kon_pattn_bwd(*[L._p(t) for t in a], 1 if ctx.use_scale else 0, ctx.mask_mode,
+                                      L.stream_ptr(q.device)), "kon_pattn_bwd")
+        return dq, dk, dv, None, None, None
+
+
+def product_attention(q, k, v, mask=None, use_scale=False, mask_mode=0):
+    """sigmoid(mask(q k^T [/ sqrt d])) v on explicit q, k, v [..., F, d] (BL:292-311).  ``mask`` [F,F]:
+    mode 1 ``score @ mask``, mode 2 ``score + mask * -1e5`` (BL:299-306); boolean masks are cast to float
+    exactly as the reference does (``tf.cast(mask, 'float')``)."""
+    if mask is None:
+        mask_mode = 0
+    else:
+        if mask_mode not in (1, 2):
+            raise L.KonError("product_attention: mask given but mask_mode is %r (must be 1 or 2)" % (mask_mode,))
+        if mask.dim() != 2:
+            raise L.KonError("product_attention: only a [F,F] mask shared by all samples is provided")
+        mask = mask.to(torch.float32).contiguous()
+    return _Pattn.apply(q, k, v, mask, bool(use_scale), int(mask_mode))
