@@ -114,15 +114,14 @@ class SparseEmbed(nn.Module):
             offs.append(offs[-1] + r)
         self.field_row_offset = tuple(offs)
         self.emb_reg = 0.0 if is_linear else float(self.sparse_info[0].emb_reg or 0.0)
-        g = torch.Generator(device="cpu").manual_seed(seed)
         arena = torch.empty(offs[-1], self.dim, device=device, dtype=torch.float32)
-        # per-table init, chunked on the device: glorot_uniform for cross tables (IL:215),
-        # Keras Embedding default 'uniform' = U(-0.05,0.05) for the linear ones (IL:220-222)
-        gd = torch.Generator(device=device).manual_seed(seed)
-        for f, r in enumerate(rows):
-            lim = 0.05 if is_linear else (6.0 / (r + self.dim)) ** 0.5
-            arena[offs[f]:offs[f + 1]].uniform_(-lim, lim, generator=gd)
-        del g
+        if arena.device.type != "meta":       # "meta": a placeholder that parallel.DistContext.attach replaces by shards
+            # per-table init, chunked on the device: glorot_uniform for cross tables (IL:215),
+            # Keras Embedding default 'uniform' = U(-0.05,0.05) for the linear ones (IL:220-222)
+            gd = torch.Generator(device=device).manual_seed(seed)
+            for f, r in enumerate(rows):
+                lim = 0.05 if is_linear else (6.0 / (r + self.dim)) ** 0.5
+                arena[offs[f]:offs[f + 1]].uniform_(-lim, lim, generator=gd)
         self.arena = nn.Parameter(arena)
 
     def load_reference_weights(self, tables: Sequence[torch.Tensor]):

@@ -228,6 +228,7 @@ class PeerRegion:
         self._flag_ptrs = (ctypes.c_void_p * self.world)(*self.ptrs)
         self._bytes = torch.as_tensor(_RawCuda(self.local_ptr, self.nbytes), device=device)
         self._used = self.FLAG_BYTES
+        self._n_barriers = 0
         self.flags = self._bytes[:self.FLAG_BYTES].view(torch.int32)
         dist.barrier(group=group)       # every mapping exists before anybody stores through one
 
@@ -246,9 +247,25 @@ class PeerRegion:
     def ptr_array(self, byte_offset: int):
         return (ctypes.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
 
-    def barrier(self, timeout_ms: int = 10000):
+    def barrier(self, timeout_ms: Optional[int] = None):
+        """Flag barrier on the current stream.  A peer that does not arrive within the timeout makes the kernel set
+        the region's error word instead of hanging the GPU; ``check()`` turns that into a ``KonError`` (the trainer
+        calls it on a cadence, see ``train.Trainer``).  Default 10 s (``KON_PEER_TIMEOUT_MS``), 60 s for the first
+        barriers of a region (lazy initialisation / graph warm-up skew between the ranks)."""
+        if timeout_ms is None:
+            timeout_ms = int(os.environ.get("KON_PEER_TIMEOUT_MS", "10000"))
+            if self._n_barriers < 8:
+                timeout_ms = max(timeout_ms, 60000)
+        self._n_barriers += 1
         self.L.check(self.lib.kon_peer_barrier(self._flag_ptrs, self.world, self.rank, self.dev_index, timeout_ms,
                                                self.L.stream_ptr(self.device)), "kon_peer_barrier")
+
+    def check(self):
+        """Raise if a barrier of this region ever timed out (synchronises the device)."""
+        if self.timed_out():
+            raise self.L.KonError(
+                f"rank {self.rank}: a peer barrier timed out -- the embedding rows / gradients exchanged in that step "
+                "were incomplete; the training state is not trustworthy from that step on")
 
     def timed_out(self) -> bool:
         """True when a barrier gave up waiting for a peer (word 17 of the flag block); synchronises."""
@@ -441,6 +458,11 @@ class ShardedEmbed(nn.Module):
         self._peer[(B_l, width)] = dict(region=region, xcat=xcat, xcat_off=xo, dbuf=dbuf, dbuf_off=do)
         return self._peer[(B_l, width)]
 
+    def check_peer(self):
+        """Raise ``KonError`` if any exchange barrier of this layer timed out (synchronises)."""
+        for px in self._peer.values():
+            px["region"].check()
+
     def close_peer(self):
         """Unmap / free the exchange regions (collective; call before destroying the process group)."""
         for px in self._peer.values():
@@ -493,6 +515,18 @@ class ShardedEmbed(nn.Module):
                 if f in self.plan.rw_fields:
                     t = t[self.rank::self.world]
                 self.arena[self.all_offs[j]:self.all_offs[j + 1]].copy_(t)
+
+    def load_global_table(self, f: int, table: torch.Tensor):
+        """One field's full (global) table -> this rank's shard of it (no-op when another rank owns field f)."""
+        fields = self.plan.tw_of_rank[self.rank] + self.plan.rw_fields
+        if f not in fields:
+            return
+        j = fields.index(f)
+        with torch.no_grad():
+            t = table.to(self.arena.device)
+            if f in self.plan.rw_fields:
+                t = t[self.rank::self.world]
+            self.arena[self.all_offs[j]:self.all_offs[j + 1]].copy_(t)
 
     def lookup(self, ids: torch.Tensor) -> torch.Tensor:
         if self.use_peer:

@@ -60,6 +60,15 @@ class Trainer:
         self.presort = not isinstance(model, XDeepFM)
         self._g = None
         self.capture_error = None
+        # sharded jobs: a peer-barrier timeout must not pass silently (the consumer kernels would read partially
+        # written rows).  Checking costs a device sync, so it runs on a cadence, after graph warm-up, and on demand.
+        self.peer_check_every = 64
+        self._n_steps = 0
+
+    def check_peers(self):
+        for emb in (self.model.sparse_embed, self.model.linear_embed):
+            if emb is not None and hasattr(emb, "check_peer"):
+                emb.check_peer()
 
     def _ensure_dense_opt(self):
         if self.dense_opt is None:      # lazily: layers build their weights on first call
@@ -90,6 +99,10 @@ class Trainer:
         for so in self.sparse_opts:
             so.step()
         ops.end_step()
+        self._n_steps += 1
+        if self.dist is not None and self.peer_check_every and self._n_steps % self.peer_check_every == 0 \
+                and not torch.cuda.is_current_stream_capturing():
+            self.check_peers()
         return loss.detach()
 
     # ------------------------------------------------------------------------------------------
@@ -108,6 +121,8 @@ class Trainer:
                     self.step(*self._static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            if self.dist is not None:
+                self.check_peers()
             g = torch.cuda.CUDAGraph()
             # multi-GPU: the process group's watchdog thread issues CUDA calls of its own; only THIS
             # thread's calls may invalidate the capture
@@ -136,4 +151,7 @@ class Trainer:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._g.replay()
+        self._n_steps += 1
+        if self.dist is not None and self.peer_check_every and self._n_steps % self.peer_check_every == 0:
+            self.check_peers()
         return self._static_loss

@@ -465,6 +465,24 @@ def model_autoint(p, dense, sparse_ids):
     return merge_score_layer(final, p["head_w"], p["head_b"], use_merge=False)
 
 
+def model_autoint_stacked(p, dense, sparse_ids, n_layers: int):
+    """EXTENSION with no reference counterpart (the reference wires exactly one attention block, MD:159-163, and a
+    second one could not consume its 4-D output, BL:358): ``n_layers`` blocks of ``autoint_block`` stacked the
+    standard AutoInt way, re-packing ``[H,B,F,d] -> [B,F,H*d]`` between blocks.  Block 0 uses the reference's
+    weight names, block l >= 1 the same names with an ``_l`` suffix.  Each block is BL:356-377 + CL:205-216."""
+    sparse, _ = _embed_lists(p, sparse_ids)
+    x = stack_layer(sparse, use_flat=False, axis=1)
+    a = None
+    for l in range(n_layers):
+        sfx = "" if l == 0 else f"_{l}"
+        a = autoint_block(x, p["query_w" + sfx], p["key_w" + sfx], p["res_w" + sfx], p["ln_gamma" + sfx], p["ln_beta" + sfx])
+        if l + 1 < n_layers:
+            x = a.permute(1, 2, 0, 3).reshape(a.shape[1], a.shape[2], -1)
+    heads = [a[h] for h in range(a.shape[0])]
+    final = stack_layer(heads, use_flat=True, axis=-1)
+    return merge_score_layer(final, p["head_w"], p["head_b"], use_merge=False)
+
+
 def glorot_uniform(shape, gen: torch.Generator, dtype=torch.float32):
     """``glorot_uniform``: U(+-sqrt(6/(fan_in+fan_out))) with Keras fan rules
     (2-D: (in,out); >2-D: receptive field * in/out channels).  The TF RNG stream
