@@ -300,6 +300,16 @@ int kon_pattn_bwd(const DLTensor* q, const DLTensor* k, const DLTensor* v, const
                   const DLTensor* g_out, DLTensor* dq, DLTensor* dk, DLTensor* dv, int32_t use_scale,
                   int32_t mask_mode, void* stream);
 
+/* compile(loss=binary_crossentropy) on probabilities (example/ctr_example/un_seq.py:61), forward and backward in
+ * one kernel each instead of ~30 elementwise launches:
+ *   p' = clip(p, eps, 1-eps);  loss = mean over all elements of -(y log(p'+eps) + (1-y) log(1-p'+eps))
+ *   p, y compact f32 of one size ([B,2] softmax heads with one-hot labels, [B,1,1] sigmoid heads); loss f32[1];
+ *   workspace >= kon_bce_workspace_bytes() uint8 (per-CTA partials, summed in fixed order: deterministic).
+ * Backward: dp = g_loss * dloss/dp (zero where the clip is active, as tf.clip_by_value). */
+size_t kon_bce_workspace_bytes(void);
+int kon_bce_fwd(const DLTensor* p, const DLTensor* y, DLTensor* loss, DLTensor* workspace, float eps, void* stream);
+int kon_bce_bwd(const DLTensor* p, const DLTensor* y, const DLTensor* g_loss, DLTensor* dp, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

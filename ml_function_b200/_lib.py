@@ -167,6 +167,9 @@ def lib():
         "kon_pairs_bwd": (ctypes.c_int, [T, T, T, vp]),
         "kon_pattn_fwd": (ctypes.c_int, [T] * 5 + [i32, i32, vp]),
         "kon_pattn_bwd": (ctypes.c_int, [T] * 8 + [i32, i32, vp]),
+        "kon_bce_workspace_bytes": (sz, []),
+        "kon_bce_fwd": (ctypes.c_int, [T, T, T, T, f32, vp]),
+        "kon_bce_bwd": (ctypes.c_int, [T, T, T, T, f32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)   # AttributeError here = header and library disagree
@@ -190,6 +193,7 @@ EXPORTED_SYMBOLS = (
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",
     "kon_head_fwd", "kon_head_bwd_workspace_bytes", "kon_head_bwd",
     "kon_pool_sum_fwd", "kon_pairs_fwd", "kon_pairs_bwd", "kon_pattn_fwd", "kon_pattn_bwd",
+    "kon_bce_workspace_bytes", "kon_bce_fwd", "kon_bce_bwd",
 )
 
 

@@ -314,8 +314,10 @@ struct BwdArgs {
 // One lane group (LPR lanes x float4) reduces one window of kWin sorted lookups; the CTA
 // then stitches runs that cross window boundaries through shared memory, and leaves at
 // most one head and one tail partial per CTA for embed_fixup_kernel.
-template <int LPR>
-__global__ void __launch_bounds__(kRedThreads, KON_EMB_RED_MINB) embed_reduce_kernel(const BwdArgs a) {
+// NB = gradient rows loaded per lane group before the first one is consumed.  8 covers HBM latency; rows that
+// come over NVLink (peer mode) have ~3x the latency, so that instantiation keeps a whole 16-lookup window in flight.
+template <int LPR, int NB>
+__global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) embed_reduce_kernel(const BwdArgs a) {
   constexpr int G = kRedThreads / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_head = reinterpret_cast<float4*>(smem_raw);          // [G][LPR]
@@ -353,12 +355,12 @@ __global__ void __launch_bounds__(kRedThreads, KON_EMB_RED_MINB) embed_reduce_ke
     bool first_run = true;
     float4 acc = zero;
     const int cnt = (int)(hi - lo);
-    for (int i0 = 0; i0 < cnt; i0 += 8) {
-      float4 r[8];
-      int sg[8];
-      uint32_t ky[8];
+    for (int i0 = 0; i0 < cnt; i0 += NB) {
+      float4 r[NB];
+      int sg[NB];
+      uint32_t ky[NB];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < NB; ++u) {
         r[u] = zero;
         sg[u] = cur;
         ky[u] = cur_key;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kRedThreads, KON_EMB_RED_MINB) embed_reduce_ke
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < NB; ++u) {
         if (i0 + u < cnt) {
           if (sg[u] != cur) {   // run [.., i-1] is complete at its right end
             if (first_run && !starts) {
@@ -1093,7 +1095,8 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   ProfileScope ps_red("embed_reduce_kernel", st);
 #define KON_RED_CASE(N)                                                                  \
   case N:                                                                                \
-    embed_reduce_kernel<N><<<l.n_cta, kRedThreads, smem, st>>>(a);                       \
+    if (a.n_peers > 1) embed_reduce_kernel<N, kWin><<<l.n_cta, kRedThreads, smem, st>>>(a);  \
+    else embed_reduce_kernel<N, 8><<<l.n_cta, kRedThreads, smem, st>>>(a);               \
     KON_LAUNCH_CHECK("embed_reduce_kernel");                                             \
     embed_fixup_kernel<N>                                                                \
         <<<(l.n_cta + kRedThreads / N - 1) / (kRedThreads / N), kRedThreads, 0, st>>>(a, l.n_cta); \

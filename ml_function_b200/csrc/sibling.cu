@@ -207,6 +207,64 @@ __global__ void __launch_bounds__(kPaThreads) pattn_bwd_kernel(const PattnArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Keras binary_crossentropy on probabilities (compile(loss=binary_crossentropy), EX un_seq.py:61):
+//   p' = clip(p, eps, 1-eps);  bce = -(y log(p'+eps) + (1-y) log(1-p'+eps));  loss = mean over all elements
+// (mean over the last axis, then over the batch == mean over all elements for a dense [B,C] tensor).
+// Two fixed-order stages -> deterministic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBceThreads = 256;
+constexpr int kBceMaxCtas = 1024;
+
+__device__ __forceinline__ float block_sum_256(float v, float* s_part) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kBceThreads / 32; ++w) t += s_part[w];
+  return t;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kBceThreads)
+bce_partial_kernel(const float* __restrict__ p, const float* __restrict__ y, long long n, float eps,
+                   float* __restrict__ part) {
+  __shared__ float s_part[kBceThreads / 32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)kBceThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kBceThreads) {
+    const float pc = fminf(fmaxf(p[i], eps), 1.f - eps);
+    const float yy = y[i];
+    acc -= yy * logf(pc + eps) + (1.f - yy) * logf(1.f - pc + eps);
+  }
+  const float t = block_sum_256(acc, s_part);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kBceThreads)
+bce_final_kernel(const float* __restrict__ part, int n_part, float inv_n, float* __restrict__ loss) {
+  __shared__ float s_part[kBceThreads / 32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += kBceThreads) acc += part[i];
+  const float t = block_sum_256(acc, s_part);
+  if (threadIdx.x == 0) *loss = t * inv_n;
+}
+
+// dp = g * d(mean bce)/dp; the clip passes no gradient outside [eps, 1-eps] (tf.clip_by_value)
+__global__ void __launch_bounds__(kBceThreads)
+bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ y, const float* __restrict__ g, long long n,
+               float eps, float inv_n, float* __restrict__ dp) {
+  const float gs = (*g) * inv_n;
+  for (long long i = blockIdx.x * (long long)kBceThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kBceThreads) {
+    const float pv = p[i];
+    float d = 0.f;
+    if (pv >= eps && pv <= 1.f - eps) {
+      const float yy = y[i];
+      d = gs * ((1.f - yy) / (1.f - pv + eps) - yy / (pv + eps));
+    }
+    dp[i] = d;
+  }
+}
+
 int grid_for(long long total, int sms, int mult = 16) {
   return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sms * mult));
 }
@@ -364,5 +422,57 @@ extern "C" int kon_pattn_bwd(const DLTensor* q, const DLTensor* k, const DLTenso
   const int grid = (int)std::min<long long>(a.units, (long long)sm_count_of(dev) * 8);
   pattn_bwd_kernel<<<grid, kPaThreads, smem, st>>>(a);
   KON_LAUNCH_CHECK("pattn_bwd_kernel");
+  return KON_OK;
+}
+
+static int check_bce(const DLTensor* p, const DLTensor* y, int* dev, long long* n) {
+  KON_TRY(check_cuda_tensor(p, "p"));
+  *dev = p->device.device_id;
+  KON_TRY(check_cuda_tensor(y, "y", *dev));
+  KON_REQUIRE(is_f32(p) && is_f32(y) && is_compact(p) && is_compact(y) && numel(p) == numel(y), KON_EINVAL,
+              "p and y must be compact float32 tensors of one size");
+  *n = numel(p);
+  KON_REQUIRE(*n >= 1, KON_EINVAL, "empty loss input");
+  return KON_OK;
+}
+
+extern "C" size_t kon_bce_workspace_bytes(void) { return (size_t)kBceMaxCtas * 4; }
+
+extern "C" int kon_bce_fwd(const DLTensor* p, const DLTensor* y, DLTensor* loss, DLTensor* workspace, float eps,
+                           void* stream) {
+  int dev;
+  long long n;
+  KON_TRY(check_bce(p, y, &dev, &n));
+  KON_TRY(check_cuda_tensor(loss, "loss", dev));
+  KON_TRY(check_cuda_tensor(workspace, "workspace", dev));
+  KON_REQUIRE(is_f32(loss) && numel(loss) == 1, KON_EINVAL, "loss must be float32[1]");
+  KON_REQUIRE(is_u8(workspace) && (size_t)numel(workspace) >= kon_bce_workspace_bytes() &&
+                  ((uintptr_t)data_ptr<char>(workspace) & 15u) == 0, KON_EWORKSPACE, "workspace too small or misaligned");
+  DeviceGuard guard(dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<long long>((n + kBceThreads - 1) / kBceThreads, kBceMaxCtas);
+  float* part = data_ptr<float>(workspace);
+  bce_partial_kernel<<<grid, kBceThreads, 0, st>>>(data_ptr<float>(p), data_ptr<float>(y), n, eps, part);
+  KON_LAUNCH_CHECK("bce_partial_kernel");
+  bce_final_kernel<<<1, kBceThreads, 0, st>>>(part, grid, 1.f / (float)n, data_ptr<float>(loss));
+  KON_LAUNCH_CHECK("bce_final_kernel");
+  return KON_OK;
+}
+
+extern "C" int kon_bce_bwd(const DLTensor* p, const DLTensor* y, const DLTensor* g_loss, DLTensor* dp, float eps,
+                           void* stream) {
+  int dev;
+  long long n;
+  KON_TRY(check_bce(p, y, &dev, &n));
+  KON_TRY(check_cuda_tensor(g_loss, "g_loss", dev));
+  KON_TRY(check_cuda_tensor(dp, "dp", dev));
+  KON_REQUIRE(is_f32(g_loss) && numel(g_loss) == 1, KON_EINVAL, "g_loss must be float32[1]");
+  KON_REQUIRE(is_f32(dp) && is_compact(dp) && numel(dp) == n, KON_EINVAL, "dp must be compact float32 like p");
+  DeviceGuard guard(dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<long long>((n + kBceThreads - 1) / kBceThreads, (long long)sm_count_of(dev) * 8);
+  bce_bwd_kernel<<<grid, kBceThreads, 0, st>>>(data_ptr<float>(p), data_ptr<float>(y), data_ptr<float>(g_loss), n, eps,
+                                               1.f / (float)n, data_ptr<float>(dp));
+  KON_LAUNCH_CHECK("bce_bwd_kernel");
   return KON_OK;
 }

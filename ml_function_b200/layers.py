@@ -549,6 +549,39 @@ class _DenseFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+def _mm_f32_out(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 -> fp32 GEMM (fp32 accumulate, the result is never rounded to bf16)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.mm(a, b).float()
+
+
+class _DenseCastFn(torch.autograd.Function):
+    """First MLP layer on a reduced-precision path: ``x`` arrives in fp32 (the concat buffer), is cast to the
+    compute dtype here, and its gradient goes back in fp32 straight out of the GEMM (fp32 accumulators written
+    as fp32) -- no bf16 rounding of the gradient that flows into the embedding rows, and no separate
+    bf16 -> fp32 cast pass over the [B, 13+F*k] gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xc = x.to(w.dtype)
+        ctx.save_for_backward(xc, w)
+        return torch.addmm(b, xc, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, w = ctx.saved_tensors
+        g = g.contiguous()
+        gx = _mm_f32_out(g, w.t()) if ctx.needs_input_grad[0] else None
+        gw = xc.t() @ g if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[2]:
+            ones = torch.ones((1, g.shape[0]), dtype=g.dtype, device=g.device)
+            gb = (ones @ g).reshape(-1)
+        return gx, gw, gb
+
+
 class DnnLayer(nn.Module):
     """CL:159-226 with the defaults the CTR builders use (``res_unit=1``, no BN/LN, ReLU):
     per hidden layer ``Dense`` -> ``Add([ori, x])`` when the shapes allow it (CL:206-214)
@@ -596,14 +629,17 @@ class DnnLayer(nn.Module):
         if len(self.kernels) == 0 and self.hidden_units:
             self.build(x.shape[-1], x.device)
         cd = self.compute_dtype
-        if cd is not None:
-            x = x.to(cd)
-        for w, b in zip(self.kernels, self.biases):
+        for i, (w, b) in enumerate(zip(self.kernels, self.biases)):
             ori = x
-            x = _DenseFn.apply(x, w.to(x.dtype), b.to(x.dtype))
+            if cd is not None and x.dtype != cd:
+                x = _DenseCastFn.apply(x, w.to(cd), b.to(cd)) if i == 0 else _DenseFn.apply(x.to(cd), w.to(cd), b.to(cd))
+            else:
+                x = _DenseFn.apply(x, w.to(x.dtype), b.to(x.dtype))
             if ori.shape == x.shape:
-                x = ori + x
+                x = ori.to(x.dtype) + x
             x = torch.relu(x)
+        if cd is not None and x.dtype != cd:      # no hidden layer: the logit layer still runs in the compute dtype
+            x = x.to(cd)
         if self.logit_kernel is not None:
             x = torch.addmm(self.logit_bias.to(x.dtype), x, self.logit_kernel.to(x.dtype))
         return x.float() if cd is not None else x

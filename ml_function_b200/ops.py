@@ -761,3 +761,37 @@ def product_attention(q, k, v, mask=None, use_scale=False, mask_mode=0):
             raise L.KonError("product_attention: only a [F,F] mask shared by all samples is provided")
         mask = mask.to(torch.float32).contiguous()
     return _Pattn.apply(q, k, v, mask, bool(use_scale), int(mask_mode))
+
+
+class _Bce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, y, eps):
+        lib = L.lib()
+        p, y = p.contiguous(), y.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=p.device)
+        ws = _ws(lib.kon_bce_workspace_bytes(), p.device)
+        a = [L._arg(t) for t in (p, y, loss, ws)]
+        with _prof("bce_fwd"):
+            L.check(lib.kon_bce_fwd(*[t.ptr for t in a], eps, L.stream_ptr(p.device)), "kon_bce_fwd")
+        ctx.save_for_backward(p, y)
+        ctx.eps = eps
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        p, y = ctx.saved_tensors
+        g = g.reshape(1).contiguous().float()
+        dp = torch.empty_like(p)
+        a = [L._arg(t) for t in (p, y, g, dp)]
+        with _prof("bce_bwd"):
+            L.check(lib.kon_bce_bwd(*[t.ptr for t in a], ctx.eps, L.stream_ptr(p.device)), "kon_bce_bwd")
+        return dp, None, None
+
+
+def binary_crossentropy(y_true: torch.Tensor, y_pred: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """``compile(loss=binary_crossentropy)`` on probabilities, fused: clip, log terms, mean over the last axis
+    and the batch (= mean over all elements), deterministic; the gradient in one kernel."""
+    if y_true.shape != y_pred.shape:
+        y_true = y_true.reshape(y_pred.shape)
+    return _Bce.apply(y_pred.float(), y_true.float(), float(eps))

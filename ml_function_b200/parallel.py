@@ -115,6 +115,15 @@ def _all_to_all(out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits, gro
     dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
 
 
+def _fire_backward_hook(sh):
+    """The embedding lookups are the first nodes of the forward graph, hence the LAST nodes autograd runs, and
+    AccumulateGrad nodes run at top priority: when an embedding backward starts, every dense-weight gradient of the
+    step is final.  The trainer hooks the dense all-reduce here so that it overlaps the embedding exchange / scatter."""
+    hook = getattr(sh, "backward_hook", None)
+    if hook is not None:
+        hook()
+
+
 class _ShardedLookup(torch.autograd.Function):
     """ids_local [B_l,F] -> emb [B_l,F,k] in global field order."""
 
@@ -152,6 +161,7 @@ class _ShardedLookup(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        _fire_backward_hook(ctx.sh)
         sh, arena = ctx.sh, ctx.arena
         ids_tw, ids_rw = ctx.saved_tensors
         plan, g, N, rank = sh.plan, sh.group, sh.world, sh.rank
@@ -330,6 +340,7 @@ class _PeerLookup(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        _fire_backward_hook(ctx.sh)
         from . import ops
         sh, arena, px = ctx.sh, ctx.arena, ctx.px
         ids_tw, ids_rw = ctx.saved_tensors
@@ -377,6 +388,7 @@ class _ShardedSum(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        _fire_backward_hook(ctx.sh)
         sh, arena = ctx.sh, ctx.arena
         (ids_loc,) = ctx.saved_tensors
         N = sh.world
@@ -581,6 +593,54 @@ class DistContext:
             n = g.numel()
             g.copy_(flat[o:o + n].view_as(g))
             o += n
+
+    # ---- the same all-reduce, overlapped with the embedding backward ---------------------------------
+    def arm_overlapped_allreduce(self, model, params_fn):
+        """Before ``backward()``: the first embedding backward of the step launches the dense all-reduce on a
+        side stream (see ``_fire_backward_hook``); ``finish_allreduce`` joins it (or runs it in line when no hook fired)."""
+        self._ar_done = False
+        self._ar_event = None
+        self._ar_keep = None
+
+        def hook():
+            if self._ar_done:
+                return
+            self._ar_done = True
+            if torch.device(self.device).type != "cuda":
+                self.allreduce_dense_grads(params_fn())
+                return
+            cur = torch.cuda.current_stream(self.device)
+            if getattr(self, "_ar_stream", None) is None:
+                self._ar_stream = torch.cuda.Stream(device=self.device)
+            side = self._ar_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gs = [p.grad for p in params_fn() if p.grad is not None]
+                if gs:
+                    flat = torch.cat([g.reshape(-1) for g in gs])
+                    dist.all_reduce(flat, group=self.group)
+                    o = 0
+                    for g in gs:
+                        n = g.numel()
+                        g.copy_(flat[o:o + n].view_as(g))
+                        o += n
+                    self._ar_keep = (flat, gs)          # alive until the main stream has joined
+                ev = torch.cuda.Event()
+                ev.record(side)
+            self._ar_event = ev
+        for emb in (model.sparse_embed, model.linear_embed):
+            if emb is not None and hasattr(emb, "plan"):
+                emb.backward_hook = hook
+
+    def finish_allreduce(self, model, params):
+        for emb in (model.sparse_embed, model.linear_embed):
+            if emb is not None and hasattr(emb, "plan"):
+                emb.backward_hook = None
+        if not getattr(self, "_ar_done", False):
+            self.allreduce_dense_grads(params)          # no sharded lookup took part in this backward
+        elif self._ar_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._ar_event)
+        self._ar_keep = None
 
     def describe(self) -> str:
         return self.plan.describe() if self.plan else f"dp{self.world}"

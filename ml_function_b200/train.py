@@ -78,7 +78,7 @@ class Trainer:
 
     def loss(self, dense, ids, labels):
         out = self.model(dense, ids)
-        return keras_binary_crossentropy(labels.view(out.shape), out)
+        return ops.binary_crossentropy(labels, out)        # compile(loss=binary_crossentropy), fused (kon_bce_fwd/bwd)
 
     def step(self, dense, ids, labels) -> torch.Tensor:
         """labels: one-hot ``[B,2]`` (``to_categorical``, DP:359) for the softmax(2) heads,
@@ -90,9 +90,12 @@ class Trainer:
         self._ensure_dense_opt()
         self.dense_opt.zero_grad(set_to_none=True)
         if self.dist is not None:
-            # global loss = mean over ranks of the local means; grads are summed across ranks
+            # global loss = mean over ranks of the local means; grads are summed across ranks.  The dense all-reduce
+            # starts when the first embedding backward starts (all dense grads are final by then) and overlaps the
+            # embedding exchange + scatter-add on a side stream.
+            self.dist.arm_overlapped_allreduce(self.model, lambda: self._dense_params)
             (loss / self.dist.world).backward()
-            self.dist.allreduce_dense_grads(self._dense_params)
+            self.dist.finish_allreduce(self.model, self._dense_params)
         else:
             loss.backward()
         self.dense_opt.step()

@@ -329,3 +329,29 @@ def test_model_builders_vs_reference(name):
             assert_rel(got[k_], ref, 2e-5, f"{name} d{k_}")
         checked += 1
     assert checked >= 2 or name == "fm"
+
+
+def test_fused_bce_loss_vs_reference_losses_and_keras_formula():
+    """kon_bce_fwd/bwd (what the trainer uses) on the reference's own model outputs: the loss value the
+    reference's run produced, and the gradient of the Keras formula (clip, eps inside the logs)."""
+    from ml_function_b200 import ops
+    from ml_function_b200.models import keras_binary_crossentropy
+    for name in ("fm", "deepfm", "dcn", "xdeepfm", "autoint", "nfm", "afm"):
+        c = ref_case("models", name)
+        p = d(c["out/y"]).clone().requires_grad_(True)
+        y = d(c["in/labels"])
+        loss = ops.binary_crossentropy(y, p)
+        assert abs(loss.item() - float(c["out64/loss"])) < 2e-6 * max(1.0, abs(float(c["out64/loss"]))), name
+        loss.backward()
+        q = d(c["out/y"]).double().requires_grad_(True)
+        keras_binary_crossentropy(y.double(), q).backward()
+        assert_rel(p.grad, q.grad, 1e-5, name + " d(bce)/dp")
+    # the clip: no gradient outside [eps, 1-eps], finite loss at exactly 0 and 1
+    p = torch.tensor([[0.0, 1.0], [1e-9, 0.5], [1 - 1e-9, 0.25]], device=DEV, requires_grad=True)
+    y = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 0.0]], device=DEV)
+    loss = ops.binary_crossentropy(y, p)
+    ref = keras_binary_crossentropy(y.double(), p.detach().double())
+    assert abs(loss.item() - ref.item()) < 1e-5 * ref.item() and torch.isfinite(loss)
+    loss.backward()
+    assert p.grad[0, 0].item() == 0.0 and p.grad[0, 1].item() == 0.0 and p.grad[1, 0].item() == 0.0
+    assert p.grad[1, 1].item() < 0.0
