@@ -556,7 +556,7 @@ def verify_sharded(name, args, dev, world, rank, B, rows, mlp_dtype):
         sh, se = model.sparse_embed, ref.sparse_embed
         n_loc = sh.all_offs[-1]
         loc = sum(sg.to_dense(n_loc) for sg in sh.arena.kon_sparse_grads)
-        e_e = 0.0
+        e_e = e_big = 0.0
         fields = plan.tw_of_rank[0] + plan.rw_fields
         for j, f in enumerate(fields):
             lo, hi = se.field_row_offset[f], se.field_row_offset[f + 1]
@@ -568,10 +568,16 @@ def verify_sharded(name, args, dev, world, rank, B, rows, mlp_dtype):
                 full.index_add_(0, r_[sel] - lo, sg.grads[:n][sel])
             if f in plan.rw_fields:
                 full = full[0::world]
-            e_e = max(e_e, rel(loc[sh.all_offs[j]:sh.all_offs[j + 1]], full))
+            e_f = rel(loc[sh.all_offs[j]:sh.all_offs[j + 1]], full)
+            e_e = max(e_e, e_f)
+            if rows[f] >= 1_000_000:      # few duplicates per row: no long fp32 sums whose association order could differ
+                e_big = max(e_big, e_f)
             del full
-        res = {"fwd": e_fwd, "loss": e_loss, "dense_w": e_w, "emb_rows": e_e,
-               "ok": bool(e_fwd < 1e-5 and e_loss < 1e-5 and e_w < 2e-3 and e_e < 1e-5),
+        res = {"fwd": e_fwd, "loss": e_loss, "dense_w": e_w, "emb_rows": e_e, "emb_rows_big_tables": e_big,
+               # small tables sum ~10^4-10^5 fp32 gradient rows per table row; the single-GPU model adds them chunk by
+               # chunk, the sharded owner in one pass: association-order noise up to ~1e-3 of the largest entry.  Tables
+               # with >= 1M rows (short sums) must agree to fp32 rounding.
+               "ok": bool(e_fwd < 1e-5 and e_loss < 1e-5 and e_w < 2e-3 and e_e < 5e-3 and e_big < 1e-5),
                "what": "max rel err, sharded N-rank job vs single-GPU model on the same global batch: rank-0 outputs, "
                        "global loss, dense-weight grads after all-reduce (summation order over the batch differs), "
                        "rank-0-owned embedding-row grads"}

@@ -164,6 +164,22 @@ int kon_peer_free(int device_id, void* ptr);
 int kon_peer_barrier(void* const* peer_flags, int32_t n_peers, int32_t rank, int device_id,
                      int64_t timeout_ms, void* stream);
 
+/* The small exchanges of the sharded step as peer STORES (no NCCL call, no staging): up to KON_MAX_PUTS strided
+ * 2-D copies in one launch, sources in local memory, destinations anywhere (kon_peer_open mappings).  Used for the
+ * all-to-all of the 4-byte ids (columns -> owning rank), of the output gradient rows (columns -> owning rank, so the
+ * scatter-add then reads local memory only), and of the first-order partial sums / their gradients.  All byte
+ * quantities are multiples of 4; 16-byte units are used when everything is 16-byte aligned.  A kon_peer_barrier on
+ * the same stream publishes the data. */
+#define KON_MAX_PUTS 32
+typedef struct {
+  const void* src;      /* local */
+  void*       dst;      /* local or peer mapping */
+  int64_t     src_pitch, dst_pitch;   /* bytes between rows */
+  int64_t     width;    /* bytes per row */
+  int64_t     rows;
+} KonPut2D;
+int kon_peer_put2d(const KonPut2D* puts, int32_t n, int device_id, void* stream);
+
 /* Forward: `ids` [B_global, F_local] are this rank's lookups for the GLOBAL batch (F_local = the
  * fields whose tables this rank owns, `field_row_offset` into its local `arena`).  Sample b belongs
  * to rank q = b / rows_per_peer; its row for local field f is stored at

@@ -20,6 +20,7 @@ namespace kon {
 namespace {
 
 // flag block layout (uint32 words): [0,16) arrival slots, 16 epoch, 17 error
+constexpr int kMaxPuts = KON_MAX_PUTS;
 constexpr int kEpochWord = 16;
 constexpr int kErrorWord = 17;
 
@@ -65,10 +66,77 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
   if (t == 0) mine[kEpochWord] = e;
 }
 
+// ---- generic all-to-all payload mover: up to kMaxPuts strided 2-D copies, sources local, destinations anywhere
+// (peer mappings) -- 16-byte units when every pointer / pitch / width allows it, else 4-byte units.
+// Stores are fire-and-forget, so the remote side runs at NVLink bandwidth instead of at load latency.
+struct PutTable {
+  const char* src[kMaxPuts];
+  char* dst[kMaxPuts];
+  long long src_pitch[kMaxPuts], dst_pitch[kMaxPuts];
+  long long upr[kMaxPuts];        // units per row
+  long long units[kMaxPuts];      // rows * upr
+  int n;
+};
+
+template <typename U>
+__global__ void __launch_bounds__(256) peer_put2d_kernel(const __grid_constant__ PutTable t) {
+  const int d = blockIdx.y;
+  const long long total = t.units[d];
+  const long long upr = t.upr[d];
+  const char* __restrict__ src = t.src[d];
+  char* __restrict__ dst = t.dst[d];
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+    const long long r = u / upr;
+    const long long c = u - r * upr;
+    const U v = *reinterpret_cast<const U*>(src + r * t.src_pitch[d] + c * (long long)sizeof(U));
+    *reinterpret_cast<U*>(dst + r * t.dst_pitch[d] + c * (long long)sizeof(U)) = v;
+  }
+}
+
 }  // namespace
 }  // namespace kon
 
 using namespace kon;
+
+extern "C" int kon_peer_put2d(const KonPut2D* puts, int32_t n, int device_id, void* stream) {
+  KON_REQUIRE(puts != nullptr && n >= 1 && n <= kMaxPuts, KON_EINVAL, "kon_peer_put2d: n=%d outside [1,%d]", n, kMaxPuts);
+  bool vec = true;
+  long long max_units4 = 0;
+  for (int i = 0; i < n; ++i) {
+    const KonPut2D& q = puts[i];
+    KON_REQUIRE(q.rows >= 0 && q.width >= 0, KON_EINVAL, "put %d: negative extent", i);
+    if (q.rows == 0 || q.width == 0) continue;
+    KON_REQUIRE(q.src != nullptr && q.dst != nullptr, KON_EINVAL, "put %d: NULL pointer", i);
+    KON_REQUIRE(((uintptr_t)q.src | (uintptr_t)q.dst | (uintptr_t)q.src_pitch | (uintptr_t)q.dst_pitch | (uintptr_t)q.width) % 4 == 0,
+                KON_EINVAL, "put %d: pointers, pitches and width must be multiples of 4 bytes", i);
+    KON_REQUIRE(q.src_pitch >= q.width || q.rows == 1, KON_EINVAL, "put %d: src_pitch < width", i);
+    if (((uintptr_t)q.src | (uintptr_t)q.dst | (uintptr_t)q.src_pitch | (uintptr_t)q.dst_pitch | (uintptr_t)q.width) % 16 != 0) vec = false;
+    max_units4 = std::max<long long>(max_units4, q.rows * (q.width / 4));
+  }
+  if (max_units4 == 0) return KON_OK;
+  const int unit = vec ? 16 : 4;
+  PutTable t{};
+  t.n = n;
+  for (int i = 0; i < n; ++i) {
+    const KonPut2D& q = puts[i];
+    t.src[i] = static_cast<const char*>(q.src);
+    t.dst[i] = static_cast<char*>(q.dst);
+    t.src_pitch[i] = q.src_pitch;
+    t.dst_pitch[i] = q.dst_pitch;
+    t.upr[i] = q.width / unit;
+    t.units[i] = (q.rows == 0 || q.width == 0) ? 0 : q.rows * (q.width / unit);
+    if (t.upr[i] == 0) t.upr[i] = 1;
+  }
+  DeviceGuard guard(device_id);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long max_units = max_units4 * 4 / unit;
+  const int gx = (int)std::max<long long>(1, std::min<long long>((max_units + 255) / 256, (long long)sm_count_of(device_id) * 8 / std::max(1, std::min(n, 8))));
+  dim3 grid(gx, n);
+  if (vec) peer_put2d_kernel<uint4><<<grid, 256, 0, st>>>(t);
+  else peer_put2d_kernel<uint32_t><<<grid, 256, 0, st>>>(t);
+  KON_LAUNCH_CHECK("peer_put2d_kernel");
+  return KON_OK;
+}
 
 extern "C" int kon_peer_alloc(int device_id, size_t bytes, void** ptr, void* handle64) {
   KON_REQUIRE(ptr != nullptr && handle64 != nullptr && bytes > 0, KON_EINVAL, "kon_peer_alloc: bad argument");

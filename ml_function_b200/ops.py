@@ -121,6 +121,10 @@ def new_step(presort: bool = True):
 
 def end_step():
     global _SHARE_SORT
+    # sharded jobs: a first-order gradient whose owner-side scatter was deferred to the embedding backward's barrier
+    # (parallel._ShardedSumPeer) and never picked up -- publish and scatter it now (same on every rank)
+    for key in [k_ for k_ in _STEP_CACHE if isinstance(k_, tuple) and k_ and k_[0] == "lin_bwd"]:
+        _STEP_CACHE.pop(key)(need_barrier=True)
     _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()

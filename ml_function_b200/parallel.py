@@ -295,10 +295,36 @@ class PeerRegion:
         self.local_ptr = None
 
 
+def _put2d(sh, puts):
+    """puts: list of (src_ptr, dst_ptr, src_pitch, dst_pitch, width, rows) in bytes -> one kon_peer_put2d launch."""
+    from . import _lib as L
+    puts = [p for p in puts if p[4] > 0 and p[5] > 0]
+    if not puts:
+        return
+    arr = (L.KonPut2D * len(puts))(*[L.KonPut2D(*p) for p in puts])
+    dev = sh.arena.device
+    L.check(L.lib().kon_peer_put2d(arr, len(puts), dev.index if dev.index is not None else torch.cuda.current_device(),
+                                   L.stream_ptr(dev)), "kon_peer_put2d")
+
+
 class _PeerLookup(torch.autograd.Function):
-    """ids_local [B_l,F] (+ dense [B_l,nd]) -> xcat [B_l,width] = [emb (F*k, global field order) | dense | 0]
-    with the pooled-embedding exchange fused into the gather kernel (stores over NVLink) and the dOut
-    exchange fused into the backward's segmented reduction (loads over NVLink)."""
+    """ids_local [B_l,F] (+ dense [B_l,nd]) -> xcat [B_l,width] = [emb (F*k, global field order) | dense | 0].
+
+    Everything the sharded embedding step exchanges travels as peer STORES over NVLink, published by flag barriers
+    (three per step) -- no NCCL call on this path:
+      forward   (A) the 4-byte ids: every rank stores each owner's columns into the owner's region   [kon_peer_put2d]
+                    -- barrier A --
+                (1) the owners gather for the GLOBAL batch and store every row straight into the concat buffer of
+                    the sample's rank [kon_embed_fwd_peer]; the first-order partial sums of the linear partner
+                    layer ride along [kon_peer_put2d]
+                    -- barrier 1 --
+      backward  (2) every rank stores each owner's columns of its output gradient into the owner's receive buffer
+                    [kon_peer_put2d] (stores are fire-and-forget: the 95 MB/GPU move at NVLink bandwidth, where the
+                    r1 design's row loads from the scatter kernel ran at NVLink latency); the linear partner's
+                    gradient rides along
+                    -- barrier 2 --
+                    the owner's sort-then-segment scatter-add reads LOCAL memory only [kon_embed_bwd].
+    Buffer reuse across steps is ordered by barrier A of the next step (a rank reaches it only after its backward)."""
 
     @staticmethod
     def forward(ctx, arena, ids_local, dense, sh: "ShardedEmbed", width: int):
@@ -306,10 +332,8 @@ class _PeerLookup(torch.autograd.Function):
         plan, N, rank = sh.plan, sh.world, sh.rank
         B_l, F = ids_local.shape
         k = arena.shape[1]
-        ids_tw, ids_rw = sh.exchange_ids(ids_local)      # NCCL, 4 B per lookup; also orders this step's
-        px = sh.peer_buffers(B_l, width)                 # peer stores after every rank's previous step
-        # (the side-stream routing sort of ops.embed_presort is a single-GPU optimisation for now: it has not
-        # been measured next to the NCCL / peer traffic of the sharded step)
+        px = sh.peer_buffers(B_l, width)
+        ids_tw, ids_rw = sh.exchange_ids(ids_local, px)  # (A) + barrier A
         xcat, region = px["xcat"], px["region"]
         n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
         if n_tw:
@@ -325,7 +349,17 @@ class _PeerLookup(torch.autograd.Function):
             xcat[:, F * k:F * k + nd].copy_(dense)
         if width > F * k + nd:
             xcat[:, F * k + nd:].zero_()
-        region.barrier()
+        # the linear partner's first-order partial sums ride on the same barrier
+        lp = sh.lin_partner
+        lin_ids = None
+        if lp is not None and lp._seen_use and ops._SHARE_SORT:
+            lin_ids = ids_tw if n_rw == 0 else torch.cat([ids_tw, ids_rw], dim=1).contiguous()
+            part = lp.lookup_fn(lp.arena, lin_ids, lp.all_offs, True)             # [B_g, 1]
+            _put2d(sh, [(part.data_ptr() + q * B_l * 4, region.ptrs[q] + px["linparts_off"] + rank * 4, 4, N * 4, 4, B_l)
+                        for q in range(N)])
+        region.barrier()                                  # barrier 1: rows (and partial sums) complete
+        if lin_ids is not None:
+            ops._STEP_CACHE[("lin_fwd", id(plan))] = (px["linparts"].sum(dim=1, keepdim=True), lin_ids, px)
         if not plan.identity_order:      # row-wise fields interleaved with table-wise ones: one permutation copy
             emb = xcat[:, :F * k].view(B_l, F, k).index_select(1, sh.to_global)
             out = torch.cat([emb.reshape(B_l, F * k), xcat[:, F * k:]], dim=1)
@@ -346,25 +380,76 @@ class _PeerLookup(torch.autograd.Function):
         ids_tw, ids_rw = ctx.saved_tensors
         plan, N, rank = sh.plan, sh.world, sh.rank
         B_l, F, k, nd, width = ctx.dims
-        region, dbuf = px["region"], px["dbuf"]
-        gemb = gout[:, :F * k].reshape(B_l, F, k)
-        if not plan.identity_order:
-            gemb = gemb.index_select(1, sh.to_exchange)
-        dbuf.copy_(gemb)
-        region.barrier()                 # every rank's dOut is in place
+        region = px["region"]
         n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
+        if plan.identity_order and gout.stride(1) == 1 and gout.stride(0) % 4 == 0 and gout.data_ptr() % 16 == 0:
+            gsrc, pitch = gout, gout.stride(0) * 4       # columns [0, F*k) of the concat-buffer gradient, in place
+        else:
+            gemb = gout[:, :F * k].reshape(B_l, F, k)
+            if not plan.identity_order:
+                gemb = gemb.index_select(1, sh.to_exchange)
+            gsrc, pitch = gemb.contiguous(), F * k * 4
+        puts = []
+        for q, (o, c) in enumerate(sh.tw_slabs):         # owner q's columns -> rows [rank*B_l, ...) of its receive buffer
+            puts.append((gsrc.data_ptr() + o * k * 4, region.ptrs[q] + px["drecv_tw_off"] + rank * B_l * c * k * 4,
+                         pitch, c * k * 4, c * k * 4, B_l))
+        if n_rw:                                          # row-wise columns: every rank needs them (its rows of the tables)
+            for q in range(N):
+                puts.append((gsrc.data_ptr() + n_tw_all * k * 4, region.ptrs[q] + px["drecv_rw_off"] + rank * B_l * n_rw * k * 4,
+                             pitch, n_rw * k * 4, n_rw * k * 4, B_l))
+        _put2d(sh, puts)
+        region.barrier()                                  # barrier 2: every rank's dOut (and first-order gradient) is in place
         if arena.requires_grad:
             if not hasattr(arena, "kon_sparse_grads"):
                 arena.kon_sparse_grads = []
             if n_tw:
-                col0 = sh.tw_slabs[rank][0]
-                arena.kon_sparse_grads.append(ops.embed_bwd_peer(
-                    region.ptr_array(px["dbuf_off"] + col0 * k * 4), N, B_l, F * k, k, k, ids_tw, sh.tw_offs))
+                d_tw = px["drecv_tw"][:N * B_l * n_tw * k].view(N * B_l, n_tw, k)
+                arena.kon_sparse_grads.append(ops.embed_bwd_raw(d_tw, ids_tw, sh.tw_offs))
             if n_rw:
-                arena.kon_sparse_grads.append(ops.embed_bwd_peer(
-                    region.ptr_array(px["dbuf_off"] + n_tw_all * k * 4), N, B_l, F * k, k, k, ids_rw, sh.rw_offs))
+                d_rw = px["drecv_rw"].view(N * B_l, n_rw, k)
+                arena.kon_sparse_grads.append(ops.embed_bwd_raw(d_rw, ids_rw, sh.rw_offs))
+        deferred = ops._STEP_CACHE.pop(("lin_bwd", id(plan)), None)
+        if deferred is not None:
+            deferred()
         gdense = gout[:, F * k:F * k + nd] if nd else None
         return None, None, gdense, None, None
+
+
+class _ShardedSumPeer(torch.autograd.Function):
+    """First-order sum whose exchange rode on the embedding layer's barriers (see ``_PeerLookup``): the forward value
+    was assembled there; the backward stores this rank's gradient into every owner's receive buffer and leaves the
+    owner-side scatter-add to run right after barrier 2 of the embedding backward (same step, same stream)."""
+
+    @staticmethod
+    def forward(ctx, arena, mine, lin_ids, sh: "ShardedEmbed", px):
+        ctx.sh, ctx.arena, ctx.px = sh, arena, px
+        ctx.save_for_backward(lin_ids)
+        return mine.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        _fire_backward_hook(ctx.sh)
+        from . import ops
+        sh, arena, px = ctx.sh, ctx.arena, ctx.px
+        (lin_ids,) = ctx.saved_tensors
+        N, rank = sh.world, sh.rank
+        B_l = gout.shape[0]
+        g = gout.contiguous()
+        region = px["region"]
+        sp = sh.sparse_partner
+        _put2d(sp, [(g.data_ptr(), region.ptrs[q] + px["lin_grecv_off"] + rank * B_l * 4, 4, 4, 4, B_l) for q in range(N)])
+
+        def scatter(need_barrier=False):
+            if need_barrier:                              # no embedding backward followed in this step (ops.end_step)
+                region.barrier()
+            if arena.requires_grad:
+                full = px["lin_grecv"].view(N * B_l, 1)
+                g3 = full.unsqueeze(1).expand(N * B_l, lin_ids.shape[1], 1)
+                if not hasattr(arena, "kon_sparse_grads"):
+                    arena.kon_sparse_grads = []
+                arena.kon_sparse_grads.append(sh.scatter_fn(g3, lin_ids, sh.all_offs))
+        ops._STEP_CACHE[("lin_bwd", id(sh.plan))] = scatter
+        return None, None, None, None, None
 
 
 class _ShardedSum(torch.autograd.Function):
@@ -456,19 +541,38 @@ class ShardedEmbed(nn.Module):
                          and dist.get_backend(group) == "nccl" and self.dim % 4 == 0 and self.world <= 16
                          and os.environ.get("KON_PEER_EXCHANGE", "1") != "0")
         self._peer = {}
+        # the first-order (linear) layer of the same model rides on the embedding layer's barriers (DistContext.attach
+        # links the two); `_seen_use` is set by the linear layer's first lookup_sum, so models that never read the
+        # first-order tables (DCN, AutoInt) do not pay for their partial sums
+        object.__setattr__(self, "lin_partner", None)
+        object.__setattr__(self, "sparse_partner", None)
+        self._seen_use = False
 
     def peer_buffers(self, B_l: int, width: int):
         """The rank's exchange region for one (local batch, row width); built collectively on first use
-        (every rank sees the same shapes in the same order)."""
-        F, k = len(self.plan.rows), self.dim
+        (every rank sees the same shapes in the same order).  Sub-buffers (same offsets on every rank; sizes use the
+        largest per-rank field count): ``xcat`` [B_l,width] | ``ids_tw`` int32 [N*B_l*n_tw_max] | ``ids_rw`` int32
+        [N*B_l*n_rw] | ``drecv_tw`` [N*B_l*n_tw_max*k] | ``drecv_rw`` [N*B_l*n_rw*k] | ``linparts`` [B_l,N] |
+        ``lin_grecv`` [N*B_l]."""
+        F, k, N = len(self.plan.rows), self.dim, self.world
         if (B_l, width) in self._peer:
             return self._peer[(B_l, width)]
-        nbytes = PeerRegion.FLAG_BYTES + (B_l * width * 4 + 255) // 256 * 256 + (B_l * F * k * 4 + 255) // 256 * 256
-        region = PeerRegion(self.group, self.arena.device, nbytes)
-        xcat, xo = region.carve((B_l, width))
-        dbuf, do = region.carve((B_l, F, k))
-        self._peer[(B_l, width)] = dict(region=region, xcat=xcat, xcat_off=xo, dbuf=dbuf, dbuf_off=do)
-        return self._peer[(B_l, width)]
+        n_tw_max = max(max(len(t) for t in self.plan.tw_of_rank), 1)
+        n_rw = len(self.plan.rw_fields)
+        al = lambda nb: (nb + 255) // 256 * 256
+        sizes = [B_l * width * 4, N * B_l * n_tw_max * 4, N * B_l * max(n_rw, 1) * 4, N * B_l * n_tw_max * k * 4,
+                 N * B_l * max(n_rw, 1) * k * 4, B_l * N * 4, N * B_l * 4]
+        region = PeerRegion(self.group, self.arena.device, PeerRegion.FLAG_BYTES + sum(al(x) for x in sizes))
+        px = dict(region=region)
+        px["xcat"], px["xcat_off"] = region.carve((B_l, width))
+        px["ids_tw"], px["ids_tw_off"] = region.carve((N * B_l * n_tw_max,), torch.int32)
+        px["ids_rw"], px["ids_rw_off"] = region.carve((N * B_l * max(n_rw, 1),), torch.int32)
+        px["drecv_tw"], px["drecv_tw_off"] = region.carve((N * B_l * n_tw_max * k,))
+        px["drecv_rw"], px["drecv_rw_off"] = region.carve((N * B_l * max(n_rw, 1) * k,))
+        px["linparts"], px["linparts_off"] = region.carve((B_l, N))
+        px["lin_grecv"], px["lin_grecv_off"] = region.carve((N * B_l,))
+        self._peer[(B_l, width)] = px
+        return px
 
     def check_peer(self):
         """Raise ``KonError`` if any exchange barrier of this layer timed out (synchronises)."""
@@ -481,7 +585,33 @@ class ShardedEmbed(nn.Module):
             px["region"].close()
         self._peer = {}
 
-    def exchange_ids(self, ids_local: torch.Tensor):
+    def _exchange_ids_peer(self, ids_local: torch.Tensor, px):
+        """The ids all-to-all as peer stores + one flag barrier (int32 ids, identity field order)."""
+        N, plan, rank = self.world, self.plan, self.rank
+        B_l, F = ids_local.shape
+        region = px["region"]
+        n_loc, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
+        src = ids_local if plan.identity_order else ids_local.index_select(1, self.to_exchange).contiguous()
+        base, pitch = src.data_ptr(), F * 4
+        puts = [(base + o * 4, region.ptrs[q] + px["ids_tw_off"] + rank * B_l * c * 4, pitch, c * 4, c * 4, B_l)
+                for q, (o, c) in enumerate(self.tw_slabs)]
+        if n_rw:
+            puts += [(base + n_tw_all * 4, region.ptrs[q] + px["ids_rw_off"] + rank * B_l * n_rw * 4, pitch, n_rw * 4,
+                      n_rw * 4, B_l) for q in range(N)]
+        _put2d(self, puts)
+        region.barrier()                                  # barrier A (also: every rank has finished its previous step)
+        # copies out of the region: the ids are read again by the backward's routing sort, after peers may have
+        # stored the NEXT step's ids
+        ids_tw = px["ids_tw"][:N * B_l * n_loc].view(N * B_l, n_loc).clone()
+        if n_rw:
+            r = px["ids_rw"][:N * B_l * n_rw].view(N * B_l, n_rw)
+            own = (r % N) == rank
+            ids_rw = torch.where(own, torch.div(r, N, rounding_mode="floor"), torch.full_like(r, -1)).contiguous()
+        else:
+            ids_rw = torch.empty((N * B_l, 0), dtype=ids_local.dtype, device=ids_local.device)
+        return ids_tw, ids_rw
+
+    def exchange_ids(self, ids_local: torch.Tensor, px=None):
         """Local ids ``[B_l,F]`` -> this rank's lookups for the GLOBAL batch:
         (table-wise ids ``[B_g, n_tw_loc]``, row-wise local row ids ``[B_g, n_rw]`` with -1 where the
         row lives on another rank).  Each owner only receives the columns it owns (all-to-all of
@@ -493,6 +623,11 @@ class ShardedEmbed(nn.Module):
         ckey = ("ids", id(plan), ids_local.data_ptr(), ids_local._version, tuple(ids_local.shape))
         if ops._SHARE_SORT and ckey in ops._STEP_CACHE:
             return ops._STEP_CACHE[ckey]
+        if px is not None and ids_local.dtype == torch.int32 and ids_local.is_contiguous():
+            out = self._exchange_ids_peer(ids_local, px)
+            if ops._SHARE_SORT:
+                ops._STEP_CACHE[ckey] = out
+            return out
         B_l = ids_local.shape[0]
         dev = ids_local.device
         n_loc = len(plan.tw_of_rank[self.rank])
@@ -547,6 +682,12 @@ class ShardedEmbed(nn.Module):
         return _ShardedLookup.apply(self.arena, ids, self)
 
     def lookup_sum(self, ids: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        self._seen_use = True
+        cached = ops._STEP_CACHE.pop(("lin_fwd", id(self.plan)), None) if ops._SHARE_SORT else None
+        if cached is not None and self.sparse_partner is not None:
+            mine, lin_ids, px = cached
+            return _ShardedSumPeer.apply(self.arena, mine, lin_ids, self, px)
         return _ShardedSum.apply(self.arena, ids, self)
 
     def lookup_concat(self, ids: torch.Tensor, dense: Optional[torch.Tensor], width: int) -> torch.Tensor:
@@ -579,6 +720,9 @@ class DistContext:
         model.sparse_embed = ShardedEmbed(info, self.plan, self.group, dev, is_linear=False, seed=old.seed)
         if model.linear_embed is not None:
             model.linear_embed = ShardedEmbed(info, self.plan, self.group, dev, is_linear=True, seed=old.seed)
+            if model.sparse_embed.use_peer:      # plain attributes (not sub-modules: the link is cyclic)
+                object.__setattr__(model.sparse_embed, "lin_partner", model.linear_embed)
+                object.__setattr__(model.linear_embed, "sparse_partner", model.sparse_embed)
         del old
         return model
 

@@ -366,6 +366,29 @@ def layer_cases(ns):
                 "out/score_add": CL.ScoreLayer(use_add=True)([c.t(s1), c.t(s2), c.t(s3)]),
                 "out/score": CL.ScoreLayer()(c.t(s1))}
     cases["heads"] = both(ns, heads_case)
+    # ---- DP:85-102, 294-301: the reference's own feature encoders (pandas + sklearn, no TensorFlow involved) ----
+    import pandas as pd
+    r2 = np.random.RandomState(77)
+    n_rows = 60
+    cats = np.array(["a", "b", "10", "9", "zz", "A", "-1", "x y"])
+    sdf = pd.DataFrame({"C14": cats[r2.randint(0, 8, n_rows)], "C15": r2.randint(0, 5, n_rows).astype(object),
+                        "C16": cats[r2.randint(0, 3, n_rows)]})
+    sdf.loc[[3, 17, 40], "C14"] = np.nan
+    sdf.loc[[5, 6], "C15"] = np.nan
+    ddf = pd.DataFrame({"I1": r2.rand(n_rows) * 50 - 10, "I2": r2.randint(0, 4, n_rows).astype(float), "I3": np.full(n_rows, 2.5)})
+    ddf.loc[[1, 2, 30], "I1"] = np.nan
+    ddf.loc[[9], "I2"] = np.nan
+    dp2 = DP.data_prepare(batch_size=16)
+    enc, sinfo = dp2.sparse_fea_deal(sdf.copy())
+    den, dinfo = dp2.dense_fea_deal(ddf.copy())
+    cases["data_prepare"] = {
+        "in/sparse": np.array(sdf.fillna("<nan>").astype(str).to_numpy(), dtype="U8"),
+        "in/dense": ddf.to_numpy(dtype=np.float64),
+        "out/ids": enc.to_numpy().astype(np.int64), "out/word_size": np.array([i.word_size for i in sinfo]),
+        "out/cross_unit": np.array([i.cross_unit for i in sinfo]), "out/emb_reg": np.array([i.emb_reg for i in sinfo]),
+        "out/dense": den.to_numpy(dtype=np.float64),
+        "out/fields": np.array(list(sinfo[0]._fields), dtype="U16"),
+    }
     return cases
 
 
@@ -495,7 +518,9 @@ def generate():
 
 def _same(a, b):
     a, b = np.asarray(a), np.asarray(b)
-    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    return np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
 
 
 def check(verbose=True):

@@ -69,7 +69,7 @@ def ref_case(which: str, name: str) -> RefCase:
     c = RefCase()
     for k in z.files:
         if k.startswith(pre):
-            c[k[len(pre):]] = torch.from_numpy(z[k])
+            c[k[len(pre):]] = torch.from_numpy(z[k]) if z[k].dtype.kind in "fiub" else z[k]
     assert c, "no fixture case %r in ref_%s.npz" % (name, which)
     return c
 

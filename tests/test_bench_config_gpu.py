@@ -100,8 +100,11 @@ def test_xdeepfm_at_the_benched_config_sampled_rows():
     p = torch.clamp(ref, 1e-7, 1 - 1e-7)
     part = (-(yl * torch.log(p + 1e-7) + (1 - yl) * torch.log(1 - p + 1e-7))).sum() / B
     part.backward()
-    assert_rel(xcat.grad[idx][:, :F * k], X.grad[:, :F * k], 2e-2, "xdeepfm bench-config d(loss)/d(embedding rows)")
-    assert_rel(xcat.grad[idx][:, F * k:F * k + 13], X.grad[:, F * k:F * k + 13], 2e-2, "d(loss)/d(dense features)")
+    e_emb = rel_err(xcat.grad[idx][:, :F * k], X.grad[:, :F * k])
+    e_den = rel_err(xcat.grad[idx][:, F * k:F * k + 13], X.grad[:, F * k:F * k + 13])
+    print(f"bench-config xDeepFM: out err {rel_err(out.detach()[idx], ref):.3e}, d/d(emb rows) {e_emb:.3e}, d/d(dense) {e_den:.3e}")
+    assert e_emb <= 2e-2, f"xdeepfm bench-config d(loss)/d(embedding rows): rel err {e_emb:.3e} > 2e-2"
+    assert e_den <= 2e-2, f"xdeepfm bench-config d(loss)/d(dense features): rel err {e_den:.3e} > 2e-2"
     del model
     torch.cuda.empty_cache()
 

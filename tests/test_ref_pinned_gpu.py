@@ -341,7 +341,9 @@ def test_fused_bce_loss_vs_reference_losses_and_keras_formula():
         p = d(c["out/y"]).clone().requires_grad_(True)
         y = d(c["in/labels"])
         loss = ops.binary_crossentropy(y, p)
-        assert abs(loss.item() - float(c["out64/loss"])) < 2e-6 * max(1.0, abs(float(c["out64/loss"]))), name
+        # `out/loss` is the reference's fp32 loss on exactly these fp32 outputs (the fp64 run's outputs differ in the
+        # last bits, which matters where a probability rounds to the clip boundary)
+        assert abs(loss.item() - float(c["out/loss"])) < 2e-6 * max(1.0, abs(float(c["out/loss"]))), name
         loss.backward()
         q = d(c["out/y"]).double().requires_grad_(True)
         keras_binary_crossentropy(y.double(), q).backward()
