@@ -568,7 +568,14 @@ def verify_sharded(name, args, dev, world, rank, B, rows, mlp_dtype):
                 full.index_add_(0, r_[sel] - lo, sg.grads[:n][sel])
             if f in plan.rw_fields:
                 full = full[0::world]
-            e_f = rel(loc[sh.all_offs[j]:sh.all_offs[j + 1]], full)
+            mine_f = loc[sh.all_offs[j]:sh.all_offs[j + 1]]
+            e_f = rel(mine_f, full)
+            if os.environ.get("KON_VERIFY_DETAIL"):
+                dd = (mine_f - full).abs().amax(dim=1)
+                bad = dd > 1e-5 * float(full.abs().max())
+                print(f"verify detail: field {f} rows {rows[f]} err {e_f:.3e} max|ref| {float(full.abs().max()):.3e} "
+                      f"bad rows {int(bad.sum())} of {int((full.abs().amax(dim=1) > 0).sum())} touched; "
+                      f"touched-mismatch {int(((mine_f.abs().amax(dim=1) > 0) != (full.abs().amax(dim=1) > 0)).sum())}", file=sys.stderr)
             e_e = max(e_e, e_f)
             if rows[f] >= 1_000_000:      # few duplicates per row: no long fp32 sums whose association order could differ
                 e_big = max(e_big, e_f)

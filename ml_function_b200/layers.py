@@ -527,26 +527,42 @@ class StackLayer(nn.Module):
         return torch.cat(list(inputs), dim=self.axis if self.axis else -1)
 
 
+def _bias_act_gemm(x, w, b, relu: bool):
+    """``x @ w + b`` with the bias (and ReLU) applied in the GEMM epilogue (cuBLASLt), one kernel."""
+    if relu:
+        return torch._addmm_activation(b, x, w)            # epilogue: bias + ReLU
+    return torch.addmm(b, x, w)
+
+
+def _relu_grad(g, y):
+    return torch.ops.aten.threshold_backward(g, y, 0)     # g * (y > 0), one kernel, from the saved OUTPUT
+
+
 class _DenseFn(torch.autograd.Function):
-    """``x @ w + b`` whose bias gradient is a GEMV ``ones^T @ g`` on cuBLAS instead of torch's
-    column reduction (65,536 x 256 bf16: 65 us -> a few us)."""
+    """``[ReLU](x @ w + b)`` (CL:190 + CL:216 when no residual sits in between): bias and activation live in the GEMM
+    epilogue; the bias gradient is a GEMV ``ones^T @ g`` on cuBLAS instead of torch's column reduction
+    (65,536 x 256 bf16: 65 us -> a few us)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
-        ctx.save_for_backward(x, w)
-        return torch.addmm(b, x, w)
+    def forward(ctx, x, w, b, relu=False):
+        y = _bias_act_gemm(x, w, b, relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu = relu
+        return y
 
     @staticmethod
     def backward(ctx, g):
-        x, w = ctx.saved_tensors
+        x, w, y = ctx.saved_tensors
         g = g.contiguous()
+        if ctx.relu:
+            g = _relu_grad(g, y)
         gx = g @ w.t() if ctx.needs_input_grad[0] else None
         gw = x.t() @ g if ctx.needs_input_grad[1] else None
         gb = None
         if ctx.needs_input_grad[2]:
             ones = torch.ones((1, g.shape[0]), dtype=g.dtype, device=g.device)
             gb = (ones @ g).reshape(-1)
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 def _mm_f32_out(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -564,22 +580,26 @@ class _DenseCastFn(torch.autograd.Function):
     bf16 -> fp32 cast pass over the [B, 13+F*k] gradient."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, relu=False):
         xc = x.to(w.dtype)
-        ctx.save_for_backward(xc, w)
-        return torch.addmm(b, xc, w)
+        y = _bias_act_gemm(xc, w, b, relu)
+        ctx.save_for_backward(xc, w, y if relu else None)
+        ctx.relu = relu
+        return y
 
     @staticmethod
     def backward(ctx, g):
-        xc, w = ctx.saved_tensors
+        xc, w, y = ctx.saved_tensors
         g = g.contiguous()
+        if ctx.relu:
+            g = _relu_grad(g, y)
         gx = _mm_f32_out(g, w.t()) if ctx.needs_input_grad[0] else None
         gw = xc.t() @ g if ctx.needs_input_grad[1] else None
         gb = None
         if ctx.needs_input_grad[2]:
             ones = torch.ones((1, g.shape[0]), dtype=g.dtype, device=g.device)
             gb = (ones @ g).reshape(-1)
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 class DnnLayer(nn.Module):
@@ -631,13 +651,14 @@ class DnnLayer(nn.Module):
         cd = self.compute_dtype
         for i, (w, b) in enumerate(zip(self.kernels, self.biases)):
             ori = x
+            res = w.shape[0] == w.shape[1]                 # the reference's Add([ori, x]) fires (CL:206-214)
+            fuse = not res                                 # else ReLU follows the residual add, outside the GEMM
             if cd is not None and x.dtype != cd:
-                x = _DenseCastFn.apply(x, w.to(cd), b.to(cd)) if i == 0 else _DenseFn.apply(x.to(cd), w.to(cd), b.to(cd))
+                x = _DenseCastFn.apply(x, w.to(cd), b.to(cd), fuse) if i == 0 else _DenseFn.apply(x.to(cd), w.to(cd), b.to(cd), fuse)
             else:
-                x = _DenseFn.apply(x, w.to(x.dtype), b.to(x.dtype))
-            if ori.shape == x.shape:
-                x = ori.to(x.dtype) + x
-            x = torch.relu(x)
+                x = _DenseFn.apply(x, w.to(x.dtype), b.to(x.dtype), fuse)
+            if res:
+                x = torch.relu(ori.to(x.dtype) + x)
         if cd is not None and x.dtype != cd:      # no hidden layer: the logit layer still runs in the compute dtype
             x = x.to(cd)
         if self.logit_kernel is not None:
