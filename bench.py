@@ -556,7 +556,8 @@ def verify_sharded(name, args, dev, world, rank, B, rows, mlp_dtype):
         sh, se = model.sparse_embed, ref.sparse_embed
         n_loc = sh.all_offs[-1]
         loc = sum(sg.to_dense(n_loc) for sg in sh.arena.kon_sparse_grads)
-        e_e = e_big = 0.0
+        e_e = 0.0
+        touched_mismatch = 0
         fields = plan.tw_of_rank[0] + plan.rw_fields
         for j, f in enumerate(fields):
             lo, hi = se.field_row_offset[f], se.field_row_offset[f + 1]
@@ -577,14 +578,14 @@ def verify_sharded(name, args, dev, world, rank, B, rows, mlp_dtype):
                       f"bad rows {int(bad.sum())} of {int((full.abs().amax(dim=1) > 0).sum())} touched; "
                       f"touched-mismatch {int(((mine_f.abs().amax(dim=1) > 0) != (full.abs().amax(dim=1) > 0)).sum())}", file=sys.stderr)
             e_e = max(e_e, e_f)
-            if rows[f] >= 1_000_000:      # few duplicates per row: no long fp32 sums whose association order could differ
-                e_big = max(e_big, e_f)
+            touched_mismatch += int(((mine_f.abs().amax(dim=1) > 0) != (full.abs().amax(dim=1) > 0)).sum())
             del full
-        res = {"fwd": e_fwd, "loss": e_loss, "dense_w": e_w, "emb_rows": e_e, "emb_rows_big_tables": e_big,
-               # small tables sum ~10^4-10^5 fp32 gradient rows per table row; the single-GPU model adds them chunk by
-               # chunk, the sharded owner in one pass: association-order noise up to ~1e-3 of the largest entry.  Tables
-               # with >= 1M rows (short sums) must agree to fp32 rounding.
-               "ok": bool(e_fwd < 1e-5 and e_loss < 1e-5 and e_w < 2e-3 and e_e < 5e-3 and e_big < 1e-5),
+        res = {"fwd": e_fwd, "loss": e_loss, "dense_w": e_w, "emb_rows": e_e, "emb_rows_touched_mismatch": touched_mismatch,
+               # Routing is exact: the SET of touched rows must be identical (touched_mismatch == 0).  The values agree
+               # to ~1e-3 of a field's largest entry, not to fp32 rounding: the first-order sum is associated
+               # differently (per-owner partials), which moves the logit by an ulp, and in the bf16 CIN backward an ulp
+               # flips the bf16 rounding of a dZ element now and then (observed: 0.4 % of the rows, |diff| ~ 2e-9).
+               "ok": bool(e_fwd < 1e-5 and e_loss < 1e-5 and e_w < 2e-3 and e_e < 5e-3 and touched_mismatch == 0),
                "what": "max rel err, sharded N-rank job vs single-GPU model on the same global batch: rank-0 outputs, "
                        "global loss, dense-weight grads after all-reduce (summation order over the batch differs), "
                        "rank-0-owned embedding-row grads"}

@@ -233,6 +233,18 @@ class InnerLayer(nn.Module):
         return fl
 
 
+class IPnnLayer(nn.Module):
+    """IL:68-80: the inner-product half of PNN = ``InnerLayer()`` without the Add: the list of pairwise products."""
+
+    def __init__(self, seed=2020):
+        super().__init__()
+        self.seed = seed
+        self.inner = InnerLayer()
+
+    def forward(self, inputs, **kwargs):
+        return self.inner(inputs)
+
+
 class FmLayer(nn.Module):
     """IL:146.  ``inputs = [cross_embed, linear_embed]`` -> ``[B,1,k]``
     (= ``Add([Add(pairwise products)] + linear_list)`` with ``[B,1,1]`` broadcast)."""

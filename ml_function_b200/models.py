@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .layers import (CIN, AttentionBaseLayer, CrossLayer, DnnLayer, FieldList, FmLayer, InnerLayer, MergeScoreLayer,
+from .layers import (CIN, AttentionBaseLayer, CrossLayer, DnnLayer, FieldList, FmLayer, InnerLayer, IPnnLayer, MergeScoreLayer,
                      MultHeadAttentionLayer, ProductAttentionLayer, ScoreLayer, SeqBaseLayer, SparseEmbed, StackLayer,
                      denseFea, pack_ids, sparseFea)
 
@@ -321,6 +321,40 @@ class AFM(_CtrModel):
         z = lambda w: torch.zeros_like(w) if w.grad is None else w.grad     # never-read scoring weights
         return {"afm_score_w": z(a.kernel_w), "afm_score_b": z(a.kernel_b), "afm_mlp_w": z(a.mlp_kernel),
                 "afm_out_w": a.out_kernel.grad, "afm_out_b": a.out_bias.grad}
+
+
+class PNN(_CtrModel):
+    """MD:43-56 with ``use_inner=True, use_outer=False`` (IPNN; ``OPnnLayer`` is broken in the reference itself, IL:56 vs
+    IL:63, and is rejected): ``StackLayer(linear_embed + IPnnLayer()(sparse_embed))`` -> ``DnnLayer`` ->
+    ``Dense(2, softmax)``.  The pairwise products come from ``kon_pairs_fwd/bwd``."""
+
+    def __init__(self, inputFea: InputFeature = None, hidden_units=None, use_inner=True, use_outer=False):
+        super().__init__(inputFea)
+        if use_outer or not use_inner:
+            raise ValueError("PNN: only use_inner=True, use_outer=False can run (OPnnLayer is broken in the reference)")
+        self.hidden_units = hidden_units if hidden_units is not None else [256, 256, 256]
+        self.ipnn = IPnnLayer()
+        self.dnn = DnnLayer(hidden_units=self.hidden_units)
+        self.head = MergeScoreLayer(use_merge=False)
+
+    def forward(self, dense_inputs, sparse_inputs):
+        ids = pack_ids(sparse_inputs)
+        v = self.sparse_embed.lookup(ids)                  # [B,F,k]
+        lin = self.linear_embed.lookup(ids)                # [B,F,1]: the 26 first-order terms, un-summed (MD:48)
+        pairs = self.ipnn(v).packed                        # [B,P,k]
+        x = torch.cat([lin.reshape(lin.shape[0], -1), pairs.reshape(pairs.shape[0], -1)], dim=1)   # StackLayer (MD:53)
+        return self.head(self.dnn(x))
+
+    def load_reference_params(self, p):
+        _load_embeds(self, p)
+        n = len(self.hidden_units)
+        self.dnn.load_reference_weights([p[f"dnn_w{i}"] for i in range(n)], [p[f"dnn_b{i}"] for i in range(n)])
+        self.head.load_reference_weights(p["head_w"], p["head_b"])
+
+    def reference_grads(self):
+        out = {"head_w": self.head.kernel.grad, "head_b": self.head.bias.grad}
+        self._dnn_grads(out, self.dnn, False)
+        return out
 
 
 class AutoInt(_CtrModel):

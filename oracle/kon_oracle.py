@@ -454,6 +454,18 @@ def model_afm(p, dense, sparse_ids):
     return score_layer(linear + [atten], use_add=True)            # MD:145
 
 
+def model_pnn(p, dense, sparse_ids, n_hidden=3):
+    """``PNN`` (MD:43-56) with ``use_inner=True, use_outer=False`` (``OPnnLayer`` cannot run in the reference:
+    ``InnerLayer(use_inner=False)`` reads ``self.dot``, which IL:56 comments out): ``linear_embed`` list +
+    ``IPnnLayer()`` = the 325 un-summed pairwise products (IL:68-80) -> ``StackLayer`` (flatten + concat,
+    ``[B, F + P*k]``) -> ``DnnLayer`` -> ``Dense(2, softmax)``.  The dense inputs are not used (MD:56)."""
+    sparse, linear = _embed_lists(p, sparse_ids)
+    cross_fea = list(linear) + inner_layer(sparse)                # MD:48-50
+    x = stack_layer(cross_fea)                                    # MD:53
+    dnn_ = dnn_layer(x, [p[f"dnn_w{i}"] for i in range(n_hidden)], [p[f"dnn_b{i}"] for i in range(n_hidden)])
+    return merge_score_layer(dnn_, p["head_w"], p["head_b"], use_merge=False)
+
+
 def model_autoint(p, dense, sparse_ids):
     """``AutoInt`` (MD:150-165): one attention block, heads flattened and
     concatenated, ``Dense(2, softmax)``."""

@@ -501,6 +501,8 @@ def model_cases(ns):
     cases["autoint"] = run_model(MD.AutoInt, 16, 48, 5, builder_kw=dict(attention_dim=8, attention_head_dim=2))
     cases["nfm"] = run_model(MD.NFM, 8, 48, 6, sigmoid=True, builder_kw=dict(hidden_units=[32, 16, 8]))
     cases["afm"] = run_model(MD.AFM, 8, 48, 7, sigmoid=True)
+    # IPNN (MD:43-56 with use_outer=False: OPnnLayer is broken in the reference, IL:56 vs IL:63)
+    cases["pnn"] = run_model(MD.PNN, 8, 48, 8, builder_kw=dict(hidden_units=[32, 32, 16], use_inner=True, use_outer=False))
     return cases
 
 

@@ -233,6 +233,7 @@ MODELS = {
     "autoint": (ko.model_autoint, {}),
     "nfm": (ko.model_nfm, {}),
     "afm": (ko.model_afm, {}),
+    "pnn": (ko.model_pnn, {}),
 }
 
 

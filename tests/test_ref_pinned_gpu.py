@@ -283,12 +283,13 @@ def _build(name, c):
          "xdeepfm": lambda: KM.XDeepFM(fea, conv_size=[10, 9, 8], hidden_units=hidden, cin_precision="fp32"),
          "nfm": lambda: KM.NFM(fea, hidden_units=hidden),
          "afm": lambda: KM.AFM(fea),
+         "pnn": lambda: KM.PNN(fea, hidden_units=hidden, use_inner=True, use_outer=False),
          "autoint": lambda: KM.AutoInt(fea, attention_dim=8, attention_head_dim=2)}[name]()
     m.load_reference_params({k_: d(v) for k_, v in w.items()})
     return m, rows
 
 
-@pytest.mark.parametrize("name", ["fm", "deepfm", "dcn", "xdeepfm", "autoint", "nfm", "afm"])
+@pytest.mark.parametrize("name", ["fm", "deepfm", "dcn", "xdeepfm", "autoint", "nfm", "afm", "pnn"])
 def test_model_builders_vs_reference(name):
     from ml_function_b200.models import keras_binary_crossentropy
     c = ref_case("models", name)
@@ -336,7 +337,7 @@ def test_fused_bce_loss_vs_reference_losses_and_keras_formula():
     reference's run produced, and the gradient of the Keras formula (clip, eps inside the logs)."""
     from ml_function_b200 import ops
     from ml_function_b200.models import keras_binary_crossentropy
-    for name in ("fm", "deepfm", "dcn", "xdeepfm", "autoint", "nfm", "afm"):
+    for name in ("fm", "deepfm", "dcn", "xdeepfm", "autoint", "nfm", "afm", "pnn"):
         c = ref_case("models", name)
         p = d(c["out/y"]).clone().requires_grad_(True)
         y = d(c["in/labels"])
@@ -352,7 +353,9 @@ def test_fused_bce_loss_vs_reference_losses_and_keras_formula():
     p = torch.tensor([[0.0, 1.0], [1e-9, 0.5], [1 - 1e-9, 0.25]], device=DEV, requires_grad=True)
     y = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 0.0]], device=DEV)
     loss = ops.binary_crossentropy(y, p)
-    ref = keras_binary_crossentropy(y.double(), p.detach().double())
+    # at the clip boundary 1 - eps is not representable in fp32 (the reference computes in fp32 too): compare with
+    # the same formula in fp32
+    ref = keras_binary_crossentropy(y, p.detach())
     assert abs(loss.item() - ref.item()) < 1e-5 * ref.item() and torch.isfinite(loss)
     loss.backward()
     assert p.grad[0, 0].item() == 0.0 and p.grad[0, 1].item() == 0.0 and p.grad[1, 0].item() == 0.0
