@@ -272,7 +272,10 @@ embed_keys_kernel(const IdT* __restrict__ ids, const __grid_constant__ FieldTabl
     const long long id = (long long)ids[p];
     const long long rows = s_off[f + 1] - s_off[f];
     keys[p] = (id >= 0 && id < rows) ? (uint32_t)(s_off[f] + id) : sentinel;
-    vals[p] = (uint32_t)p;
+    // the payload of the sort is the (sample, field) pair itself, packed b * 256 + f (F <= 256, B < 2^24: checked
+    // by the host), so that the segmented reduction addresses its gradient row with a shift and a mask -- the two
+    // 64-bit divisions per lookup it used to spend on p -> (b, f) were most of its 146 instructions per lookup
+    vals[p] = (uint32_t)(((bag / F) << 8) | (uint32_t)f);
   }
 }
 
@@ -294,7 +297,6 @@ struct BwdArgs {
   const float* d_out;
   long long sb, sf;   // strides of d_out dims 0 / 1 (elements)
   int F, L, dim, vec_per_row;
-  uint32_t f_magic;   // ceil(2^32 / F) when x / F == umulhi(x, f_magic) for every x < n, else 0 (plain division)
   long long n;        // lookups
   const uint32_t* keys;   // sorted
   const uint32_t* vals;   // sorted with the keys
@@ -369,13 +371,9 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
           const long long i = lo + i0 + u;
           sg[u] = a.segidx[i];
           ky[u] = a.keys[i];
-          // p < 2^31 (checked by the host): 32-bit math, the division by F as a multiply-high
-          // (f_magic = ceil(2^32 / F), exact for bag < 2^31 / F ... verified on the host for n <= 2^31 - 1)
-          const uint32_t p = a.vals[i];
-          const uint32_t bag = a.L == 1 ? p : p / (uint32_t)a.L;
-          uint32_t bq = a.f_magic ? __umulhi(bag, a.f_magic) : bag / (uint32_t)a.F;
-          long long b = bq;
-          const int f = (int)(bag - bq * (uint32_t)a.F);
+          const uint32_t bf = a.vals[i];               // b * 256 + f, packed by embed_keys_kernel
+          long long b = bf >> 8;
+          const int f = (int)(bf & 255u);
           const float* src = a.d_out;
           if (a.n_peers) {
             const long long q = b / a.peer_rows;
@@ -995,6 +993,8 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
               "embedding dim must be 1 or a multiple of 4 (got %lld)", (long long)dim);
   const int64_t n = v.B * v.F * v.L;
   KON_REQUIRE(n <= 0x7fffffffLL, KON_EUNSUPPORTED, "more than 2^31-1 lookups per call");
+  KON_REQUIRE(v.B < (1LL << 24), KON_EUNSUPPORTED, "batch of %lld samples: the routing packs (sample, field) in 32 bits, B < 2^24",
+              (long long)v.B);
   const int64_t total_rows = ft.off[n_fields];
   KON_REQUIRE(total_rows < 0xffffffffLL, KON_EUNSUPPORTED, "arena with >= 2^32-1 rows");
   if (!sort_only) {
@@ -1066,17 +1066,6 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   for (int q = 0; q < kMaxPeers; ++q) a.peer[q] = src.peer[q];
   a.F = (int)v.F;
   a.L = (int)v.L;
-  {
-    // x / F == (x * m) >> 32 with m = ceil(2^32 / F) holds for all x < 2^32 / (m * F - 2^32) (Granlund-Montgomery);
-    // F = 1 has no 32-bit magic (m = 2^32): plain path.
-    a.f_magic = 0;
-    if (v.F > 1) {
-      const unsigned long long m = ((1ull << 32) + (unsigned long long)v.F - 1) / (unsigned long long)v.F;
-      const unsigned long long err = m * (unsigned long long)v.F - (1ull << 32);     // in [0, F)
-      const unsigned long long bags = (unsigned long long)(n / v.L) + 1;
-      if (m < (1ull << 32) && (err == 0 || bags < (1ull << 32) / err)) a.f_magic = (uint32_t)m;
-    }
-  }
   a.dim = rdim;
   a.vec_per_row = l.vpr;
   a.n = n;
