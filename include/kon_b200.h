@@ -170,7 +170,7 @@ int kon_peer_barrier(void* const* peer_flags, int32_t n_peers, int32_t rank, int
  * scatter-add then reads local memory only), and of the first-order partial sums / their gradients.  All byte
  * quantities are multiples of 4; 16-byte units are used when everything is 16-byte aligned.  A kon_peer_barrier on
  * the same stream publishes the data. */
-#define KON_MAX_PUTS 32
+#define KON_MAX_PUTS 64
 typedef struct {
   const void* src;      /* local */
   void*       dst;      /* local or peer mapping */
@@ -192,6 +192,13 @@ int kon_embed_fwd_peer(const DLTensor* arena, const DLTensor* ids, const int64_t
                        int32_t n_fields, void* const* peer_out, int32_t n_peers,
                        int64_t rows_per_peer, int64_t out_stride_b, int64_t out_stride_f,
                        DLTensor* oob, int32_t flags, void* stream);
+/* Same, with an explicit destination column per local field: the row of local field f lands at float offset
+ * field_col[f] of the destination row (instead of f*out_stride_f), so an owner's fields need not be adjacent in the
+ * model's field order (cost-balanced table placement) and the receiver's buffer is still in model order. */
+int kon_embed_fwd_peer_cols(const DLTensor* arena, const DLTensor* ids, const int64_t* field_row_offset,
+                            int32_t n_fields, void* const* peer_out, int32_t n_peers,
+                            int64_t rows_per_peer, int64_t out_stride_b, int64_t out_stride_f,
+                            const int32_t* field_col, DLTensor* oob, int32_t flags, void* stream);
 /* Backward: kon_embed_bwd with the gradient row of (sample b, local field f) loaded from
  *     peer_d_out[q] + (b - q*rows_per_peer)*stride_b + f*stride_f,   q = b / rows_per_peer.
  * Out-of-range ids (rows owned by another rank) carry no gradient.  reuse_sort != 0: as

@@ -152,6 +152,7 @@ def lib():
         "kon_peer_barrier": (ctypes.c_int, [ctypes.POINTER(vp), i32, i32, ctypes.c_int, i64, vp]),
         "kon_peer_put2d": (ctypes.c_int, [ctypes.POINTER(KonPut2D), i32, ctypes.c_int, vp]),
         "kon_embed_fwd_peer": (ctypes.c_int, [T, T, i64p, i32, ctypes.POINTER(vp), i32, i64, i64, i64, T, i32, vp]),
+        "kon_embed_fwd_peer_cols": (ctypes.c_int, [T, T, i64p, i32, ctypes.POINTER(vp), i32, i64, i64, i64, i32p, T, i32, vp]),
         "kon_embed_bwd_peer": (ctypes.c_int, [ctypes.POINTER(vp), i32, i64, i64, i64, i32, T, i64p, i32, T, T, T, T, i32, vp]),
         "kon_fm_fwd": (ctypes.c_int, [T, T, T, vp]),
         "kon_fm_bwd": (ctypes.c_int, [T, T, T, T, vp]),
@@ -193,7 +194,7 @@ EXPORTED_SYMBOLS = (
     "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_bwd_reuse", "kon_embed_sort", "kon_embed_sgd", "kon_embed_adam",
     "kon_embed_adam_devstep",
     "kon_peer_alloc", "kon_peer_open", "kon_peer_close", "kon_peer_free", "kon_peer_barrier", "kon_peer_put2d",
-    "kon_embed_fwd_peer", "kon_embed_bwd_peer",
+    "kon_embed_fwd_peer", "kon_embed_fwd_peer_cols", "kon_embed_bwd_peer",
     "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",

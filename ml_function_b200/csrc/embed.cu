@@ -58,6 +58,8 @@ struct PeerTable {
   int n;                // peers (0 = off)
   int skip_invalid;     // forward: leave the destination untouched for out-of-range ids (row-wise
                         // shards: the id belongs to another rank, which writes the row itself)
+  int use_col;          // forward: local field f lands at column col[f] (floats) of the destination row instead
+  int col[kMaxFields];  // of f * out_stride_f -- owners whose fields are not adjacent in the model's field order
 };
 
 // -------------------------------------------------------------------------------------
@@ -171,7 +173,8 @@ embed_fwd_vec_kernel(const float4* __restrict__ arena, const IdT* __restrict__ i
               dst = pt.base[q];
               b -= q * pt.rows;
             }
-            *reinterpret_cast<float4*>(dst + b * out_sb + fs[u] * out_sf + lane * 4) = r[u];
+            const long long fcol = (PEER && pt.use_col) ? (long long)pt.col[fs[u]] : fs[u] * out_sf;
+            *reinterpret_cast<float4*>(dst + b * out_sb + fcol + lane * 4) = r[u];
           }
         }
       }
@@ -743,6 +746,15 @@ extern "C" int kon_embed_fwd_peer(const DLTensor* arena, const DLTensor* ids,
                                   void* const* peer_out, int32_t n_peers, int64_t rows_per_peer,
                                   int64_t out_stride_b, int64_t out_stride_f, DLTensor* oob,
                                   int32_t flags, void* stream) {
+  return kon_embed_fwd_peer_cols(arena, ids, field_row_offset, n_fields, peer_out, n_peers, rows_per_peer,
+                                 out_stride_b, out_stride_f, nullptr, oob, flags, stream);
+}
+
+extern "C" int kon_embed_fwd_peer_cols(const DLTensor* arena, const DLTensor* ids,
+                                       const int64_t* field_row_offset, int32_t n_fields,
+                                       void* const* peer_out, int32_t n_peers, int64_t rows_per_peer,
+                                       int64_t out_stride_b, int64_t out_stride_f, const int32_t* field_col,
+                                       DLTensor* oob, int32_t flags, void* stream) {
   KON_TRY(check_cuda_tensor(arena, "arena"));
   const int dev = arena->device.device_id;
   IdsView v;
@@ -771,6 +783,13 @@ extern "C" int kon_embed_fwd_peer(const DLTensor* arena, const DLTensor* ids,
     KON_REQUIRE(peer_out[q] != nullptr && aligned16(peer_out[q]), KON_EINVAL,
                 "peer_out[%d] is NULL or not 16-B aligned", q);
     pt.base[q] = static_cast<float*>(peer_out[q]);
+  }
+  if (field_col) {
+    pt.use_col = 1;
+    for (int f = 0; f < n_fields; ++f) {
+      KON_REQUIRE(field_col[f] >= 0 && field_col[f] % 4 == 0, KON_EINVAL, "field_col[%d]=%d must be a non-negative multiple of 4 floats", f, field_col[f]);
+      pt.col[f] = field_col[f];
+    }
   }
   int* oob_p = nullptr;
   if (oob) {

@@ -19,6 +19,10 @@ from . import _lib as L
 PROFILE = None
 
 
+# KON_NVTX=1: every C-ABI call is wrapped in an NVTX range named after the op (nsys / ncu --nvtx timelines).
+NVTX = os.environ.get("KON_NVTX", "0") == "1"
+
+
 class _prof:
     __slots__ = ("name", "e0")
 
@@ -26,6 +30,8 @@ class _prof:
         self.name = name
 
     def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push("kon." + self.name)
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
@@ -35,6 +41,8 @@ class _prof:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             PROFILE.setdefault(self.name, []).append((self.e0, e1))
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
         return False
 
 
@@ -216,18 +224,19 @@ def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optio
 
 # ---- sharded embeddings over NVLink peer memory ----------------------------------
 def embed_fwd_peer(arena, ids, field_row_offset: Sequence[int], peer_out, n_peers: int, rows_per_peer: int,
-                   stride_b: int, stride_f: int, skip_invalid=False, oob=None):
+                   stride_b: int, stride_f: int, skip_invalid=False, oob=None, field_col: Optional[Sequence[int]] = None):
     """kon_embed_fwd_peer: gather this rank's tables for the GLOBAL batch ``ids`` [B_g, F_loc] and store
     every row into the buffer of the rank that owns the sample.  ``peer_out``: ctypes ``c_void_p`` array
     (this process's mappings of the ranks' buffers, already offset to this rank's first column)."""
     lib = L.lib()
     offs = L.i64_array(list(field_row_offset))
     a, i, ob = L._arg(arena), L._arg(ids), L._arg(oob)
+    cols = None if field_col is None else L.i32_array(list(field_col))      # float offset of each local field's column
     with _prof("embed_fwd_peer"):
-        L.check(lib.kon_embed_fwd_peer(a.ptr, i.ptr, offs, ids.shape[1], peer_out, n_peers, rows_per_peer,
-                                       stride_b, stride_f, L._p(ob),
-                                       L.KON_EMBED_SKIP_INVALID if skip_invalid else 0,
-                                       L.stream_ptr(arena.device)), "kon_embed_fwd_peer")
+        L.check(lib.kon_embed_fwd_peer_cols(a.ptr, i.ptr, offs, ids.shape[1], peer_out, n_peers, rows_per_peer,
+                                            stride_b, stride_f, cols, L._p(ob),
+                                            L.KON_EMBED_SKIP_INVALID if skip_invalid else 0,
+                                            L.stream_ptr(arena.device)), "kon_embed_fwd_peer_cols")
 
 
 def embed_bwd_peer(peer_d_out, n_peers: int, rows_per_peer: int, stride_b: int, stride_f: int, dim: int,

@@ -41,24 +41,41 @@ from torch import nn
 class ShardPlan:
     """Which rank owns which (field, row)."""
 
-    def __init__(self, rows: Sequence[int], world: int, row_wise_min_rows: int = 50_000_000):
+    def __init__(self, rows: Sequence[int], world: int, row_wise_min_rows: int = 50_000_000, balance: str = "count",
+                 row_bytes: int = 64):
         self.rows = [int(r) for r in rows]
         self.world = world
+        self.balance = balance
         F = len(self.rows)
         self.rw_fields = [f for f in range(F) if world > 1 and self.rows[f] >= row_wise_min_rows]
         self.tw_fields = [f for f in range(F) if f not in self.rw_fields]
-        # Every table-wise field costs the same number of lookups per step, so ranks are balanced by
-        # field COUNT; contiguous blocks of fields per rank keep the exchanged layout identical to the
-        # model's field order (no permutation copy after the all-to-all).
         self.tw_owner = {}
         n_tw = len(self.tw_fields)
-        base, extra = divmod(n_tw, world)
-        pos = 0
-        for p in range(world):
-            cnt = base + (1 if p < extra else 0)
-            for f in self.tw_fields[pos:pos + cnt]:
+        if balance == "cost" and world > 1:
+            # Every field costs the same number of lookups and the same NVLink bytes, but not the same HBM time: a
+            # lookup into a table that stays in the 126 MB L2 is a hit, a lookup into a multi-GB table is a random
+            # DRAM row (gather, scatter-add and row-wise Adam alike).  Contiguous count-balanced blocks put the two
+            # largest Criteo tables on rank 0 and none on four other ranks, and everybody waits for rank 0 at the
+            # barriers.  Greedy placement, heaviest first, onto the least loaded rank, with the per-rank field count
+            # capped so that the NVLink egress stays balanced too.
+            cap = (n_tw + world - 1) // world
+            wgt = {f: 1.0 + 3.0 * min(1.0, self.rows[f] * row_bytes / 64e6) for f in self.tw_fields}
+            load, cnt = [0.0] * world, [0] * world
+            for f in sorted(self.tw_fields, key=lambda f_: (-wgt[f_], f_)):
+                p = min((q for q in range(world) if cnt[q] < cap), key=lambda q: (load[q], cnt[q], q))
                 self.tw_owner[f] = p
-            pos += cnt
+                load[p] += wgt[f]
+                cnt[p] += 1
+        else:
+            # balanced by field COUNT; contiguous blocks of fields per rank keep the exchanged layout identical to
+            # the model's field order (no permutation copy after an NCCL all-to-all)
+            base, extra = divmod(n_tw, world)
+            pos = 0
+            for p in range(world):
+                cnt = base + (1 if p < extra else 0)
+                for f in self.tw_fields[pos:pos + cnt]:
+                    self.tw_owner[f] = p
+                pos += cnt
         self.tw_of_rank = [[f for f in self.tw_fields if self.tw_owner[f] == p] for p in range(world)]
         # field order after the exchange ("rank-major"): rank 0's tw fields, rank 1's, ..., then rw fields
         self.exchange_order = [f for p in range(world) for f in self.tw_of_rank[p]] + self.rw_fields
@@ -84,9 +101,21 @@ class ShardPlan:
             o.append(o[-1] + self.local_rows(rank, f))
         return tw, o
 
+    @staticmethod
+    def runs(fields: Sequence[int]):
+        """Ascending field list -> [(first global field, position of it in the list, length)] of maximal runs of
+        ADJACENT global fields (one strided 2-D copy each)."""
+        out = []
+        for j, f in enumerate(fields):
+            if out and out[-1][0] + out[-1][2] == f:
+                out[-1] = (out[-1][0], out[-1][1], out[-1][2] + 1)
+            else:
+                out.append((f, j, 1))
+        return out
+
     def describe(self) -> str:
-        return (f"dp{self.world} dense + sharded embeddings ({len(self.tw_fields)} table-wise, "
-                f"{len(self.rw_fields)} row-wise fields)")
+        return (f"dp{self.world} dense + sharded embeddings ({len(self.tw_fields)} table-wise"
+                f"{' cost-balanced' if self.balance == 'cost' else ''}, {len(self.rw_fields)} row-wise fields)")
 
 
 # ------------------------------------------------------------------------------------------
@@ -336,13 +365,13 @@ class _PeerLookup(torch.autograd.Function):
         ids_tw, ids_rw = sh.exchange_ids(ids_local, px)  # (A) + barrier A
         xcat, region = px["xcat"], px["region"]
         n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
+        base = region.ptr_array(px["xcat_off"])          # every field lands at ITS column of the model's order
         if n_tw:
-            col0 = sh.tw_slabs[rank][0]
-            ops.embed_fwd_peer(arena.detach(), ids_tw, sh.tw_offs, region.ptr_array(px["xcat_off"] + col0 * k * 4),
-                               N, B_l, width, k)
+            ops.embed_fwd_peer(arena.detach(), ids_tw, sh.tw_offs, base, N, B_l, width, k,
+                               field_col=[f * k for f in plan.tw_of_rank[rank]])
         if n_rw:
-            ops.embed_fwd_peer(arena.detach(), ids_rw, sh.rw_offs, region.ptr_array(px["xcat_off"] + n_tw_all * k * 4),
-                               N, B_l, width, k, skip_invalid=True)
+            ops.embed_fwd_peer(arena.detach(), ids_rw, sh.rw_offs, base, N, B_l, width, k, skip_invalid=True,
+                               field_col=[f * k for f in plan.rw_fields])
         nd = 0
         if dense is not None:
             nd = dense.shape[1]
@@ -360,11 +389,7 @@ class _PeerLookup(torch.autograd.Function):
         region.barrier()                                  # barrier 1: rows (and partial sums) complete
         if lin_ids is not None:
             ops._STEP_CACHE[("lin_fwd", id(plan))] = (px["linparts"].sum(dim=1, keepdim=True), lin_ids, px)
-        if not plan.identity_order:      # row-wise fields interleaved with table-wise ones: one permutation copy
-            emb = xcat[:, :F * k].view(B_l, F, k).index_select(1, sh.to_global)
-            out = torch.cat([emb.reshape(B_l, F * k), xcat[:, F * k:]], dim=1)
-        else:
-            out = xcat
+        out = xcat
         ctx.sh, ctx.arena, ctx.px = sh, arena, px
         ctx.save_for_backward(ids_tw, ids_rw)
         ctx.dims = (B_l, F, k, nd, width)
@@ -382,22 +407,23 @@ class _PeerLookup(torch.autograd.Function):
         B_l, F, k, nd, width = ctx.dims
         region = px["region"]
         n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
-        if plan.identity_order and gout.stride(1) == 1 and gout.stride(0) % 4 == 0 and gout.data_ptr() % 16 == 0:
+        if gout.stride(1) == 1 and gout.stride(0) % 4 == 0 and gout.data_ptr() % 16 == 0:
             gsrc, pitch = gout, gout.stride(0) * 4       # columns [0, F*k) of the concat-buffer gradient, in place
         else:
-            gemb = gout[:, :F * k].reshape(B_l, F, k)
-            if not plan.identity_order:
-                gemb = gemb.index_select(1, sh.to_exchange)
-            gsrc, pitch = gemb.contiguous(), F * k * 4
+            gsrc, pitch = gout[:, :F * k].contiguous(), F * k * 4
         puts = []
-        for q, (o, c) in enumerate(sh.tw_slabs):         # owner q's columns -> rows [rank*B_l, ...) of its receive buffer
-            puts.append((gsrc.data_ptr() + o * k * 4, region.ptrs[q] + px["drecv_tw_off"] + rank * B_l * c * k * 4,
-                         pitch, c * k * 4, c * k * 4, B_l))
-        if n_rw:                                          # row-wise columns: every rank needs them (its rows of the tables)
-            for q in range(N):
-                puts.append((gsrc.data_ptr() + n_tw_all * k * 4, region.ptrs[q] + px["drecv_rw_off"] + rank * B_l * n_rw * k * 4,
-                             pitch, n_rw * k * 4, n_rw * k * 4, B_l))
-        _put2d(sh, puts)
+        for q in range(N):                                # owner q's columns -> rows [rank*B_l, ...) of its receive buffer
+            c = len(plan.tw_of_rank[q])
+            for f0, j0, cnt in sh.runs_tw[q]:
+                puts.append((gsrc.data_ptr() + f0 * k * 4,
+                             region.ptrs[q] + px["drecv_tw_off"] + (rank * B_l * c + j0) * k * 4,
+                             pitch, c * k * 4, cnt * k * 4, B_l))
+            for f0, j0, cnt in sh.runs_rw:                # row-wise columns: every rank needs them (its rows of the tables)
+                puts.append((gsrc.data_ptr() + f0 * k * 4,
+                             region.ptrs[q] + px["drecv_rw_off"] + (rank * B_l * n_rw + j0) * k * 4,
+                             pitch, n_rw * k * 4, cnt * k * 4, B_l))
+        for i in range(0, len(puts), 64):
+            _put2d(sh, puts[i:i + 64])
         region.barrier()                                  # barrier 2: every rank's dOut (and first-order gradient) is in place
         if arena.requires_grad:
             if not hasattr(arena, "kon_sparse_grads"):
@@ -535,6 +561,8 @@ class ShardedEmbed(nn.Module):
             slabs.append((o, len(plan.tw_of_rank[p])))
             o += len(plan.tw_of_rank[p])
         self.tw_slabs = slabs
+        self.runs_tw = [ShardPlan.runs(plan.tw_of_rank[p]) for p in range(self.world)]
+        self.runs_rw = ShardPlan.runs(plan.rw_fields)
         self.tw_idx_of = [torch.tensor(plan.tw_of_rank[p], dtype=torch.long, device=device) for p in range(self.world)]
         # fused NVLink exchange: NCCL process group + CUDA + vector-width rows (KON_PEER_EXCHANGE=0: NCCL baseline)
         self.use_peer = (not is_linear and self.world > 1 and torch.device(device).type == "cuda"
@@ -591,14 +619,18 @@ class ShardedEmbed(nn.Module):
         B_l, F = ids_local.shape
         region = px["region"]
         n_loc, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
-        src = ids_local if plan.identity_order else ids_local.index_select(1, self.to_exchange).contiguous()
-        base, pitch = src.data_ptr(), F * 4
-        puts = [(base + o * 4, region.ptrs[q] + px["ids_tw_off"] + rank * B_l * c * 4, pitch, c * 4, c * 4, B_l)
-                for q, (o, c) in enumerate(self.tw_slabs)]
-        if n_rw:
-            puts += [(base + n_tw_all * 4, region.ptrs[q] + px["ids_rw_off"] + rank * B_l * n_rw * 4, pitch, n_rw * 4,
-                      n_rw * 4, B_l) for q in range(N)]
-        _put2d(self, puts)
+        base, pitch = ids_local.data_ptr(), F * 4
+        puts = []
+        for q in range(N):
+            c = len(plan.tw_of_rank[q])
+            for f0, j0, cnt in self.runs_tw[q]:
+                puts.append((base + f0 * 4, region.ptrs[q] + px["ids_tw_off"] + (rank * B_l * c + j0) * 4, pitch, c * 4,
+                             cnt * 4, B_l))
+            for f0, j0, cnt in self.runs_rw:
+                puts.append((base + f0 * 4, region.ptrs[q] + px["ids_rw_off"] + (rank * B_l * n_rw + j0) * 4, pitch,
+                             n_rw * 4, cnt * 4, B_l))
+        for i in range(0, len(puts), 64):
+            _put2d(self, puts[i:i + 64])
         region.barrier()                                  # barrier A (also: every rank has finished its previous step)
         # copies out of the region: the ids are read again by the backward's routing sort, after peers may have
         # stored the NEXT step's ids
@@ -705,16 +737,22 @@ class ShardedEmbed(nn.Module):
 
 
 class DistContext:
-    def __init__(self, group, device, row_wise_min_rows: int = 50_000_000):
+    def __init__(self, group, device, row_wise_min_rows: int = 50_000_000, balance: Optional[str] = None):
         self.group, self.device = group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.row_wise_min_rows = row_wise_min_rows
+        # cost-balanced placement needs the peer path (fields of an owner are not adjacent); the NCCL baseline keeps
+        # contiguous blocks (KON_SHARD_BALANCE=count|cost overrides)
+        self.balance = balance or os.environ.get("KON_SHARD_BALANCE") or (
+            "cost" if (torch.device(device).type == "cuda" and os.environ.get("KON_PEER_EXCHANGE", "1") != "0") else "count")
         self.plan: Optional[ShardPlan] = None
 
     def attach(self, model):
         """Replace the model's replicated embedding layers by sharded ones (in place)."""
         info = model.sparse_embed.sparse_info
-        self.plan = ShardPlan([i.word_size for i in info], self.world, self.row_wise_min_rows)
+        dim = info[0].cross_unit
+        self.plan = ShardPlan([i.word_size for i in info], self.world, self.row_wise_min_rows, balance=self.balance,
+                              row_bytes=4 * int(dim))
         dev = self.device
         old = model.sparse_embed
         model.sparse_embed = ShardedEmbed(info, self.plan, self.group, dev, is_linear=False, seed=old.seed)

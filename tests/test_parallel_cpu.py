@@ -110,6 +110,25 @@ def test_shard_plan_covers_every_row_once():
                 assert len(p.rw_fields) == 5
 
 
+def test_cost_balanced_plan_spreads_the_big_tables():
+    from ml_function_b200.parallel import ShardPlan
+    rows = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27,
+            14992, 5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+    big = [f for f, r in enumerate(rows) if r >= 1_000_000]
+    for world in (2, 4, 8):
+        p = ShardPlan(rows, world, balance="cost")
+        assert sorted(f for fs in p.tw_of_rank for f in fs) == list(range(26))          # every table exactly once
+        per_rank_big = [sum(1 for f in fs if f in big) for fs in p.tw_of_rank]
+        assert max(per_rank_big) - min(per_rank_big) <= 1                               # count plan: rank 0 had 2, four ranks 0
+        assert max(len(fs) for fs in p.tw_of_rank) <= (26 + world - 1) // world         # NVLink egress stays capped
+        for fs in p.tw_of_rank:
+            assert fs == sorted(fs)
+            rr = ShardPlan.runs(fs)
+            assert sum(c for _, _, c in rr) == len(fs) and [f for f0, _, c in rr for f in range(f0, f0 + c)] == fs
+            assert [j for _, j, _ in rr] == [fs.index(f0) for f0, _, _ in rr]
+    assert ShardPlan(rows, 8).tw_of_rank[0] == [0, 1, 2, 3]                             # default stays contiguous
+
+
 def _worker_step_cache(rank, world, port, ret):
     """Inside a training step (ops.new_step() ... end_step()) the embedding and the first-order tables share
     ONE ids exchange; outside a step nothing is cached (a recycled address must never hit)."""
