@@ -418,10 +418,19 @@ class _PeerLookup(torch.autograd.Function):
                 puts.append((gsrc.data_ptr() + f0 * k * 4,
                              region.ptrs[q] + px["drecv_tw_off"] + (rank * B_l * c + j0) * k * 4,
                              pitch, c * k * 4, cnt * k * 4, B_l))
-            for f0, j0, cnt in sh.runs_rw:                # row-wise columns: every rank needs them (its rows of the tables)
-                puts.append((gsrc.data_ptr() + f0 * k * 4,
-                             region.ptrs[q] + px["drecv_rw_off"] + (rank * B_l * n_rw + j0) * k * 4,
-                             pitch, n_rw * k * 4, cnt * k * 4, B_l))
+        if n_rw:
+            # row-wise columns: EVERY rank needs them (its rows of the tables).  Scattered over the row they would go
+            # out as N x (#runs) narrow stores; packed once locally they go out as one wide row per sample and peer.
+            if len(sh.runs_rw) > 1:
+                stage = torch.empty((B_l, n_rw * k), dtype=gout.dtype, device=gout.device)
+                _put2d(sh, [(gsrc.data_ptr() + f0 * k * 4, stage.data_ptr() + j0 * k * 4, pitch, n_rw * k * 4, cnt * k * 4, B_l)
+                            for f0, j0, cnt in sh.runs_rw])
+                rsrc, rpitch = stage.data_ptr(), n_rw * k * 4
+            else:
+                rsrc, rpitch = gsrc.data_ptr() + sh.runs_rw[0][0] * k * 4, pitch
+            for q in range(N):
+                puts.append((rsrc, region.ptrs[q] + px["drecv_rw_off"] + rank * B_l * n_rw * k * 4, rpitch, n_rw * k * 4,
+                             n_rw * k * 4, B_l))
         for i in range(0, len(puts), 64):
             _put2d(sh, puts[i:i + 64])
         region.barrier()                                  # barrier 2: every rank's dOut (and first-order gradient) is in place
@@ -743,8 +752,12 @@ class DistContext:
         self.row_wise_min_rows = row_wise_min_rows
         # cost-balanced placement needs the peer path (fields of an owner are not adjacent); the NCCL baseline keeps
         # contiguous blocks (KON_SHARD_BALANCE=count|cost overrides)
-        self.balance = balance or os.environ.get("KON_SHARD_BALANCE") or (
-            "cost" if (torch.device(device).type == "cuda" and os.environ.get("KON_PEER_EXCHANGE", "1") != "0") else "count")
+        # "count" (default): contiguous blocks of fields per rank -> every peer store / put moves 192-256 contiguous
+        # bytes per sample.  "cost" (KON_SHARD_BALANCE=cost): one multi-GB table per rank; measured on 8xB200 it removes
+        # the HBM skew (rank-0 gather 0.22 -> 0.16 ms, scatter 0.25 -> 0.18, Adam 0.10 -> 0.06) but scatters every
+        # owner's fields over the row, so the NVLink writes shrink to 64-byte runs and the step does not get faster
+        # (8.73 vs 8.86 ms): kept as an option, not the default.
+        self.balance = balance or os.environ.get("KON_SHARD_BALANCE") or "count"
         self.plan: Optional[ShardPlan] = None
 
     def attach(self, model):

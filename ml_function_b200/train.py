@@ -95,12 +95,15 @@ class Trainer:
             # embedding exchange + scatter-add on a side stream.
             self.dist.arm_overlapped_allreduce(self.model, lambda: self._dense_params)
             (loss / self.dist.world).backward()
+            for so in self.sparse_opts:         # the row-wise Adam does not wait for the dense all-reduce
+                so.step()
             self.dist.finish_allreduce(self.model, self._dense_params)
+            self.dense_opt.step()
         else:
             loss.backward()
-        self.dense_opt.step()
-        for so in self.sparse_opts:
-            so.step()
+            self.dense_opt.step()
+            for so in self.sparse_opts:
+                so.step()
         ops.end_step()
         self._n_steps += 1
         if self.dist is not None and self.peer_check_every and self._n_steps % self.peer_check_every == 0 \
