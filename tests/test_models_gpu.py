@@ -188,3 +188,34 @@ def test_train_step_updates_only_touched_rows_and_lowers_loss():
     changed = (model.sparse_embed.arena.detach() != before).any(dim=1).nonzero().flatten().cpu()
     touched = torch.unique((ids.cpu().long() + torch.tensor(offsets(rows)[:-1])).reshape(-1))
     assert torch.equal(changed, touched)
+
+
+def test_data_pipeline_feeds_the_trainer_from_hbm_and_pinned_memory():
+    """DP:335-337 pipeline (shuffle(2048).repeat(2).batch().prefetch(2)) over a dataset resident in HBM / in pinned
+    host memory -> Trainer.step: every sample is seen exactly twice, batches arrive on the device as int32 ids."""
+    import numpy as np
+    from ml_function_b200.data_prepare import data_prepare
+    from ml_function_b200.train import Trainer
+    g = gen(13)
+    rows = [50, 3000, 7]
+    n, k = 3000, 8
+    p = _params("deepfm", rows, k, g)
+    ids = torch.stack([torch.randint(0, r, (n,), generator=g) for r in rows], 1).numpy().astype(np.int32)
+    ids[:, 1] = np.arange(n) % rows[1]                    # field 1 identifies the sample (mod 3000 = identity)
+    dense = torch.rand(n, 13, generator=g).numpy()
+    y = (torch.rand(n, generator=g) < 0.3).float()
+    labels = torch.stack([1 - y, y], 1).numpy()
+    for resident in ("device", "host"):
+        model = _build("deepfm", rows, k, p)
+        tr = Trainer(model, lr=1e-3)
+        dp = data_prepare(batch_size=512, device=DEV)
+        pipe = dp.data_pipeline(((ids, dense), labels), resident=resident)
+        seen, losses = [], []
+        for d_, i_, y_ in pipe:
+            assert i_.is_cuda and i_.dtype == torch.int32 and d_.is_cuda and y_.shape[1] == 2
+            seen.append(i_[:, 1].clone())
+            losses.append(tr.step(d_, i_, y_))
+        torch.cuda.synchronize()
+        counts = torch.bincount(torch.cat(seen).long().cpu(), minlength=n)
+        assert bool((counts == 2).all()) and len(losses) == len(pipe) == (2 * n + 511) // 512
+        assert all(torch.isfinite(l) for l in losses)
