@@ -423,87 +423,108 @@ __global__ void __launch_bounds__(kPoolThreads, 2) cin_last_pool_kernel(const La
 }
 
 
-// Same computation with the two mat-vecs on warp-level tensor-core MMAs: one warp owns a 16-row tile (the 16
-// coordinates d of one sample when D == 16) and computes t[d,h] = sum_i x0[d,i] wsum[h,i] as m16n8k16 bf16 MMAs
-// (K = 26 fields padded to 32, N = the feature maps in tiles of 8), multiplies the accumulator fragment by the
-// matching pre[b,h,d] fragment (fp32) and row-sums.  ~470 warp instructions per 16 rows instead of ~2250 on the
-// FFMA2 path: the kernel becomes HBM-bound on the 419 MB of `pre`.  (Legacy mma.sync on purpose: 13 GFLOP.)
+// Same computation on warp-level tensor-core MMAs: one warp owns a 16-row tile (the 16 coordinates d of one sample
+// when D == 16) and computes t[h,d] = sum_i wsum[h,i] x0[d,i] as m16n8k16 bf16 MMAs with M = feature maps (13 tiles
+// of 16), N = coordinates (2 tiles of 8), K = 26 fields padded to 32.  In this orientation a thread's accumulator
+// pair (h, d..d+1) sits on ONE 32-bit word of `pre` ([B,H,D] bf16: d is the contiguous axis), so the multiply by
+// pre[b,h,d] costs one 4-byte load per two products; the wsum fragments are pre-arranged in shared memory so that
+// each A fragment is one conflict-free LDS.128.  ~390 warp instructions per sample (FFMA2 kernel: ~2250, the first
+// MMA version with M = coordinates: 1350): the kernel streams the 419 MB of `pre` at the pace of its loads.
+// (Legacy mma.sync on purpose: 13 GFLOP of side work.)
 constexpr int kPoolMmaWarps = 8;
-constexpr int kPoolTbRow = 20;      // words per wsum row in shared memory (32 bf16 + pad): conflict-free B fragments
 
-__device__ __forceinline__ void pool_mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void pool_mma_16816(float* c, const uint4& a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
 template <int MF>
 __global__ void __launch_bounds__(32 * kPoolMmaWarps) cin_last_pool_mma_kernel(const LastPoolArgs a) {
   static_assert(MF <= 32, "field count");
-  extern __shared__ __align__(16) uint32_t sTb[];               // [Hp8][kPoolTbRow] bf16x2 words
+  extern __shared__ __align__(16) uint4 sA[];                   // [n_mt][2 k-steps][32 lanes]: A fragments of wsum
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < a.Hp8 * kPoolTbRow; e += blockDim.x) {
-    const int h = e / kPoolTbRow, w = e - h * kPoolTbRow;       // word w holds fields 2w, 2w+1
-    float lo = 0.f, hi = 0.f;
-    if (2 * w < MF) lo = a.T[h * kPoolTRow + 2 * w];
-    if (2 * w + 1 < MF) hi = a.T[h * kPoolTRow + 2 * w + 1];
-    sTb[e] = tc::pack_bf16(lo, hi);
+  const int n_mt = a.Hp8 / 16 + ((a.Hp8 % 16) ? 1 : 0);
+  for (int e = tid; e < n_mt * 2 * 32; e += blockDim.x) {
+    const int l = e & 31, ks = (e >> 5) & 1, mt = e >> 6;
+    const int gg = l >> 2, tt = l & 3;
+    auto w2 = [&](int h, int i) -> uint32_t {                   // (wsum[h][i], wsum[h][i+1]) as bf16x2, zero outside
+      float lo = 0.f, hi = 0.f;
+      if (h < a.Hp8) {
+        if (i < MF) lo = a.T[h * kPoolTRow + i];
+        if (i + 1 < MF) hi = a.T[h * kPoolTRow + i + 1];
+      }
+      return tc::pack_bf16(lo, hi);
+    };
+    const int h0 = 16 * mt + gg, i0 = 16 * ks + 2 * tt;
+    sA[e] = make_uint4(w2(h0, i0), w2(h0 + 8, i0), w2(h0, i0 + 8), w2(h0 + 8, i0 + 8));
   }
   __syncthreads();
   const float bs = *a.bsum;
   const int g = lane >> 2, t = lane & 3;
   const int tiles_per_b = a.D / 16;
   const long long n_tiles = a.rows / 16;
-  const int n_nt = a.Hp8 / 8;
   for (long long tile = (long long)blockIdx.x * kPoolMmaWarps + warp; tile < n_tiles;
        tile += (long long)gridDim.x * kPoolMmaWarps) {
     const long long b = tile / tiles_per_b;
     const int d0 = (int)(tile - b * tiles_per_b) * 16;
     const float* xb = a.x0 + b * a.x0_sb + d0;                  // x0[b,i,d0+d] = xb[i*D + d]
     const unsigned short* pb = a.pre + b * (long long)a.Hp * a.D + d0;   // pre[b,h,d0+d] = pb[h*D + d]
-    // A fragments (row-major 16x16 per k-step): a0 (g, 2t..), a1 (g+8, 2t..), a2 (g, 2t+8..), a3 (g+8, 2t+8..)
-    uint32_t af[2][4];
+    // B fragments of x0^T (k = field i, n = coordinate d): b0 = (i = 16ks+2t, +1 ; d = 8nt+g), b1 = fields +8
+    uint32_t bf[2][2][2];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = 16 * ks + 2 * t + (q >> 1) * 8;
-        const int d = g + (q & 1) * 8;
-        const float lo = i < MF ? __ldg(xb + (long long)i * a.D + d) : 0.f;
-        const float hi = i + 1 < MF ? __ldg(xb + (long long)(i + 1) * a.D + d) : 0.f;
-        af[ks][q] = tc::pack_bf16(lo, hi);
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int i = 16 * ks + 2 * t + 8 * q;
+          const int d = 8 * nt + g;
+          const float lo = i < MF ? __ldg(xb + (long long)i * a.D + d) : 0.f;
+          const float hi = i + 1 < MF ? __ldg(xb + (long long)(i + 1) * a.D + d) : 0.f;
+          bf[nt][ks][q] = tc::pack_bf16(lo, hi);
+        }
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};                 // [nt][d = 8nt + 2t, +1], partial over this lane's h rows
+#pragma unroll 13
+    for (int mt = 0; mt < n_mt; ++mt) {
+      const int hA = min(16 * mt + g, a.Hp - 1), hB = min(16 * mt + g + 8, a.Hp - 1);   // rows >= Hp: wsum is 0 there
+      uint32_t pw[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        pw[nt][0] = __ldg(reinterpret_cast<const uint32_t*>(pb + (long long)hA * a.D + 8 * nt + 2 * t));
+        pw[nt][1] = __ldg(reinterpret_cast<const uint32_t*>(pb + (long long)hB * a.D + 8 * nt + 2 * t));
+      }
+      const uint4 a0 = sA[(mt * 2 + 0) * 32 + lane], a1 = sA[(mt * 2 + 1) * 32 + lane];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        pool_mma_16816(c, a0, bf[nt][0][0], bf[nt][0][1]);
+        pool_mma_16816(c, a1, bf[nt][1][0], bf[nt][1][1]);
+        acc[nt][0] = fmaf(__uint_as_float(pw[nt][0] << 16), c[0], acc[nt][0]);
+        acc[nt][1] = fmaf(__uint_as_float(pw[nt][0] & 0xffff0000u), c[1], acc[nt][1]);
+        acc[nt][0] = fmaf(__uint_as_float(pw[nt][1] << 16), c[2], acc[nt][0]);
+        acc[nt][1] = fmaf(__uint_as_float(pw[nt][1] & 0xffff0000u), c[3], acc[nt][1]);
       }
     }
-    float acc_lo = 0.f, acc_hi = 0.f;                           // rows g and g+8
-#pragma unroll 5
-    for (int nt = 0; nt < n_nt; ++nt) {
-      const int h0 = nt * 8 + 2 * t;                            // this thread's accumulator columns: h0, h0+1
-      // pre fragment first (global / L2 latency), masked beyond Hp
-      const bool v0 = h0 < a.Hp, v1 = h0 + 1 < a.Hp;
-      const int hc0 = v0 ? h0 : a.Hp - 1, hc1 = v1 ? h0 + 1 : a.Hp - 1;
-      const unsigned short p00 = __ldg(pb + (long long)hc0 * a.D + g);
-      const unsigned short p01 = __ldg(pb + (long long)hc1 * a.D + g);
-      const unsigned short p10 = __ldg(pb + (long long)hc0 * a.D + g + 8);
-      const unsigned short p11 = __ldg(pb + (long long)hc1 * a.D + g + 8);
-      const uint32_t* brow = sTb + (nt * 8 + g) * kPoolTbRow;   // B[k=i][n=h]: thread needs wsum[h = nt*8+g][i]
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      pool_mma_16816(c, af[0], brow[t], brow[t + 4]);
-      pool_mma_16816(c, af[1], brow[t + 8], brow[t + 12]);
-      acc_lo = fmaf(v0 ? bf16_to_f32(p00) : 0.f, c[0], acc_lo);
-      acc_lo = fmaf(v1 ? bf16_to_f32(p01) : 0.f, c[1], acc_lo);
-      acc_hi = fmaf(v0 ? bf16_to_f32(p10) : 0.f, c[2], acc_hi);
-      acc_hi = fmaf(v1 ? bf16_to_f32(p11) : 0.f, c[3], acc_hi);
-    }
-    // the 4 lanes of a quad hold disjoint column subsets of the same two rows: fixed-order butterfly
-    acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, 1);
-    acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, 1);
-    acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, 2);
-    acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, 2);
-    if (t == 0) {
+    // the 8 lanes with the same t hold disjoint feature maps of the same coordinates: fixed-order butterfly over g
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v = acc[nt][q];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        acc[nt][q] = v;
+      }
+    if (g == 0) {
       float* pp = a.pooled + b * a.pooled_stride + a.pooled_col0 + d0;
-      pp[g] = acc_lo + bs;
-      pp[g + 8] = acc_hi + bs;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        pp[8 * nt + 2 * t] = acc[nt][0] + bs;
+        pp[8 * nt + 2 * t + 1] = acc[nt][1] + bs;
+      }
     }
   }
 }
@@ -572,7 +593,8 @@ int cin_tc_fwd(const float* x0, long long x0_sb, const float* const* w, const fl
         const long long tiles = rows / 16;
         const int grid = (int)std::min<long long>((tiles + kPoolMmaWarps - 1) / kPoolMmaWarps, (long long)sms * 6);
         ProfileScope ps("cin_last_pool_kernel", st);
-        cin_last_pool_mma_kernel<26><<<grid, 32 * kPoolMmaWarps, (size_t)Hp8 * kPoolTbRow * 4, st>>>(z);
+        const int n_mt = (Hp8 + 15) / 16;
+        cin_last_pool_mma_kernel<26><<<grid, 32 * kPoolMmaWarps, (size_t)n_mt * 2 * 32 * 16, st>>>(z);
       } else {
         const long long tiles = (rows + kPoolThreads * kPoolRows - 1) / (kPoolThreads * kPoolRows);
         const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);

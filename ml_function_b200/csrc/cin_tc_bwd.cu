@@ -1003,6 +1003,32 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
     const uint32_t colD = sub ? kDaColD1 : kDaColD0;
     uint32_t d_use = 0;
     uint32_t tile_it = 0;
+    // dx0 of a tile is folded into global memory (read-modify-write, two dependent DRAM round trips) AFTER the next
+    // tile's A operand has been staged and handed to the MMA warp: the tensor core then works on the new tile while
+    // the old tile's rows are updated, instead of idling behind them at every tile boundary.
+#ifndef KON_DA_DEFER_RMW
+#define KON_DA_DEFER_RMW 1
+#endif
+    float2 dx2_prev[MF / 2];
+    float* dxr_prev = nullptr;
+    const float* dq_prev = nullptr;
+    auto fold_dx0 = [&](float* dxr, const float* dq, const float2* dxv) {
+      float old[MF];
+#pragma unroll
+      for (int i = 0; i < MF; ++i) old[i] = dxr[(long long)i * a.D];          // all loads first
+      if (!a.dz_prev) {                                                       // layer 0: + dpre (written by this thread)
+        float t[MF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) t[i] = dq[(long long)i * a.D];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) old[i] += t[i];
+      }
+#pragma unroll
+      for (int i = 0; i < MF / 2; ++i) {
+        dxr[(long long)(2 * i) * a.D] = old[2 * i] + dxv[i].x;
+        dxr[(long long)(2 * i + 1) * a.D] = old[2 * i + 1] + dxv[i].y;
+      }
+    };
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x, ++tile_it) {
       const long long r = pair * 256 + sub * 128 + (warp & 3) * 32 + lane;
       const bool valid = r < a.rows;
@@ -1032,6 +1058,10 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
         tc::fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.a_full[sub]);
+      }
+      if (KON_DA_DEFER_RMW && dxr_prev) {          // previous tile's dx0, now behind this tile's first MMAs
+        fold_dx0(dxr_prev, dq_prev, dx2_prev);
+        dxr_prev = nullptr;
       }
       // ---- per-row constants -------------------------------------------------------------------
       const unsigned short* xrow = a.x0b + b * (long long)MF * a.D + d;      // x0[b,i,d] = xrow[i*D]
@@ -1120,24 +1150,18 @@ __global__ void __launch_bounds__(320, 1) cin_da_tc_kernel(const DaArgs a) {
       }
       if (valid) {
         float* dxr = a.dx0 + b * a.dx_sb + d;
-        float old[MF];
+        const float* dq = a.dpre0 + b * (long long)MF * a.D + d;
+        if (KON_DA_DEFER_RMW) {
 #pragma unroll
-        for (int i = 0; i < MF; ++i) old[i] = dxr[(long long)i * a.D];          // all loads first
-        if (!a.dz_prev) {                                                       // layer 0: + dpre (written by this thread)
-          const float* dq = a.dpre0 + b * (long long)MF * a.D + d;
-          float t[MF];
-#pragma unroll
-          for (int i = 0; i < MF; ++i) t[i] = dq[(long long)i * a.D];
-#pragma unroll
-          for (int i = 0; i < MF; ++i) old[i] += t[i];
-        }
-#pragma unroll
-        for (int i = 0; i < MF / 2; ++i) {
-          dxr[(long long)(2 * i) * a.D] = old[2 * i] + dx2[i].x;
-          dxr[(long long)(2 * i + 1) * a.D] = old[2 * i + 1] + dx2[i].y;
+          for (int i = 0; i < MF / 2; ++i) dx2_prev[i] = dx2[i];
+          dxr_prev = dxr;
+          dq_prev = dq;
+        } else {
+          fold_dx0(dxr, dq, dx2);
         }
       }
     }
+    if (KON_DA_DEFER_RMW && dxr_prev) fold_dx0(dxr_prev, dq_prev, dx2_prev);
   } else if (warp == 8) {
     // MMA role: warp-uniform control flow, one elected lane issues (see stream_mma_role)
     {
