@@ -1015,7 +1015,8 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   KON_REQUIRE(v.B < (1LL << 24), KON_EUNSUPPORTED, "batch of %lld samples: the routing packs (sample, field) in 32 bits, B < 2^24",
               (long long)v.B);
   const int64_t total_rows = ft.off[n_fields];
-  KON_REQUIRE(total_rows < 0xffffffffLL, KON_EUNSUPPORTED, "arena with >= 2^32-1 rows");
+  KON_REQUIRE(total_rows < 0x7fffffffLL, KON_EUNSUPPORTED,
+              "arena with >= 2^31-1 rows: unique_rows is int32 (shard the tables over ranks / arenas)");
   if (!sort_only) {
     KON_REQUIRE(is_i32(unique_rows) && numel(unique_rows) >= n && is_compact(unique_rows),
                 KON_EINVAL, "unique_rows must be compact int32 [>=N]");

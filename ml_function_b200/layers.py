@@ -276,25 +276,43 @@ class CrossLayer(nn.Module):
     """IL:255.  ``[B,D] -> [B,D,1]``; weights ``outer_weight_i`` / ``outer_bias_i`` ``[D,1]``
     stored stacked as ``kernel [L,D]`` / ``bias [L,D]``."""
 
-    def __init__(self, cross_hidden=3, seed=2020, **kwargs):
+    def __init__(self, cross_hidden=3, seed=2020, n_valid=None, **kwargs):
         super().__init__()
         self.cross_hidden, self.seed = cross_hidden, seed
+        # ``n_valid``: the reference's D when the input carries zero alignment columns behind it (the models'
+        # concat buffer is padded to a multiple of 4 floats).  Pad columns are inert: x0 = 0 there, the kernels'
+        # pad entries are 0 and get a zero gradient, and the pad BIAS gradient (the only thing that could make
+        # them a learnt constant feature) is masked.
+        self.n_valid = n_valid
         self.kernel = nn.UninitializedParameter()
         self.bias = nn.UninitializedParameter()
 
+    def _mask_pad(self):
+        D = self.bias.shape[1]
+        nv = D if self.n_valid is None else self.n_valid
+        if nv < D:
+            mask = torch.ones(1, D, device=self.bias.device)
+            mask[:, nv:] = 0
+            self.bias.register_hook(lambda g: g * mask)
+
     def build(self, D: int, device):
+        nv = D if self.n_valid is None else self.n_valid
         g = torch.Generator(device="cpu").manual_seed(self.seed)
-        lim = (6.0 / (D + 1)) ** 0.5                       # glorot_uniform on [D,1]
+        lim = (6.0 / (nv + 1)) ** 0.5                      # glorot_uniform on the reference's [D,1]
         # the reference passes the same seeded initializer object to every layer (IL:267)
-        w = torch.stack([(torch.rand(D, generator=g) * 2 - 1) * lim for _ in range(self.cross_hidden)])
+        w = torch.zeros(self.cross_hidden, D)
+        for i in range(self.cross_hidden):
+            w[i, :nv] = (torch.rand(nv, generator=g) * 2 - 1) * lim
         self.kernel = nn.Parameter(w.to(device))
         self.bias = nn.Parameter(torch.zeros(self.cross_hidden, D, device=device))
+        self._mask_pad()
 
     def load_reference_weights(self, kernels: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
         w = torch.stack([k.reshape(-1) for k in kernels])
         b = torch.stack([k.reshape(-1) for k in biases])
         self.kernel = nn.Parameter(w.contiguous())
         self.bias = nn.Parameter(b.contiguous())
+        self._mask_pad()
 
     def forward(self, inputs, **kwargs):
         if isinstance(self.kernel, nn.UninitializedParameter):

@@ -182,7 +182,7 @@ class DCN(_CtrModel):
     def __init__(self, inputFea: InputFeature = None, hidden_units=None, cross_hidden=3):
         super().__init__(inputFea)
         self.hidden_units = hidden_units if hidden_units is not None else [256, 128, 64]
-        self.cross = CrossLayer(cross_hidden=cross_hidden)
+        self.cross = CrossLayer(cross_hidden=cross_hidden, n_valid=self.Fk + self.n_dense)
         self.dnn = DnnLayer(hidden_units=self.hidden_units)
         self.head = MergeScoreLayer()
 

@@ -67,10 +67,11 @@ class SparseGrad:
     """Result of kon_embed_bwd: ``rows[:n]`` ascending unique arena rows and their summed
     gradients ``grads[:n]``; ``n`` stays on the device (no host sync)."""
 
-    __slots__ = ("rows", "grads", "n")
+    __slots__ = ("rows", "grads", "n", "disjoint")
 
-    def __init__(self, rows, grads, n):
+    def __init__(self, rows, grads, n, disjoint=False):
         self.rows, self.grads, self.n = rows, grads, n
+        self.disjoint = disjoint        # True: shares no row with the other gradients of its arena in this step
 
     def to_dense(self, n_rows: int) -> torch.Tensor:
         n = int(self.n.item())
@@ -148,11 +149,12 @@ def _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort):
     key = (ids.data_ptr(), ids._version, tuple(field_row_offset), n)
     cached = _SORT_CACHE.get(key) if share_sort else None
     need = lib.kon_embed_bwd_workspace_bytes(n, dim)
-    if cached is not None and cached.numel() >= need:
+    if cached is not None:
         ev = _SORT_EVENTS.pop(key, None)
-        if ev is not None:               # routed on the side stream: join it once
-            torch.cuda.current_stream(dev).wait_event(ev)
-        return cached, True
+        if ev is not None:               # routed on the side stream: join it once -- also before the buffer may be
+            torch.cuda.current_stream(dev).wait_event(ev)      # dropped below (the sort may still be writing it)
+        if cached.numel() >= need:
+            return cached, True
     # sized for the widest payload seen in practice plus the dim-1 path, so a later call can reuse it
     ws = _ws(max(need, lib.kon_embed_bwd_workspace_bytes(n, 1), lib.kon_embed_bwd_workspace_bytes(n, 32)), dev)
     if share_sort:

@@ -217,8 +217,10 @@ class _ShardedLookup(torch.autograd.Function):
         if arena.requires_grad:
             if not hasattr(arena, "kon_sparse_grads"):
                 arena.kon_sparse_grads = []
+            first = len(arena.kon_sparse_grads) == 0
             for gg, ii, oo in grads:
                 arena.kon_sparse_grads.append(sh.scatter_fn(gg, ii, oo))
+                arena.kon_sparse_grads[-1].disjoint = first
         return None, None, None
 
 
@@ -437,12 +439,15 @@ class _PeerLookup(torch.autograd.Function):
         if arena.requires_grad:
             if not hasattr(arena, "kon_sparse_grads"):
                 arena.kon_sparse_grads = []
+            first = len(arena.kon_sparse_grads) == 0          # table-wise and row-wise fields: disjoint row ranges
             if n_tw:
                 d_tw = px["drecv_tw"][:N * B_l * n_tw * k].view(N * B_l, n_tw, k)
                 arena.kon_sparse_grads.append(ops.embed_bwd_raw(d_tw, ids_tw, sh.tw_offs))
+                arena.kon_sparse_grads[-1].disjoint = first
             if n_rw:
                 d_rw = px["drecv_rw"].view(N * B_l, n_rw, k)
                 arena.kon_sparse_grads.append(ops.embed_bwd_raw(d_rw, ids_rw, sh.rw_offs))
+                arena.kon_sparse_grads[-1].disjoint = first
         deferred = ops._STEP_CACHE.pop(("lin_bwd", id(plan)), None)
         if deferred is not None:
             deferred()

@@ -36,6 +36,14 @@ class SparseAdam:
         if not sgs:
             return
         self.t += 1
+        if len(sgs) > 1 and not all(getattr(sg, "disjoint", False) for sg in sgs):
+            # the arena was looked up more than once in this step: Adam must see the SUM of the gradients of a row
+            # once, not one update per lookup (rare path: merged with torch ops; needs one host sync per gradient)
+            rows = torch.cat([sg.rows[:int(sg.n)] for sg in sgs]).long()
+            grads = torch.cat([sg.grads[:int(sg.n)] for sg in sgs])
+            uniq, inv = torch.unique(rows, return_inverse=True)
+            merged = torch.zeros((uniq.numel(), grads.shape[1]), dtype=grads.dtype, device=grads.device).index_add_(0, inv, grads)
+            sgs = [ops.SparseGrad(uniq.to(torch.int32), merged, torch.tensor([uniq.numel()], dtype=torch.int32, device=grads.device))]
         for sg in sgs:
             ops.embed_adam_devstep(self.arena.data, self.m, self.v, sg, self.lr, self.beta1, self.beta2,
                                    self.eps, self.l2, self.t)

@@ -219,3 +219,59 @@ def test_data_pipeline_feeds_the_trainer_from_hbm_and_pinned_memory():
         counts = torch.bincount(torch.cat(seen).long().cpu(), minlength=n)
         assert bool((counts == 2).all()) and len(losses) == len(pipe) == (2 * n + 511) // 512
         assert all(torch.isfinite(l) for l in losses)
+
+
+def test_sparse_adam_sums_the_gradients_of_an_arena_looked_up_twice():
+    """Keras' optimizer sees ONE gradient per variable (the sum over its uses): a row hit by two lookups of
+    the same arena in one step gets one Adam update on the summed gradient, not two updates."""
+    from ml_function_b200 import ops
+    from ml_function_b200.train import SparseAdam
+    g = gen(31)
+    rows, k, B = [40, 9], 4, 64
+    offs = offsets(rows)
+    arena = torch.nn.Parameter(torch.randn(sum(rows), k, generator=g).to(DEV))
+    w0 = arena.detach().clone()
+    ids_a = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).to(DEV)
+    ids_b = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).to(DEV)
+    da = torch.randn(B, 2, k, generator=g).to(DEV)
+    db = torch.randn(B, 2, k, generator=g).to(DEV)
+    arena.kon_sparse_grads = [ops.embed_bwd_raw(da, ids_a, offs[:-1]), ops.embed_bwd_raw(db, ids_b, offs[:-1])]
+    opt = SparseAdam(arena, lr=1e-2)
+    opt.step()
+    # oracle: dense Adam on the summed gradient, rows without a gradient untouched (lazy)
+    dense = torch.zeros(sum(rows), k, dtype=torch.float64)
+    o = torch.tensor(offs[:-1])
+    for ids, d in ((ids_a, da), (ids_b, db)):
+        dense.index_add_(0, (ids.cpu().long() + o).reshape(-1), d.cpu().double().reshape(-1, k))
+    m = 0.1 * dense
+    v = 0.001 * dense * dense
+    upd = 1e-2 * (m / (1 - 0.9)) / ((v / (1 - 0.999)).sqrt() + 1e-7)
+    want = w0.cpu().double() - torch.where(dense != 0, upd, torch.zeros_like(upd))
+    assert_rel(arena.detach().cpu().double(), want, 1e-5)
+
+
+def test_dcn_alignment_columns_stay_inert_through_training():
+    """The concat buffer is padded to a multiple of 4 floats; the cross layer's pad bias must never train
+    (else the pad columns become learnt constant features the reference does not have)."""
+    from ml_function_b200 import layers as KL, models as KM
+    from ml_function_b200.train import Trainer
+    g = gen(12)
+    rows = [50, 30, 7]
+    B, k = 256, 4                                     # 3*4 + 13 = 25 -> W = 28: three alignment columns
+    sparse = [KL.make_sparse_fea(f"s{i}", r, cross_unit=k) for i, r in enumerate(rows)]
+    dense_info = [KL.denseFea(f"d{i}", None) for i in range(13)]
+    fea = KM.FeatureInput(sparse, dense_info, useLinear=True, useAddLinear=True, device=DEV)
+    model = KM.DCN(fea, hidden_units=[16, 8], cross_hidden=3).to(DEV)
+    nv = model.Fk + model.n_dense
+    assert model.W > nv
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).to(DEV)
+    dense = torch.rand(B, 13, generator=g).to(DEV)
+    y = (torch.rand(B, generator=g) < 0.3).float()
+    labels = torch.stack([1 - y, y], 1).to(DEV)
+    tr = Trainer(model, lr=1e-2)
+    for _ in range(5):
+        tr.step(dense, ids, labels)
+    assert model.cross.kernel.shape[1] == model.W
+    assert torch.count_nonzero(model.cross.bias.detach()[:, nv:]) == 0
+    assert torch.count_nonzero(model.cross.kernel.detach()[:, nv:]) == 0
+    assert torch.count_nonzero(model.cross.bias.detach()[:, :nv]) > 0
