@@ -688,7 +688,18 @@ def run_gpu(args):
         for kn, fn in (("embed_fwd_vec_kernel", lambda i: ops.embed_fwd_raw(emb.arena.detach(), resident[i % len(resident)][1],
                                                                             emb.field_row_offset, out=outv)),
                        ("embed_bwd", lambda i: ops.embed_bwd_raw(gv, resident[i % len(resident)][1],
-                                                                 emb.field_row_offset, share_sort=False))):
+                                                                 emb.field_row_offset, share_sort=False)),
+                       # what the step's backward waits for: the routing was sorted at lookup time on the side stream
+                       # (kon_embed_sort), the backward runs the segmented reduce + fixup only -- here with the
+                       # first-order tables' gradient riding along (kon_embed_bwd_pair), as in the training step
+                       ("embed_bwd_presorted", lambda i: ops.embed_bwd_raw(gv, resident[i % len(resident)][1],
+                                                                           emb.field_row_offset, lin=g1v))):
+            if kn == "embed_bwd_presorted":
+                g1v = torch.randn((B, 1), device=dev).unsqueeze(1).expand(B, 26, 1)
+                ops.new_step()
+                for _, ids_r, _ in resident:
+                    ops.embed_presort(ids_r, emb.field_row_offset)
+                ops._join_side_streams()
             for i in range(3):
                 fn(i)
             torch.cuda.synchronize()
@@ -711,6 +722,8 @@ def run_gpu(args):
             except Exception as e:      # noqa: BLE001
                 print("isolated timing of", kn, "failed:", repr(e), file=sys.stderr)
                 torch.cuda.synchronize()
+            if kn == "embed_bwd_presorted":
+                ops.end_step()
         del xc, outv, gv
     # ---- the same step replayed from a CUDA graph (kernel stats above come from the eager pass:
     # events cannot be recorded inside a capture).  `value` and `e2e` are each the MEDIAN of
@@ -825,8 +838,12 @@ def run_gpu(args):
             "bound": "hbm", "launches_per_step": 1.0, "ms_per_launch": ms_iso, "work_per_launch": amount,
             "achieved": amount / (ms_iso * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
             "frac": amount / (ms_iso * 1e-3) / 1e9 / pk["hbm"], "share_of_step": ms_iso / (ms_eager / args.steps),
-            "note": ("embed_bwd = routing (keys, radix partition + sort, run heads) + segmented reduce + fixup; algorithmic "
-                     "bytes are the all-rows-unique worst case" if op == "embed_bwd" else "single launch, distinct id batches")}
+            "note": {"embed_bwd": "embed_bwd = routing (keys, radix partition + sort, run heads) + segmented reduce + fixup; "
+                                  "algorithmic bytes are the all-rows-unique worst case",
+                     "embed_bwd_presorted": "the backward's critical path in the training step: segmented reduce + fixup of the "
+                                            "embedding AND the first-order gradient in one pass (kon_embed_bwd_pair); the routing "
+                                            "was sorted at lookup time on a side stream (kon_embed_sort)"}.get(
+                         kn, "single launch, distinct id batches")}
     dom = max((kn for kn in kstats if "back-to-back" not in kn), key=lambda kn: kstats[kn]["share_of_step"], default=None)
     roof = None
     if dom is not None:

@@ -125,6 +125,16 @@ int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids, const int64_
 int kon_embed_sort(const DLTensor* ids, const int64_t* field_row_offset, int32_t n_fields,
                    DLTensor* workspace, void* stream);
 
+/* Two gradients over ONE routing, one pass: d_out [B,F,dim] (dim % 4 == 0) for the embedding arena and
+ * d_lin [B,F,1] (any strides; stride_f = 0 for a sum-pooled first-order term) for the dim-1 "linear" arena that
+ * FeatureInput(useLinear=True) (DP:65-76) looks up with the SAME ids and per-field row counts.  unique_rows /
+ * n_unique are shared; grads [>=N,dim], grads_lin [>=N,1].  reuse_sort != 0: the sorted routing of these ids is
+ * already at the front of `workspace` (kon_embed_sort).  Workspace: kon_embed_bwd_workspace_bytes(N, dim). */
+int kon_embed_bwd_pair(const DLTensor* d_out, const DLTensor* d_lin, const DLTensor* ids,
+                       const int64_t* field_row_offset, int32_t n_fields, DLTensor* unique_rows,
+                       DLTensor* grads, DLTensor* grads_lin, DLTensor* n_unique, DLTensor* workspace,
+                       int32_t reuse_sort, void* stream);
+
 /* Sparse row-wise SGD on the arena: w[r] -= lr * (g + 2*l2*w[r]) for the n_unique rows
  * (the L2 term is the reference's embeddings_regularizer, IL:217, applied lazily). */
 int kon_embed_sgd(DLTensor* arena, const DLTensor* unique_rows, const DLTensor* grads,

@@ -30,6 +30,15 @@ namespace kon {
 #ifndef KON_EMB_WIN
 #define KON_EMB_WIN 16
 #endif
+#ifndef KON_EMB_RED_MINB_LIN
+#define KON_EMB_RED_MINB_LIN 3   // fused first-order gradient (kon_embed_bwd_pair)
+#endif
+#ifndef KON_EMB_RED_NB_LIN
+#define KON_EMB_RED_NB_LIN 4     // 8 spills (80-register cap at 3 CTAs/SM): 91 us instead of 61 us at 1.7 M lookups
+#endif
+#ifndef KON_EMB_RED_NB
+#define KON_EMB_RED_NB 8
+#endif
 #ifndef KON_EMB_RED_MINB
 #define KON_EMB_RED_MINB 3
 #endif
@@ -311,6 +320,13 @@ struct BwdArgs {
   float* cta_head;  // [n_cta, dim]
   float* cta_tail;  // [n_cta, dim]
   int* cta_meta;    // [n_cta]
+  // fused first-order gradient (kon_embed_bwd_pair): a second, one-float-per-lookup gradient reduced over the
+  // same routing in the same pass (the dim-1 "linear" tables are looked up with the same ids)
+  const float* d1;
+  long long sb1, sf1;
+  float* grads1;      // [n_unique]
+  float* cta_head1;   // [n_cta]
+  float* cta_tail1;   // [n_cta]
   // peer mode (n_peers > 0): sample b's gradient row is read from rank b / peer_rows over NVLink
   int n_peers;
   long long peer_rows;
@@ -322,8 +338,11 @@ struct BwdArgs {
 // most one head and one tail partial per CTA for embed_fixup_kernel.
 // NB = gradient rows loaded per lane group before the first one is consumed.  8 covers HBM latency; rows that
 // come over NVLink (peer mode) have ~3x the latency, so that instantiation keeps a whole 16-lookup window in flight.
-template <int LPR, int NB>
-__global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) embed_reduce_kernel(const BwdArgs a) {
+// LIN: also reduce the one-float gradient a.d1 (see BwdArgs) -- one extra 4-byte load per lookup (the same address
+// for the LPR lanes of a group), one extra accumulator.
+template <int LPR, int NB, bool LIN = false>
+__global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : (LIN ? KON_EMB_RED_MINB_LIN : KON_EMB_RED_MINB))
+embed_reduce_kernel(const BwdArgs a) {
   constexpr int G = kRedThreads / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_head = reinterpret_cast<float4*>(smem_raw);          // [G][LPR]
@@ -331,6 +350,8 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
   __shared__ int s_meta[G];
   __shared__ int s_tailseg[G];
   __shared__ uint32_t s_tailkey[G];
+  __shared__ float s_head1[LIN ? G : 1];
+  __shared__ float s_tail1[LIN ? G : 1];
 
   const int tid = threadIdx.x;
   const int g = tid / LPR, lane = tid % LPR;
@@ -342,14 +363,18 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
 
   int meta = 0;
   float4 head = zero, tail = zero;
+  float head1 = 0.f, tail1 = 0.f;
   int tail_seg = 0;
   uint32_t tail_key = 0;
 
-  auto emit_final = [&](int seg, uint32_t key, float4 v) {
+  auto emit_final = [&](int seg, uint32_t key, float4 v, float v1) {
     if (key == a.sentinel) return;   // out-of-range ids carry no gradient
     if (lane_on)
       *reinterpret_cast<float4*>(a.grads + (long long)(seg - 1) * a.dim + lane * 4) = v;
-    if (lane == 0) a.unique_rows[seg - 1] = (int)key;
+    if (lane == 0) {
+      a.unique_rows[seg - 1] = (int)key;
+      if (LIN) a.grads1[seg - 1] = v1;
+    }
   };
 
   if (lo < a.n) {
@@ -360,14 +385,17 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
     uint32_t cur_key = a.keys[lo];
     bool first_run = true;
     float4 acc = zero;
+    float acc1 = 0.f;
     const int cnt = (int)(hi - lo);
     for (int i0 = 0; i0 < cnt; i0 += NB) {
       float4 r[NB];
+      float r1[LIN ? NB : 1];
       int sg[NB];
       uint32_t ky[NB];
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
         r[u] = zero;
+        if (LIN) r1[u] = 0.f;
         sg[u] = cur;
         ky[u] = cur_key;
         if (i0 + u < cnt) {
@@ -386,6 +414,7 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
           if (lane_on)
             r[u] = ldg_stream_f4(
                 reinterpret_cast<const float4*>(src + b * a.sb + f * a.sf) + lane);
+          if (LIN) r1[u] = __ldg(a.d1 + b * a.sb1 + f * a.sf1);
         }
       }
 #pragma unroll
@@ -394,27 +423,32 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
           if (sg[u] != cur) {   // run [.., i-1] is complete at its right end
             if (first_run && !starts) {
               head = acc;
+              head1 = acc1;
               meta |= kHeadEnded;
             } else {
-              emit_final(cur, cur_key, acc);
+              emit_final(cur, cur_key, acc, acc1);
             }
             first_run = false;
             acc = zero;
+            acc1 = 0.f;
             cur = sg[u];
             cur_key = ky[u];
           }
           acc.x += r[u].x; acc.y += r[u].y; acc.z += r[u].z; acc.w += r[u].w;
+          if (LIN) acc1 += r1[u];
         }
       }
     }
     // last run of the window
     if (first_run && !starts) {
       head = acc;
+      head1 = acc1;
       if (ends) meta |= kHeadEnded;
     } else if (ends) {
-      emit_final(cur, cur_key, acc);
+      emit_final(cur, cur_key, acc, acc1);
     } else {
       tail = acc;
+      tail1 = acc1;
       tail_seg = cur;
       tail_key = cur_key;
       meta |= kHasTail;
@@ -430,6 +464,10 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
     s_meta[g] = meta;
     s_tailseg[g] = tail_seg;
     s_tailkey[g] = tail_key;
+    if (LIN) {
+      s_head1[g] = head1;
+      s_tail1[g] = tail1;
+    }
   }
   __syncthreads();
 
@@ -437,6 +475,7 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
   // (a) a run that started in window g (tail) walks right through the heads of g+1..
   if (meta & kHasTail) {
     float4 acc = tail;
+    float acc1 = tail1;
     int w = g + 1;
     bool ended = false;
     for (; w < G; ++w) {
@@ -444,13 +483,15 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
       if (!(m & kHasHead)) break;   // cannot happen while the run continues; defensive
       const float4 h = s_head[w * LPR + lane];
       acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+      if (LIN) acc1 += s_head1[w];
       if (m & kHeadEnded) { ended = true; break; }
     }
     if (ended) {
-      emit_final(tail_seg, tail_key, acc);
+      emit_final(tail_seg, tail_key, acc, acc1);
     } else {   // runs off the CTA: it is the CTA's tail partial
       if (lane_on)
         *reinterpret_cast<float4*>(a.cta_tail + (long long)blockIdx.x * a.dim + lane * 4) = acc;
+      if (LIN && lane == 0) a.cta_tail1[blockIdx.x] = acc1;
     }
   }
   // (b) the run entering the CTA from the left: group 0 walks it
@@ -459,17 +500,20 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
     if (s_meta[0] & kHasHead) {
       cmeta |= kHasHead;
       float4 acc = s_head[lane];
+      float acc1 = LIN ? s_head1[0] : 0.f;
       bool ended = (s_meta[0] & kHeadEnded) != 0;
       for (int w = 1; w < G && !ended; ++w) {
         const int m = s_meta[w];
         if (!(m & kHasHead)) break;   // window w is empty (past n): the run ended with n
         const float4 h = s_head[w * LPR + lane];
         acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+        if (LIN) acc1 += s_head1[w];
         if (m & kHeadEnded) ended = true;
       }
       if (ended) cmeta |= kHeadEnded;
       if (lane_on)
         *reinterpret_cast<float4*>(a.cta_head + (long long)blockIdx.x * a.dim + lane * 4) = acc;
+      if (LIN && lane == 0) a.cta_head1[blockIdx.x] = acc1;
     }
     // does some run leave the CTA on the right?  It is the tail of the last non-empty
     // window, or a head run that never ended.
@@ -492,7 +536,7 @@ __global__ void __launch_bounds__(kRedThreads, NB > 8 ? 2 : KON_EMB_RED_MINB) em
 }
 
 // Runs that cross CTA boundaries: one lane group per CTA that owns a tail partial.
-template <int LPR>
+template <int LPR, bool LIN = false>
 __global__ void __launch_bounds__(kRedThreads) embed_fixup_kernel(const BwdArgs a, int n_cta) {
   constexpr int G = kRedThreads / LPR;
   const int c = blockIdx.x * G + threadIdx.x / LPR;
@@ -501,7 +545,9 @@ __global__ void __launch_bounds__(kRedThreads) embed_fixup_kernel(const BwdArgs 
   if (!(a.cta_meta[c] & kHasTail)) return;
   const bool lane_on = lane < a.vec_per_row;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc1 = 0.f;
   if (lane_on) acc = *reinterpret_cast<const float4*>(a.cta_tail + (long long)c * a.dim + lane * 4);
+  if (LIN) acc1 = a.cta_tail1[c];
   for (int w = c + 1; w < n_cta; ++w) {
     const int m = a.cta_meta[w];
     if (!(m & kHasHead)) break;
@@ -509,6 +555,7 @@ __global__ void __launch_bounds__(kRedThreads) embed_fixup_kernel(const BwdArgs 
       const float4 h = *reinterpret_cast<const float4*>(a.cta_head + (long long)w * a.dim + lane * 4);
       acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
     }
+    if (LIN) acc1 += a.cta_head1[w];
     if (m & kHeadEnded) break;
   }
   // the run's identity: last sorted lookup of CTA c
@@ -517,7 +564,10 @@ __global__ void __launch_bounds__(kRedThreads) embed_fixup_kernel(const BwdArgs 
   const uint32_t key = a.keys[last];
   if (key == a.sentinel) return;
   if (lane_on) *reinterpret_cast<float4*>(a.grads + (long long)(seg - 1) * a.dim + lane * 4) = acc;
-  if (lane == 0) a.unique_rows[seg - 1] = (int)key;
+  if (lane == 0) {
+    a.unique_rows[seg - 1] = (int)key;
+    if (LIN) a.grads1[seg - 1] = acc1;
+  }
 }
 
 // -------------------------------------------------------------------------------------
@@ -820,7 +870,7 @@ extern "C" int kon_embed_fwd_peer_cols(const DLTensor* arena, const DLTensor* id
 // ---- backward workspace layout ----------------------------------------------------------
 namespace {
 struct BwdLayout {
-  size_t keys_in, vals_in, keys_out, vals_out, segidx, cta_head, cta_tail, cta_meta, cub, total;
+  size_t keys_in, vals_in, keys_out, vals_out, segidx, cta_head, cta_tail, cta_meta, cub, cta_lin, total;
   size_t cub_bytes;
   int n_cta;
   int lpr, vpr, dim_pad;
@@ -859,6 +909,7 @@ int bwd_layout(int64_t n, int32_t dim, BwdLayout* l) {
   l->cta_tail = take((size_t)l->n_cta * l->lpr * 16);
   l->cta_meta = take((size_t)l->n_cta * 4);
   l->cub = take(l->cub_bytes);
+  l->cta_lin = take((size_t)l->n_cta * 8);   // kon_embed_bwd_pair: per-CTA head / tail partials of the 1-float gradient
   l->total = o;
   return 0;
 }
@@ -905,6 +956,10 @@ struct GradSrc {
   int n_peers = 0;
   long long peer_rows = 0;
   const float* peer[kMaxPeers] = {};
+  // kon_embed_bwd_pair: the fused one-float gradient and its output
+  const float* lin = nullptr;
+  long long lin_sb = 0, lin_sf = 0;
+  float* lin_grads = nullptr;
 };
 }  // namespace
 
@@ -945,6 +1000,43 @@ extern "C" int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids,
                                    DLTensor* workspace, void* stream) {
   return embed_bwd_impl(d_out, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 1,
                         stream);
+}
+
+// Two gradients over one routing: the embedding tables' [B,F,dim] gradient and the first-order ("linear", dim-1)
+// tables' [B,F,1] gradient (any strides; a sum-pooled first-order term has stride_f = 0) when both tables were
+// looked up with the same ids and per-field row counts -- the reference's FeatureInput(useLinear=True) (DP:65-76).
+// One pass over the sorted lookups yields both; unique_rows / n_unique are shared.  Replaces a second
+// pad + reduce + fixup + unpad chain (63 us at 1.7 M lookups).
+extern "C" int kon_embed_bwd_pair(const DLTensor* d_out, const DLTensor* d_lin, const DLTensor* ids,
+                                  const int64_t* field_row_offset, int32_t n_fields,
+                                  DLTensor* unique_rows, DLTensor* grads, DLTensor* grads_lin,
+                                  DLTensor* n_unique, DLTensor* workspace, int32_t reuse_sort, void* stream) {
+  KON_TRY(check_cuda_tensor(d_out, "d_out"));
+  const int dev = d_out->device.device_id;
+  KON_TRY(check_cuda_tensor(d_lin, "d_lin", dev));
+  KON_TRY(check_cuda_tensor(ids, "ids", dev));
+  KON_TRY(check_cuda_tensor(grads_lin, "grads_lin", dev));
+  KON_REQUIRE(is_f32(d_out) && d_out->ndim == 3 && ids->ndim == 2 && d_out->shape[0] == ids->shape[0] &&
+                  d_out->shape[1] == ids->shape[1] && d_out->shape[2] >= 4 && d_out->shape[2] % 4 == 0,
+              KON_EINVAL, "d_out must be float32 [B,F,dim], dim a multiple of 4, ids [B,F]");
+  KON_REQUIRE(is_f32(d_lin) && d_lin->ndim == 3 && d_lin->shape[0] == ids->shape[0] &&
+                  d_lin->shape[1] == ids->shape[1] && d_lin->shape[2] == 1,
+              KON_EINVAL, "d_lin must be float32 [B,F,1]");
+  KON_REQUIRE(is_f32(grads_lin) && is_compact(grads_lin) && numel(grads_lin) >= numel(ids), KON_EINVAL,
+              "grads_lin must be compact float32 [>=N,1]");
+  KON_REQUIRE(stride_of(d_out, 2) == 1, KON_EINVAL, "d_out last dim must be compact");
+  GradSrc src;
+  src.p = data_ptr<float>(d_out);
+  src.sb = stride_of(d_out, 0);
+  src.sf = stride_of(d_out, 1);
+  src.dim = d_out->shape[2];
+  src.device = dev;
+  src.lin = data_ptr<float>(d_lin);
+  src.lin_sb = stride_of(d_lin, 0);
+  src.lin_sf = stride_of(d_lin, 1);
+  src.lin_grads = data_ptr<float>(grads_lin);
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
+                        reuse_sort ? 1 : 0, stream);
 }
 
 // Routing only: builds the (arena row, position) keys, sorts them and scans the run heads into the front
@@ -1099,6 +1191,12 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   a.cta_head = (float*)(ws + l.cta_head);
   a.cta_tail = (float*)(ws + l.cta_tail);
   a.cta_meta = (int*)(ws + l.cta_meta);
+  a.d1 = src.lin;
+  a.sb1 = src.lin_sb;
+  a.sf1 = src.lin_sf;
+  a.grads1 = src.lin_grads;
+  a.cta_head1 = (float*)(ws + l.cta_lin);
+  a.cta_tail1 = a.cta_head1 + l.n_cta;
   float* padded_grads = nullptr;
   if (dim == 1) {
     float4* padded = (float4*)(ws + pad_off);
@@ -1119,8 +1217,16 @@ static int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t
   ProfileScope ps_red("embed_reduce_kernel", st);
 #define KON_RED_CASE(N)                                                                  \
   case N:                                                                                \
+    if (a.d1 != nullptr) {                                                               \
+      embed_reduce_kernel<N, KON_EMB_RED_NB_LIN, true><<<l.n_cta, kRedThreads, smem, st>>>(a); \
+      KON_LAUNCH_CHECK("embed_reduce_kernel");                                           \
+      embed_fixup_kernel<N, true>                                                        \
+          <<<(l.n_cta + kRedThreads / N - 1) / (kRedThreads / N), kRedThreads, 0, st>>>(a, l.n_cta); \
+      KON_LAUNCH_CHECK("embed_fixup_kernel");                                            \
+      break;                                                                             \
+    }                                                                                    \
     if (a.n_peers > 1) embed_reduce_kernel<N, kWin><<<l.n_cta, kRedThreads, smem, st>>>(a);  \
-    else embed_reduce_kernel<N, 8><<<l.n_cta, kRedThreads, smem, st>>>(a);               \
+    else embed_reduce_kernel<N, KON_EMB_RED_NB><<<l.n_cta, kRedThreads, smem, st>>>(a);  \
     KON_LAUNCH_CHECK("embed_reduce_kernel");                                             \
     embed_fixup_kernel<N>                                                                \
         <<<(l.n_cta + kRedThreads / N - 1) / (kRedThreads / N), kRedThreads, 0, st>>>(a, l.n_cta); \

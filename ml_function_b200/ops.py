@@ -134,6 +134,7 @@ def end_step():
     # (parallel._ShardedSumPeer) and never picked up -- publish and scatter it now (same on every rank)
     for key in [k_ for k_ in _STEP_CACHE if isinstance(k_, tuple) and k_ and k_[0] == "lin_bwd"]:
         _STEP_CACHE.pop(key)(need_barrier=True)
+    flush_deferred()
     _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
@@ -204,8 +205,10 @@ def embed_presort(ids, field_row_offset: Sequence[int]):
     _SORT_EVENTS[key] = ev
 
 
-def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None) -> SparseGrad:
-    """d_out [B,F,dim] (any strides on dims 0/1, e.g. an expanded [B,1,dim])."""
+def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optional[bool] = None, lin=None):
+    """d_out [B,F,dim] (any strides on dims 0/1, e.g. an expanded [B,1,dim]) -> SparseGrad.
+    ``lin``: a second gradient [B,F,1] (any strides) of dim-1 tables looked up with the same ids / offsets, reduced
+    in the same pass (kon_embed_bwd_pair) -> (SparseGrad, SparseGrad of the dim-1 tables; rows and n shared)."""
     lib = L.lib()
     F = ids.shape[1]
     dim = d_out.shape[2]
@@ -215,6 +218,14 @@ def embed_bwd_raw(d_out, ids, field_row_offset: Sequence[int], share_sort: Optio
     grads = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
     nu = torch.zeros(1, dtype=torch.int32, device=dev)
     ws, reuse = _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort)
+    if lin is not None:
+        grads1 = torch.empty((max(n, 1), 1), dtype=torch.float32, device=dev)
+        offs = L.i64_array(list(field_row_offset))
+        a = [L._arg(t) for t in (d_out, lin, ids, rows, grads, grads1, nu, ws)]
+        with _prof("embed_bwd"):
+            L.check(lib.kon_embed_bwd_pair(a[0].ptr, a[1].ptr, a[2].ptr, offs, F, a[3].ptr, a[4].ptr, a[5].ptr, a[6].ptr,
+                                           a[7].ptr, 1 if reuse else 0, L.stream_ptr(dev)), "kon_embed_bwd_pair")
+        return SparseGrad(rows, grads, nu), SparseGrad(rows, grads1, nu)
     fn, what = (lib.kon_embed_bwd_reuse, "kon_embed_bwd_reuse") if reuse else (lib.kon_embed_bwd, "kon_embed_bwd")
     offs = L.i64_array(list(field_row_offset))
     a = [L._arg(t) for t in (d_out, ids, rows, grads, nu, ws)]
@@ -261,11 +272,57 @@ def embed_bwd_peer(peer_d_out, n_peers: int, rows_per_peer: int, stride_b: int, 
     return SparseGrad(rows, grads, nu)
 
 
+# The first-order ("linear", dim-1) tables of a model are looked up with the same ids as its embedding tables
+# (FeatureInput(useLinear=True), DP:65-76).  Inside new_step() ... end_step() their gradient -- which autograd
+# delivers FIRST, the linear term sits at the end of the forward -- is parked until the embedding tables' backward
+# and reduced in the same pass over the shared routing (kon_embed_bwd_pair).  ``flush_deferred()`` (Trainer: right
+# after backward(); also end_step()) scatters whatever was parked and never picked up.
+FUSE_LIN = os.environ.get("KON_FUSE_LIN", "1") != "0"
+
+
+def _route_key(ids, field_row_offset):
+    return (ids.data_ptr(), ids._version, tuple(field_row_offset), ids.numel())
+
+
+def _announce_main(arena, ids, field_row_offset):
+    if FUSE_LIN and _SHARE_SORT and arena.requires_grad and ids.dim() == 2 and arena.shape[1] % 4 == 0:
+        _STEP_CACHE[("emb_main", _route_key(ids, field_row_offset))] = True
+
+
+def _append_grad(arena, sg):
+    if not hasattr(arena, "kon_sparse_grads"):
+        arena.kon_sparse_grads = []
+    arena.kon_sparse_grads.append(sg)
+
+
+def _main_backward(arena, g3, ids, field_row_offset):
+    """The embedding tables' scatter-add, taking a parked first-order gradient of the same routing along."""
+    key = _route_key(ids, field_row_offset)
+    _STEP_CACHE.pop(("emb_main", key), None)
+    parked = _STEP_CACHE.pop(("lin_parked", key), None)
+    if parked is None:
+        _append_grad(arena, embed_bwd_raw(g3, ids, field_row_offset))
+        return
+    lin_arena, g1 = parked
+    sg, sg1 = embed_bwd_raw(g3, ids, field_row_offset, lin=g1)
+    _append_grad(arena, sg)
+    _append_grad(lin_arena, sg1)
+
+
+def flush_deferred():
+    for key in [k_ for k_ in _STEP_CACHE if isinstance(k_, tuple) and k_ and k_[0] == "lin_parked"]:
+        lin_arena, g1 = _STEP_CACHE.pop(key)
+        ids = _STEP_CACHE.pop(("lin_ids", key[1]))
+        _append_grad(lin_arena, embed_bwd_raw(g1, ids, key[1][2]))
+
+
 class _EmbedLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, arena, ids, field_row_offset, sum_fields):
         if arena.requires_grad:
             embed_presort(ids, field_row_offset)
+            if arena.shape[1] > 1:
+                _announce_main(arena, ids, field_row_offset)
         out = embed_fwd_raw(arena.detach(), ids, field_row_offset, sum_fields)
         ctx.save_for_backward(ids)
         ctx.arena = arena
@@ -282,10 +339,16 @@ class _EmbedLookup(torch.autograd.Function):
                 g3 = g.contiguous().unsqueeze(1).expand(g.shape[0], ids.shape[1], g.shape[1])
             else:
                 g3 = g.contiguous()
-            sg = embed_bwd_raw(g3, ids, ctx.offs)
-            if not hasattr(arena, "kon_sparse_grads"):
-                arena.kon_sparse_grads = []
-            arena.kon_sparse_grads.append(sg)
+            key = _route_key(ids, ctx.offs)
+            if arena.shape[1] == 1 and ids.dim() == 2 and ("emb_main", key) in _STEP_CACHE \
+                    and ("lin_parked", key) not in _STEP_CACHE:
+                _STEP_CACHE[("lin_parked", key)] = (arena, g3)       # reduced by the embedding tables' backward
+                _STEP_CACHE[("lin_ids", key)] = ids
+            elif arena.shape[1] > 1 and g3.dim() == 3 and g3.stride(2) == 1 and g3.stride(0) % 4 == 0 \
+                    and g3.stride(1) % 4 == 0 and g3.data_ptr() % 16 == 0:
+                _main_backward(arena, g3, ids, ctx.offs)
+            else:
+                _append_grad(arena, embed_bwd_raw(g3, ids, ctx.offs))
         return None, None, None, None
 
 
@@ -646,6 +709,7 @@ class _EmbedConcat(torch.autograd.Function):
         assert width % 4 == 0 and width >= Fk + nd
         if arena.requires_grad:
             embed_presort(ids, field_row_offset)
+            _announce_main(arena, ids, field_row_offset)
         xcat = torch.empty((B, width), dtype=arena.dtype, device=arena.device)
         embed_fwd_raw(arena.detach(), ids, field_row_offset, False, out=xcat[:, :Fk].view(B, F, dim))
         if nd:
@@ -665,10 +729,7 @@ class _EmbedConcat(torch.autograd.Function):
         if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
             g = g.contiguous()
         if arena.requires_grad:
-            sg = embed_bwd_raw(g[:, :ctx.Fk].view(B, F, ctx.Fk // F), ids, ctx.offs)
-            if not hasattr(arena, "kon_sparse_grads"):
-                arena.kon_sparse_grads = []
-            arena.kon_sparse_grads.append(sg)
+            _main_backward(arena, g[:, :ctx.Fk].view(B, F, ctx.Fk // F), ids, ctx.offs)
         gd = g[:, ctx.Fk:ctx.Fk + ctx.nd] if ctx.dense_grad else None
         return None, None, None, gd, None
 

@@ -298,8 +298,10 @@ class PeerRegion:
             if self._n_barriers < 8:
                 timeout_ms = max(timeout_ms, 60000)
         self._n_barriers += 1
-        self.L.check(self.lib.kon_peer_barrier(self._flag_ptrs, self.world, self.rank, self.dev_index, timeout_ms,
-                                               self.L.stream_ptr(self.device)), "kon_peer_barrier")
+        from . import ops
+        with ops._prof("peer_barrier"):                   # device time of the barrier = flag round trip + waiting for the slowest rank
+            self.L.check(self.lib.kon_peer_barrier(self._flag_ptrs, self.world, self.rank, self.dev_index, timeout_ms,
+                                                   self.L.stream_ptr(self.device)), "kon_peer_barrier")
 
     def check(self):
         """Raise if a barrier of this region ever timed out (synchronises the device)."""
@@ -334,8 +336,10 @@ def _put2d(sh, puts):
         return
     arr = (L.KonPut2D * len(puts))(*[L.KonPut2D(*p) for p in puts])
     dev = sh.arena.device
-    L.check(L.lib().kon_peer_put2d(arr, len(puts), dev.index if dev.index is not None else torch.cuda.current_device(),
-                                   L.stream_ptr(dev)), "kon_peer_put2d")
+    from . import ops
+    with ops._prof("peer_put"):
+        L.check(L.lib().kon_peer_put2d(arr, len(puts), dev.index if dev.index is not None else torch.cuda.current_device(),
+                                       L.stream_ptr(dev)), "kon_peer_put2d")
 
 
 class _PeerLookup(torch.autograd.Function):
@@ -442,7 +446,14 @@ class _PeerLookup(torch.autograd.Function):
             first = len(arena.kon_sparse_grads) == 0          # table-wise and row-wise fields: disjoint row ranges
             if n_tw:
                 d_tw = px["drecv_tw"][:N * B_l * n_tw * k].view(N * B_l, n_tw, k)
-                arena.kon_sparse_grads.append(ops.embed_bwd_raw(d_tw, ids_tw, sh.tw_offs))
+                sg = None
+                if n_rw == 0 and ops.FUSE_LIN:            # the first-order gradient rides the same segmented reduce
+                    deferred = ops._STEP_CACHE.pop(("lin_bwd", id(plan)), None)
+                    if deferred is not None:
+                        sg = deferred(main=(d_tw, ids_tw, sh.tw_offs))
+                if sg is None:
+                    sg = ops.embed_bwd_raw(d_tw, ids_tw, sh.tw_offs)
+                arena.kon_sparse_grads.append(sg)
                 arena.kon_sparse_grads[-1].disjoint = first
             if n_rw:
                 d_rw = px["drecv_rw"].view(N * B_l, n_rw, k)
@@ -479,15 +490,26 @@ class _ShardedSumPeer(torch.autograd.Function):
         sp = sh.sparse_partner
         _put2d(sp, [(g.data_ptr(), region.ptrs[q] + px["lin_grecv_off"] + rank * B_l * 4, 4, 4, 4, B_l) for q in range(N)])
 
-        def scatter(need_barrier=False):
+        def scatter(need_barrier=False, main=None):
+            """``main`` = (d_out, ids, offsets) of the embedding tables' scatter-add about to run on the same routing:
+            both gradients are then reduced in one pass and the embedding tables' SparseGrad is returned."""
             if need_barrier:                              # no embedding backward followed in this step (ops.end_step)
                 region.barrier()
-            if arena.requires_grad:
-                full = px["lin_grecv"].view(N * B_l, 1)
-                g3 = full.unsqueeze(1).expand(N * B_l, lin_ids.shape[1], 1)
-                if not hasattr(arena, "kon_sparse_grads"):
-                    arena.kon_sparse_grads = []
-                arena.kon_sparse_grads.append(sh.scatter_fn(g3, lin_ids, sh.all_offs))
+            if not arena.requires_grad:
+                return None
+            full = px["lin_grecv"].view(N * B_l, 1)
+            g3 = full.unsqueeze(1).expand(N * B_l, lin_ids.shape[1], 1)
+            if not hasattr(arena, "kon_sparse_grads"):
+                arena.kon_sparse_grads = []
+            if main is not None:
+                d_m, ids_m, offs_m = main
+                if ids_m.data_ptr() == lin_ids.data_ptr() and ids_m.shape == lin_ids.shape \
+                        and tuple(offs_m) == tuple(sh.all_offs) and sh.scatter_fn is _kon_scatter:
+                    sg, sg1 = ops.embed_bwd_raw(d_m, ids_m, offs_m, lin=g3)
+                    arena.kon_sparse_grads.append(sg1)
+                    return sg
+            arena.kon_sparse_grads.append(sh.scatter_fn(g3, lin_ids, sh.all_offs))
+            return None
         ops._STEP_CACHE[("lin_bwd", id(sh.plan))] = scatter
         return None, None, None, None, None
 
@@ -839,7 +861,9 @@ class DistContext:
         if not getattr(self, "_ar_done", False):
             self.allreduce_dense_grads(params)          # no sharded lookup took part in this backward
         elif self._ar_event is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._ar_event)
+            from . import ops
+            with ops._prof("allreduce_wait"):             # what the overlapped dense all-reduce still costs the main stream
+                torch.cuda.current_stream(self.device).wait_event(self._ar_event)
         self._ar_keep = None
 
     def describe(self) -> str:

@@ -103,12 +103,14 @@ class Trainer:
             # embedding exchange + scatter-add on a side stream.
             self.dist.arm_overlapped_allreduce(self.model, lambda: self._dense_params)
             (loss / self.dist.world).backward()
+            ops.flush_deferred()
             for so in self.sparse_opts:         # the row-wise Adam does not wait for the dense all-reduce
                 so.step()
             self.dist.finish_allreduce(self.model, self._dense_params)
             self.dense_opt.step()
         else:
             loss.backward()
+            ops.flush_deferred()                # a first-order gradient parked for an embedding backward that never came
             self.dense_opt.step()
             for so in self.sparse_opts:
                 so.step()

@@ -348,6 +348,80 @@ def test_embed_bwd_shared_sort_matches_separate():
         assert torch.equal(x.rows[:n], y.rows[:n]) and torch.equal(x.grads[:n], y.grads[:n])
 
 
+@pytest.mark.parametrize("dim", [4, 16, 32, 64])
+@pytest.mark.parametrize("B,rows", [(5000, [50, 3000, 7, 100000]), (3, [5, 5]), (70000, [3, 2, 40])])
+def test_embed_bwd_pair_is_bit_identical_to_two_calls(dim, B, rows):
+    """kon_embed_bwd_pair: the first-order gradient rides the embedding tables' segmented reduction (same routing).
+    Rows, counts and the embedding gradient are bit-identical to two kon_embed_bwd calls; the first-order sums see
+    the same lookups in the same order but are associated at other CTA boundaries than the stand-alone dim-1 launch
+    (1,024 instead of 4,096 lookups per CTA), so they agree to fp32 rounding (1e-6 of the largest sum) and are
+    bit-identical between the pre-sorted and the sort-inside call.  Per-field [B,F,1] gradient and the stride-0
+    gradient of a sum-pooled first-order term; runs crossing window / CTA boundaries (3 hot rows over 70,000
+    samples) included."""
+    ops = _ops()
+    g = gen(22)
+    F = len(rows)
+    ids = make_ids(B, rows, g).to(DEV)
+    offs = offsets(rows)
+    gd = torch.randn(B, F, dim, generator=g).to(DEV)
+    for g1 in (torch.randn(B, F, 1, generator=g).to(DEV), torch.randn(B, 1, generator=g).to(DEV).unsqueeze(1).expand(B, F, 1)):
+        a, a1 = ops.embed_bwd_raw(gd, ids, offs, share_sort=False), ops.embed_bwd_raw(g1, ids, offs, share_sort=False)
+        b, b1 = ops.embed_bwd_raw(gd, ids, offs, share_sort=False, lin=g1)
+        ops.new_step()
+        ops.embed_presort(ids, offs)
+        c, c1 = ops.embed_bwd_raw(gd, ids, offs, lin=g1)
+        ops.end_step()
+        n = int(a.n.item())
+        for x, x1 in ((b, b1), (c, c1)):
+            assert int(x.n.item()) == n and int(x1.n.item()) == n
+            assert torch.equal(x.rows[:n], a.rows[:n]) and torch.equal(x1.rows[:n], a1.rows[:n])
+            assert torch.equal(x.grads[:n], a.grads[:n])
+            assert (x1.grads[:n] - a1.grads[:n]).abs().max() <= 1e-6 * a1.grads[:n].abs().max()
+        assert torch.equal(b1.grads[:n], c1.grads[:n])
+
+
+def test_first_order_gradient_parked_for_the_embedding_backward():
+    """Inside new_step() ... end_step() the dim-1 tables' gradient is reduced by the embedding tables' backward
+    (ops._main_backward); a parked gradient nobody picks up is scattered by flush_deferred().  Both give the
+    gradients of the un-fused path."""
+    ops = _ops()
+    g = gen(23)
+    rows = [50, 3000, 7]
+    B, k = 777, 8
+    offs = offsets(rows)
+    ids = make_ids(B, rows, g).to(DEV)
+    arena = torch.nn.Parameter(torch.randn(sum(rows), k, generator=g).to(DEV))
+    lin = torch.nn.Parameter(torch.randn(sum(rows), 1, generator=g).to(DEV))
+    w = torch.randn(B, 3 * k, generator=g).to(DEV)
+
+    def run(fused, use_main):
+        arena.kon_sparse_grads, lin.kon_sparse_grads = [], []
+        if fused:
+            ops.new_step()
+        x = ops.embed_lookup_concat(arena, ids, offs, None, 3 * k)
+        l1 = ops.embed_lookup(lin, ids, offs, True)
+        loss = (l1 * l1).sum() + ((x * w).sum() if use_main else 0.0)
+        loss.backward()
+        if fused:
+            if use_main:
+                assert not any(isinstance(k_, tuple) and k_[0] == "lin_parked" for k_ in ops._STEP_CACHE)
+            ops.flush_deferred()
+            ops.end_step()
+        out = []
+        for a in (arena, lin):
+            out.append([(sg.rows[:int(sg.n)].clone(), sg.grads[:int(sg.n)].clone()) for sg in a.kon_sparse_grads])
+        return out
+
+    for use_main in (True, False):
+        ref, got = run(False, use_main), run(True, use_main)
+        for r_, g_ in zip(ref, got):
+            assert len(r_) == len(g_)
+            for (rr, rg), (gr, gg) in zip(r_, g_):
+                assert torch.equal(rr, gr)
+                assert (rg - gg).abs().max() <= 1e-6 * rg.abs().max()
+        assert len(got[1]) == 1 and len(got[0]) == (1 if use_main else 0)
+
+
 @pytest.mark.parametrize("B,F,kin,H", [(37, 26, 16, 2), (5, 32, 32, 3), (64, 7, 16, 1), (300, 26, 64, 2)])
 @pytest.mark.parametrize("flags", [(True, True, True, True), (False, False, False, False), (True, True, False, True)])
 def test_attention_bf16_tensor_core(B, F, kin, H, flags):
@@ -569,4 +643,9 @@ def test_embed_presort_on_side_stream_matches_inline_sort():
     for x, y in ((a16, b16), (a1, b1)):
         n = int(x.n.item())
         assert n == int(y.n.item())
-        assert torch.equal(x.rows[:n], y.rows[:n]) and torch.equal(x.grads[:n], y.grads[:n])
+        assert torch.equal(x.rows[:n], y.rows[:n])
+    n = int(a16.n.item())
+    assert torch.equal(a16.grads[:n], b16.grads[:n])
+    # in a step the first-order gradient rides the embedding tables' reduction (kon_embed_bwd_pair): same lookups,
+    # same order, partial sums joined at other CTA boundaries than the stand-alone dim-1 launch -> fp32 rounding
+    assert (a1.grads[:n] - b1.grads[:n]).abs().max() <= 1e-6 * a1.grads[:n].abs().max()

@@ -235,7 +235,7 @@ def test_sparse_adam_sums_the_gradients_of_an_arena_looked_up_twice():
     ids_b = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).to(DEV)
     da = torch.randn(B, 2, k, generator=g).to(DEV)
     db = torch.randn(B, 2, k, generator=g).to(DEV)
-    arena.kon_sparse_grads = [ops.embed_bwd_raw(da, ids_a, offs[:-1]), ops.embed_bwd_raw(db, ids_b, offs[:-1])]
+    arena.kon_sparse_grads = [ops.embed_bwd_raw(da, ids_a, offs), ops.embed_bwd_raw(db, ids_b, offs)]
     opt = SparseAdam(arena, lr=1e-2)
     opt.step()
     # oracle: dense Adam on the summed gradient, rows without a gradient untouched (lazy)

@@ -1,0 +1,6 @@
+set -x
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_models_gpu.py -m gpu -q 2>&1 | tail -30 > gpurun_out/r02p_pytest.log
+tail -3 gpurun_out/r02p_pytest.log
+for v in b200 v1 v2 v3; do
+KON_B200_LIB=$PWD/ml_function_b200/libkon_$v.so python bench.py --model deepfm --no-cpu-baseline --no-other-models > gpurun_out/r02p_deepfm_$v.json 2>> gpurun_out/r02p_bench.err
+done
