@@ -390,11 +390,12 @@ class _PeerLookup(torch.autograd.Function):
         if lp is not None and lp._seen_use and ops._SHARE_SORT:
             lin_ids = ids_tw if n_rw == 0 else torch.cat([ids_tw, ids_rw], dim=1).contiguous()
             part = lp.lookup_fn(lp.arena, lin_ids, lp.all_offs, True)             # [B_g, 1]
-            _put2d(sh, [(part.data_ptr() + q * B_l * 4, region.ptrs[q] + px["linparts_off"] + rank * 4, 4, N * 4, 4, B_l)
-                        for q in range(N)])
+            # one contiguous B_l-float block per (source rank, sample owner): 16-byte NVLink stores, not B_l 4-byte ones
+            _put2d(sh, [(part.data_ptr() + q * B_l * 4, region.ptrs[q] + px["linparts_off"] + rank * B_l * 4,
+                         B_l * 4, B_l * 4, B_l * 4, 1) for q in range(N)])
         region.barrier()                                  # barrier 1: rows (and partial sums) complete
         if lin_ids is not None:
-            ops._STEP_CACHE[("lin_fwd", id(plan))] = (px["linparts"].sum(dim=1, keepdim=True), lin_ids, px)
+            ops._STEP_CACHE[("lin_fwd", id(plan))] = (px["linparts"].sum(dim=0).unsqueeze(1), lin_ids, px)
         out = xcat
         ctx.sh, ctx.arena, ctx.px = sh, arena, px
         ctx.save_for_backward(ids_tw, ids_rw)
@@ -488,7 +489,8 @@ class _ShardedSumPeer(torch.autograd.Function):
         g = gout.contiguous()
         region = px["region"]
         sp = sh.sparse_partner
-        _put2d(sp, [(g.data_ptr(), region.ptrs[q] + px["lin_grecv_off"] + rank * B_l * 4, 4, 4, 4, B_l) for q in range(N)])
+        _put2d(sp, [(g.data_ptr(), region.ptrs[q] + px["lin_grecv_off"] + rank * B_l * 4, B_l * 4, B_l * 4, B_l * 4, 1)
+                    for q in range(N)])
 
         def scatter(need_barrier=False, main=None):
             """``main`` = (d_out, ids, offsets) of the embedding tables' scatter-add about to run on the same routing:
@@ -616,7 +618,7 @@ class ShardedEmbed(nn.Module):
         """The rank's exchange region for one (local batch, row width); built collectively on first use
         (every rank sees the same shapes in the same order).  Sub-buffers (same offsets on every rank; sizes use the
         largest per-rank field count): ``xcat`` [B_l,width] | ``ids_tw`` int32 [N*B_l*n_tw_max] | ``ids_rw`` int32
-        [N*B_l*n_rw] | ``drecv_tw`` [N*B_l*n_tw_max*k] | ``drecv_rw`` [N*B_l*n_rw*k] | ``linparts`` [B_l,N] |
+        [N*B_l*n_rw] | ``drecv_tw`` [N*B_l*n_tw_max*k] | ``drecv_rw`` [N*B_l*n_rw*k] | ``linparts`` [N,B_l] |
         ``lin_grecv`` [N*B_l]."""
         F, k, N = len(self.plan.rows), self.dim, self.world
         if (B_l, width) in self._peer:
@@ -633,7 +635,7 @@ class ShardedEmbed(nn.Module):
         px["ids_rw"], px["ids_rw_off"] = region.carve((N * B_l * max(n_rw, 1),), torch.int32)
         px["drecv_tw"], px["drecv_tw_off"] = region.carve((N * B_l * n_tw_max * k,))
         px["drecv_rw"], px["drecv_rw_off"] = region.carve((N * B_l * max(n_rw, 1) * k,))
-        px["linparts"], px["linparts_off"] = region.carve((B_l, N))
+        px["linparts"], px["linparts_off"] = region.carve((N, B_l))
         px["lin_grecv"], px["lin_grecv_off"] = region.carve((N * B_l,))
         self._peer[(B_l, width)] = px
         return px
