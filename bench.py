@@ -433,6 +433,19 @@ class Job:
             ms = float(t.item())
         return ms
 
+    def spin_up(self, fn, seconds):
+        """Untimed steps for ~`seconds` of device time right before the timed windows (on top of --warmup).  With
+        N > 1 the ranks wait on each other while rank 0 verifies / captures, their GPUs fall back to idle clocks, and
+        the first 0.2 s window of a max-over-ranks timing then measures the clock ramp (8.18 / 7.76 / 7.54 ms for three
+        consecutive windows at N = 2, gpurun_out/r02q_bench_n2.json) instead of the steady state."""
+        if seconds <= 0:
+            return
+        ms10 = self.timed(fn, 10)                    # max over ranks: every rank derives the same step count
+        n = int(min(2000, max(0, seconds * 1e3 / max(ms10 / 10, 1e-3) - 10)))
+        for i in range(n):
+            fn(i)
+        self.barrier()
+
     def step_eager(self, i):
         d, ids, y = self.resident[i % len(self.resident)]
         return self.trainer.step(d, ids, y)
@@ -474,6 +487,7 @@ def quick_measure(name, args, dev, world, rank, B, rows, mlp_dtype, windows=3, r
                 step = job.step_graph
                 for i in range(3):
                     step(i)
+        job.spin_up(step, args.spinup)
         ms = median([job.timed(step, args.steps) for _ in range(windows)])
         job.check_peer()
         out = {"value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / args.steps,
@@ -739,6 +753,7 @@ def run_gpu(args):
                 step_fn(i)
         elif rank == 0:
             print("CUDA-graph capture failed, staying eager:", trainer.capture_error, file=sys.stderr)
+    job.spin_up(step_fn, args.spinup)
     win_value = [timed(step_fn, args.steps) for _ in range(args.windows)]
     ms = median(win_value)
     # ---- end-to-end timing (H2D + step + D2H) ---------------------------------------------
@@ -880,7 +895,8 @@ def run_gpu(args):
                 "cin": args.cin_precision + (" tcgen05, fp32 accumulate" if args.cin_precision == "bf16" else ""),
                 "mlp_dtype": args.mlp_dtype,
                 "cache": f"working set per step (>1 GB) exceeds the 126 MB L2; {args.n_batches} distinct batches rotate",
-                "timing": f"median of {args.windows} windows of {args.steps} steps each (value and e2e alike)",
+                "timing": f"median of {args.windows} windows of {args.steps} steps each (value and e2e alike), after --warmup "
+                          f"steps and {args.spinup} s of untimed steps (clock ramp of ranks that idled during capture / verify)",
                 "parallelism": parallelism, "embedding_exchange": exchange},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "windows_ms_per_step": [w / args.steps for w in win_e2e]},
@@ -931,6 +947,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--windows", type=int, default=3, help="timed windows of --steps steps each; the median is reported")
+    ap.add_argument("--spinup", type=float, default=1.5,
+                    help="seconds of untimed steps right before the timed windows (clock ramp; see Job.spin_up)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: --batch is the GLOBAL batch, split over the ranks")
     ap.add_argument("--big-tables", default="", help="TxR: replace the T largest tables by R-row tables (config 5: 8x100000000)")

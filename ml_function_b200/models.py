@@ -230,8 +230,12 @@ class XDeepFM(_CtrModel):
     def logit(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
         linear = self.linear_embed.lookup_sum(ids)         # [B,1] (useAddLinear, IL:233-234)
-        cin_out = self.cin(xcat, fields=(self.F, self.k))  # [B,1]; reads xcat[:, :F*k] in place
+        # the MLP runs BEFORE the CIN (the sum below keeps the reference's operand order): its short kernels share
+        # the GPU with the backward's routing sort on the side stream; the persistent CIN kernels then start on an
+        # idle GPU (ops.join_presort)
         dnn_out = self.dnn(xcat)                           # [B,1]
+        ops.join_presort()
+        cin_out = self.cin(xcat, fields=(self.F, self.k))  # [B,1]; reads xcat[:, :F*k] in place
         return ScoreLayer.summed([linear.unsqueeze(1), cin_out, dnn_out])   # [B,1,1]
 
     def forward(self, dense_inputs, sparse_inputs):

@@ -179,6 +179,16 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
+def join_presort():
+    """Make the current stream wait for the routing sorts in flight on the side stream.  Called before a kernel
+    that owns the whole GPU (the persistent tcgen05 CIN kernels: one CTA per SM, ~200 KB of shared memory): a sort
+    still running when such a kernel launches keeps some SMs busy, those CTAs start late and the whole persistent
+    kernel ends late -- worse than not overlapping at all."""
+    for key, ev in list(_SORT_EVENTS.items()):
+        torch.cuda.current_stream().wait_event(ev)
+    _SORT_EVENTS.clear()
+
+
 def embed_presort(ids, field_row_offset: Sequence[int]):
     """Start the routing sort for ``ids`` on the side stream (no-op outside new_step() ... end_step(), or when
     the same ids / offsets were already routed in this step)."""

@@ -371,6 +371,11 @@ class _PeerLookup(torch.autograd.Function):
         ids_tw, ids_rw = sh.exchange_ids(ids_local, px)  # (A) + barrier A
         xcat, region = px["xcat"], px["region"]
         n_tw, n_rw, n_tw_all = len(plan.tw_of_rank[rank]), len(plan.rw_fields), len(plan.tw_fields)
+        if arena.requires_grad:                           # the backward's routing: on the side stream, from here on
+            if n_tw:
+                ops.embed_presort(ids_tw, sh.tw_offs)
+            if n_rw:
+                ops.embed_presort(ids_rw, sh.rw_offs)
         base = region.ptr_array(px["xcat_off"])          # every field lands at ITS column of the model's order
         if n_tw:
             ops.embed_fwd_peer(arena.detach(), ids_tw, sh.tw_offs, base, N, B_l, width, k,

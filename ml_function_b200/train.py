@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -65,7 +67,9 @@ class Trainer:
         self.is_sigmoid = isinstance(model, XDeepFM)
         # routing sort of the embedding backward on a side stream at lookup time -- except next to the
         # persistent tcgen05 CIN kernels, which lose more to the co-scheduled sort kernels than the overlap hides
-        self.presort = not isinstance(model, XDeepFM)
+        # KON_PRESORT_X=0: keep xDeepFM's routing sort in the backward (the round-1 setting, when the sort contended
+        # with the persistent CIN kernels; the forward now joins the side stream before the CIN, XDeepFM.logit)
+        self.presort = not isinstance(model, XDeepFM) or os.environ.get("KON_PRESORT_X", "1") != "0"
         self._g = None
         self.capture_error = None
         # sharded jobs: a peer-barrier timeout must not pass silently (the consumer kernels would read partially
