@@ -1,0 +1,1183 @@
+// a4: embedding backward -- the implicit IndexedSlices -> unique -> unsorted_segment_sum of Model.fit over the
+// 26 Keras Embedding layers of SparseEmbed (IL:217-242), as a deterministic sort-then-segment scatter-add.
+//
+// HBM-bound integer routing + fp32 payload; no library call on the path (r1 used CUB's 4-pass onesweep radix sort
+// and DeviceScan: 144 us of latency-bound launches for 1.7 M lookups).
+//
+//   routing : the arena row of a lookup is (field, id) and the field is known from the POSITION of the lookup,
+//             so the global sort falls apart into F independent per-field sorts of B*L ids with log2(rows_f) bits.
+//             Each field is sorted by a stable LSD counting sort with digits of up to 12 bits: one pass for tables
+//             of up to 4096 rows, two passes up to 16.7 M rows, three beyond.  A pass is three kernels over all
+//             fields at once -- per-tile digit histograms (route_hist), an in-place exclusive scan in (digit, tile)
+//             order that also places the fields back to back in the output (route_scan), and a scatter whose
+//             in-tile ranks come from warp match + per-warp shared-memory counters (route_scatter: no atomics, the
+//             order inside a digit is the order of the positions => stable => the summation order is fixed).
+//             Fields with fewer passes join in the last slot(s) and read the ids directly.  Out-of-range ids are
+//             routed behind all valid lookups (count in the header) and never reach the reduction.
+//             route_heads counts the run heads (first lookup of every distinct row) per 32 lookups / per 8192
+//             lookups (exclusive prefixes; the last CTA to finish scans the per-CTA totals), which is all the
+//             reduction needs to know the output slot of every run.
+//   segsum  : lane groups of LPR lanes x float4 walk 8 consecutive sorted lookups each (8 independent row loads in
+//             flight per thread).  Runs inside a window are stored straight from registers; runs crossing windows
+//             are stitched by a segmented scan over the lane groups of the warp (shuffles, fixed tree), then over
+//             the 8 warps of the CTA (shared memory, left to right), then over CTAs (embed_fixup_kernel).  Every
+//             association order is a function of the sorted positions only => bit-reproducible.
+#include "common.cuh"
+#include "embed_common.cuh"
+
+#include <algorithm>
+
+namespace kon {
+namespace {
+
+// -------------------------------------------------------------------------------------
+// routing: per-field LSD counting sort
+// -------------------------------------------------------------------------------------
+constexpr int kRtTile = 4096;                       // lookups of ONE field per CTA
+constexpr int kRtThreads = 256;
+constexpr int kRtWarps = kRtThreads / 32;
+constexpr int kRtRounds = kRtTile / kRtThreads;     // items per thread
+constexpr int kRtWarpItems = kRtTile / kRtWarps;    // consecutive items per warp
+constexpr int kRtMaxBits = 12;
+constexpr int kRtMaxBins = 1 << kRtMaxBits;
+constexpr int kScanThreads = 1024;
+constexpr int kScanPerThread = kRtMaxBins / kScanThreads;
+constexpr int kHeadsPerThread = 32;
+constexpr int kHeadsTile = 256 * kHeadsPerThread;   // sorted lookups per route_heads CTA
+constexpr uint32_t kSkipKey = 0xffffffffu;          // lane past the end of the field
+
+struct RouteHdr {
+  int n_valid;        // lookups with an in-range id = length of the sorted prefix the reduction walks
+  int n_unique;       // distinct arena rows among them
+  unsigned ticket;    // route_heads: CTAs finished
+  int pad;
+};
+
+struct FieldPass {
+  bool active, first, last;
+  int shift;
+  uint32_t mask;
+  int bins;           // digits of this pass; the out-of-range lookups take the extra digit `bins`
+};
+
+__host__ __device__ inline int bits_for(long long rows) {   // ids of a table with `rows` rows fit in this many bits
+  int b = 0;
+  while (b < 62 && (1LL << b) < rows) ++b;
+  return b;
+}
+__host__ __device__ inline int passes_for(int bits) {
+  return bits <= kRtMaxBits ? 1 : (bits + kRtMaxBits - 1) / kRtMaxBits;
+}
+// A field with P passes runs them in the LAST P of the job's max_p slots, so every field finishes in the last slot.
+__host__ __device__ inline FieldPass field_pass(long long rows, int slot, int max_p) {
+  FieldPass fp;
+  const int bits = bits_for(rows);
+  const int P = passes_for(bits);
+  const int w = (bits + P - 1) / P;
+  const int i = slot - (max_p - P);
+  fp.active = i >= 0;
+  fp.first = i == 0;
+  fp.last = i == P - 1;
+  fp.shift = i > 0 ? i * w : 0;
+  fp.mask = fp.last ? 0xffffffffu : ((1u << w) - 1u);
+  fp.bins = fp.last ? (int)((rows > 0 ? (rows - 1) >> fp.shift : 0) + 1) : (1 << w);
+  return fp;
+}
+
+struct RouteArgs {
+  const void* ids;
+  FieldTable ft;
+  int F, L;
+  long long nf;         // lookups per field (B * L)
+  int NT;               // tiles per field
+  int max_p;
+  int hs;               // row stride of `hist` (uint32 words)
+  uint32_t sentinel;    // key of an out-of-range lookup (= total rows)
+  uint32_t *tmp_keys, *tmp_vals, *out_keys, *out_vals;
+  uint32_t* hist;           // [F][NT][hs]: counts (route_hist) -> destination bases (route_scan), in place
+  uint32_t* tile_inv;       // [F][NT]: out-of-range lookups per tile
+  uint32_t* tile_inv_base;  // [F][NT]: where they go
+  RouteHdr* hdr;
+};
+
+// slot s writes the final buffers when an even number of slots follows, else the scratch pair
+__device__ __forceinline__ void route_bufs(const RouteArgs& a, int slot, const uint32_t*& sk, const uint32_t*& sv,
+                                           uint32_t*& dk, uint32_t*& dv) {
+  const bool to_out = ((a.max_p - 1 - slot) & 1) == 0;
+  dk = to_out ? a.out_keys : a.tmp_keys;
+  dv = to_out ? a.out_vals : a.tmp_vals;
+  sk = to_out ? a.tmp_keys : a.out_keys;
+  sv = to_out ? a.tmp_vals : a.out_vals;
+}
+
+// (key, payload) of the kRtRounds items of a thread.  First pass of a field: straight from the ids ([B,F,L], the
+// field's column); payload = (sample << 8) | field, the address of the gradient row.  Later passes: the scratch pair.
+template <typename IdT>
+__device__ __forceinline__ void route_load(const RouteArgs& a, const FieldPass& fp, int f, long long off, long long rows,
+                                           const uint32_t* sk, const uint32_t* sv, long long jw, int lane,
+                                           uint32_t (&key)[kRtRounds], uint32_t (&val)[kRtRounds]) {
+  if (fp.first) {
+    const IdT* ids = static_cast<const IdT*>(a.ids);
+    long long id[kRtRounds];
+#pragma unroll
+    for (int r = 0; r < kRtRounds; ++r) {
+      const long long j = jw + r * 32 + lane;
+      id[r] = -1;
+      val[r] = 0;
+      if (j < a.nf) {
+        long long b = j, p;
+        if (a.L == 1) {
+          p = b * a.F + f;
+        } else {
+          b = j / a.L;
+          p = (b * a.F + f) * a.L + (j - b * a.L);
+        }
+        id[r] = (long long)__ldg(ids + p);
+        val[r] = (uint32_t)((b << 8) | (long long)f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRtRounds; ++r) {
+      const long long j = jw + r * 32 + lane;
+      key[r] = j < a.nf ? ((id[r] >= 0 && id[r] < rows) ? (uint32_t)(off + id[r]) : a.sentinel) : kSkipKey;
+    }
+  } else {
+    const uint32_t* k = sk + (long long)f * a.nf;
+    const uint32_t* v = sv + (long long)f * a.nf;
+#pragma unroll
+    for (int r = 0; r < kRtRounds; ++r) {
+      const long long j = jw + r * 32 + lane;
+      key[r] = kSkipKey;
+      val[r] = 0;
+      if (j < a.nf) {
+        key[r] = k[j];
+        val[r] = v[j];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t route_digit(uint32_t key, const FieldPass& fp, long long off, uint32_t sentinel) {
+  if (key == kSkipKey) return (uint32_t)fp.bins + 1u;      // dummy counter
+  if (key == sentinel) return (uint32_t)fp.bins;
+  return (uint32_t)(((long long)key - off) >> fp.shift) & fp.mask;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kRtThreads) route_hist_kernel(const __grid_constant__ RouteArgs a, int slot) {
+  extern __shared__ uint32_t s_hist[];   // [bins + 2]
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const long long off = a.ft.off[f], rows = a.ft.off[f + 1] - off;
+  const FieldPass fp = field_pass(rows, slot, a.max_p);
+  if (!fp.active) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < fp.bins + 2; i += kRtThreads) s_hist[i] = 0;
+  __syncthreads();
+  const uint32_t *sk, *sv;
+  uint32_t *dk, *dv;
+  route_bufs(a, slot, sk, sv, dk, dv);
+  uint32_t key[kRtRounds], val[kRtRounds];
+  route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
+#pragma unroll
+  for (int r = 0; r < kRtRounds; ++r) {
+    const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    if (lane == __ffs(m) - 1) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+  }
+  __syncthreads();
+  uint32_t* out = a.hist + ((size_t)f * a.NT + tile) * a.hs;
+  for (int i = tid; i < fp.bins; i += kRtThreads) out[i] = s_hist[i];
+  if (tid == 0) a.tile_inv[f * a.NT + tile] = s_hist[fp.bins];
+}
+
+// exclusive prefix of one value per thread over the CTA (blockDim.x threads, a multiple of 32, <= 1024)
+__device__ __forceinline__ long long block_excl_scan(long long v, long long* s_warp, long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long p = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += p;
+  }
+  __syncthreads();   // s_warp may still be read by a previous call
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  long long base = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) {
+    const long long x = s_warp[w];
+    if (w < warp) base += x;
+    tot += x;
+  }
+  if (total) *total = tot;
+  return base + inc - v;
+}
+
+// One CTA per field: counts [tile][digit] -> destination of the first such lookup of the tile, in (digit, tile) order.
+// Last slot: the fields follow one another without gaps (out-of-range lookups of ALL fields behind them) and the
+// header gets n_valid.
+__global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_constant__ RouteArgs a, int slot) {
+  __shared__ long long s_warp[32];
+  const int f = blockIdx.x;
+  const long long rows = a.ft.off[f + 1] - a.ft.off[f];
+  const FieldPass fp = field_pass(rows, slot, a.max_p);
+  if (!fp.active) return;
+  const bool fin = slot == a.max_p - 1;
+  const int t = threadIdx.x;
+  long long inv_before = 0, inv_all = 0, inv_mine = 0;
+  {
+    long long lb = 0, la = 0, lm = 0;
+    if (fin) {
+      const int tot = a.F * a.NT;
+      for (int i = t; i < tot; i += kScanThreads) {
+        const int g = i / a.NT;
+        const long long v = a.tile_inv[i];
+        la += v;
+        if (g < f) lb += v;
+        if (g == f) lm += v;
+      }
+    } else {
+      for (int i = t; i < a.NT; i += kScanThreads) lm += a.tile_inv[f * a.NT + i];
+    }
+    block_excl_scan(lb, s_warp, &inv_before);
+    block_excl_scan(la, s_warp, &inv_all);
+    block_excl_scan(lm, s_warp, &inv_mine);
+  }
+  const long long n_all = (long long)a.F * a.nf;
+  const long long base0 = fin ? (long long)f * a.nf - inv_before : (long long)f * a.nf;
+  const long long inv_base = fin ? (n_all - inv_all) + inv_before : (long long)f * a.nf + (a.nf - inv_mine);
+
+  const int c = (fp.bins + kScanThreads - 1) / kScanThreads;    // consecutive digits per thread (<= kScanPerThread)
+  uint32_t* h0 = a.hist + (size_t)f * a.NT * a.hs;
+  uint32_t tot[kScanPerThread];
+  long long mine = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    tot[k] = 0;
+    const int b = t * c + k;
+    if (k < c && b < fp.bins) {
+      uint32_t s = 0;
+      for (int tile = 0; tile < a.NT; ++tile) s += h0[(size_t)tile * a.hs + b];
+      tot[k] = s;
+      mine += s;
+    }
+  }
+  long long run0 = base0 + block_excl_scan(mine, s_warp, nullptr);
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    const int b = t * c + k;
+    if (k < c && b < fp.bins) {
+      uint32_t run = (uint32_t)run0;
+      for (int tile = 0; tile < a.NT; ++tile) {
+        uint32_t* p = h0 + (size_t)tile * a.hs + b;
+        const uint32_t cnt = *p;
+        *p = run;
+        run += cnt;
+      }
+      run0 += tot[k];
+    }
+  }
+  long long carry = inv_base;
+  for (int t0 = 0; t0 < a.NT; t0 += kScanThreads) {
+    const bool on = t0 + t < a.NT;
+    const long long v = on ? (long long)a.tile_inv[f * a.NT + t0 + t] : 0;
+    long long total;
+    const long long ex = block_excl_scan(v, s_warp, &total);
+    if (on) a.tile_inv_base[f * a.NT + t0 + t] = (uint32_t)(carry + ex);
+    carry += total;
+  }
+  if (fin && f == 0 && t == 0) {
+    a.hdr->n_valid = (int)(n_all - inv_all);
+    a.hdr->ticket = 0;
+  }
+}
+
+// Stable scatter of one tile.  Warp w owns items [w*512, (w+1)*512) of the tile and walks them 32 at a time in
+// order; the rank of an item among the equal digits of its warp is (count so far, a uint16 in shared memory private
+// to the warp) + (matching lanes below it).  Then: exclusive prefix over the warps per digit, + the tile's base.
+template <typename IdT>
+__global__ void __launch_bounds__(kRtThreads) route_scatter_kernel(const __grid_constant__ RouteArgs a, int slot) {
+  extern __shared__ uint32_t s_dyn[];
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const long long off = a.ft.off[f], rows = a.ft.off[f + 1] - off;
+  const FieldPass fp = field_pass(rows, slot, a.max_p);
+  if (!fp.active) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = fp.bins + 1;                 // digits incl. the out-of-range one
+  const int stride = (fp.bins + 3) & ~1;      // + out-of-range + dummy, even
+  uint32_t* s_base = s_dyn;                                             // [nb]
+  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + ((nb + 1) & ~1));   // [kRtWarps][stride]
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(s_cnt);
+    for (int i = tid; i < kRtWarps * stride / 2; i += kRtThreads) z[i] = 0;
+    const uint32_t* h = a.hist + ((size_t)f * a.NT + tile) * a.hs;
+    for (int i = tid; i < fp.bins; i += kRtThreads) s_base[i] = h[i];
+    if (tid == 0) s_base[fp.bins] = a.tile_inv_base[f * a.NT + tile];
+  }
+  const uint32_t *sk, *sv;
+  uint32_t *dk, *dv;
+  route_bufs(a, slot, sk, sv, dk, dv);
+  uint32_t key[kRtRounds], val[kRtRounds];
+  route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
+  __syncthreads();
+  uint16_t* cnt = s_cnt + warp * stride;
+  uint32_t dr[kRtRounds];   // digit << 16 | rank inside the warp
+  const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < kRtRounds; ++r) {
+    const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const uint32_t prev = cnt[d];
+    __syncwarp();
+    if (lane == __ffs(m) - 1) cnt[d] = (uint16_t)(prev + __popc(m));
+    __syncwarp();
+    dr[r] = (d << 16) | (prev + __popc(m & below));
+  }
+  __syncthreads();
+  for (int b = tid; b < nb; b += kRtThreads) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kRtWarps; ++w) {
+      const uint32_t c = s_cnt[w * stride + b];
+      s_cnt[w * stride + b] = (uint16_t)run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRtRounds; ++r) {
+    if (key[r] != kSkipKey) {
+      const uint32_t d = dr[r] >> 16;
+      const uint32_t pos = s_base[d] + cnt[d] + (dr[r] & 0xffffu);
+      dk[pos] = key[r];
+      dv[pos] = val[r];
+    }
+  }
+}
+
+// Run heads of the sorted valid prefix: blk_base[i / 32] = heads in [tile start, i) for i a multiple of 32,
+// cta_base[i / 8192] = heads before the tile (filled by the last CTA to finish), hdr->n_unique.
+__global__ void __launch_bounds__(256) route_heads_kernel(const uint32_t* __restrict__ keys, RouteHdr* hdr,
+                                                          int* __restrict__ blk_base, int* __restrict__ cta_tot,
+                                                          int* __restrict__ cta_base) {
+  __shared__ long long s_warp[32];
+  __shared__ unsigned s_ticket;
+  const int nv = hdr->n_valid;
+  const int t = threadIdx.x;
+  const long long i0 = (long long)blockIdx.x * kHeadsTile + (long long)t * kHeadsPerThread;
+  int c = 0;
+  if (i0 < nv) {
+    uint32_t prev = i0 > 0 ? keys[i0 - 1] : ~keys[0];
+    const uint4* p = reinterpret_cast<const uint4*>(keys + i0);
+#pragma unroll
+    for (int q = 0; q < kHeadsPerThread / 4; ++q) {
+      if (i0 + q * 4 < nv) {        // the buffer is padded to a multiple of 32 keys: whole vectors are readable
+        const uint4 k = p[q];
+        const long long i = i0 + q * 4;
+        c += (k.x != prev) ? 1 : 0;
+        c += (i + 1 < nv && k.y != k.x) ? 1 : 0;
+        c += (i + 2 < nv && k.z != k.y) ? 1 : 0;
+        c += (i + 3 < nv && k.w != k.z) ? 1 : 0;
+        prev = k.w;
+      }
+    }
+  }
+  long long total;
+  const long long ex = block_excl_scan(c, s_warp, &total);
+  blk_base[(long long)blockIdx.x * 256 + t] = (int)ex;
+  if (t == 0) {
+    cta_tot[blockIdx.x] = (int)total;
+    __threadfence();
+    s_ticket = atomicAdd(&hdr->ticket, 1u);
+  }
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  long long carry = 0;
+  for (int b0 = 0; b0 < (int)gridDim.x; b0 += 256) {
+    const bool on = b0 + t < (int)gridDim.x;
+    const long long v = on ? (long long)__ldcg(cta_tot + b0 + t) : 0;
+    long long tot;
+    const long long e = block_excl_scan(v, s_warp, &tot);
+    if (on) cta_base[b0 + t] = (int)(carry + e);
+    carry += tot;
+  }
+  if (t == 0) {
+    hdr->n_unique = (int)carry;
+    hdr->ticket = 0;
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// segmented sum over the sorted lookups
+// -------------------------------------------------------------------------------------
+constexpr int kSegThreads = 256;
+constexpr int kSegWarps = kSegThreads / 32;
+constexpr int kSegWin = 8;       // sorted lookups per lane group and chunk = row loads in flight per thread
+#ifndef KON_SEG_CHUNKS
+#define KON_SEG_CHUNKS 4
+#endif
+constexpr int kSegChunks = KON_SEG_CHUNKS;   // chunks per warp
+
+__host__ __device__ constexpr int seg_tile(int lpr) { return kSegWarps * kSegChunks * (32 / lpr) * kSegWin; }
+
+struct SegArgs {
+  const float* d_out;
+  long long sb, sf;   // strides of d_out dims 0 / 1 (elements)
+  int dim, vec_per_row;
+  const uint32_t* keys;   // sorted
+  const uint32_t* vals;   // (sample << 8) | field, sorted with the keys
+  const RouteHdr* hdr;
+  const int* blk_base;
+  const int* cta_base;
+  int* unique_rows;
+  float* grads;
+  int* n_unique;
+  float* cta_head;   // [n_cta, dim]  sum of the CTA's lookups before its first run head (all of them if it has none)
+  float* cta_tail;   // [n_cta, dim]  sum from its last run head to its end
+  int* cta_meta;     // [n_cta] 1 = the CTA holds a run head
+  int* cta_tid;      // [n_cta] output slot of the run open at the CTA's end (-1: none)
+  uint32_t* cta_tkey;
+  // fused first-order gradient (kon_embed_bwd_pair): a second, one-float-per-lookup gradient reduced over the
+  // same routing in the same pass (the dim-1 "linear" tables are looked up with the same ids)
+  const float* d1;
+  long long sb1, sf1;
+  float* grads1;      // [n_unique]
+  float* cta_head1;   // [n_cta]
+  float* cta_tail1;   // [n_cta]
+  // peer mode (n_peers > 0): sample b's gradient row is read from rank b / peer_rows over NVLink
+  int n_peers;
+  long long peer_rows;
+  const float* peer[kMaxPeers];
+};
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_shfl_up(float4 v, int d) {
+  return make_float4(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d),
+                     __shfl_up_sync(0xffffffffu, v.z, d), __shfl_up_sync(0xffffffffu, v.w, d));
+}
+__device__ __forceinline__ float4 f4_shfl(float4 v, int l) {
+  return make_float4(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l),
+                     __shfl_sync(0xffffffffu, v.z, l), __shfl_sync(0xffffffffu, v.w, l));
+}
+
+template <int LPR, bool LIN>
+__global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(const __grid_constant__ SegArgs a) {
+  constexpr int GPW = 32 / LPR;               // lane groups per warp
+  constexpr int CHUNK = GPW * kSegWin;        // sorted lookups per warp and chunk
+  constexpr int SPAN = CHUNK * kSegChunks;    // per warp
+  constexpr int TILE = SPAN * kSegWarps;      // per CTA
+  __shared__ uint32_t s_key[kSegWarps][CHUNK + 4];   // [0] = the lookup before the chunk
+  __shared__ uint32_t s_val[kSegWarps][CHUNK];
+  __shared__ float4 s_wh[kSegWarps][LPR], s_wt[kSegWarps][LPR];
+  __shared__ float s_wh1[kSegWarps], s_wt1[kSegWarps];
+  __shared__ int s_wflag[kSegWarps], s_wtid[kSegWarps];
+  __shared__ uint32_t s_wtkey[kSegWarps];
+
+  const long long nv = a.hdr->n_valid;
+  const long long cta_lo = (long long)blockIdx.x * TILE;
+  if (cta_lo > nv) return;      // the CTA that holds position nv (the virtual head closing the last run) still runs
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int g = lane / LPR, sub = lane % LPR;
+  const bool lane_on = sub < a.vec_per_row;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && tid == 0) *a.n_unique = a.hdr->n_unique;
+
+  auto emit = [&](int id, uint32_t key, float4 v, float v1) {
+    if (id < 0) return;
+    if (lane_on) *reinterpret_cast<float4*>(a.grads + (long long)id * a.dim + sub * 4) = v;
+    if (sub == 0) {
+      a.unique_rows[id] = (int)key;
+      if (LIN) a.grads1[id] = v1;
+    }
+  };
+
+  const long long s = cta_lo + (long long)w * SPAN;
+  // state of the warp's walk: (cf: a run head was seen; cv: sum since the last head, or since s; ccnt: heads)
+  float4 cv = zero;
+  float cv1 = 0.f;
+  bool cf = false;
+  int ccnt = 0;
+  float4 wh = zero;      // sum of the warp's lookups before its first head (this lane's slice), group-uniform copies
+  float wh1 = 0.f;
+  bool wh_set = false;
+  int run_base = 0;
+  if (s <= nv) {
+    // heads before s; at s == nv (only the virtual head is left) the tables may end one entry short
+    run_base = s < nv ? a.cta_base[s / kHeadsTile] + a.blk_base[s >> 5] : a.hdr->n_unique;
+#pragma unroll 1
+    for (int ch = 0; ch < kSegChunks; ++ch) {
+      const long long cs = s + (long long)ch * CHUNK;
+      if (cs > nv) break;
+      __syncwarp();
+      for (int i = lane; i < CHUNK + 1; i += 32) {
+        const long long idx = cs - 1 + i;
+        s_key[w][i] = (idx >= 0 && idx < nv) ? a.keys[idx] : 0u;
+        if (i < CHUNK) s_val[w][i] = (cs + i < nv) ? a.vals[cs + i] : 0u;
+      }
+      __syncwarp();
+      const long long ws = cs + g * kSegWin;
+      const int rel = (int)max(-1LL, min((long long)kSegWin + 1, nv - ws));   // items of the window below nv
+      uint32_t k[kSegWin + 1];
+#pragma unroll
+      for (int u = 0; u <= kSegWin; ++u) k[u] = s_key[w][g * kSegWin + u];
+      unsigned hb = 0;
+#pragma unroll
+      for (int u = 0; u < kSegWin; ++u) {
+        const bool h = (u == rel) || (u < rel && (k[u + 1] != k[u] || ws + u == 0));
+        hb |= h ? (1u << u) : 0u;
+      }
+      float4 r[kSegWin];
+      float r1[LIN ? kSegWin : 1];
+#pragma unroll
+      for (int u = 0; u < kSegWin; ++u) {
+        r[u] = zero;
+        if (LIN) r1[u] = 0.f;
+        if (u < rel) {
+          const uint32_t bf = s_val[w][g * kSegWin + u];
+          long long b = bf >> 8;
+          const int f = (int)(bf & 255u);
+          const float* src = a.d_out;
+          if (a.n_peers) {
+            const long long q = b / a.peer_rows;
+            src = a.peer[q];
+            b -= q * a.peer_rows;
+          }
+          if (lane_on) r[u] = ldg_stream_f4(reinterpret_cast<const float4*>(src + b * a.sb + f * a.sf) + sub);
+          if (LIN) r1[u] = __ldg(a.d1 + b * a.sb1 + f * a.sf1);
+        }
+      }
+      // heads before the window / does a head precede it inside the warp: known before the rows arrive
+      const bool seen = hb != 0;
+      const unsigned hmask = __ballot_sync(0xffffffffu, seen);
+      unsigned gm = 0;    // bit q: group q of this chunk holds a head
+#pragma unroll
+      for (int q = 0; q < GPW; ++q) gm |= ((hmask >> (q * LPR)) & 1u) << q;
+      const int hc = __popc(hb);
+      int inc_c = hc;
+#pragma unroll
+      for (int d = 1; d < GPW; d <<= 1) {
+        const int p = __shfl_up_sync(0xffffffffu, inc_c, d * LPR);
+        if (g >= d) inc_c += p;
+      }
+      const bool ex_f = (gm & ((1u << g) - 1u)) != 0;
+      const bool in_f = cf || ex_f;
+      const int wbase = run_base + ccnt + inc_c - hc;
+      // the window: runs that start and end inside it go straight to their slot
+      float4 acc = zero, H = zero;
+      float acc1 = 0.f, H1 = 0.f;
+      bool first = true;
+      int lh = 0;
+#pragma unroll
+      for (int u = 0; u < kSegWin; ++u) {
+        if ((hb >> u) & 1u) {
+          if (first) {
+            H = acc;
+            H1 = acc1;
+            first = false;
+          } else {
+            emit(wbase + lh - 1, k[u], acc, acc1);
+          }
+          ++lh;
+          acc = r[u];
+          if (LIN) acc1 = r1[u];
+        } else {
+          acc = f4_add(acc, r[u]);
+          if (LIN) acc1 += r1[u];
+        }
+      }
+      // segmented scan over the lane groups: element = (window holds a head ? its tail : its whole sum)
+      float4 inc = acc;
+      float inc1 = acc1;
+#pragma unroll
+      for (int d = 1; d < GPW; d <<= 1) {
+        const float4 p = f4_shfl_up(inc, d * LPR);
+        float p1 = 0.f;
+        if (LIN) p1 = __shfl_up_sync(0xffffffffu, inc1, d * LPR);
+        const int lo = g - d + 1;
+        const unsigned range = (lo <= 0 ? ((2u << g) - 1u) : (((2u << g) - 1u) & ~((1u << lo) - 1u)));
+        if (g >= d && !(gm & range)) {
+          inc = f4_add(p, inc);
+          if (LIN) inc1 = p1 + inc1;
+        }
+      }
+      float4 ex = f4_shfl_up(inc, LPR);
+      float ex1 = 0.f;
+      if (LIN) ex1 = __shfl_up_sync(0xffffffffu, inc1, LPR);
+      if (g == 0) {
+        ex = zero;
+        ex1 = 0.f;
+      }
+      const float4 in_v = ex_f ? ex : f4_add(cv, ex);
+      const float in_v1 = ex_f ? ex1 : cv1 + ex1;
+      if (seen) {   // the run entering the window ends at its first head
+        const float4 tot = f4_add(in_v, H);
+        const float tot1 = in_v1 + H1;
+        if (in_f) {
+          emit(wbase - 1, k[0], tot, tot1);
+        } else {      // it entered the warp from the left: the warp's head partial
+          wh = tot;
+          wh1 = tot1;
+          wh_set = true;
+        }
+      }
+      const float4 lv = f4_shfl(inc, (GPW - 1) * LPR + sub);
+      float lv1 = 0.f;
+      if (LIN) lv1 = __shfl_sync(0xffffffffu, inc1, (GPW - 1) * LPR);
+      const int lc = __shfl_sync(0xffffffffu, inc_c, (GPW - 1) * LPR);
+      if (gm) {
+        cv = lv;
+        cv1 = lv1;
+        cf = true;
+      } else {
+        cv = f4_add(cv, lv);
+        cv1 += lv1;
+      }
+      ccnt += lc;
+    }
+  }
+  // ---- the warp's head / tail partials ---------------------------------------------------
+  if (wh_set) {       // exactly one lane group of the warp
+    s_wh[w][sub] = wh;
+    if (LIN && sub == 0) s_wh1[w] = wh1;
+  }
+  if (g == 0) {
+    if (!cf) {        // no head in the warp (or nothing to do): everything belongs to the run entering it
+      s_wh[w][sub] = cv;
+      if (LIN && sub == 0) s_wh1[w] = cv1;
+    } else {
+      s_wt[w][sub] = cv;
+      if (LIN && sub == 0) s_wt1[w] = cv1;
+    }
+    if (sub == 0) {
+      s_wflag[w] = cf ? 1 : 0;
+      const long long last = s + SPAN - 1;
+      const bool real = cf && last < nv;       // else the open run is the virtual one behind position nv
+      s_wtid[w] = real ? run_base + ccnt - 1 : -1;
+      s_wtkey[w] = real ? a.keys[last] : 0u;
+    }
+  }
+  __syncthreads();
+  // ---- stitch the warps, left to right --------------------------------------------------
+  if (w == 0 && g == 0) {
+    float4 pre = zero, ov = zero;
+    float pre1 = 0.f, ov1 = 0.f;
+    bool open = false;
+    int oid = -1;
+    uint32_t okey = 0;
+    float4 chead = zero;
+    float chead1 = 0.f;
+    for (int ww = 0; ww < kSegWarps; ++ww) {
+      const float4 h = s_wh[ww][sub];
+      const float h1 = LIN ? s_wh1[ww] : 0.f;
+      if (s_wflag[ww]) {
+        if (open) {
+          emit(oid, okey, f4_add(ov, h), ov1 + h1);
+        } else {
+          chead = f4_add(pre, h);
+          chead1 = pre1 + h1;
+        }
+        open = true;
+        ov = s_wt[ww][sub];
+        ov1 = LIN ? s_wt1[ww] : 0.f;
+        oid = s_wtid[ww];
+        okey = s_wtkey[ww];
+      } else if (open) {
+        ov = f4_add(ov, h);
+        ov1 += h1;
+      } else {
+        pre = f4_add(pre, h);
+        pre1 += h1;
+      }
+    }
+    if (!open) {
+      chead = pre;
+      chead1 = pre1;
+    }
+    const long long c = blockIdx.x;
+    if (lane_on) {
+      *reinterpret_cast<float4*>(a.cta_head + c * a.dim + sub * 4) = chead;
+      *reinterpret_cast<float4*>(a.cta_tail + c * a.dim + sub * 4) = ov;
+    }
+    if (sub == 0) {
+      a.cta_meta[c] = open ? 1 : 0;
+      a.cta_tid[c] = open ? oid : -1;
+      a.cta_tkey[c] = okey;
+      if (LIN) {
+        a.cta_head1[c] = chead1;
+        a.cta_tail1[c] = ov1;
+      }
+    }
+  }
+}
+
+// Runs that cross CTA boundaries: one lane group per CTA closes the run open at that CTA's end -- its tail plus the
+// head partials of the CTAs to the right, up to and including the first one that holds a run head.
+template <int LPR, bool LIN>
+__global__ void __launch_bounds__(kSegThreads) embed_fixup_kernel(const __grid_constant__ SegArgs a) {
+  constexpr int G = kSegThreads / LPR;
+  constexpr int TILE = seg_tile(LPR);
+  constexpr int NB = 4;
+  const long long nv = a.hdr->n_valid;
+  const int n_act = (int)(nv / TILE) + 1;
+  const int c = blockIdx.x * G + threadIdx.x / LPR;
+  const int sub = threadIdx.x % LPR;
+  if (c >= n_act) return;
+  const int id = a.cta_tid[c];
+  if (!a.cta_meta[c] || id < 0) return;
+  const bool lane_on = sub < a.vec_per_row;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = zero;
+  float acc1 = 0.f;
+  if (lane_on) acc = *reinterpret_cast<const float4*>(a.cta_tail + (long long)c * a.dim + sub * 4);
+  if (LIN) acc1 = a.cta_tail1[c];
+  bool done = false;
+  for (int w0 = c + 1; w0 < n_act && !done; w0 += NB) {
+    float4 h[NB];
+    float h1[NB];
+    int m[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      h[q] = zero;
+      h1[q] = 0.f;
+      m[q] = 1;
+      if (w0 + q < n_act) {
+        m[q] = a.cta_meta[w0 + q];
+        if (lane_on) h[q] = *reinterpret_cast<const float4*>(a.cta_head + (long long)(w0 + q) * a.dim + sub * 4);
+        if (LIN) h1[q] = a.cta_head1[w0 + q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      if (!done) {
+        acc = f4_add(acc, h[q]);
+        acc1 += h1[q];
+        if (m[q]) done = true;
+      }
+    }
+  }
+  if (lane_on) *reinterpret_cast<float4*>(a.grads + (long long)id * a.dim + sub * 4) = acc;
+  if (sub == 0) {
+    a.unique_rows[id] = (int)a.cta_tkey[c];
+    if (LIN) a.grads1[id] = acc1;
+  }
+}
+
+// dim == 1 (linear tables) reuses the float4 machinery by treating each gradient as a
+// one-lane row: the reduce kernel needs 16-B rows, so dim==1 is routed through a padded
+// copy.  This small kernel spreads [B,F] -> [B,F,4] (x, 0, 0, 0) and the inverse.
+__global__ void pad1_kernel(const float* __restrict__ src, long long sb, long long sf, int F,
+                            long long n_bags, float4* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_bags;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / F;
+    const int f = (int)(i - b * F);
+    dst[i] = make_float4(src[b * sb + f * sf], 0.f, 0.f, 0.f);
+  }
+}
+
+// grads [N,4] (column 0 valid) -> [N,1]; only the n_unique leading rows carry data
+__global__ void __launch_bounds__(256)
+unpad1_kernel(const float4* __restrict__ src, const int* __restrict__ n_unique, long long n,
+              float* __restrict__ dst) {
+  const long long nu = min((long long)*n_unique, n);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nu;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i].x;
+}
+
+// ---- workspace layout -----------------------------------------------------------------------
+// Everything the routing produces comes first and depends on n alone, so the first-order tables (and, sharded,
+// the peer backward) reuse one routing whatever their row width.
+struct BwdLayout {
+  size_t hdr, tmp_keys, tmp_vals, out_keys, out_vals, blk_base, cta_tot, cta_base, hist, tile_inv, tile_inv_base;
+  size_t cta_head, cta_tail, cta_meta, cta_tid, cta_tkey, cta_lin, total;
+  int n_cta, n_heads_cta, hist_rows;
+  int lpr, vpr;
+};
+
+int bwd_layout(int64_t n, int32_t dim, BwdLayout* l) {
+  // the segmented reduction works on float4 lanes; dims that are not a multiple of 4 are
+  // handled by the caller padding d_out (not needed by any reference configuration except
+  // the dim-1 linear tables, which take the dim==1 scalar route below).
+  l->vpr = (dim + 3) / 4;
+  l->lpr = pow2_ge(l->vpr);
+  if (l->lpr > 32) return -1;
+  const int64_t tile = seg_tile(l->lpr);
+  l->n_cta = (int)((n + 1 + tile - 1) / tile);      // position n (the virtual head) is covered too
+  l->n_heads_cta = (int)((n + kHeadsTile - 1) / kHeadsTile);
+  if (l->n_heads_cta < 1) l->n_heads_cta = 1;
+  l->hist_rows = (int)(n / kRtTile) + kMaxFields + 1;   // >= F * tiles-per-field for any F <= kMaxFields
+  const size_t n32 = align_up((size_t)n, 32) + 32;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o = align_up(o + bytes, 256);
+    return r;
+  };
+  l->hdr = take(sizeof(RouteHdr));
+  l->tmp_keys = take(n32 * 4);
+  l->tmp_vals = take(n32 * 4);
+  l->out_keys = take(n32 * 4);
+  l->out_vals = take(n32 * 4);
+  l->blk_base = take((size_t)l->n_heads_cta * 256 * 4);
+  l->cta_tot = take((size_t)l->n_heads_cta * 4);
+  l->cta_base = take((size_t)l->n_heads_cta * 4 + 4);
+  l->hist = take((size_t)l->hist_rows * (kRtMaxBins + 1) * 4);
+  l->tile_inv = take((size_t)l->hist_rows * 4);
+  l->tile_inv_base = take((size_t)l->hist_rows * 4);
+  l->cta_head = take((size_t)l->n_cta * l->lpr * 16);
+  l->cta_tail = take((size_t)l->n_cta * l->lpr * 16);
+  l->cta_meta = take((size_t)l->n_cta * 4);
+  l->cta_tid = take((size_t)l->n_cta * 4);
+  l->cta_tkey = take((size_t)l->n_cta * 4);
+  l->cta_lin = take((size_t)l->n_cta * 8);   // kon_embed_bwd_pair: per-CTA head / tail partials of the 1-float gradient
+  l->total = o;
+  return 0;
+}
+
+// where the upstream gradient rows live: one local [B,F,dim] view, or per-rank slabs over NVLink
+struct GradSrc {
+  const float* p = nullptr;
+  long long sb = 0, sf = 0;
+  int64_t dim = 0;
+  int device = 0;
+  int n_peers = 0;
+  long long peer_rows = 0;
+  const float* peer[kMaxPeers] = {};
+  // kon_embed_bwd_pair: the fused one-float gradient and its output
+  const float* lin = nullptr;
+  long long lin_sb = 0, lin_sf = 0;
+  float* lin_grads = nullptr;
+};
+
+size_t scatter_smem(int bins) {
+  const int nb = bins + 1, stride = (bins + 3) & ~1;
+  return (size_t)((nb + 1) & ~1) * 4 + (size_t)kRtWarps * stride * 2;
+}
+
+template <typename IdT>
+int launch_route(const RouteArgs& a, const int* slot_bins, cudaStream_t st) {
+  KON_CUDA(cudaFuncSetAttribute(route_scatter_kernel<IdT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)scatter_smem(kRtMaxBins)));     // per device; not a stream operation
+  const dim3 grid(a.NT, a.F);
+  for (int slot = 0; slot < a.max_p; ++slot) {
+    route_hist_kernel<IdT><<<grid, kRtThreads, (size_t)(slot_bins[slot] + 2) * 4, st>>>(a, slot);
+    KON_LAUNCH_CHECK("route_hist_kernel");
+    route_scan_kernel<<<a.F, kScanThreads, 0, st>>>(a, slot);
+    KON_LAUNCH_CHECK("route_scan_kernel");
+    route_scatter_kernel<IdT><<<grid, kRtThreads, scatter_smem(slot_bins[slot]), st>>>(a, slot);
+    KON_LAUNCH_CHECK("route_scatter_kernel");
+  }
+  return KON_OK;
+}
+
+int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field_row_offset,
+                   int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                   DLTensor* workspace, int reuse_sort, void* stream) {
+  const int dev = src.device;
+  IdsView v;
+  FieldTable ft;
+  KON_TRY(parse_common(ids, field_row_offset, n_fields, dev, &v, &ft));
+  const bool sort_only = reuse_sort == 2;     // kon_embed_sort: routing only
+  if (!sort_only) {
+    KON_TRY(check_cuda_tensor(unique_rows, "unique_rows", dev));
+    KON_TRY(check_cuda_tensor(grads, "grads", dev));
+    KON_TRY(check_cuda_tensor(n_unique, "n_unique", dev));
+  }
+  KON_TRY(check_cuda_tensor(workspace, "workspace", dev));
+  const int64_t dim = src.dim;
+  KON_REQUIRE(dim % 4 == 0 || dim == 1, KON_EUNSUPPORTED,
+              "embedding dim must be 1 or a multiple of 4 (got %lld)", (long long)dim);
+  const int64_t n = v.B * v.F * v.L;
+  KON_REQUIRE(n <= 0x7fffffffLL - 2 * kHeadsTile, KON_EUNSUPPORTED, "more than 2^31 - 16385 lookups per call");
+  KON_REQUIRE(v.B < (1LL << 24), KON_EUNSUPPORTED, "batch of %lld samples: the routing packs (sample, field) in 32 bits, B < 2^24",
+              (long long)v.B);
+  const int64_t total_rows = ft.off[n_fields];
+  KON_REQUIRE(total_rows < 0x7fffffffLL, KON_EUNSUPPORTED,
+              "arena with >= 2^31-1 rows: unique_rows is int32 (shard the tables over ranks / arenas)");
+  if (!sort_only) {
+    KON_REQUIRE(is_i32(unique_rows) && numel(unique_rows) >= n && is_compact(unique_rows),
+                KON_EINVAL, "unique_rows must be compact int32 [>=N]");
+    KON_REQUIRE(is_f32(grads) && grads->ndim == 2 && grads->shape[0] >= n && grads->shape[1] == dim &&
+                    is_compact(grads),
+                KON_EINVAL, "grads must be compact float32 [>=N,dim]");
+    KON_REQUIRE(is_i32(n_unique) && numel(n_unique) >= 1, KON_EINVAL, "n_unique must be int32[1]");
+  }
+  DeviceGuard guard(dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    if (!sort_only) KON_CUDA(cudaMemsetAsync(data_ptr<int>(n_unique), 0, 4, st));
+    return KON_OK;
+  }
+  const int rdim = dim == 1 ? 4 : (int)dim;   // row width seen by the reduce kernels
+  BwdLayout l;
+  KON_REQUIRE(bwd_layout(n, rdim, &l) == 0, KON_EUNSUPPORTED, "embedding dim %lld too large",
+              (long long)dim);
+  size_t need = l.total;
+  size_t pad_off = 0;
+  if (dim == 1) {   // padded d_out copy + padded grads live behind the regular layout
+    pad_off = need;
+    need += align_up((size_t)v.B * v.F * 16, 256) + align_up((size_t)n * 16, 256);
+  }
+  KON_REQUIRE(is_u8(workspace) && (size_t)numel(workspace) >= need, KON_EWORKSPACE,
+              "workspace has %lld bytes, need %zu", (long long)numel(workspace), need);
+  char* ws = data_ptr<char>(workspace);
+  KON_REQUIRE(((uintptr_t)ws & 255u) == 0, KON_EINVAL, "workspace must be 256-B aligned");
+  const int sms = sm_count_of(dev);
+  RouteHdr* hdr = (RouteHdr*)(ws + l.hdr);
+  uint32_t* keys_out = (uint32_t*)(ws + l.out_keys);
+  uint32_t* vals_out = (uint32_t*)(ws + l.out_vals);
+  int* blk_base = (int*)(ws + l.blk_base);
+  int* cta_base = (int*)(ws + l.cta_base);
+
+  if (reuse_sort != 1) {
+    RouteArgs ra;
+    ra.ids = ids->data ? (const void*)data_ptr<char>(ids) : nullptr;
+    ra.ft = ft;
+    ra.F = (int)v.F;
+    ra.L = (int)v.L;
+    ra.nf = v.B * v.L;
+    ra.NT = (int)((ra.nf + kRtTile - 1) / kRtTile);
+    KON_REQUIRE((int64_t)ra.F * ra.NT <= l.hist_rows, KON_EINVAL, "routing histogram rows");   // cannot fire
+    ra.sentinel = (uint32_t)total_rows;
+    ra.tmp_keys = (uint32_t*)(ws + l.tmp_keys);
+    ra.tmp_vals = (uint32_t*)(ws + l.tmp_vals);
+    ra.out_keys = keys_out;
+    ra.out_vals = vals_out;
+    ra.hist = (uint32_t*)(ws + l.hist);
+    ra.tile_inv = (uint32_t*)(ws + l.tile_inv);
+    ra.tile_inv_base = (uint32_t*)(ws + l.tile_inv_base);
+    ra.hdr = hdr;
+    int max_p = 1;
+    for (int f = 0; f < n_fields; ++f) max_p = std::max(max_p, passes_for(bits_for(ft.off[f + 1] - ft.off[f])));
+    ra.max_p = max_p;
+    int slot_bins[8] = {0};
+    int hs = 2;
+    for (int slot = 0; slot < max_p; ++slot)
+      for (int f = 0; f < n_fields; ++f) {
+        const FieldPass fp = field_pass(ft.off[f + 1] - ft.off[f], slot, max_p);
+        if (fp.active) slot_bins[slot] = std::max(slot_bins[slot], fp.bins);
+      }
+    for (int slot = 0; slot < max_p; ++slot) hs = std::max(hs, slot_bins[slot]);
+    ra.hs = hs;
+    ProfileScope ps("embed_bwd_sort", st);
+    if (v.i64)
+      KON_TRY(launch_route<long long>(ra, slot_bins, st));
+    else
+      KON_TRY(launch_route<int>(ra, slot_bins, st));
+    route_heads_kernel<<<l.n_heads_cta, 256, 0, st>>>(keys_out, hdr, blk_base, (int*)(ws + l.cta_tot), cta_base);
+    KON_LAUNCH_CHECK("route_heads_kernel");
+  }
+  if (sort_only) return KON_OK;
+
+  SegArgs a;
+  a.d_out = src.p;
+  a.sb = src.sb;
+  a.sf = src.sf;
+  a.n_peers = src.n_peers;
+  a.peer_rows = src.peer_rows;
+  for (int q = 0; q < kMaxPeers; ++q) a.peer[q] = src.peer[q];
+  a.dim = rdim;
+  a.vec_per_row = l.vpr;
+  a.keys = keys_out;
+  a.vals = vals_out;
+  a.hdr = hdr;
+  a.blk_base = blk_base;
+  a.cta_base = cta_base;
+  a.unique_rows = data_ptr<int>(unique_rows);
+  a.grads = data_ptr<float>(grads);
+  a.n_unique = data_ptr<int>(n_unique);
+  a.cta_head = (float*)(ws + l.cta_head);
+  a.cta_tail = (float*)(ws + l.cta_tail);
+  a.cta_meta = (int*)(ws + l.cta_meta);
+  a.cta_tid = (int*)(ws + l.cta_tid);
+  a.cta_tkey = (uint32_t*)(ws + l.cta_tkey);
+  a.d1 = src.lin;
+  a.sb1 = src.lin_sb;
+  a.sf1 = src.lin_sf;
+  a.grads1 = src.lin_grads;
+  a.cta_head1 = (float*)(ws + l.cta_lin);
+  a.cta_tail1 = a.cta_head1 + l.n_cta;
+  float* padded_grads = nullptr;
+  if (dim == 1) {
+    float4* padded = (float4*)(ws + pad_off);
+    padded_grads = (float*)(ws + pad_off + align_up((size_t)v.B * v.F * 16, 256));
+    const long long nb = v.B * v.F;
+    pad1_kernel<<<(int)std::min<long long>((nb + 255) / 256, (long long)sms * 16), 256, 0, st>>>(
+        a.d_out, a.sb, a.sf, (int)v.F, nb, padded);
+    KON_LAUNCH_CHECK("pad1_kernel");
+    a.d_out = (const float*)padded;
+    a.sb = v.F * 4;
+    a.sf = 4;
+    a.grads = padded_grads;
+  } else {
+    KON_REQUIRE(aligned16(a.d_out) && a.sb % 4 == 0 && a.sf % 4 == 0, KON_EINVAL,
+                "d_out rows must be 16-B aligned");
+  }
+  {
+    ProfileScope ps_red("embed_reduce_kernel", st);
+    const int fix_grid = (l.n_cta + kSegThreads / l.lpr - 1) / (kSegThreads / l.lpr);
+#define KON_SEG_CASE(N)                                                          \
+  case N:                                                                        \
+    if (a.d1 != nullptr) {                                                       \
+      embed_segsum_kernel<N, true><<<l.n_cta, kSegThreads, 0, st>>>(a);          \
+      KON_LAUNCH_CHECK("embed_segsum_kernel");                                   \
+      embed_fixup_kernel<N, true><<<fix_grid, kSegThreads, 0, st>>>(a);          \
+    } else {                                                                     \
+      embed_segsum_kernel<N, false><<<l.n_cta, kSegThreads, 0, st>>>(a);         \
+      KON_LAUNCH_CHECK("embed_segsum_kernel");                                   \
+      embed_fixup_kernel<N, false><<<fix_grid, kSegThreads, 0, st>>>(a);         \
+    }                                                                            \
+    KON_LAUNCH_CHECK("embed_fixup_kernel");                                      \
+    break;
+    switch (l.lpr) {
+      KON_SEG_CASE(1)
+      KON_SEG_CASE(2)
+      KON_SEG_CASE(4)
+      KON_SEG_CASE(8)
+      KON_SEG_CASE(16)
+      KON_SEG_CASE(32)
+      default:
+        return fail(KON_EUNSUPPORTED, "embedding dim too large");
+    }
+#undef KON_SEG_CASE
+  }
+  if (dim == 1) {   // compact [N,4] -> [N,1]  (a 2-D memcpy with 4-byte rows takes 160 us for 1.7 M rows)
+    unpad1_kernel<<<(int)std::min<long long>((n + 255) / 256, (long long)sms * 16), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(padded_grads), a.n_unique, n, data_ptr<float>(grads));
+    KON_LAUNCH_CHECK("unpad1_kernel");
+  }
+  return KON_OK;
+}
+
+int embed_bwd_impl(const DLTensor* d_out, const DLTensor* ids, const int64_t* field_row_offset,
+                   int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                   DLTensor* workspace, int reuse_sort, void* stream) {
+  KON_TRY(check_cuda_tensor(d_out, "d_out"));
+  KON_TRY(check_cuda_tensor(ids, "ids", d_out->device.device_id));
+  KON_REQUIRE(is_f32(d_out) && d_out->ndim == 3 && (ids->ndim == 2 || ids->ndim == 3) &&
+                  d_out->shape[0] == ids->shape[0] && d_out->shape[1] == ids->shape[1],
+              KON_EINVAL, "d_out must be float32 [B,F,dim]");
+  GradSrc src;
+  src.p = data_ptr<float>(d_out);
+  src.sb = stride_of(d_out, 0);
+  src.sf = stride_of(d_out, 1);
+  src.dim = d_out->shape[2];
+  src.device = d_out->device.device_id;
+  KON_REQUIRE(src.dim == 1 || stride_of(d_out, 2) == 1, KON_EINVAL, "d_out last dim must be compact");
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
+                        reuse_sort, stream);
+}
+
+}  // namespace
+}  // namespace kon
+
+using namespace kon;
+
+extern "C" size_t kon_embed_bwd_workspace_bytes(int64_t n_lookups, int32_t dim) {
+  BwdLayout l;
+  if (n_lookups <= 0) return 256;
+  if (n_lookups > 0x7fffffffLL - 2 * kHeadsTile || bwd_layout(n_lookups, dim == 1 ? 4 : dim, &l) != 0) return 0;
+  if (dim == 1) return l.total + 2 * align_up((size_t)n_lookups * 16, 256);
+  return l.total;
+}
+
+extern "C" int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids,
+                             const int64_t* field_row_offset, int32_t n_fields,
+                             DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                             DLTensor* workspace, void* stream) {
+  return embed_bwd_impl(d_out, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 0,
+                        stream);
+}
+
+extern "C" int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids,
+                                   const int64_t* field_row_offset, int32_t n_fields,
+                                   DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
+                                   DLTensor* workspace, void* stream) {
+  return embed_bwd_impl(d_out, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace, 1,
+                        stream);
+}
+
+// Two gradients over one routing: the embedding tables' [B,F,dim] gradient and the first-order ("linear", dim-1)
+// tables' [B,F,1] gradient (any strides; a sum-pooled first-order term has stride_f = 0) when both tables were
+// looked up with the same ids and per-field row counts -- the reference's FeatureInput(useLinear=True) (DP:65-76).
+// One pass over the sorted lookups yields both; unique_rows / n_unique are shared.
+extern "C" int kon_embed_bwd_pair(const DLTensor* d_out, const DLTensor* d_lin, const DLTensor* ids,
+                                  const int64_t* field_row_offset, int32_t n_fields,
+                                  DLTensor* unique_rows, DLTensor* grads, DLTensor* grads_lin,
+                                  DLTensor* n_unique, DLTensor* workspace, int32_t reuse_sort, void* stream) {
+  KON_TRY(check_cuda_tensor(d_out, "d_out"));
+  const int dev = d_out->device.device_id;
+  KON_TRY(check_cuda_tensor(d_lin, "d_lin", dev));
+  KON_TRY(check_cuda_tensor(ids, "ids", dev));
+  KON_TRY(check_cuda_tensor(grads_lin, "grads_lin", dev));
+  KON_REQUIRE(is_f32(d_out) && d_out->ndim == 3 && ids->ndim == 2 && d_out->shape[0] == ids->shape[0] &&
+                  d_out->shape[1] == ids->shape[1] && d_out->shape[2] >= 4 && d_out->shape[2] % 4 == 0,
+              KON_EINVAL, "d_out must be float32 [B,F,dim], dim a multiple of 4, ids [B,F]");
+  KON_REQUIRE(is_f32(d_lin) && d_lin->ndim == 3 && d_lin->shape[0] == ids->shape[0] &&
+                  d_lin->shape[1] == ids->shape[1] && d_lin->shape[2] == 1,
+              KON_EINVAL, "d_lin must be float32 [B,F,1]");
+  KON_REQUIRE(is_f32(grads_lin) && is_compact(grads_lin) && numel(grads_lin) >= numel(ids), KON_EINVAL,
+              "grads_lin must be compact float32 [>=N,1]");
+  KON_REQUIRE(stride_of(d_out, 2) == 1, KON_EINVAL, "d_out last dim must be compact");
+  GradSrc src;
+  src.p = data_ptr<float>(d_out);
+  src.sb = stride_of(d_out, 0);
+  src.sf = stride_of(d_out, 1);
+  src.dim = d_out->shape[2];
+  src.device = dev;
+  src.lin = data_ptr<float>(d_lin);
+  src.lin_sb = stride_of(d_lin, 0);
+  src.lin_sf = stride_of(d_lin, 1);
+  src.lin_grads = data_ptr<float>(grads_lin);
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
+                        reuse_sort ? 1 : 0, stream);
+}
+
+// Routing only: sorts the lookups by arena row and counts the run heads into the front of `workspace`, where
+// kon_embed_bwd_reuse / kon_embed_bwd_pair / kon_embed_bwd_peer(reuse_sort = 1) pick them up.  The routing
+// depends on the ids alone, so a trainer runs it on a side stream at the START of the step, off the
+// critical path of the backward.
+extern "C" int kon_embed_sort(const DLTensor* ids, const int64_t* field_row_offset, int32_t n_fields,
+                              DLTensor* workspace, void* stream) {
+  KON_TRY(check_cuda_tensor(ids, "ids"));
+  GradSrc src;
+  src.dim = 4;
+  src.device = ids->device.device_id;
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, nullptr, nullptr, nullptr, workspace, 2, stream);
+}
+
+// Sharded backward over peer memory: the owner of the tables reads the gradient row of sample b
+// from the gradient buffer of rank b / rows_per_peer while it reduces the sorted segments.
+extern "C" int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers,
+                                  int64_t rows_per_peer, int64_t stride_b, int64_t stride_f,
+                                  int32_t dim, const DLTensor* ids, const int64_t* field_row_offset,
+                                  int32_t n_fields, DLTensor* unique_rows, DLTensor* grads,
+                                  DLTensor* n_unique, DLTensor* workspace, int32_t reuse_sort,
+                                  void* stream) {
+  KON_TRY(check_cuda_tensor(ids, "ids"));
+  KON_REQUIRE(peer_d_out != nullptr && n_peers >= 1 && n_peers <= kMaxPeers, KON_EINVAL,
+              "n_peers=%d outside [1,%d]", n_peers, kMaxPeers);
+  KON_REQUIRE(ids->ndim == 2, KON_EUNSUPPORTED, "the peer exchange takes [B,F] ids");
+  KON_REQUIRE(rows_per_peer >= 1 && ids->shape[0] <= rows_per_peer * n_peers, KON_EINVAL,
+              "ids has %lld samples, peers hold %lld x %d", (long long)ids->shape[0],
+              (long long)rows_per_peer, n_peers);
+  KON_REQUIRE(dim >= 4 && dim % 4 == 0, KON_EUNSUPPORTED, "the peer exchange needs dim %% 4 == 0");
+  GradSrc src;
+  src.sb = stride_b;
+  src.sf = stride_f;
+  src.dim = dim;
+  src.device = ids->device.device_id;
+  src.n_peers = n_peers;
+  src.peer_rows = rows_per_peer;
+  for (int q = 0; q < n_peers; ++q) {
+    KON_REQUIRE(peer_d_out[q] != nullptr && aligned16(peer_d_out[q]), KON_EINVAL,
+                "peer_d_out[%d] is NULL or not 16-B aligned", q);
+    src.peer[q] = static_cast<const float*>(peer_d_out[q]);
+  }
+  src.p = src.peer[0];
+  return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
+                        reuse_sort ? 1 : 0, stream);
+}

@@ -152,6 +152,79 @@ def test_embed_bwd_tiny():
     _check_embed_bwd([4, 4], 17, 16, seed=6)
 
 
+def test_embed_bwd_three_pass_table_and_several_tiles():
+    # 20 M rows = 25 bits -> three 9-bit counting passes; the 3-row table joins in the last slot (one pass), the
+    # 5000- / 70000-row tables in the last two; 9001 samples = 3 routing tiles per field, the last one ragged
+    _check_embed_bwd([3, 20_000_000, 5000, 70000], 9001, 16, seed=21)
+    _check_embed_bwd([4096, 4097, 1], 4097, 8, seed=22)      # exactly 12 bits / one bit more; tile boundary + 1
+
+
+@pytest.mark.parametrize("dim", [16, 1])
+def test_embed_bwd_out_of_range_ids_are_dropped(dim):
+    """Out-of-range ids carry no gradient (TF-GPU gather semantics): the routing puts them behind every valid lookup
+    and the reduction never sees them -- also when a whole field, or everything, is out of range."""
+    ops = _ops()
+    g = gen(31)
+    rows = [7, 50000, 300, 9]
+    B, F = 5003, len(rows)
+    for mode in ("some", "field", "all"):
+        ids = make_ids(B, rows, g)
+        bad = torch.rand(B, F, generator=g) < 0.2
+        if mode == "field":
+            bad[:, 1] = True
+        if mode == "all":
+            bad[:] = True
+        junk = torch.where(torch.rand(B, F, generator=g) < 0.5, torch.full((B, F), -3),
+                           torch.tensor(rows).expand(B, F) + 11)
+        ids = torch.where(bad, junk, ids.long()).to(torch.int32)
+        d_out = torch.randn(B, F, dim, generator=g)
+        sg = ops.embed_bwd_raw(d_out.to(DEV), ids.to(DEV), offsets(rows))
+        n = int(sg.n.item())
+        off = offsets(rows)
+        exp_rows, exp_grads = [], []
+        for f in range(F):
+            ok = ~bad[:, f].numpy()
+            if ok.any():
+                u, gr = ko.embedding_grad(ids[:, f].numpy()[ok], d_out[:, f].numpy()[ok], rows[f])
+                exp_rows.append(u + off[f])
+                exp_grads.append(gr)
+        exp_rows = np.concatenate(exp_rows) if exp_rows else np.zeros(0, np.int64)
+        exp_grads = np.concatenate(exp_grads) if exp_grads else np.zeros((0, dim), np.float32)
+        assert n == exp_rows.shape[0], mode
+        assert np.array_equal(sg.rows[:n].cpu().numpy().astype(np.int64), exp_rows), mode
+        if n:
+            scale = np.abs(exp_grads).max()
+            assert np.abs(sg.grads[:n].cpu().numpy() - exp_grads).max() <= 1e-5 * scale + 1e-30, mode
+
+
+def test_embed_bwd_is_bit_reproducible_and_graph_capturable():
+    ops = _ops()
+    g = gen(41)
+    rows = [3, 70000, 10, 500, 5_000_000]
+    B = 20000
+    ids = make_ids(B, rows, g).to(DEV)
+    d_out = torch.randn(B, len(rows), 16, generator=g).to(DEV)
+    a = ops.embed_bwd_raw(d_out, ids, offsets(rows), share_sort=False)
+    b = ops.embed_bwd_raw(d_out, ids, offsets(rows), share_sort=False)
+    n = int(a.n.item())
+    assert n == int(b.n.item())
+    assert torch.equal(a.rows[:n], b.rows[:n]) and torch.equal(a.grads[:n], b.grads[:n])
+    # the whole backward (routing kernels, head count with its last-CTA scan, reduction) replays from a CUDA graph
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.embed_bwd_raw(d_out, ids, offsets(rows), share_sort=False)     # warm the workspace cache
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            c = ops.embed_bwd_raw(d_out, ids, offsets(rows), share_sort=False)
+        for _ in range(3):
+            c.grads.zero_()
+            gr.replay()
+    torch.cuda.synchronize()
+    assert int(c.n.item()) == n
+    assert torch.equal(a.rows[:n], c.rows[:n]) and torch.equal(a.grads[:n], c.grads[:n])
+
+
 def test_embed_autograd_and_sgd():
     ops = _ops()
     g = gen(11)
