@@ -40,8 +40,9 @@ constexpr int kRtRounds = kRtTile / kRtThreads;     // items per thread
 constexpr int kRtWarpItems = kRtTile / kRtWarps;    // consecutive items per warp
 constexpr int kRtMaxBits = 12;
 constexpr int kRtMaxBins = 1 << kRtMaxBits;
-constexpr int kScanThreads = 1024;
-constexpr int kScanPerThread = kRtMaxBins / kScanThreads;
+constexpr int kRtGroups = 8;                        // route_scan: CTAs per field ...
+constexpr int kRtGroupBins = kRtMaxBins / kRtGroups;   // ... of this many digits each
+constexpr int kScanThreads = 256;
 constexpr int kHeadsPerThread = 32;
 constexpr int kHeadsTile = 256 * kHeadsPerThread;   // sorted lookups per route_heads CTA
 constexpr uint32_t kSkipKey = 0xffffffffu;          // lane past the end of the field
@@ -95,6 +96,7 @@ struct RouteArgs {
   uint32_t sentinel;    // key of an out-of-range lookup (= total rows)
   uint32_t *tmp_keys, *tmp_vals, *out_keys, *out_vals;
   uint32_t* hist;           // [F][NT][hs]: counts (route_hist) -> destination bases (route_scan), in place
+  uint32_t* gsum;           // [F][NT][kRtGroups]: counts summed over groups of kRtGroupBins digits
   uint32_t* tile_inv;       // [F][NT]: out-of-range lookups per tile
   uint32_t* tile_inv_base;  // [F][NT]: where they go
   RouteHdr* hdr;
@@ -112,55 +114,86 @@ __device__ __forceinline__ void route_bufs(const RouteArgs& a, int slot, const u
 
 // (key, payload) of the kRtRounds items of a thread.  First pass of a field: straight from the ids ([B,F,L], the
 // field's column); payload = (sample << 8) | field, the address of the gradient row.  Later passes: the scratch pair.
+// Every load is unconditional (lanes past the end of the field re-read its last item and are masked afterwards):
+// a guarded load is a branch, and 16 branches are 16 dependent trips to memory instead of 16 loads in flight.
 template <typename IdT>
 __device__ __forceinline__ void route_load(const RouteArgs& a, const FieldPass& fp, int f, long long off, long long rows,
                                            const uint32_t* sk, const uint32_t* sv, long long jw, int lane,
                                            uint32_t (&key)[kRtRounds], uint32_t (&val)[kRtRounds]) {
+  const long long last = a.nf - 1;
+  const long long jb = min(jw, last);
+  const int rem = (int)min(last - jb, (long long)(kRtWarpItems - 1));   // items of this warp's span after its first
   if (fp.first) {
     const IdT* ids = static_cast<const IdT*>(a.ids);
-    long long id[kRtRounds];
+    IdT raw[kRtRounds];
+    if (a.L == 1) {
+      const IdT* p0 = ids + jb * a.F + f;
 #pragma unroll
-    for (int r = 0; r < kRtRounds; ++r) {
-      const long long j = jw + r * 32 + lane;
-      id[r] = -1;
-      val[r] = 0;
-      if (j < a.nf) {
-        long long b = j, p;
-        if (a.L == 1) {
-          p = b * a.F + f;
-        } else {
-          b = j / a.L;
-          p = (b * a.F + f) * a.L + (j - b * a.L);
-        }
-        id[r] = (long long)__ldg(ids + p);
-        val[r] = (uint32_t)((b << 8) | (long long)f);
+      for (int r = 0; r < kRtRounds; ++r) raw[r] = __ldg(p0 + (unsigned)(min(r * 32 + lane, rem) * a.F));
+#pragma unroll
+      for (int r = 0; r < kRtRounds; ++r) {
+        const int o = r * 32 + lane;
+        const long long id = (long long)raw[r];
+        const uint32_t kk = (id >= 0 && id < rows) ? (uint32_t)(off + id) : a.sentinel;
+        key[r] = (jw + o <= last) ? kk : kSkipKey;
+        val[r] = (uint32_t)(((jb + o) << 8) | (long long)f);
       }
-    }
+    } else {
 #pragma unroll
-    for (int r = 0; r < kRtRounds; ++r) {
-      const long long j = jw + r * 32 + lane;
-      key[r] = j < a.nf ? ((id[r] >= 0 && id[r] < rows) ? (uint32_t)(off + id[r]) : a.sentinel) : kSkipKey;
+      for (int r = 0; r < kRtRounds; ++r) {
+        const long long j = jb + min(r * 32 + lane, rem);
+        const long long b = j / a.L;
+        raw[r] = __ldg(ids + (b * a.F + f) * a.L + (j - b * a.L));
+      }
+#pragma unroll
+      for (int r = 0; r < kRtRounds; ++r) {
+        const int o = r * 32 + lane;
+        const long long id = (long long)raw[r];
+        const uint32_t kk = (id >= 0 && id < rows) ? (uint32_t)(off + id) : a.sentinel;
+        key[r] = (jw + o <= last) ? kk : kSkipKey;
+        val[r] = (uint32_t)((((jb + min(o, rem)) / a.L) << 8) | (long long)f);
+      }
     }
   } else {
-    const uint32_t* k = sk + (long long)f * a.nf;
-    const uint32_t* v = sv + (long long)f * a.nf;
+    const uint32_t* k = sk + (long long)f * a.nf + jb;
+    const uint32_t* v = sv + (long long)f * a.nf + jb;
 #pragma unroll
     for (int r = 0; r < kRtRounds; ++r) {
-      const long long j = jw + r * 32 + lane;
-      key[r] = kSkipKey;
-      val[r] = 0;
-      if (j < a.nf) {
-        key[r] = k[j];
-        val[r] = v[j];
-      }
+      const int o = min(r * 32 + lane, rem);
+      key[r] = k[o];
+      val[r] = v[o];
     }
+#pragma unroll
+    for (int r = 0; r < kRtRounds; ++r)
+      if (jw + r * 32 + lane > last) key[r] = kSkipKey;
   }
 }
 
 __device__ __forceinline__ uint32_t route_digit(uint32_t key, const FieldPass& fp, long long off, uint32_t sentinel) {
-  if (key == kSkipKey) return (uint32_t)fp.bins + 1u;      // dummy counter
-  if (key == sentinel) return (uint32_t)fp.bins;
-  return (uint32_t)(((long long)key - off) >> fp.shift) & fp.mask;
+  const uint32_t d = ((uint32_t)(key - (uint32_t)off) >> fp.shift) & fp.mask;
+  return key == kSkipKey ? (uint32_t)fp.bins + 1u          // dummy counter
+                         : (key == sentinel ? (uint32_t)fp.bins : d);
+}
+
+// `hist` is [F][NT tiles][hs digits]; `gsum` [F][NT][kRtGroups] holds the per-tile sums over groups of kRtGroupBins
+// digits, so that route_scan can split the digits of a field over kRtGroups CTAs
+__device__ __forceinline__ size_t hist_at(const RouteArgs& a, int f, int tile) {
+  return ((size_t)f * a.NT + tile) * a.hs;
+}
+
+// lanes of the warp holding the same digit as this one.  match.any does this in one instruction but at about one
+// result per 70 clocks and SM (measured: 360 matches per SM took 23 k clocks); nbits votes cost ~4 issue slots each.
+__device__ __forceinline__ unsigned match_bits(uint32_t d, int nbits) {
+  unsigned m = 0xffffffffu;
+  for (int b = 0; b < nbits; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned v = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? v : ~v;
+  }
+  return m;
+}
+__device__ __forceinline__ int digit_bits(int bins) {   // digits run over [0, bins + 1]
+  return 32 - __clz(bins + 1);
 }
 
 template <typename IdT>
@@ -172,22 +205,36 @@ __global__ void __launch_bounds__(kRtThreads) route_hist_kernel(const __grid_con
   if (!fp.active) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < fp.bins + 2; i += kRtThreads) s_hist[i] = 0;
-  __syncthreads();
   const uint32_t *sk, *sv;
   uint32_t *dk, *dv;
   route_bufs(a, slot, sk, sv, dk, dv);
   uint32_t key[kRtRounds], val[kRtRounds];
   route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
+  __syncthreads();
+  if (fp.bins >= 64) {     // mostly distinct digits in a warp: one shared-memory atomic per lookup
 #pragma unroll
-  for (int r = 0; r < kRtRounds; ++r) {
-    const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
-    const unsigned m = __match_any_sync(0xffffffffu, d);
-    if (lane == __ffs(m) - 1) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+    for (int r = 0; r < kRtRounds; ++r) atomicAdd(&s_hist[route_digit(key[r], fp, off, a.sentinel)], 1u);
+  } else {                 // few digits, long runs of equal ones: one atomic per distinct digit of the warp
+    const int nbits = digit_bits(fp.bins);
+#pragma unroll
+    for (int r = 0; r < kRtRounds; ++r) {
+      const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
+      const unsigned m = match_bits(d, nbits);
+      if (lane == __ffs(m) - 1) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+    }
   }
   __syncthreads();
-  uint32_t* out = a.hist + ((size_t)f * a.NT + tile) * a.hs;
+  uint32_t* out = a.hist + hist_at(a, f, tile);
   for (int i = tid; i < fp.bins; i += kRtThreads) out[i] = s_hist[i];
   if (tid == 0) a.tile_inv[f * a.NT + tile] = s_hist[fp.bins];
+  // sums over groups of kRtGroupBins digits: warp w adds up group w
+  if (warp < kRtGroups) {
+    uint32_t g = 0;
+    for (int i = warp * kRtGroupBins + lane; i < min(fp.bins, (warp + 1) * kRtGroupBins); i += 32) g += s_hist[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    if (lane == 0) a.gsum[((size_t)f * a.NT + tile) * kRtGroups + warp] = g;
+  }
 }
 
 // exclusive prefix of one value per thread over the CTA (blockDim.x threads, a multiple of 32, <= 1024)
@@ -212,20 +259,21 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long* s_w
   return base + inc - v;
 }
 
-// One CTA per field: counts [tile][digit] -> destination of the first such lookup of the tile, in (digit, tile) order.
-// Last slot: the fields follow one another without gaps (out-of-range lookups of ALL fields behind them) and the
-// header gets n_valid.
+// CTA (g, f) owns the digits [g*512, g*512 + 512) of field f: counts [tile][digit] -> destination of the first such
+// lookup of the tile, in (digit, tile) order.  Last slot: the fields follow one another without gaps (out-of-range
+// lookups of ALL fields behind them) and the header gets n_valid.
+constexpr int kScanChunk = 16;   // tiles of one digit loaded at once
 __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_constant__ RouteArgs a, int slot) {
   __shared__ long long s_warp[32];
-  const int f = blockIdx.x;
+  const int f = blockIdx.y, grp = blockIdx.x;
   const long long rows = a.ft.off[f + 1] - a.ft.off[f];
   const FieldPass fp = field_pass(rows, slot, a.max_p);
-  if (!fp.active) return;
+  if (!fp.active || grp * kRtGroupBins >= fp.bins) return;
   const bool fin = slot == a.max_p - 1;
   const int t = threadIdx.x;
-  long long inv_before = 0, inv_all = 0, inv_mine = 0;
+  long long inv_before = 0, inv_all = 0, inv_mine = 0, before = 0;
   {
-    long long lb = 0, la = 0, lm = 0;
+    long long lb = 0, la = 0, lm = 0, lg = 0;
     if (fin) {
       const int tot = a.F * a.NT;
       for (int i = t; i < tot; i += kScanThreads) {
@@ -238,45 +286,54 @@ __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_c
     } else {
       for (int i = t; i < a.NT; i += kScanThreads) lm += a.tile_inv[f * a.NT + i];
     }
+    // lookups of this field with a digit below my group
+    for (int i = t; i < a.NT * kRtGroups; i += kScanThreads)
+      if (i % kRtGroups < grp) lg += a.gsum[(size_t)f * a.NT * kRtGroups + i];
     block_excl_scan(lb, s_warp, &inv_before);
     block_excl_scan(la, s_warp, &inv_all);
     block_excl_scan(lm, s_warp, &inv_mine);
+    block_excl_scan(lg, s_warp, &before);
   }
   const long long n_all = (long long)a.F * a.nf;
-  const long long base0 = fin ? (long long)f * a.nf - inv_before : (long long)f * a.nf;
+  const long long base0 = (fin ? (long long)f * a.nf - inv_before : (long long)f * a.nf) + before;
   const long long inv_base = fin ? (n_all - inv_all) + inv_before : (long long)f * a.nf + (a.nf - inv_mine);
 
-  const int c = (fp.bins + kScanThreads - 1) / kScanThreads;    // consecutive digits per thread (<= kScanPerThread)
-  uint32_t* h0 = a.hist + (size_t)f * a.NT * a.hs;
-  uint32_t tot[kScanPerThread];
-  long long mine = 0;
+  // thread t owns the digits g*512 + t and g*512 + t + 256: consecutive threads, consecutive counters
+  uint32_t* h = a.hist + hist_at(a, f, 0);
+  long long carry = base0;
+#pragma unroll 1
+  for (int k = 0; k < kRtGroupBins / kScanThreads; ++k) {
+    const int b = grp * kRtGroupBins + k * kScanThreads + t;
+    const bool on = b < fp.bins;
+    const int bb = on ? b : 0;
+    long long mine = 0;
+    for (int t0 = 0; t0 < a.NT; t0 += kScanChunk) {
+      uint32_t v[kScanChunk];
 #pragma unroll
-  for (int k = 0; k < kScanPerThread; ++k) {
-    tot[k] = 0;
-    const int b = t * c + k;
-    if (k < c && b < fp.bins) {
-      uint32_t s = 0;
-      for (int tile = 0; tile < a.NT; ++tile) s += h0[(size_t)tile * a.hs + b];
-      tot[k] = s;
-      mine += s;
+      for (int q = 0; q < kScanChunk; ++q) v[q] = h[(size_t)min(t0 + q, a.NT - 1) * a.hs + bb];
+#pragma unroll
+      for (int q = 0; q < kScanChunk; ++q) mine += (t0 + q < a.NT) ? v[q] : 0u;
     }
-  }
-  long long run0 = base0 + block_excl_scan(mine, s_warp, nullptr);
+    if (!on) mine = 0;
+    long long total;
+    uint32_t run = (uint32_t)(carry + block_excl_scan(mine, s_warp, &total));
+    carry += total;
+    if (on) {
+      for (int t0 = 0; t0 < a.NT; t0 += kScanChunk) {
+        uint32_t v[kScanChunk];
 #pragma unroll
-  for (int k = 0; k < kScanPerThread; ++k) {
-    const int b = t * c + k;
-    if (k < c && b < fp.bins) {
-      uint32_t run = (uint32_t)run0;
-      for (int tile = 0; tile < a.NT; ++tile) {
-        uint32_t* p = h0 + (size_t)tile * a.hs + b;
-        const uint32_t cnt = *p;
-        *p = run;
-        run += cnt;
+        for (int q = 0; q < kScanChunk; ++q) v[q] = h[(size_t)min(t0 + q, a.NT - 1) * a.hs + b];
+#pragma unroll
+        for (int q = 0; q < kScanChunk; ++q)
+          if (t0 + q < a.NT) {
+            h[(size_t)(t0 + q) * a.hs + b] = run;
+            run += v[q];
+          }
       }
-      run0 += tot[k];
     }
   }
-  long long carry = inv_base;
+  if (grp != 0) return;
+  carry = inv_base;
   for (int t0 = 0; t0 < a.NT; t0 += kScanThreads) {
     const bool on = t0 + t < a.NT;
     const long long v = on ? (long long)a.tile_inv[f * a.NT + t0 + t] : 0;
@@ -295,7 +352,7 @@ __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_c
 // order; the rank of an item among the equal digits of its warp is (count so far, a uint16 in shared memory private
 // to the warp) + (matching lanes below it).  Then: exclusive prefix over the warps per digit, + the tile's base.
 template <typename IdT>
-__global__ void __launch_bounds__(kRtThreads) route_scatter_kernel(const __grid_constant__ RouteArgs a, int slot) {
+__global__ void __launch_bounds__(kRtThreads, 2) route_scatter_kernel(const __grid_constant__ RouteArgs a, int slot) {
   extern __shared__ uint32_t s_dyn[];
   const int f = blockIdx.y, tile = blockIdx.x;
   const long long off = a.ft.off[f], rows = a.ft.off[f + 1] - off;
@@ -306,26 +363,27 @@ __global__ void __launch_bounds__(kRtThreads) route_scatter_kernel(const __grid_
   const int stride = (fp.bins + 3) & ~1;      // + out-of-range + dummy, even
   uint32_t* s_base = s_dyn;                                             // [nb]
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + ((nb + 1) & ~1));   // [kRtWarps][stride]
-  {
-    uint32_t* z = reinterpret_cast<uint32_t*>(s_cnt);
-    for (int i = tid; i < kRtWarps * stride / 2; i += kRtThreads) z[i] = 0;
-    const uint32_t* h = a.hist + ((size_t)f * a.NT + tile) * a.hs;
-    for (int i = tid; i < fp.bins; i += kRtThreads) s_base[i] = h[i];
-    if (tid == 0) s_base[fp.bins] = a.tile_inv_base[f * a.NT + tile];
-  }
   const uint32_t *sk, *sv;
   uint32_t *dk, *dv;
   route_bufs(a, slot, sk, sv, dk, dv);
   uint32_t key[kRtRounds], val[kRtRounds];
   route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(s_cnt);
+    for (int i = tid; i < kRtWarps * stride / 2; i += kRtThreads) z[i] = 0;
+    const uint32_t* h = a.hist + hist_at(a, f, tile);
+    for (int i = tid; i < fp.bins; i += kRtThreads) s_base[i] = h[i];
+    if (tid == 0) s_base[fp.bins] = a.tile_inv_base[f * a.NT + tile];
+  }
   __syncthreads();
   uint16_t* cnt = s_cnt + warp * stride;
   uint32_t dr[kRtRounds];   // digit << 16 | rank inside the warp
   const unsigned below = (1u << lane) - 1u;
+  const int nbits = digit_bits(fp.bins);
 #pragma unroll
   for (int r = 0; r < kRtRounds; ++r) {
     const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
-    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const unsigned m = match_bits(d, nbits);
     const uint32_t prev = cnt[d];
     __syncwarp();
     if (lane == __ffs(m) - 1) cnt[d] = (uint16_t)(prev + __popc(m));
@@ -366,19 +424,21 @@ __global__ void __launch_bounds__(256) route_heads_kernel(const uint32_t* __rest
   const long long i0 = (long long)blockIdx.x * kHeadsTile + (long long)t * kHeadsPerThread;
   int c = 0;
   if (i0 < nv) {
-    uint32_t prev = i0 > 0 ? keys[i0 - 1] : ~keys[0];
+    // the buffer is padded to a multiple of 32 keys (+32): whole vectors are readable
     const uint4* p = reinterpret_cast<const uint4*>(keys + i0);
+    uint4 k[kHeadsPerThread / 4];
+    const uint32_t before = keys[max(i0 - 1, 0LL)];
+#pragma unroll
+    for (int q = 0; q < kHeadsPerThread / 4; ++q) k[q] = p[q];
+    uint32_t prev = i0 > 0 ? before : ~k[0].x;
 #pragma unroll
     for (int q = 0; q < kHeadsPerThread / 4; ++q) {
-      if (i0 + q * 4 < nv) {        // the buffer is padded to a multiple of 32 keys: whole vectors are readable
-        const uint4 k = p[q];
-        const long long i = i0 + q * 4;
-        c += (k.x != prev) ? 1 : 0;
-        c += (i + 1 < nv && k.y != k.x) ? 1 : 0;
-        c += (i + 2 < nv && k.z != k.y) ? 1 : 0;
-        c += (i + 3 < nv && k.w != k.z) ? 1 : 0;
-        prev = k.w;
-      }
+      const long long i = i0 + q * 4;
+      c += (i < nv && k[q].x != prev) ? 1 : 0;
+      c += (i + 1 < nv && k[q].y != k[q].x) ? 1 : 0;
+      c += (i + 2 < nv && k[q].z != k[q].y) ? 1 : 0;
+      c += (i + 3 < nv && k[q].w != k[q].z) ? 1 : 0;
+      prev = k[q].w;
     }
   }
   long long total;
@@ -413,16 +473,12 @@ __global__ void __launch_bounds__(256) route_heads_kernel(const uint32_t* __rest
 constexpr int kSegThreads = 256;
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegWin = 8;       // sorted lookups per lane group and chunk = row loads in flight per thread
-#ifndef KON_SEG_CHUNKS
-#define KON_SEG_CHUNKS 4
-#endif
-constexpr int kSegChunks = KON_SEG_CHUNKS;   // chunks per warp
-
-__host__ __device__ constexpr int seg_tile(int lpr) { return kSegWarps * kSegChunks * (32 / lpr) * kSegWin; }
+constexpr int kSegSpan = 256;    // sorted lookups per warp (its keys / payloads are staged in shared memory at once)
+constexpr int kSegTile = kSegSpan * kSegWarps;
 
 struct SegArgs {
   const float* d_out;
-  long long sb, sf;   // strides of d_out dims 0 / 1 (elements)
+  unsigned sb4, sf4;  // strides of d_out dims 0 / 1 in float4 units
   int dim, vec_per_row;
   const uint32_t* keys;   // sorted
   const uint32_t* vals;   // (sample << 8) | field, sorted with the keys
@@ -440,7 +496,7 @@ struct SegArgs {
   // fused first-order gradient (kon_embed_bwd_pair): a second, one-float-per-lookup gradient reduced over the
   // same routing in the same pass (the dim-1 "linear" tables are looked up with the same ids)
   const float* d1;
-  long long sb1, sf1;
+  unsigned sb1, sf1;
   float* grads1;      // [n_unique]
   float* cta_head1;   // [n_cta]
   float* cta_tail1;   // [n_cta]
@@ -453,6 +509,9 @@ struct SegArgs {
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
+__device__ __forceinline__ float4 f4_sel(bool c, float4 a, float4 b) {
+  return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
 __device__ __forceinline__ float4 f4_shfl_up(float4 v, int d) {
   return make_float4(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d),
                      __shfl_up_sync(0xffffffffu, v.z, d), __shfl_up_sync(0xffffffffu, v.w, d));
@@ -462,91 +521,108 @@ __device__ __forceinline__ float4 f4_shfl(float4 v, int l) {
                      __shfl_sync(0xffffffffu, v.z, l), __shfl_sync(0xffffffffu, v.w, l));
 }
 
-template <int LPR, bool LIN>
-__global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(const __grid_constant__ SegArgs a) {
+template <int LPR, bool LIN, bool PEER>
+__global__ void __launch_bounds__(kSegThreads, (LIN || PEER) ? 2 : 3)
+embed_segsum_kernel(const __grid_constant__ SegArgs a) {
   constexpr int GPW = 32 / LPR;               // lane groups per warp
   constexpr int CHUNK = GPW * kSegWin;        // sorted lookups per warp and chunk
-  constexpr int SPAN = CHUNK * kSegChunks;    // per warp
-  constexpr int TILE = SPAN * kSegWarps;      // per CTA
-  __shared__ uint32_t s_key[kSegWarps][CHUNK + 4];   // [0] = the lookup before the chunk
-  __shared__ uint32_t s_val[kSegWarps][CHUNK];
+  constexpr int NCH = kSegSpan / CHUNK;
+  __shared__ __align__(16) uint32_t s_key[kSegWarps][kSegSpan + 4];   // [0] = the lookup before the span
+  __shared__ __align__(16) uint32_t s_val[kSegWarps][kSegSpan];
   __shared__ float4 s_wh[kSegWarps][LPR], s_wt[kSegWarps][LPR];
   __shared__ float s_wh1[kSegWarps], s_wt1[kSegWarps];
   __shared__ int s_wflag[kSegWarps], s_wtid[kSegWarps];
   __shared__ uint32_t s_wtkey[kSegWarps];
 
   const long long nv = a.hdr->n_valid;
-  const long long cta_lo = (long long)blockIdx.x * TILE;
+  const long long cta_lo = (long long)blockIdx.x * kSegTile;
   if (cta_lo > nv) return;      // the CTA that holds position nv (the virtual head closing the last run) still runs
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int g = lane / LPR, sub = lane % LPR;
   const bool lane_on = sub < a.vec_per_row;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   if (blockIdx.x == 0 && tid == 0) *a.n_unique = a.hdr->n_unique;
+  const unsigned dim4 = (unsigned)a.dim >> 2;
+  float4* const grads4 = reinterpret_cast<float4*>(a.grads);
+  const float4* const src4 = reinterpret_cast<const float4*>(a.d_out);
+  const unsigned sb4 = a.sb4, sf4 = a.sf4, sb1 = a.sb1, sf1 = a.sf1;
 
   auto emit = [&](int id, uint32_t key, float4 v, float v1) {
-    if (id < 0) return;
-    if (lane_on) *reinterpret_cast<float4*>(a.grads + (long long)id * a.dim + sub * 4) = v;
+    if (lane_on) grads4[(unsigned)id * dim4 + sub] = v;
     if (sub == 0) {
       a.unique_rows[id] = (int)key;
       if (LIN) a.grads1[id] = v1;
     }
   };
 
-  const long long s = cta_lo + (long long)w * SPAN;
+  const long long s = cta_lo + (long long)w * kSegSpan;
   // state of the warp's walk: (cf: a run head was seen; cv: sum since the last head, or since s; ccnt: heads)
   float4 cv = zero;
   float cv1 = 0.f;
   bool cf = false;
   int ccnt = 0;
-  float4 wh = zero;      // sum of the warp's lookups before its first head (this lane's slice), group-uniform copies
-  float wh1 = 0.f;
-  bool wh_set = false;
   int run_base = 0;
   if (s <= nv) {
     // heads before s; at s == nv (only the virtual head is left) the tables may end one entry short
     run_base = s < nv ? a.cta_base[s / kHeadsTile] + a.blk_base[s >> 5] : a.hdr->n_unique;
+    {   // keys s-1 .. s+255 and payloads s .. s+255 of the span, all loads in flight at once
+      uint32_t kk[kSegSpan / 32 + 1], vv[kSegSpan / 32];
+#pragma unroll
+      for (int q = 0; q <= kSegSpan / 32; ++q) {
+        const long long idx = s - 1 + q * 32 + lane;
+        kk[q] = a.keys[min(max(idx, 0LL), nv)];        // the buffers are readable up to n + 32
+      }
+#pragma unroll
+      for (int q = 0; q < kSegSpan / 32; ++q) vv[q] = a.vals[min(s + q * 32 + lane, max(nv - 1, 0LL))];
+#pragma unroll
+      for (int q = 0; q <= kSegSpan / 32; ++q)
+        if (q < kSegSpan / 32 || lane == 0) s_key[w][q * 32 + lane] = kk[q];
+#pragma unroll
+      for (int q = 0; q < kSegSpan / 32; ++q) s_val[w][q * 32 + lane] = vv[q];
+    }
+    __syncwarp();
 #pragma unroll 1
-    for (int ch = 0; ch < kSegChunks; ++ch) {
+    for (int ch = 0; ch < NCH; ++ch) {
       const long long cs = s + (long long)ch * CHUNK;
       if (cs > nv) break;
-      __syncwarp();
-      for (int i = lane; i < CHUNK + 1; i += 32) {
-        const long long idx = cs - 1 + i;
-        s_key[w][i] = (idx >= 0 && idx < nv) ? a.keys[idx] : 0u;
-        if (i < CHUNK) s_val[w][i] = (cs + i < nv) ? a.vals[cs + i] : 0u;
+      const int wo = ch * CHUNK + g * kSegWin;          // window offset inside the span
+      const long long ws = s + wo;
+      const int rel = (int)max(-1LL, min((long long)kSegWin + 1, nv - ws));   // lookups of the window below nv
+      uint32_t k[kSegWin + 1], v[kSegWin];
+      {
+        const uint4 k0 = *reinterpret_cast<const uint4*>(&s_key[w][wo]);
+        const uint4 k1 = *reinterpret_cast<const uint4*>(&s_key[w][wo + 4]);
+        const uint4 v0 = *reinterpret_cast<const uint4*>(&s_val[w][wo]);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(&s_val[w][wo + 4]);
+        k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w;
+        k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
+        k[8] = s_key[w][wo + 8];
+        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+        v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
       }
-      __syncwarp();
-      const long long ws = cs + g * kSegWin;
-      const int rel = (int)max(-1LL, min((long long)kSegWin + 1, nv - ws));   // items of the window below nv
-      uint32_t k[kSegWin + 1];
+      unsigned hb = ws == 0 ? 1u : 0u;
 #pragma unroll
-      for (int u = 0; u <= kSegWin; ++u) k[u] = s_key[w][g * kSegWin + u];
-      unsigned hb = 0;
-#pragma unroll
-      for (int u = 0; u < kSegWin; ++u) {
-        const bool h = (u == rel) || (u < rel && (k[u + 1] != k[u] || ws + u == 0));
-        hb |= h ? (1u << u) : 0u;
+      for (int u = 0; u < kSegWin; ++u) hb |= (k[u + 1] != k[u]) ? (1u << u) : 0u;
+      if (rel < kSegWin) {        // the window reaches past the valid prefix: head bits below nv, + the virtual head at nv
+        hb &= rel > 0 ? ((1u << rel) - 1u) : 0u;
+        if (rel >= 0) hb |= 1u << rel;
       }
       float4 r[kSegWin];
       float r1[LIN ? kSegWin : 1];
 #pragma unroll
       for (int u = 0; u < kSegWin; ++u) {
-        r[u] = zero;
-        if (LIN) r1[u] = 0.f;
-        if (u < rel) {
-          const uint32_t bf = s_val[w][g * kSegWin + u];
-          long long b = bf >> 8;
-          const int f = (int)(bf & 255u);
-          const float* src = a.d_out;
-          if (a.n_peers) {
-            const long long q = b / a.peer_rows;
-            src = a.peer[q];
-            b -= q * a.peer_rows;
-          }
-          if (lane_on) r[u] = ldg_stream_f4(reinterpret_cast<const float4*>(src + b * a.sb + f * a.sf) + sub);
-          if (LIN) r1[u] = __ldg(a.d1 + b * a.sb1 + f * a.sf1);
+        // lookups at / past nv re-read the row of the last valid one and are zeroed below (no guarded loads)
+        const uint32_t bf = v[u];
+        unsigned b = bf >> 8;
+        const unsigned f = bf & 255u;
+        const float4* src = src4;
+        if (PEER) {
+          const unsigned q = b / (unsigned)a.peer_rows;
+          src = reinterpret_cast<const float4*>(a.peer[q]);
+          b -= q * (unsigned)a.peer_rows;
         }
+        r[u] = ldg_stream_f4(src + (b * sb4 + f * sf4 + (lane_on ? sub : 0)));
+        if (LIN) r1[u] = __ldg(a.d1 + (b * sb1 + f * sf1));
       }
       // heads before the window / does a head precede it inside the warp: known before the rows arrive
       const bool seen = hb != 0;
@@ -564,28 +640,28 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
       const bool ex_f = (gm & ((1u << g) - 1u)) != 0;
       const bool in_f = cf || ex_f;
       const int wbase = run_base + ccnt + inc_c - hc;
+      const int fu = seen ? __ffs(hb) - 1 : kSegWin;
+      if (rel < kSegWin) {
+#pragma unroll
+        for (int u = 0; u < kSegWin; ++u)
+          if (u >= rel) {
+            r[u] = zero;
+            if (LIN) r1[u] = 0.f;
+          }
+      }
       // the window: runs that start and end inside it go straight to their slot
       float4 acc = zero, H = zero;
       float acc1 = 0.f, H1 = 0.f;
-      bool first = true;
-      int lh = 0;
 #pragma unroll
       for (int u = 0; u < kSegWin; ++u) {
-        if ((hb >> u) & 1u) {
-          if (first) {
-            H = acc;
-            H1 = acc1;
-            first = false;
-          } else {
-            emit(wbase + lh - 1, k[u], acc, acc1);
-          }
-          ++lh;
-          acc = r[u];
-          if (LIN) acc1 = r1[u];
-        } else {
-          acc = f4_add(acc, r[u]);
-          if (LIN) acc1 += r1[u];
+        const bool hd = (hb >> u) & 1u;
+        if (hd && u > fu) emit(wbase + __popc(hb & ((1u << u) - 1u)) - 1, k[u], acc, acc1);
+        if (u == fu) {
+          H = acc;
+          H1 = acc1;
         }
+        acc = f4_sel(hd, r[u], f4_add(acc, r[u]));
+        if (LIN) acc1 = hd ? r1[u] : acc1 + r1[u];
       }
       // segmented scan over the lane groups: element = (window holds a head ? its tail : its whole sum)
       float4 inc = acc;
@@ -595,9 +671,9 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
         const float4 p = f4_shfl_up(inc, d * LPR);
         float p1 = 0.f;
         if (LIN) p1 = __shfl_up_sync(0xffffffffu, inc1, d * LPR);
-        const int lo = g - d + 1;
-        const unsigned range = (lo <= 0 ? ((2u << g) - 1u) : (((2u << g) - 1u) & ~((1u << lo) - 1u)));
-        if (g >= d && !(gm & range)) {
+        // groups (g - d, g] hold no head <=> the partner's sum still belongs to my run
+        const bool take = g >= d && ((gm >> (g - d + 1)) & ((1u << d) - 1u)) == 0;
+        if (take) {
           inc = f4_add(p, inc);
           if (LIN) inc1 = p1 + inc1;
         }
@@ -616,10 +692,9 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
         const float tot1 = in_v1 + H1;
         if (in_f) {
           emit(wbase - 1, k[0], tot, tot1);
-        } else {      // it entered the warp from the left: the warp's head partial
-          wh = tot;
-          wh1 = tot1;
-          wh_set = true;
+        } else {      // it entered the warp from the left: the warp's head partial (one lane group per warp gets here)
+          s_wh[w][sub] = tot;
+          if (LIN && sub == 0) s_wh1[w] = tot1;
         }
       }
       const float4 lv = f4_shfl(inc, (GPW - 1) * LPR + sub);
@@ -638,10 +713,6 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
     }
   }
   // ---- the warp's head / tail partials ---------------------------------------------------
-  if (wh_set) {       // exactly one lane group of the warp
-    s_wh[w][sub] = wh;
-    if (LIN && sub == 0) s_wh1[w] = wh1;
-  }
   if (g == 0) {
     if (!cf) {        // no head in the warp (or nothing to do): everything belongs to the run entering it
       s_wh[w][sub] = cv;
@@ -652,7 +723,7 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
     }
     if (sub == 0) {
       s_wflag[w] = cf ? 1 : 0;
-      const long long last = s + SPAN - 1;
+      const long long last = s + kSegSpan - 1;
       const bool real = cf && last < nv;       // else the open run is the virtual one behind position nv
       s_wtid[w] = real ? run_base + ccnt - 1 : -1;
       s_wtkey[w] = real ? a.keys[last] : 0u;
@@ -673,7 +744,7 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
       const float h1 = LIN ? s_wh1[ww] : 0.f;
       if (s_wflag[ww]) {
         if (open) {
-          emit(oid, okey, f4_add(ov, h), ov1 + h1);
+          if (oid >= 0) emit(oid, okey, f4_add(ov, h), ov1 + h1);
         } else {
           chead = f4_add(pre, h);
           chead1 = pre1 + h1;
@@ -717,10 +788,9 @@ __global__ void __launch_bounds__(kSegThreads, LIN ? 2 : 3) embed_segsum_kernel(
 template <int LPR, bool LIN>
 __global__ void __launch_bounds__(kSegThreads) embed_fixup_kernel(const __grid_constant__ SegArgs a) {
   constexpr int G = kSegThreads / LPR;
-  constexpr int TILE = seg_tile(LPR);
   constexpr int NB = 4;
   const long long nv = a.hdr->n_valid;
-  const int n_act = (int)(nv / TILE) + 1;
+  const int n_act = (int)(nv / kSegTile) + 1;
   const int c = blockIdx.x * G + threadIdx.x / LPR;
   const int sub = threadIdx.x % LPR;
   if (c >= n_act) return;
@@ -739,19 +809,15 @@ __global__ void __launch_bounds__(kSegThreads) embed_fixup_kernel(const __grid_c
     int m[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-      h[q] = zero;
-      h1[q] = 0.f;
-      m[q] = 1;
-      if (w0 + q < n_act) {
-        m[q] = a.cta_meta[w0 + q];
-        if (lane_on) h[q] = *reinterpret_cast<const float4*>(a.cta_head + (long long)(w0 + q) * a.dim + sub * 4);
-        if (LIN) h1[q] = a.cta_head1[w0 + q];
-      }
+      const int cc = min(w0 + q, n_act - 1);
+      m[q] = w0 + q < n_act ? a.cta_meta[cc] : 1;
+      h[q] = *reinterpret_cast<const float4*>(a.cta_head + (long long)cc * a.dim + (lane_on ? sub : 0) * 4);
+      h1[q] = LIN ? a.cta_head1[cc] : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-      if (!done) {
-        acc = f4_add(acc, h[q]);
+      if (!done && w0 + q < n_act) {
+        if (lane_on) acc = f4_add(acc, h[q]);
         acc1 += h1[q];
         if (m[q]) done = true;
       }
@@ -791,7 +857,7 @@ unpad1_kernel(const float4* __restrict__ src, const int* __restrict__ n_unique, 
 // Everything the routing produces comes first and depends on n alone, so the first-order tables (and, sharded,
 // the peer backward) reuse one routing whatever their row width.
 struct BwdLayout {
-  size_t hdr, tmp_keys, tmp_vals, out_keys, out_vals, blk_base, cta_tot, cta_base, hist, tile_inv, tile_inv_base;
+  size_t hdr, tmp_keys, tmp_vals, out_keys, out_vals, blk_base, cta_tot, cta_base, hist, gsum, tile_inv, tile_inv_base;
   size_t cta_head, cta_tail, cta_meta, cta_tid, cta_tkey, cta_lin, total;
   int n_cta, n_heads_cta, hist_rows;
   int lpr, vpr;
@@ -804,8 +870,7 @@ int bwd_layout(int64_t n, int32_t dim, BwdLayout* l) {
   l->vpr = (dim + 3) / 4;
   l->lpr = pow2_ge(l->vpr);
   if (l->lpr > 32) return -1;
-  const int64_t tile = seg_tile(l->lpr);
-  l->n_cta = (int)((n + 1 + tile - 1) / tile);      // position n (the virtual head) is covered too
+  l->n_cta = (int)((n + 1 + kSegTile - 1) / kSegTile);      // position n (the virtual head) is covered too
   l->n_heads_cta = (int)((n + kHeadsTile - 1) / kHeadsTile);
   if (l->n_heads_cta < 1) l->n_heads_cta = 1;
   l->hist_rows = (int)(n / kRtTile) + kMaxFields + 1;   // >= F * tiles-per-field for any F <= kMaxFields
@@ -825,6 +890,7 @@ int bwd_layout(int64_t n, int32_t dim, BwdLayout* l) {
   l->cta_tot = take((size_t)l->n_heads_cta * 4);
   l->cta_base = take((size_t)l->n_heads_cta * 4 + 4);
   l->hist = take((size_t)l->hist_rows * (kRtMaxBins + 1) * 4);
+  l->gsum = take((size_t)l->hist_rows * kRtGroups * 4);
   l->tile_inv = take((size_t)l->hist_rows * 4);
   l->tile_inv_base = take((size_t)l->hist_rows * 4);
   l->cta_head = take((size_t)l->n_cta * l->lpr * 16);
@@ -865,7 +931,7 @@ int launch_route(const RouteArgs& a, const int* slot_bins, cudaStream_t st) {
   for (int slot = 0; slot < a.max_p; ++slot) {
     route_hist_kernel<IdT><<<grid, kRtThreads, (size_t)(slot_bins[slot] + 2) * 4, st>>>(a, slot);
     KON_LAUNCH_CHECK("route_hist_kernel");
-    route_scan_kernel<<<a.F, kScanThreads, 0, st>>>(a, slot);
+    route_scan_kernel<<<dim3((slot_bins[slot] + kRtGroupBins - 1) / kRtGroupBins, a.F), kScanThreads, 0, st>>>(a, slot);
     KON_LAUNCH_CHECK("route_scan_kernel");
     route_scatter_kernel<IdT><<<grid, kRtThreads, scatter_smem(slot_bins[slot]), st>>>(a, slot);
     KON_LAUNCH_CHECK("route_scatter_kernel");
@@ -947,6 +1013,7 @@ int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field
     ra.out_keys = keys_out;
     ra.out_vals = vals_out;
     ra.hist = (uint32_t*)(ws + l.hist);
+    ra.gsum = (uint32_t*)(ws + l.gsum);
     ra.tile_inv = (uint32_t*)(ws + l.tile_inv);
     ra.tile_inv_base = (uint32_t*)(ws + l.tile_inv_base);
     ra.hdr = hdr;
@@ -974,8 +1041,7 @@ int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field
 
   SegArgs a;
   a.d_out = src.p;
-  a.sb = src.sb;
-  a.sf = src.sf;
+  long long sb = src.sb, sf = src.sf;
   a.n_peers = src.n_peers;
   a.peer_rows = src.peer_rows;
   for (int q = 0; q < kMaxPeers; ++q) a.peer[q] = src.peer[q];
@@ -995,26 +1061,40 @@ int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field
   a.cta_tid = (int*)(ws + l.cta_tid);
   a.cta_tkey = (uint32_t*)(ws + l.cta_tkey);
   a.d1 = src.lin;
-  a.sb1 = src.lin_sb;
-  a.sf1 = src.lin_sf;
   a.grads1 = src.lin_grads;
   a.cta_head1 = (float*)(ws + l.cta_lin);
   a.cta_tail1 = a.cta_head1 + l.n_cta;
+  a.sb1 = a.sf1 = 0;
+  if (src.lin) {
+    KON_REQUIRE(src.lin_sb >= 0 && src.lin_sf >= 0 &&
+                    (v.B - 1) * src.lin_sb + (v.F - 1) * src.lin_sf < 0xffffffffLL,
+                KON_EUNSUPPORTED, "d_lin strides outside the 32-bit addressing of the reduction");
+    a.sb1 = (unsigned)src.lin_sb;
+    a.sf1 = (unsigned)src.lin_sf;
+  }
+  KON_REQUIRE((long long)n * (rdim / 4) < 0xffffffffLL, KON_EUNSUPPORTED, "N * dim / 4 >= 2^32");
   float* padded_grads = nullptr;
   if (dim == 1) {
     float4* padded = (float4*)(ws + pad_off);
     padded_grads = (float*)(ws + pad_off + align_up((size_t)v.B * v.F * 16, 256));
     const long long nb = v.B * v.F;
     pad1_kernel<<<(int)std::min<long long>((nb + 255) / 256, (long long)sms * 16), 256, 0, st>>>(
-        a.d_out, a.sb, a.sf, (int)v.F, nb, padded);
+        a.d_out, sb, sf, (int)v.F, nb, padded);
     KON_LAUNCH_CHECK("pad1_kernel");
     a.d_out = (const float*)padded;
-    a.sb = v.F * 4;
-    a.sf = 4;
+    sb = v.F * 4;
+    sf = 4;
     a.grads = padded_grads;
   } else {
-    KON_REQUIRE(aligned16(a.d_out) && a.sb % 4 == 0 && a.sf % 4 == 0, KON_EINVAL,
+    KON_REQUIRE(aligned16(a.d_out) && sb % 4 == 0 && sf % 4 == 0, KON_EINVAL,
                 "d_out rows must be 16-B aligned");
+  }
+  {
+    const long long rows_b = src.n_peers ? std::min<long long>(src.peer_rows, v.B) : v.B;
+    KON_REQUIRE(sb >= 0 && sf >= 0 && ((rows_b - 1) * sb + (v.F - 1) * sf) / 4 + 64 < 0xffffffffLL, KON_EUNSUPPORTED,
+                "d_out strides outside the 32-bit (float4) addressing of the reduction");
+    a.sb4 = (unsigned)(sb / 4);
+    a.sf4 = (unsigned)(sf / 4);
   }
   {
     ProfileScope ps_red("embed_reduce_kernel", st);
@@ -1022,11 +1102,12 @@ int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field
 #define KON_SEG_CASE(N)                                                          \
   case N:                                                                        \
     if (a.d1 != nullptr) {                                                       \
-      embed_segsum_kernel<N, true><<<l.n_cta, kSegThreads, 0, st>>>(a);          \
+      embed_segsum_kernel<N, true, false><<<l.n_cta, kSegThreads, 0, st>>>(a);   \
       KON_LAUNCH_CHECK("embed_segsum_kernel");                                   \
       embed_fixup_kernel<N, true><<<fix_grid, kSegThreads, 0, st>>>(a);          \
     } else {                                                                     \
-      embed_segsum_kernel<N, false><<<l.n_cta, kSegThreads, 0, st>>>(a);         \
+      if (a.n_peers > 1) embed_segsum_kernel<N, false, true><<<l.n_cta, kSegThreads, 0, st>>>(a);  \
+      else embed_segsum_kernel<N, false, false><<<l.n_cta, kSegThreads, 0, st>>>(a);               \
       KON_LAUNCH_CHECK("embed_segsum_kernel");                                   \
       embed_fixup_kernel<N, false><<<fix_grid, kSegThreads, 0, st>>>(a);         \
     }                                                                            \
