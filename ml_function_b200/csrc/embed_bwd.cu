@@ -351,26 +351,30 @@ __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_c
 // Stable scatter of one tile.  Warp w owns items [w*512, (w+1)*512) of the tile and walks them 32 at a time in
 // order; the rank of an item among the equal digits of its warp is (count so far, a uint16 in shared memory private
 // to the warp) + (matching lanes below it).  Then: exclusive prefix over the warps per digit, + the tile's base.
+// A counter holds count (10 bits) | lane tag (5 bits): every lane bumps its digit's counter tagged with its lane id
+// and reads it back -- if every lane finds its own tag the 32 digits of the round are distinct (88 % of the rounds of
+// a 4096-digit pass) and the vote-based match is skipped.
+constexpr uint32_t kCntMask = 0x3ffu;
 template <typename IdT>
 __global__ void __launch_bounds__(kRtThreads, 2) route_scatter_kernel(const __grid_constant__ RouteArgs a, int slot) {
-  extern __shared__ uint32_t s_dyn[];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
   const int f = blockIdx.y, tile = blockIdx.x;
   const long long off = a.ft.off[f], rows = a.ft.off[f + 1] - off;
   const FieldPass fp = field_pass(rows, slot, a.max_p);
   if (!fp.active) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = fp.bins + 1;                 // digits incl. the out-of-range one
-  const int stride = (fp.bins + 3) & ~1;      // + out-of-range + dummy, even
+  const int stride = (fp.bins + 9) & ~7;      // + out-of-range + dummy; a multiple of 8 uint16 = 16 bytes
   uint32_t* s_base = s_dyn;                                             // [nb]
-  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + ((nb + 1) & ~1));   // [kRtWarps][stride]
+  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + ((nb + 3) & ~3));   // [kRtWarps][stride]
   const uint32_t *sk, *sv;
   uint32_t *dk, *dv;
   route_bufs(a, slot, sk, sv, dk, dv);
   uint32_t key[kRtRounds], val[kRtRounds];
   route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
   {
-    uint32_t* z = reinterpret_cast<uint32_t*>(s_cnt);
-    for (int i = tid; i < kRtWarps * stride / 2; i += kRtThreads) z[i] = 0;
+    uint4* z = reinterpret_cast<uint4*>(s_cnt);
+    for (int i = tid; i < kRtWarps * stride / 8; i += kRtThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t* h = a.hist + hist_at(a, f, tile);
     for (int i = tid; i < fp.bins; i += kRtThreads) s_base[i] = h[i];
     if (tid == 0) s_base[fp.bins] = a.tile_inv_base[f * a.NT + tile];
@@ -380,24 +384,40 @@ __global__ void __launch_bounds__(kRtThreads, 2) route_scatter_kernel(const __gr
   uint32_t dr[kRtRounds];   // digit << 16 | rank inside the warp
   const unsigned below = (1u << lane) - 1u;
   const int nbits = digit_bits(fp.bins);
+  const bool wide = fp.bins >= 256;
 #pragma unroll
   for (int r = 0; r < kRtRounds; ++r) {
     const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
-    const unsigned m = match_bits(d, nbits);
-    const uint32_t prev = cnt[d];
+    const uint32_t prev = cnt[d] & kCntMask;
     __syncwarp();
-    if (lane == __ffs(m) - 1) cnt[d] = (uint16_t)(prev + __popc(m));
+    bool dup = true;
+    if (wide) {
+      cnt[d] = (uint16_t)(((uint32_t)lane << 10) | (prev + 1u));
+      __syncwarp();
+      dup = __any_sync(0xffffffffu, (uint32_t)(cnt[d] >> 10) != (uint32_t)lane);
+    }
+    uint32_t rank = prev;
+    if (dup) {
+      const unsigned m = match_bits(d, nbits);
+      if (lane == __ffs(m) - 1) cnt[d] = (uint16_t)(prev + __popc(m));
+      rank += __popc(m & below);
+    }
     __syncwarp();
-    dr[r] = (d << 16) | (prev + __popc(m & below));
+    dr[r] = (d << 16) | rank;
   }
   __syncthreads();
-  for (int b = tid; b < nb; b += kRtThreads) {
-    uint32_t run = 0;
+  // exclusive prefix over the warps, two digits (one 32-bit word) at a time: counts stay below 2^16, no carry between halves
+  {
+    uint32_t* c32 = reinterpret_cast<uint32_t*>(s_cnt);
+    const int words = (nb + 1) / 2, wstride = stride / 2;
+    for (int b = tid; b < words; b += kRtThreads) {
+      uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < kRtWarps; ++w) {
-      const uint32_t c = s_cnt[w * stride + b];
-      s_cnt[w * stride + b] = (uint16_t)run;
-      run += c;
+      for (int w = 0; w < kRtWarps; ++w) {
+        const uint32_t c = c32[w * wstride + b] & (kCntMask | (kCntMask << 16));
+        c32[w * wstride + b] = run;
+        run += c;
+      }
     }
   }
   __syncthreads();
@@ -919,8 +939,8 @@ struct GradSrc {
 };
 
 size_t scatter_smem(int bins) {
-  const int nb = bins + 1, stride = (bins + 3) & ~1;
-  return (size_t)((nb + 1) & ~1) * 4 + (size_t)kRtWarps * stride * 2;
+  const int nb = bins + 1, stride = (bins + 9) & ~7;
+  return (size_t)((nb + 3) & ~3) * 4 + (size_t)kRtWarps * stride * 2;
 }
 
 template <typename IdT>

@@ -45,10 +45,30 @@ for name, fn in (("fwd", lambda: ops.embed_fwd_raw(arena, ids, offs, out=out)),
         ms, n = L.profile_read(kn)
         if n:
             res[name + ":" + kn] = ms / n
+# back to back from a CUDA graph (no host gaps): the whole backward, and the presorted backward (reduce + fixup only)
+def graph_time(fn, reps=20):
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fn(); fn()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(reps):
+                fn()
+        gr.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); gr.replay(); e1.record(st); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+res["bwd_graph"] = graph_time(lambda: ops.embed_bwd_raw(gout, ids, offs, share_sort=False))
+ws = torch.empty(lib.kon_embed_bwd_workspace_bytes(ids.numel(), 32), dtype=torch.uint8, device=dev)
+def sort_only():
+    a, w = L._arg(ids), L._arg(ws)
+    L.check(lib.kon_embed_sort(a.ptr, L.i64_array(offs), 26, w.ptr, torch.cuda.current_stream().cuda_stream), "sort")
+res["sort_graph"] = graph_time(sort_only)
 fwd_bytes = B * 26 * (4 + 2 * k * 4)
 uniq = int(ops.embed_bwd_raw(gout, ids, offs).n.item())
 bwd_bytes = B * 26 * (4 + k * 4) + uniq * (k * 4 + 4)
 print(json.dumps({"ids": "zipf" if zipf else "uniform", "ms": {a: round(b, 4) for a, b in res.items()},
                   "fwd_GBs": fwd_bytes / res["fwd:embed_fwd_vec_kernel"] / 1e6,
                   "bwd_reduce_GBs": bwd_bytes / res["bwd:embed_reduce_kernel"] / 1e6,
-                  "bwd_total_GBs": bwd_bytes / res["bwd"] / 1e6, "unique_rows": uniq}))
+                  "bwd_total_GBs": bwd_bytes / res["bwd"] / 1e6,
+                  "bwd_graph_GBs": bwd_bytes / res["bwd_graph"] / 1e6, "unique_rows": uniq}))
