@@ -853,7 +853,7 @@ def run_gpu(args):
             "bound": "hbm", "launches_per_step": 1.0, "ms_per_launch": ms_iso, "work_per_launch": amount,
             "achieved": amount / (ms_iso * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
             "frac": amount / (ms_iso * 1e-3) / 1e9 / pk["hbm"], "share_of_step": ms_iso / (ms_eager / args.steps),
-            "note": {"embed_bwd": "embed_bwd = routing (keys, radix partition + sort, run heads) + segmented reduce + fixup; "
+            "note": {"embed_bwd": "embed_bwd = routing (per-field counting sort: hist / scan / scatter per pass slot, run heads) + segmented sum + fixup; "
                                   "algorithmic bytes are the all-rows-unique worst case",
                      "embed_bwd_presorted": "the backward's critical path in the training step: segmented reduce + fixup of the "
                                             "embedding AND the first-order gradient in one pass (kon_embed_bwd_pair); the routing "

@@ -61,7 +61,7 @@ enum {
 int         kon_abi_version(void);
 const char* kon_last_error(void);
 /* Number of kernels of THIS library launched by the process so far (every __global__ of
- * libkon_b200 counts once per launch; CUB primitives called by kon_embed_bwd do not). */
+ * libkon_b200 counts once per launch). */
 long long   kon_launch_count(void);
 /* Per-kernel device timing for roofline reports.  While enabled, entry points that launch
  * several kernels (kon_cin_fwd/bwd, kon_embed_fwd/bwd) bracket their main kernels with CUDA
@@ -110,7 +110,7 @@ int kon_embed_bwd(const DLTensor* d_out, const DLTensor* ids, const int64_t* fie
                   int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                   DLTensor* workspace, void* stream);
 
-/* Same as kon_embed_bwd, but skips the key build / radix sort / run-head scan and reuses the sorted
+/* Same as kon_embed_bwd, but skips the routing (per-field counting sort, run-head count) and reuses the sorted
  * (key, position, run id) arrays a previous kon_embed_bwd call left at the front of the SAME
  * `workspace` for the SAME ids and field_row_offset (e.g. the first-order tables after the
  * embedding tables of one step: identical routing, different payload width).  The workspace must be
@@ -119,7 +119,7 @@ int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids, const int64_
                         int32_t n_fields, DLTensor* unique_rows, DLTensor* grads, DLTensor* n_unique,
                         DLTensor* workspace, void* stream);
 
-/* Routing only (key build, radix sort, run-head scan) into the front of `workspace`; the routing depends on
+/* Routing only (per-field counting sort, run-head count) into the front of `workspace`; the routing depends on
  * the ids alone, so a trainer can run it on a side stream at the start of the step and call
  * kon_embed_bwd_reuse (or kon_embed_bwd_peer with reuse_sort = 1) with the same workspace in the backward. */
 int kon_embed_sort(const DLTensor* ids, const int64_t* field_row_offset, int32_t n_fields,

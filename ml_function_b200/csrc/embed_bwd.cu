@@ -10,8 +10,8 @@
 //             of up to 4096 rows, two passes up to 16.7 M rows, three beyond.  A pass is three kernels over all
 //             fields at once -- per-tile digit histograms (route_hist), an in-place exclusive scan in (digit, tile)
 //             order that also places the fields back to back in the output (route_scan), and a scatter whose
-//             in-tile ranks come from warp match + per-warp shared-memory counters (route_scatter: no atomics, the
-//             order inside a digit is the order of the positions => stable => the summation order is fixed).
+//             in-tile ranks come from a vote-based warp match + per-warp shared-memory counters (route_scatter: no
+//             atomics, the order inside a digit is the order of the positions => stable => the summation order is fixed).
 //             Fields with fewer passes join in the last slot(s) and read the ids directly.  Out-of-range ids are
 //             routed behind all valid lookups (count in the header) and never reach the reduction.
 //             route_heads counts the run heads (first lookup of every distinct row) per 32 lookups / per 8192
@@ -495,6 +495,9 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegWin = 8;       // sorted lookups per lane group and chunk = row loads in flight per thread
 constexpr int kSegSpan = 256;    // sorted lookups per warp (its keys / payloads are staged in shared memory at once)
 constexpr int kSegTile = kSegSpan * kSegWarps;
+#ifndef KON_SEG_LIN_MINB
+#define KON_SEG_LIN_MINB 2       // CTAs per SM the fused first-order variant is compiled for
+#endif
 
 struct SegArgs {
   const float* d_out;
@@ -542,7 +545,7 @@ __device__ __forceinline__ float4 f4_shfl(float4 v, int l) {
 }
 
 template <int LPR, bool LIN, bool PEER>
-__global__ void __launch_bounds__(kSegThreads, (LIN || PEER) ? 2 : 3)
+__global__ void __launch_bounds__(kSegThreads, (LIN ? KON_SEG_LIN_MINB : (PEER ? 2 : 3)))
 embed_segsum_kernel(const __grid_constant__ SegArgs a) {
   constexpr int GPW = 32 / LPR;               // lane groups per warp
   constexpr int CHUNK = GPW * kSegWin;        // sorted lookups per warp and chunk

@@ -163,7 +163,7 @@ def _bwd_workspace(ids, field_row_offset, n, dim, dev, share_sort):
     return ws, False
 
 
-# The routing of the backward (keys, radix sort, run-head scan: ~0.14 ms of latency-bound launches for 1.7 M
+# The routing of the backward (per-field counting sort, run-head count: ~0.1 ms of latency-bound launches for 1.7 M
 # lookups) depends on the ids alone.  Inside a training step it is therefore issued at the START of the step on
 # a side stream (kon_embed_sort), overlapped with the forward / interaction kernels; the backward waits on its
 # event and runs only the segmented reduction (kon_embed_bwd_reuse).  KON_PRESORT=0 keeps it in the backward.
