@@ -31,6 +31,7 @@ import os
 # NCCL's version/debug banner goes to stdout by default; stdout carries exactly one JSON line
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
+import re
 import subprocess
 import sys
 import time
@@ -166,6 +167,27 @@ def sample_clocks_stop(proc, f, path, dev_index):
     # "under load": upper half of the samples (the sampler also sees the idle edges)
     load = sm[len(sm) // 2:]
     return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def nvlink_counters(dev_index):
+    """Cumulative NVLink data bytes (tx, rx) of one GPU, summed over its links: `nvidia-smi nvlink -gt d`
+    (the NVML throughput counters; KiB).  None when the tool / counters are not there."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(dev_index)], capture_output=True,
+                             text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = rx = 0
+    seen = False
+    for line in out.splitlines():
+        m = re.search(r"Data (Tx|Rx):\s*(\d+)\s*KiB", line)
+        if m:
+            seen = True
+            if m.group(1) == "Tx":
+                tx += int(m.group(2)) * 1024
+            else:
+                rx += int(m.group(2)) * 1024
+    return (tx, rx) if seen else None
 
 
 # ------------------------------------------------------------------------------------------
@@ -754,7 +776,21 @@ def run_gpu(args):
         elif rank == 0:
             print("CUDA-graph capture failed, staying eager:", trainer.capture_error, file=sys.stderr)
     job.spin_up(step_fn, args.spinup)
+    nvl0 = nvlink_counters(local) if (world > 1 and rank == 0) else None
     win_value = [timed(step_fn, args.steps) for _ in range(args.windows)]
+    nvlink = None
+    if nvl0 is not None:
+        nvl1 = nvlink_counters(local)
+        if nvl1 is not None:
+            n_st = args.steps * args.windows
+            k_emb = model.sparse_embed.dim if hasattr(model.sparse_embed, "dim") else 16
+            frac = (world - 1) / world
+            nvlink = {"source": "nvidia-smi nvlink -gt d (NVML data counters of rank 0's GPU, all links) around the timed windows",
+                      "tx_bytes_per_step": (nvl1[0] - nvl0[0]) / n_st, "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / n_st,
+                      # per GPU and direction: embedding rows out + output-gradient rows back for the (N-1)/N of the
+                      # global batch that lives on other ranks, the 4-byte ids, first-order terms; dense all-reduce apart
+                      "algorithmic_exchange_bytes_per_step_per_direction":
+                          frac * B * 26 * (2 * k_emb * 4 + 4 + 8)}
     ms = median(win_value)
     # ---- end-to-end timing (H2D + step + D2H) ---------------------------------------------
     for i in range(2):
@@ -904,6 +940,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "cuda_graph": graphed, "ms_per_step_eager": ms_eager / args.steps,
         "clocks": clocks,
+        "nvlink": nvlink,
         "roofline": roof,
         "kernel_stats": kstats,
         "op_stats": kernels,
