@@ -12,7 +12,8 @@
 //             order that also places the fields back to back in the output (route_scan), and a scatter whose
 //             in-tile ranks come from a vote-based warp match + per-warp shared-memory counters (route_scatter: no
 //             atomics, the order inside a digit is the order of the positions => stable => the summation order is fixed).
-//             Fields with fewer passes join in the last slot(s) and read the ids directly.  Out-of-range ids are
+//             Every field starts in slot 0 (reading the ids directly) and its last pass writes the final buffers;
+//             later slots only hold the fields with digits left.  Out-of-range ids are
 //             routed behind all valid lookups (count in the header) and never reach the reduction.
 //             route_heads counts the run heads (first lookup of every distinct row) per 32 lookups / per 8192
 //             lookups (exclusive prefixes; the last CTA to finish scans the per-CTA totals), which is all the
@@ -69,14 +70,17 @@ __host__ __device__ inline int bits_for(long long rows) {   // ids of a table wi
 __host__ __device__ inline int passes_for(int bits) {
   return bits <= kRtMaxBits ? 1 : (bits + kRtMaxBits - 1) / kRtMaxBits;
 }
-// A field with P passes runs them in the LAST P of the job's max_p slots, so every field finishes in the last slot.
+// A field with P passes runs them in the FIRST P of the job's max_p slots (its last pass writes the final buffers):
+// every field counts its out-of-range lookups in slot 0, which is all the final layout needs to know of the others,
+// and the later slots only see the fields that still have digits left (slot 1 of the Criteo job: 14 of 26).
 __host__ __device__ inline FieldPass field_pass(long long rows, int slot, int max_p) {
   FieldPass fp;
   const int bits = bits_for(rows);
   const int P = passes_for(bits);
   const int w = (bits + P - 1) / P;
-  const int i = slot - (max_p - P);
-  fp.active = i >= 0;
+  const int i = slot;
+  (void)max_p;
+  fp.active = i < P;
   fp.first = i == 0;
   fp.last = i == P - 1;
   fp.shift = i > 0 ? i * w : 0;
@@ -94,7 +98,8 @@ struct RouteArgs {
   int max_p;
   int hs;               // row stride of `hist` (uint32 words)
   uint32_t sentinel;    // key of an out-of-range lookup (= total rows)
-  uint32_t *tmp_keys, *tmp_vals, *out_keys, *out_vals;
+  uint32_t *tmp_keys, *tmp_vals, *tmp2_keys, *tmp2_vals, *out_keys, *out_vals;
+  unsigned char order[kMaxFields];   // blockIdx.y -> field, widest digits first: the long CTAs of a launch start first
   uint32_t* hist;           // [F][NT][hs]: counts (route_hist) -> destination bases (route_scan), in place
   uint32_t* gsum;           // [F][NT][kRtGroups]: counts summed over groups of kRtGroupBins digits
   uint32_t* tile_inv;       // [F][NT]: out-of-range lookups per tile
@@ -102,14 +107,14 @@ struct RouteArgs {
   RouteHdr* hdr;
 };
 
-// slot s writes the final buffers when an even number of slots follows, else the scratch pair
-__device__ __forceinline__ void route_bufs(const RouteArgs& a, int slot, const uint32_t*& sk, const uint32_t*& sv,
-                                           uint32_t*& dk, uint32_t*& dv) {
-  const bool to_out = ((a.max_p - 1 - slot) & 1) == 0;
-  dk = to_out ? a.out_keys : a.tmp_keys;
-  dv = to_out ? a.out_vals : a.tmp_vals;
-  sk = to_out ? a.tmp_keys : a.out_keys;
-  sv = to_out ? a.tmp_vals : a.out_vals;
+// the last pass of a field writes the final buffers, the others ping-pong between the two scratch pairs
+__device__ __forceinline__ void route_bufs(const RouteArgs& a, const FieldPass& fp, int slot, const uint32_t*& sk,
+                                           const uint32_t*& sv, uint32_t*& dk, uint32_t*& dv) {
+  const bool even = (slot & 1) == 0;
+  dk = fp.last ? a.out_keys : (even ? a.tmp_keys : a.tmp2_keys);
+  dv = fp.last ? a.out_vals : (even ? a.tmp_vals : a.tmp2_vals);
+  sk = even ? a.tmp2_keys : a.tmp_keys;      // written by slot - 1
+  sv = even ? a.tmp2_vals : a.tmp_vals;
 }
 
 // (key, payload) of the kRtRounds items of a thread.  First pass of a field: straight from the ids ([B,F,L], the
@@ -199,7 +204,7 @@ __device__ __forceinline__ int digit_bits(int bins) {   // digits run over [0, b
 template <typename IdT>
 __global__ void __launch_bounds__(kRtThreads) route_hist_kernel(const __grid_constant__ RouteArgs a, int slot) {
   extern __shared__ uint32_t s_hist[];   // [bins + 2]
-  const int f = blockIdx.y, tile = blockIdx.x;
+  const int f = a.order[blockIdx.y], tile = blockIdx.x;
   const long long off = a.ft.off[f], rows = a.ft.off[f + 1] - off;
   const FieldPass fp = field_pass(rows, slot, a.max_p);
   if (!fp.active) return;
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(kRtThreads) route_hist_kernel(const __grid_con
   for (int i = tid; i < fp.bins + 2; i += kRtThreads) s_hist[i] = 0;
   const uint32_t *sk, *sv;
   uint32_t *dk, *dv;
-  route_bufs(a, slot, sk, sv, dk, dv);
+  route_bufs(a, fp, slot, sk, sv, dk, dv);
   uint32_t key[kRtRounds], val[kRtRounds];
   route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
   __syncthreads();
@@ -265,16 +270,16 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long* s_w
 constexpr int kScanChunk = 16;   // tiles of one digit loaded at once
 __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_constant__ RouteArgs a, int slot) {
   __shared__ long long s_warp[32];
-  const int f = blockIdx.y, grp = blockIdx.x;
+  const int f = a.order[blockIdx.y], grp = blockIdx.x;
   const long long rows = a.ft.off[f + 1] - a.ft.off[f];
   const FieldPass fp = field_pass(rows, slot, a.max_p);
   if (!fp.active || grp * kRtGroupBins >= fp.bins) return;
-  const bool fin = slot == a.max_p - 1;
+  const bool fin = fp.last;
   const int t = threadIdx.x;
   long long inv_before = 0, inv_all = 0, inv_mine = 0, before = 0;
   {
     long long lb = 0, la = 0, lm = 0, lg = 0;
-    if (fin) {
+    if (fin || slot == 0) {
       const int tot = a.F * a.NT;
       for (int i = t; i < tot; i += kScanThreads) {
         const int g = i / a.NT;
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_c
     if (on) a.tile_inv_base[f * a.NT + t0 + t] = (uint32_t)(carry + ex);
     carry += total;
   }
-  if (fin && f == 0 && t == 0) {
+  if (slot == 0 && f == 0 && t == 0) {      // every field is active in slot 0 and has counted its out-of-range lookups
     a.hdr->n_valid = (int)(n_all - inv_all);
     a.hdr->ticket = 0;
   }
@@ -358,7 +363,7 @@ constexpr uint32_t kCntMask = 0x3ffu;
 template <typename IdT>
 __global__ void __launch_bounds__(kRtThreads, 2) route_scatter_kernel(const __grid_constant__ RouteArgs a, int slot) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
-  const int f = blockIdx.y, tile = blockIdx.x;
+  const int f = a.order[blockIdx.y], tile = blockIdx.x;
   const long long off = a.ft.off[f], rows = a.ft.off[f + 1] - off;
   const FieldPass fp = field_pass(rows, slot, a.max_p);
   if (!fp.active) return;
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) route_scatter_kernel(const __gr
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + ((nb + 3) & ~3));   // [kRtWarps][stride]
   const uint32_t *sk, *sv;
   uint32_t *dk, *dv;
-  route_bufs(a, slot, sk, sv, dk, dv);
+  route_bufs(a, fp, slot, sk, sv, dk, dv);
   uint32_t key[kRtRounds], val[kRtRounds];
   route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
   {
@@ -880,7 +885,7 @@ unpad1_kernel(const float4* __restrict__ src, const int* __restrict__ n_unique, 
 // Everything the routing produces comes first and depends on n alone, so the first-order tables (and, sharded,
 // the peer backward) reuse one routing whatever their row width.
 struct BwdLayout {
-  size_t hdr, tmp_keys, tmp_vals, out_keys, out_vals, blk_base, cta_tot, cta_base, hist, gsum, tile_inv, tile_inv_base;
+  size_t hdr, tmp_keys, tmp_vals, tmp2_keys, tmp2_vals, out_keys, out_vals, blk_base, cta_tot, cta_base, hist, gsum, tile_inv, tile_inv_base;
   size_t cta_head, cta_tail, cta_meta, cta_tid, cta_tkey, cta_lin, total;
   int n_cta, n_heads_cta, hist_rows;
   int lpr, vpr;
@@ -907,6 +912,8 @@ int bwd_layout(int64_t n, int32_t dim, BwdLayout* l) {
   l->hdr = take(sizeof(RouteHdr));
   l->tmp_keys = take(n32 * 4);
   l->tmp_vals = take(n32 * 4);
+  l->tmp2_keys = take(n32 * 4);     // second scratch pair: only tables with more than 2^24 rows (3 passes) use it
+  l->tmp2_vals = take(n32 * 4);
   l->out_keys = take(n32 * 4);
   l->out_vals = take(n32 * 4);
   l->blk_base = take((size_t)l->n_heads_cta * 256 * 4);
@@ -1033,6 +1040,8 @@ int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field
     ra.sentinel = (uint32_t)total_rows;
     ra.tmp_keys = (uint32_t*)(ws + l.tmp_keys);
     ra.tmp_vals = (uint32_t*)(ws + l.tmp_vals);
+    ra.tmp2_keys = (uint32_t*)(ws + l.tmp2_keys);
+    ra.tmp2_vals = (uint32_t*)(ws + l.tmp2_vals);
     ra.out_keys = keys_out;
     ra.out_vals = vals_out;
     ra.hist = (uint32_t*)(ws + l.hist);
@@ -1043,6 +1052,14 @@ int embed_bwd_core(const GradSrc& src, const DLTensor* ids, const int64_t* field
     int max_p = 1;
     for (int f = 0; f < n_fields; ++f) max_p = std::max(max_p, passes_for(bits_for(ft.off[f + 1] - ft.off[f])));
     ra.max_p = max_p;
+    {
+      int idx[kMaxFields];
+      for (int f = 0; f < n_fields; ++f) idx[f] = f;
+      std::stable_sort(idx, idx + n_fields, [&](int x, int y) {
+        return bits_for(ft.off[x + 1] - ft.off[x]) > bits_for(ft.off[y + 1] - ft.off[y]);
+      });
+      for (int f = 0; f < n_fields; ++f) ra.order[f] = (unsigned char)idx[f];
+    }
     int slot_bins[8] = {0};
     int hs = 2;
     for (int slot = 0; slot < max_p; ++slot)
