@@ -358,7 +358,11 @@ __global__ void __launch_bounds__(kScanThreads) route_scan_kernel(const __grid_c
 // to the warp) + (matching lanes below it).  Then: exclusive prefix over the warps per digit, + the tile's base.
 // A counter holds count (10 bits) | lane tag (5 bits): every lane bumps its digit's counter tagged with its lane id
 // and reads it back -- if every lane finds its own tag the 32 digits of the round are distinct (88 % of the rounds of
-// a 4096-digit pass) and the vote-based match is skipped.
+// a 4096-digit pass) and the vote-based match is skipped.  Lanes with EQUAL digits store different tags to one
+// address in one instruction on purpose: "which thread performs the final write is undefined", but exactly one of
+// the stores lands (CUDA C++ Programming Guide, shared-memory write conflicts within a warp), which is all the
+// read-back test needs -- the counter is then rewritten by the leader of the match.  compute-sanitizer racecheck
+// reports these (and only these) accesses; memcheck and synccheck are clean (tools/sanitize_embed_bwd.sh).
 constexpr uint32_t kCntMask = 0x3ffu;
 template <typename IdT>
 __global__ void __launch_bounds__(kRtThreads, 2) route_scatter_kernel(const __grid_constant__ RouteArgs a, int slot) {

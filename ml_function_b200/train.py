@@ -52,8 +52,48 @@ class SparseAdam:
         self.arena.kon_sparse_grads = []
 
 
+class KerasAdam:
+    """``compile(optimizer='adam')`` exactly as Keras 2.x applies it -- the reference's optimizer, for parity runs:
+
+        m <- b1 m + (1-b1) g,  v <- b2 v + (1-b2) g^2,  w <- w - lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
+
+    on EVERY element of every weight at every step (Keras turns the IndexedSlices gradient of an Embedding into a dense
+    update: rows a step does not touch still get the m / v decay, the dense ``2 l2 w`` regulariser term (IL:217) and a
+    weight update).  For an embedding arena that is three full passes over the table per step, which is why the
+    default is the row-wise lazy kernel (``SparseAdam``); trained weights of the two modes drift apart on rows that
+    are not touched every step.  torch ops on the device (not CUDA-graph capturable: the step count lives on the host)."""
+
+    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.state = {}
+        self.t = 0
+
+    def begin_step(self):
+        self.t += 1
+
+    def apply(self, w: torch.Tensor, g: torch.Tensor):
+        key = (w.data_ptr(), tuple(w.shape))        # `p.data` is a fresh Python object on every access
+        st = self.state.get(key)
+        if st is None:
+            st = self.state[key] = (torch.zeros_like(w), torch.zeros_like(w))
+        m, v = st
+        m.mul_(self.beta1).add_(g, alpha=1.0 - self.beta1)
+        v.mul_(self.beta2).addcmul_(g, g, value=1.0 - self.beta2)
+        lr_t = self.lr * (1.0 - self.beta2 ** self.t) ** 0.5 / (1.0 - self.beta1 ** self.t)
+        w.addcdiv_(m, v.sqrt().add_(self.eps), value=-lr_t)
+
+
 class Trainer:
-    def __init__(self, model, lr: float = 1e-3, dist_ctx=None):
+    def __init__(self, model, lr: float = 1e-3, dist_ctx=None, optimizer: str = "lazy"):
+        """``optimizer``: "lazy" (default) = torch fused Adam on the dense weights + row-wise lazy Adam with a lazy L2
+        term on the embedding arenas; "keras" = the reference's own dense Adam on everything (``KerasAdam``; single
+        GPU, eager steps only)."""
+        if optimizer not in ("lazy", "keras"):
+            raise ValueError("optimizer must be 'lazy' or 'keras'")
+        if optimizer == "keras" and dist_ctx is not None:
+            raise ValueError("optimizer='keras' is the single-GPU parity mode")
+        self.optimizer = optimizer
+        self.keras_opt = KerasAdam(lr=lr) if optimizer == "keras" else None
         self.model = model
         self.dist = dist_ctx
         dense = model.dense_parameters()
@@ -88,6 +128,24 @@ class Trainer:
             self.dense_opt = torch.optim.Adam(self._dense_params, lr=self.lr, eps=1e-7, fused=True,
                                               capturable=True)
 
+    def _keras_step(self):
+        """The reference's optimizer step: dense Adam on every weight, the embedding gradients densified and the
+        regulariser's dense ``2 l2 w`` added (Keras adds ``l2 * sum(w^2)`` to the loss, IL:217)."""
+        ko = self.keras_opt
+        ko.begin_step()
+        for p in self._dense_params:
+            if p.grad is not None:
+                ko.apply(p.data, p.grad)
+        for so in self.sparse_opts:
+            w = so.arena.data
+            g = torch.zeros_like(w)
+            for sg in getattr(so.arena, "kon_sparse_grads", None) or []:
+                g += sg.to_dense(w.shape[0])
+            if so.l2:
+                g.add_(w, alpha=2.0 * so.l2)
+            ko.apply(w, g)
+            so.arena.kon_sparse_grads = []
+
     def loss(self, dense, ids, labels):
         out = self.model(dense, ids)
         return ops.binary_crossentropy(labels, out)        # compile(loss=binary_crossentropy), fused (kon_bce_fwd/bwd)
@@ -112,6 +170,10 @@ class Trainer:
                 so.step()
             self.dist.finish_allreduce(self.model, self._dense_params)
             self.dense_opt.step()
+        elif self.keras_opt is not None:
+            loss.backward()
+            ops.flush_deferred()
+            self._keras_step()
         else:
             loss.backward()
             ops.flush_deferred()                # a first-order gradient parked for an embedding backward that never came
@@ -132,6 +194,9 @@ class Trainer:
         """Capture ``step`` for this batch shape; afterwards ``step_graph`` copies a batch into the
         static buffers and replays.  Returns False (and stays eager) if the capture fails."""
         self._g = None
+        if self.keras_opt is not None:
+            self.capture_error = "optimizer='keras' keeps its step count on the host: eager steps only"
+            return False
         self._static = tuple(t.clone() for t in (dense, ids, labels))
         try:
             side = torch.cuda.Stream()

@@ -275,3 +275,65 @@ def test_dcn_alignment_columns_stay_inert_through_training():
     assert torch.count_nonzero(model.cross.bias.detach()[:, nv:]) == 0
     assert torch.count_nonzero(model.cross.kernel.detach()[:, nv:]) == 0
     assert torch.count_nonzero(model.cross.bias.detach()[:, :nv]) > 0
+
+
+def test_keras_optimizer_mode_matches_the_reference_update_over_several_steps():
+    """``Trainer(optimizer="keras")``: the reference's own ``compile(optimizer='adam')`` -- dense Adam on EVERY row of
+    the embedding tables incl. the regulariser's dense ``2 l2 w`` term (IL:217) -- against an fp64 restatement of the
+    Keras update rule over three steps on different batches.  The default (row-wise lazy) mode provably differs:
+    rows no batch touches stay put there, and move here."""
+    from ml_function_b200.train import Trainer
+    g = gen(77)
+    rows = [7, 300, 5, 41, 2, 1000]
+    B, k, steps, lr, l2 = 96, 8, 3, 1e-3, 1e-8
+    p = _params("deepfm", rows, k, g)
+    batches = []
+    for _ in range(steps):
+        ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32)
+        y = (torch.rand(B, generator=g) < 0.3).float()
+        batches.append((torch.rand(B, 13, generator=g), ids, torch.stack([1 - y, y], 1)))
+    # fp64 truth: autograd over the oracle's DeepFM + the Keras Adam formulas on every weight
+    w = {n: v.double().clone().requires_grad_(True) for n, v in p.items()}
+    m = {n: torch.zeros_like(v) for n, v in w.items()}
+    vv = {n: torch.zeros_like(v) for n, v in w.items()}
+    b1, b2, eps = 0.9, 0.999, 1e-7
+    for t, (dense, ids, labels) in enumerate(batches, 1):
+        loss = ko.binary_crossentropy(labels.double(), ko.model_deepfm(w, dense.double(), ids))
+        grads = torch.autograd.grad(loss, list(w.values()), allow_unused=True)
+        lr_t = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        with torch.no_grad():
+            for (n, wt), gr in zip(w.items(), grads):
+                gr = torch.zeros_like(wt) if gr is None else gr.clone()
+                if n.startswith("emb_"):
+                    gr += 2 * l2 * wt
+                m[n].mul_(b1).add_(gr, alpha=1 - b1)
+                vv[n].mul_(b2).addcmul_(gr, gr, value=1 - b2)
+                wt -= lr_t * m[n] / (vv[n].sqrt() + eps)
+    model = _build("deepfm", rows, k, p)
+    tr = Trainer(model, lr=lr, optimizer="keras")
+    for dense, ids, labels in batches:
+        tr.step(dense.to(DEV), ids.to(DEV), labels.to(DEV))
+    assert tr.capture(*[t.to(DEV) for t in batches[0]]) is False        # host-side step count: eager only
+    off = offsets(rows)
+    arena, lin = model.sparse_embed.arena.detach().cpu().double(), model.linear_embed.arena.detach().cpu().double()
+    tol = 2e-5
+    for f in range(len(rows)):
+        assert (arena[off[f]:off[f + 1]] - w[f"emb_{f}"].detach()).abs().max() < tol, f
+        assert (lin[off[f]:off[f + 1]] - w[f"lin_{f}"].detach()).abs().max() < tol, f
+    k0 = model.phys_to_ref_rows(model.dnn.kernels[0].detach()).cpu().double()
+    assert (k0 - w["dnn_w0"].detach()).abs().max() < tol
+    for i in (1, 2):
+        assert (model.dnn.kernels[i].detach().cpu().double() - w[f"dnn_w{i}"].detach()).abs().max() < tol
+    for i in range(3):
+        assert (model.dnn.biases[i].detach().cpu().double() - w[f"dnn_b{i}"].detach()).abs().max() < tol
+    # a row of the 1000-row table that no batch looked up: moved by the dense regulariser / Adam here ...
+    seen = torch.cat([b[1][:, 5] for b in batches]).unique()
+    untouched = next(r for r in range(1000) if r not in set(seen.tolist()))
+    moved = (arena[off[5] + untouched] - p["emb_5"][untouched].double()).abs().max()
+    assert moved > 1e-7
+    # ... and left alone by the default lazy mode
+    lazy = _build("deepfm", rows, k, p)
+    tl = Trainer(lazy, lr=lr)
+    for dense, ids, labels in batches:
+        tl.step(dense.to(DEV), ids.to(DEV), labels.to(DEV))
+    assert torch.equal(lazy.sparse_embed.arena.detach().cpu()[off[5] + untouched], p["emb_5"][untouched])
