@@ -682,12 +682,34 @@ def run_gpu(args):
     stage = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
+    # end to end: every step moves its batch host -> device (pinned memory) and reads the loss back.  The copies are
+    # double-buffered on a copy stream, like the reference's dataset.prefetch(2) (DP:335-337): while step i runs, the
+    # batch of step i + 1 is already on its way; one batch is copied per step inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    staged = [None, None]          # which host batch sits (or is arriving) in stage[s]
+
+    def prefetch(i):
+        s = i % 2
+        copy_stream.wait_event(ev_free[s])               # the step that last read stage[s] is done with it
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(stage[s], host[i % len(host)]):
+                dst.copy_(src, non_blocking=True)
+            ev_copied[s].record(copy_stream)
+        staged[s] = i % len(host)
+
     def step_e2e(i):
-        hb = host[i % len(host)]
-        st = stage[i % 2]
-        for dst, src in zip(st, hb):
-            dst.copy_(src, non_blocking=True)
-        loss = trainer.step_graph(*st)
+        s = i % 2
+        if staged[s] != i % len(host):
+            prefetch(i)
+        if args.e2e_prefetch:
+            prefetch(i + 1)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev_copied[s])
+        loss = trainer.step_graph(*stage[s])
+        ev_free[s].record(cur)
+        staged[s] = None                                  # consumed
         loss_host.copy_(loss.view(1), non_blocking=True)
 
     for i in range(max(args.warmup, 3)):
@@ -935,6 +957,8 @@ def run_gpu(args):
                           f"steps and {args.spinup} s of untimed steps (clock ramp of ranks that idled during capture / verify)",
                 "parallelism": parallelism, "embedding_exchange": exchange},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "h2d": ("double-buffered on a copy stream: the batch of step i+1 is copied while step i runs "
+                        "(the reference's dataset.prefetch(2), DP:335-337)" if args.e2e_prefetch else "on the compute stream"),
                 "ms_per_step": ms_e2e / args.steps, "windows_ms_per_step": [w / args.steps for w in win_e2e]},
         "windows_ms_per_step": [w / args.steps for w in win_value],
         "gpu_launches": int(launches),
@@ -980,6 +1004,8 @@ def main():
     ap.add_argument("--cin-precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "f32", "tf32"])
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--no-e2e-prefetch", dest="e2e_prefetch", action="store_false",
+                    help="end-to-end steps copy their batch on the compute stream (no overlap with the previous step)")
     ap.add_argument("--n-batches", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
