@@ -217,8 +217,16 @@ __global__ void __launch_bounds__(kRtThreads) route_hist_kernel(const __grid_con
   route_load<IdT>(a, fp, f, off, rows, sk, sv, (long long)tile * kRtTile + warp * kRtWarpItems, lane, key, val);
   __syncthreads();
   if (fp.bins >= 64) {     // mostly distinct digits in a warp: one shared-memory atomic per lookup
+    // out-of-range lookups are counted by vote: row-wise shards hand in 1 - 1/N of their ids as "not mine", which
+    // would be that many atomics on ONE address
+    uint32_t n_inv = 0;
 #pragma unroll
-    for (int r = 0; r < kRtRounds; ++r) atomicAdd(&s_hist[route_digit(key[r], fp, off, a.sentinel)], 1u);
+    for (int r = 0; r < kRtRounds; ++r) {
+      const uint32_t d = route_digit(key[r], fp, off, a.sentinel);
+      n_inv += __popc(__ballot_sync(0xffffffffu, d == (uint32_t)fp.bins));
+      if (d < (uint32_t)fp.bins) atomicAdd(&s_hist[d], 1u);
+    }
+    if (lane == 0 && n_inv) atomicAdd(&s_hist[fp.bins], n_inv);
   } else {                 // few digits, long runs of equal ones: one atomic per distinct digit of the warp
     const int nbits = digit_bits(fp.bins);
 #pragma unroll
