@@ -229,6 +229,10 @@ int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers, int64_t r
 int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out, void* stream);
 /* dv[b,f,:] = g[b,:] * (S[b,:] - v[b,f,:]);  dlin[b,f] = sum_k g[b,k]  (dlin [B,Fl] or NULL) */
 int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin, void* stream);
+/* Same, but dv += ...: `dv` already holds another consumer's gradient of the same buffer (DeepFM: the first Dense
+ * layer's input gradient, CL:190, of the concat buffer the FM window is cut from), so the `Add` autograd would run
+ * over two [B, 13+F*k] tensors is folded into this pass.  dlin is written, not accumulated. */
+int kon_fm_bwd_acc(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin, void* stream);
 
 /* ============================ a7: DCN cross ====================================== */
 /* Replaces CrossLayer.call (IL:275-282): x_{l+1} = x0 * (x_l . w_l) + x_l + b_l.
@@ -239,6 +243,11 @@ int kon_cross_fwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b, DLTe
                   DLTensor* s, void* stream);
 size_t kon_cross_bwd_workspace_bytes(int64_t batch, int32_t dim, int32_t layers, int device_id);
 int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b, const DLTensor* s,
+                  const DLTensor* g, DLTensor* dx0, DLTensor* dw, DLTensor* db,
+                  DLTensor* workspace, void* stream);
+/* Same, but dx0 += ...: `dx0` already holds another consumer's gradient of x0 (DCN: the first Dense layer's input
+ * gradient of the concat buffer both branches read, MD:98-101); dw / db are written as usual. */
+int kon_cross_bwd_acc(const DLTensor* x0, const DLTensor* w, const DLTensor* b, const DLTensor* s,
                   const DLTensor* g, DLTensor* dx0, DLTensor* dw, DLTensor* db,
                   DLTensor* workspace, void* stream);
 

@@ -157,9 +157,11 @@ def lib():
         "kon_embed_bwd_peer": (ctypes.c_int, [ctypes.POINTER(vp), i32, i64, i64, i64, i32, T, i64p, i32, T, T, T, T, i32, vp]),
         "kon_fm_fwd": (ctypes.c_int, [T, T, T, vp]),
         "kon_fm_bwd": (ctypes.c_int, [T, T, T, T, vp]),
+        "kon_fm_bwd_acc": (ctypes.c_int, [T, T, T, T, vp]),
         "kon_cross_fwd": (ctypes.c_int, [T, T, T, T, T, vp]),
         "kon_cross_bwd_workspace_bytes": (sz, [i64, i32, i32, ctypes.c_int]),
         "kon_cross_bwd": (ctypes.c_int, [T] * 9 + [vp]),
+        "kon_cross_bwd_acc": (ctypes.c_int, [T] * 9 + [vp]),
         "kon_cin_saved_bytes": (sz, [i64, i32, i32, i32p, i32, i32]),
         "kon_cin_workspace_bytes": (sz, [i64, i32, i32, i32p, i32, i32, ctypes.c_int]),
         "kon_cin_fwd": (ctypes.c_int, [T, TT, TT, i32, T, T, T, i32, vp]),
@@ -196,7 +198,8 @@ EXPORTED_SYMBOLS = (
     "kon_embed_adam_devstep",
     "kon_peer_alloc", "kon_peer_open", "kon_peer_close", "kon_peer_free", "kon_peer_barrier", "kon_peer_put2d",
     "kon_embed_fwd_peer", "kon_embed_fwd_peer_cols", "kon_embed_bwd_peer",
-    "kon_fm_fwd", "kon_fm_bwd", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
+    "kon_fm_fwd", "kon_fm_bwd", "kon_fm_bwd_acc", "kon_cross_fwd", "kon_cross_bwd_workspace_bytes", "kon_cross_bwd",
+    "kon_cross_bwd_acc",
     "kon_cin_saved_bytes", "kon_cin_workspace_bytes", "kon_cin_fwd", "kon_cin_bwd",
     "kon_attn_fwd", "kon_attn_bwd_workspace_bytes", "kon_attn_bwd",
     "kon_head_fwd", "kon_head_bwd_workspace_bytes", "kon_head_bwd",

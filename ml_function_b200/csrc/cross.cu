@@ -58,6 +58,17 @@ __device__ __forceinline__ void cross_store4(float* __restrict__ p, bool vec, in
   }
 }
 
+// 4 columns of a row this kernel also writes (no read-only path)
+__device__ __forceinline__ float4 cross_load4_rw(const float* p, bool vec, int D, int d0) {
+  if (vec && d0 + 3 < D) return *reinterpret_cast<const float4*>(p + d0);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (d0 < D) v.x = p[d0];
+  if (d0 + 1 < D) v.y = p[d0 + 1];
+  if (d0 + 2 < D) v.z = p[d0 + 2];
+  if (d0 + 3 < D) v.w = p[d0 + 3];
+  return v;
+}
+
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc);
   acc = fmaf(a.y, b.y, acc);
@@ -177,7 +188,8 @@ __global__ void __launch_bounds__(kCrossThreads, 2)
 cross_bwd_kernel(const float* __restrict__ x0, long long xs, const float* __restrict__ w,
                  const float* __restrict__ s, const float* __restrict__ g, long long gs,
                  float* __restrict__ dx0, float* __restrict__ u, float* __restrict__ partial_cg,
-                 float* __restrict__ partial_T, long long B, int D, int L, int vec_x, int vec_g, int vec_dx) {
+                 float* __restrict__ partial_T, long long B, int D, int L, int vec_x, int vec_g, int vec_dx,
+                 int acc_dx) {
   constexpr int Dp = NJ * 128;
   extern __shared__ __align__(16) float smem[];
   float* w_s = smem;                    // [L][Dp]
@@ -242,10 +254,17 @@ cross_bwd_kernel(const float* __restrict__ x0, long long xs, const float* __rest
     // dx0 = c_L g + sum_l u_l w_l
     const float cL = cl[kCrossMaxL];
     float* dp = dx0 + r * (long long)D;
+    if (acc_dx) {        // dx0 already holds another consumer's gradient of x0 (kon_cross_bwd_acc): all of the row's
+#pragma unroll           // loads in flight at once, in the registers x0 no longer needs
+      for (int j = 0; j < NJ; ++j) x[j] = cross_load4_rw(dp, vec_dx != 0, D, 128 * j + 4 * lane);
+    }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int d0 = 128 * j + 4 * lane;
       float4 o = make_float4(cL * G[j].x, cL * G[j].y, cL * G[j].z, cL * G[j].w);
+      if (acc_dx) {
+        o.x += x[j].x; o.y += x[j].y; o.z += x[j].z; o.w += x[j].w;
+      }
 #pragma unroll
       for (int l = 0; l < kCrossMaxL; ++l) {
         if (l < L) {
@@ -523,9 +542,9 @@ extern "C" size_t kon_cross_bwd_workspace_bytes(int64_t batch, int32_t dim, int3
   return cross_ws_layout(batch, dim, layers, sm_count_of(device_id)).total;
 }
 
-extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
-                             const DLTensor* s, const DLTensor* g, DLTensor* dx0, DLTensor* dw,
-                             DLTensor* db, DLTensor* workspace, void* stream) {
+static int cross_bwd_impl(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
+                          const DLTensor* s, const DLTensor* g, DLTensor* dx0, DLTensor* dw,
+                          DLTensor* db, DLTensor* workspace, int acc_dx, void* stream) {
   int64_t B, D, L;
   KON_TRY(cross_check(x0, w, b, &B, &D, &L));
   const int dev = x0->device.device_id;
@@ -573,7 +592,7 @@ extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTens
   cross_bwd_kernel<N><<<g1, kCrossThreads, smem, st>>>(                                          \
       data_ptr<float>(x0), stride_of(x0, 0), data_ptr<float>(w), data_ptr<float>(s),             \
       data_ptr<float>(g), stride_of(g, 0), data_ptr<float>(dx0), u, pcg, pt, B, (int)D, (int)L,  \
-      vx, vg, vdx)
+      vx, vg, vdx, acc_dx)
   KON_CROSS_DISPATCH(D, CALL);
 #undef CALL
   KON_LAUNCH_CHECK("cross_bwd_kernel");
@@ -588,4 +607,16 @@ extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTens
                                                                     (int)D, (int)L);
   KON_LAUNCH_CHECK("cross_bwd_finalize_kernel");
   return KON_OK;
+}
+
+extern "C" int kon_cross_bwd(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
+                             const DLTensor* s, const DLTensor* g, DLTensor* dx0, DLTensor* dw,
+                             DLTensor* db, DLTensor* workspace, void* stream) {
+  return cross_bwd_impl(x0, w, b, s, g, dx0, dw, db, workspace, 0, stream);
+}
+
+extern "C" int kon_cross_bwd_acc(const DLTensor* x0, const DLTensor* w, const DLTensor* b,
+                                 const DLTensor* s, const DLTensor* g, DLTensor* dx0, DLTensor* dw,
+                                 DLTensor* db, DLTensor* workspace, void* stream) {
+  return cross_bwd_impl(x0, w, b, s, g, dx0, dw, db, workspace, 1, stream);
 }

@@ -22,6 +22,7 @@ struct Vec<4> {
   float4 v;
   __device__ static Vec zero() { return {make_float4(0.f, 0.f, 0.f, 0.f)}; }
   __device__ static Vec load(const float* p) { return {__ldg(reinterpret_cast<const float4*>(p))}; }
+  __device__ static Vec load_rw(const float* p) { return {*reinterpret_cast<const float4*>(p)}; }   // memory this kernel also writes
   __device__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
   __device__ void fma(const Vec& a, const Vec& b) {
     v.x = fmaf(a.v.x, b.v.x, v.x); v.y = fmaf(a.v.y, b.v.y, v.y);
@@ -41,6 +42,7 @@ struct Vec<1> {
   float v;
   __device__ static Vec zero() { return {0.f}; }
   __device__ static Vec load(const float* p) { return {__ldg(p)}; }
+  __device__ static Vec load_rw(const float* p) { return {*p}; }
   __device__ void store(float* p) const { *p = v; }
   __device__ void fma(const Vec& a, const Vec& b) { v = fmaf(a.v, b.v, v); }
   __device__ void add(const Vec& a) { v += a.v; }
@@ -82,7 +84,9 @@ fm_fwd_kernel(const float* __restrict__ v, long long sb, long long sf, const flo
 
 // One thread per (sample, chunk); threads of one sample are adjacent lanes (cpr is a power
 // of two <= 32 on this path) so dlin's sum over k finishes with shuffles.
-template <int V>
+// ACC: dv += ... -- the gradient lands in a buffer that already holds another consumer's gradient of the same
+// concat buffer (the first MLP layer's input gradient), instead of autograd summing two [B,W] tensors afterwards.
+template <int V, bool ACC>
 __global__ void __launch_bounds__(256)
 fm_bwd_kernel(const float* __restrict__ v, long long sb, long long sf, const float* __restrict__ g,
               float* __restrict__ dv, long long dsb, long long dsf, float* __restrict__ dlin,
@@ -108,13 +112,19 @@ fm_bwd_kernel(const float* __restrict__ v, long long sb, long long sf, const flo
       }
       float* dbase = dv + b * dsb + c * V;
       for (int f0 = 0; f0 < F; f0 += 8) {   // second read of v hits L1/L2
-        Vec<V> r[8];
+        Vec<V> r[8], o[ACC ? 8 : 1];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 8; ++u) {
           r[u] = (f0 + u < F) ? Vec<V>::load(base + (long long)(f0 + u) * sf) : Vec<V>::zero();
+          if (ACC) o[u] = (f0 + u < F) ? Vec<V>::load_rw(dbase + (long long)(f0 + u) * dsf) : Vec<V>::zero();
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (f0 + u < F) Vec<V>::gsub(gv, S, r[u]).store(dbase + (long long)(f0 + u) * dsf);
+          if (f0 + u < F) {
+            Vec<V> d = Vec<V>::gsub(gv, S, r[u]);
+            if (ACC) d.add(o[u]);
+            d.store(dbase + (long long)(f0 + u) * dsf);
+          }
       }
     }
     if (dlin) {
@@ -188,8 +198,8 @@ extern "C" int kon_fm_fwd(const DLTensor* v, const DLTensor* lin, DLTensor* out,
   return KON_OK;
 }
 
-extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin,
-                          void* stream) {
+static int fm_bwd_impl(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin, bool acc,
+                       void* stream) {
   KON_TRY(fm_check_v(v, "v", -1));
   const int dev = v->device.device_id;
   const int64_t B = v->shape[0], F = v->shape[1], k = v->shape[2];
@@ -227,8 +237,12 @@ extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DL
     const int cpr = (int)(k / 4), cpr_pad = pow2_ge_i(cpr);
     const long long total = B * cpr_pad;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
-    fm_bwd_kernel<4><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
-                                           (int)F, cpr, cpr_pad);
+    if (acc)
+      fm_bwd_kernel<4, true><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
+                                                   (int)F, cpr, cpr_pad);
+    else
+      fm_bwd_kernel<4, false><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
+                                                    (int)F, cpr, cpr_pad);
   } else {
     KON_REQUIRE(k <= 32, KON_EUNSUPPORTED,
                 "FM backward needs k %% 4 == 0 (16-B aligned rows) or k <= 32; got k=%lld",
@@ -236,9 +250,23 @@ extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DL
     const int cpr = (int)k, cpr_pad = pow2_ge_i(cpr);
     const long long total = B * cpr_pad;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
-    fm_bwd_kernel<1><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
-                                           (int)F, cpr, cpr_pad);
+    if (acc)
+      fm_bwd_kernel<1, true><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
+                                                   (int)F, cpr, cpr_pad);
+    else
+      fm_bwd_kernel<1, false><<<grid, 256, 0, st>>>(vp, sb, sf, gp, dvp, dsb, dsf, dlp, dlsb, dlsf, Fl, B,
+                                                    (int)F, cpr, cpr_pad);
   }
   KON_LAUNCH_CHECK("fm_bwd_kernel");
   return KON_OK;
+}
+
+extern "C" int kon_fm_bwd(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin,
+                          void* stream) {
+  return fm_bwd_impl(v, g, dv, dlin, false, stream);
+}
+
+extern "C" int kon_fm_bwd_acc(const DLTensor* v, const DLTensor* g, DLTensor* dv, DLTensor* dlin,
+                              void* stream) {
+  return fm_bwd_impl(v, g, dv, dlin, true, stream);
 }

@@ -578,6 +578,7 @@ class _DenseFn(torch.autograd.Function):
         y = _bias_act_gemm(x, w, b, relu)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.relu = relu
+        ctx.x_key = ops.xgrad_key(x)
         return y
 
     @staticmethod
@@ -587,6 +588,7 @@ class _DenseFn(torch.autograd.Function):
         if ctx.relu:
             g = _relu_grad(g, y)
         gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        ops.offer_xgrad(ctx.x_key, gx)      # a later branch on the same input adds its gradient into gx (ops._XGRAD)
         gw = x.t() @ g if ctx.needs_input_grad[1] else None
         gb = None
         if ctx.needs_input_grad[2]:
@@ -615,6 +617,7 @@ class _DenseCastFn(torch.autograd.Function):
         y = _bias_act_gemm(xc, w, b, relu)
         ctx.save_for_backward(xc, w, y if relu else None)
         ctx.relu = relu
+        ctx.x_key = ops.xgrad_key(x)
         return y
 
     @staticmethod
@@ -624,6 +627,7 @@ class _DenseCastFn(torch.autograd.Function):
         if ctx.relu:
             g = _relu_grad(g, y)
         gx = _mm_f32_out(g, w.t()) if ctx.needs_input_grad[0] else None
+        ops.offer_xgrad(ctx.x_key, gx)
         gw = xc.t() @ g if ctx.needs_input_grad[1] else None
         gb = None
         if ctx.needs_input_grad[2]:

@@ -117,6 +117,32 @@ def _join_side_streams():
 _STEP_PRESORT = True
 
 
+# Gradient of the concat buffer, accumulated in place.  ``xcat [B,W]`` feeds several branches (MLP + FM in DeepFM,
+# MLP + cross in DCN); autograd would sum their full-width gradients with an extra pass over two [B,W] tensors
+# (43 us for DeepFM, ~100 us for DCN at B = 65,536).  Inside new_step() ... end_step() the first branch whose backward
+# produces a full-width fp32 gradient (the first Dense layer: its dgrad GEMM output) offers that buffer here; a later
+# branch finds it, adds its own gradient INTO it (kon_fm_bwd_acc / kon_cross_bwd_acc) and returns None to autograd.
+# Whichever order autograd picks is fine: a branch that finds nothing returns its gradient the ordinary way.
+ACC_XGRAD = os.environ.get("KON_ACC_XGRAD", "1") != "0"
+_XGRAD = {}
+
+
+def offer_xgrad(key, g: torch.Tensor):
+    if ACC_XGRAD and _SHARE_SORT and g is not None and g.dtype == torch.float32 and g.is_contiguous():
+        _XGRAD[key] = g
+
+
+def take_xgrad(key, shape):
+    g = _XGRAD.get(key) if (ACC_XGRAD and _SHARE_SORT) else None
+    if g is not None and tuple(g.shape) == tuple(shape):
+        return g
+    return None
+
+
+def xgrad_key(x: torch.Tensor):
+    return (x.data_ptr(), tuple(x.shape))
+
+
 def new_step(presort: bool = True):
     """``presort=False``: keep the routing sort in the backward (steps dominated by the persistent tcgen05 CIN
     kernels: sort kernels co-scheduled with them cost more than they hide, 9.95 -> 10.11 ms measured)."""
@@ -124,6 +150,7 @@ def new_step(presort: bool = True):
     _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
+    _XGRAD.clear()
     _SHARE_SORT = True
     _STEP_PRESORT = presort
 
@@ -138,6 +165,7 @@ def end_step():
     _join_side_streams()
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
+    _XGRAD.clear()
     _SHARE_SORT = False
 
 
@@ -449,12 +477,19 @@ class _FmXcat(torch.autograd.Function):
         F, k = ctx.F, ctx.k
         B, W = xcat.shape
         g = g.contiguous()
+        v = xcat[:, :F * k].view(B, F, k)
+        dlin = torch.empty(ctx.lin_shape, dtype=xcat.dtype, device=xcat.device) if ctx.lin_shape is not None else None
+        acc = take_xgrad(xgrad_key(xcat), (B, W))
+        if acc is not None:           # another branch's gradient of xcat is already there: add into it
+            dv = acc[:, :F * k].view(B, F, k)
+            a, b, c, d = L._arg(v), L._arg(g), L._arg(dv), L._arg(dlin)
+            with _prof("fm_bwd"):
+                L.check(lib.kon_fm_bwd_acc(a.ptr, b.ptr, c.ptr, L._p(d), L.stream_ptr(xcat.device)), "kon_fm_bwd_acc")
+            return None, dlin, None, None
         gx = torch.empty((B, W), dtype=xcat.dtype, device=xcat.device)
         if W > F * k:
             gx[:, F * k:].zero_()
-        v = xcat[:, :F * k].view(B, F, k)
         dv = gx[:, :F * k].view(B, F, k)
-        dlin = torch.empty(ctx.lin_shape, dtype=xcat.dtype, device=xcat.device) if ctx.lin_shape is not None else None
         a, b, c, d = L._arg(v), L._arg(g), L._arg(dv), L._arg(dlin)
         with _prof("fm_bwd"):
             L.check(lib.kon_fm_bwd(a.ptr, b.ptr, c.ptr, L._p(d), L.stream_ptr(xcat.device)), "kon_fm_bwd")
@@ -496,14 +531,16 @@ class _Cross(torch.autograd.Function):
         if g.stride(-1) != 1:
             g = g.contiguous()
         dev = x0.device
-        dx0 = torch.empty(x0.shape, dtype=x0.dtype, device=dev)
+        acc = take_xgrad(xgrad_key(x0), x0.shape)        # another branch's gradient of x0 (the concat buffer)
+        dx0 = acc if acc is not None else torch.empty(x0.shape, dtype=x0.dtype, device=dev)
         dw = torch.empty_like(w)
         db = torch.empty_like(b)
         ws = _ws(lib.kon_cross_bwd_workspace_bytes(x0.shape[0], x0.shape[1], w.shape[0], dev.index or 0), dev)
         a = [L._arg(t) for t in (x0, w, b, s, g, dx0, dw, db, ws)]
+        fn, what = (lib.kon_cross_bwd_acc, "kon_cross_bwd_acc") if acc is not None else (lib.kon_cross_bwd, "kon_cross_bwd")
         with _prof("cross_bwd"):
-            L.check(lib.kon_cross_bwd(*[t.ptr for t in a], L.stream_ptr(dev)), "kon_cross_bwd")
-        return dx0, dw, db
+            L.check(fn(*[t.ptr for t in a], L.stream_ptr(dev)), what)
+        return (None if acc is not None else dx0), dw, db
 
 
 def cross(x0, w, b):

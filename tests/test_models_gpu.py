@@ -337,3 +337,45 @@ def test_keras_optimizer_mode_matches_the_reference_update_over_several_steps():
     for dense, ids, labels in batches:
         tl.step(dense.to(DEV), ids.to(DEV), labels.to(DEV))
     assert torch.equal(lazy.sparse_embed.arena.detach().cpu()[off[5] + untouched], p["emb_5"][untouched])
+
+
+@pytest.mark.parametrize("name", ["deepfm", "dcn"])
+def test_concat_buffer_gradient_accumulated_in_place_equals_autograd_sum(name):
+    """Inside a Trainer step the FM / cross backward adds its gradient of the concat buffer INTO the first Dense
+    layer's input gradient (kon_fm_bwd_acc / kon_cross_bwd_acc) instead of letting autograd sum two [B,W] tensors:
+    same weights after the step as with the fusion switched off, and the fused path is really the one taken."""
+    from ml_function_b200 import ops
+    from ml_function_b200.train import Trainer
+    g = gen(5)
+    rows = [7, 300, 5, 41, 2, 1000]
+    B, k = 257, 8
+    p = _params(name, rows, k, g)
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).to(DEV)
+    dense = torch.rand(B, 13, generator=g).to(DEV)
+    y = (torch.rand(B, generator=g) < 0.3).float()
+    labels = torch.stack([1 - y, y], 1).to(DEV)
+    res, hits = {}, {}
+    real_take = ops.take_xgrad
+    for mode in (True, False):
+        ops.ACC_XGRAD = mode
+        n = [0]
+
+        def counting(key, shape, _n=n):
+            r = real_take(key, shape)
+            _n[0] += r is not None
+            return r
+        ops.take_xgrad = counting
+        try:
+            model = _build(name, rows, k, p)
+            tr = Trainer(model, lr=1e-2)
+            tr.step(dense, ids, labels)
+            tr.step(dense, ids, labels)
+        finally:
+            ops.take_xgrad = real_take
+            ops.ACC_XGRAD = True
+        hits[mode] = n[0]
+        res[mode] = [model.sparse_embed.arena.detach().clone(), model.linear_embed.arena.detach().clone()] + \
+                    [w.detach().clone() for w in model.dnn.kernels]
+    assert hits[True] == 2 and hits[False] == 0          # one fused accumulation per step
+    for a, b in zip(res[True], res[False]):
+        assert_rel(a, b.double(), 1e-6, name + " weights after two steps, fused vs autograd sum")
