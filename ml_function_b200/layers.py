@@ -636,6 +636,42 @@ class _DenseCastFn(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+class _DenseMasterFn(torch.autograd.Function):
+    """Reduced-precision Dense layer over fp32 MASTER weights: ``w`` / ``b`` are the fp32 parameters (their gradients
+    leave the weight-gradient GEMM and the bias GEMV as fp32 accumulators, no bf16 gradient and no bf16 -> fp32 cast
+    pass per parameter), ``wc`` / ``bc`` their compute-dtype copies (made by the layer for all its weights in one
+    multi-tensor launch).  A fp32 ``x`` (the concat buffer) is cast here and gets its gradient back in fp32, straight
+    out of the dgrad GEMM, like ``_DenseCastFn``."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, wc, bc, relu=False):
+        ctx.x_f32 = x.dtype == torch.float32
+        ctx.x_key = ops.xgrad_key(x)
+        xc = x.to(wc.dtype) if x.dtype != wc.dtype else x
+        y = _bias_act_gemm(xc, wc, bc, relu)
+        ctx.save_for_backward(xc, wc, y if relu else None)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, wc, y = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.relu:
+            g = _relu_grad(g, y)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = _mm_f32_out(g, wc.t()) if ctx.x_f32 else g @ wc.t()
+            if ctx.x_f32:
+                ops.offer_xgrad(ctx.x_key, gx)
+        gw = _mm_f32_out(xc.t(), g) if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[2]:
+            ones = torch.ones((1, g.shape[0]), dtype=g.dtype, device=g.device)
+            gb = _mm_f32_out(ones, g).reshape(-1)
+        return gx, gw, gb, None, None, None
+
+
 class DnnLayer(nn.Module):
     """CL:159-226 with the defaults the CTR builders use (``res_unit=1``, no BN/LN, ReLU):
     per hidden layer ``Dense`` -> ``Add([ori, x])`` when the shapes allow it (CL:206-214)
@@ -669,6 +705,19 @@ class DnnLayer(nn.Module):
             self.logit_kernel = nn.Parameter(((torch.rand(d, self.output_dim, generator=g) * 2 - 1) * lim).to(device))
             self.logit_bias = nn.Parameter(torch.zeros(self.output_dim, device=device))
 
+    def _shadow_weights(self, cd):
+        """Compute-dtype copies of all kernels / biases, refreshed from the fp32 masters in ONE multi-tensor launch
+        per forward (the per-parameter ``w.to(bf16)`` were 2 small launches per layer, and autograd cast every
+        bf16 gradient back to fp32 with another one)."""
+        params = [t for wb in zip(self.kernels, self.biases) for t in wb]
+        sh = getattr(self, "_shadow", None)
+        if sh is None or len(sh) != len(params) or sh[0].dtype != cd or any(
+                a.shape != b.shape or a.device != b.device for a, b in zip(sh, params)):
+            sh = self._shadow = [torch.empty_like(t, dtype=cd) for t in params]
+        with torch.no_grad():
+            torch._foreach_copy_(sh, [t.detach() for t in params])
+        return sh
+
     def load_reference_weights(self, kernels, biases, logit_kernel=None, logit_bias=None):
         self.kernels = nn.ParameterList([nn.Parameter(k.clone()) for k in kernels])
         self.biases = nn.ParameterList([nn.Parameter(b.clone()) for b in biases])
@@ -683,11 +732,14 @@ class DnnLayer(nn.Module):
         if len(self.kernels) == 0 and self.hidden_units:
             self.build(x.shape[-1], x.device)
         cd = self.compute_dtype
+        shadow = self._shadow_weights(cd) if (cd is not None and cd != torch.float32 and x.is_cuda) else None
         for i, (w, b) in enumerate(zip(self.kernels, self.biases)):
             ori = x
             res = w.shape[0] == w.shape[1]                 # the reference's Add([ori, x]) fires (CL:206-214)
             fuse = not res                                 # else ReLU follows the residual add, outside the GEMM
-            if cd is not None and x.dtype != cd:
+            if shadow is not None:
+                x = _DenseMasterFn.apply(x, w, b, shadow[2 * i], shadow[2 * i + 1], fuse)
+            elif cd is not None and x.dtype != cd:
                 x = _DenseCastFn.apply(x, w.to(cd), b.to(cd), fuse) if i == 0 else _DenseFn.apply(x.to(cd), w.to(cd), b.to(cd), fuse)
             else:
                 x = _DenseFn.apply(x, w.to(x.dtype), b.to(x.dtype), fuse)
