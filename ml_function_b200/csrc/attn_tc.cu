@@ -252,7 +252,9 @@ constexpr int kPStride = 40;   // bf16 per row of the parked P / gZ tiles: 80 B 
                                // stores and the ldmatrix row reads free of bank conflicts
 constexpr int kAtBwdThreads = 32 * kAtBwdWarps;
 
-template <int KS, int HT>
+// ALL: use_scale, use_res, use_ln and the ReLU are all on (the AutoInt block as the builders make it, MD:159-163):
+// the four run-time flags become constants and their selects / branches disappear from the 1800-instruction body.
+template <int KS, int HT, bool ALL>
 __global__ void __launch_bounds__(kAtBwdThreads, KON_ATB_MINB)
 attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, const float* __restrict__ wk,
                    const float* __restrict__ wr, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -262,6 +264,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
   extern __shared__ __align__(16) uint32_t smem_dyn[];
   // dynamic smem: [W fragments 3*H*KS*64] [W^T fragments 3*H*(KIN/8)*32]
   const int H = p.H, F = p.F;
+  const bool f_scale = ALL || p.use_scale, f_res = ALL || p.use_res, f_ln = ALL || p.use_ln, f_relu = ALL || p.relu;
   uint32_t* w_frag = smem_dyn;
   uint32_t* wt_frag = w_frag + 3 * H * KS * 64;
   __shared__ __align__(16) unsigned short s_buf[kAtBwdWarps][6][32 * 8];     // K, q', gO, gQ, gK, gR  (bf16 [row][8])
@@ -282,10 +285,10 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
     wt_frag[idx] = W ? pack2(W[((long long)c * H + h) * 8 + e], W[((long long)c * H + h) * 8 + e + 1]) : 0u;
   }
   __syncthreads();
-  const float sc = p.use_scale ? rsqrtf(8.f) : 1.f;
+  const float sc = f_scale ? rsqrtf(8.f) : 1.f;
   float gam[2], bet[2];
-  gam[0] = p.use_ln ? gamma[2 * t] : 1.f;  gam[1] = p.use_ln ? gamma[2 * t + 1] : 1.f;
-  bet[0] = p.use_ln ? beta[2 * t] : 0.f;   bet[1] = p.use_ln ? beta[2 * t + 1] : 0.f;
+  gam[0] = f_ln ? gamma[2 * t] : 1.f;  gam[1] = f_ln ? gamma[2 * t + 1] : 1.f;
+  bet[0] = f_ln ? beta[2 * t] : 0.f;   bet[1] = f_ln ? beta[2 * t + 1] : 0.f;
   unsigned short* ksm = s_buf[warp][0];
   unsigned short* qsm = s_buf[warp][1];
   unsigned short* gosm = s_buf[warp][2];
@@ -361,7 +364,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
           for (int mt = 0; mt < 2; ++mt) {
             mma16816(qc[mt], ax[mt][ks], wq_[lane], wq_[32 + lane]);
             mma16816(kc[mt], ax[mt][ks], wk_[lane], wk_[32 + lane]);
-            if (p.use_res) mma16816(rc[mt], ax[mt][ks], wr_[lane], wr_[32 + lane]);
+            if (f_res) mma16816(rc[mt], ax[mt][ks], wr_[lane], wr_[32 + lane]);
           }
         }
         __syncwarp();
@@ -414,7 +417,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
             const int row = 16 * mt + g + 8 * half;
             float v0 = o[2 * half], v1 = o[2 * half + 1];
             float mean = 0.f, rstd = 1.f;
-            if (p.use_ln) {
+            if (f_ln) {
               float sum = v0 + v1;
               sum += __shfl_xor_sync(0xffffffffu, sum, 1);
               sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -425,18 +428,18 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
               rstd = rsqrtf(var * 0.125f + p.ln_eps);
             }
             const float xh0 = (v0 - mean) * rstd, xh1 = (v1 - mean) * rstd;
-            float pre0 = p.use_ln ? xh0 * gam[0] + bet[0] : v0;
-            float pre1 = p.use_ln ? xh1 * gam[1] + bet[1] : v1;
-            if (p.use_res) { pre0 += rc[mt][2 * half]; pre1 += rc[mt][2 * half + 1]; }
+            float pre0 = f_ln ? xh0 * gam[0] + bet[0] : v0;
+            float pre1 = f_ln ? xh1 * gam[1] + bet[1] : v1;
+            if (f_res) { pre0 += rc[mt][2 * half]; pre1 += rc[mt][2 * half + 1]; }
             float g0 = 0.f, g1 = 0.f;
             if (row < F) {
               const float2 gv = __ldg(reinterpret_cast<const float2*>(gy + h * p.gsh + b * p.gsb + row * p.gsf + 2 * t));
-              g0 = (p.relu && !(pre0 > 0.f)) ? 0.f : gv.x;
-              g1 = (p.relu && !(pre1 > 0.f)) ? 0.f : gv.y;
+              g0 = (f_relu && !(pre0 > 0.f)) ? 0.f : gv.x;
+              g1 = (f_relu && !(pre1 > 0.f)) ? 0.f : gv.y;
             }
-            gR[mt][2 * half] = p.use_res ? g0 : 0.f;
-            gR[mt][2 * half + 1] = p.use_res ? g1 : 0.f;
-            if (p.use_ln) {
+            gR[mt][2 * half] = f_res ? g0 : 0.f;
+            gR[mt][2 * half + 1] = f_res ? g1 : 0.f;
+            if (f_ln) {
               dgam[0] = fmaf(g0, xh0, dgam[0]); dgam[1] = fmaf(g1, xh1, dgam[1]);
               dbet[0] += g0; dbet[1] += g1;
               const float gx0 = g0 * gam[0], gx1 = g1 * gam[1];
@@ -512,7 +515,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
           for (int n = 0; n < KIN / 8; ++n) {
             mma16816(dxc[mt][n], a12, wt_frag[((0 * H + h) * (KIN / 8) + n) * 32 + lane],
                      wt_frag[((1 * H + h) * (KIN / 8) + n) * 32 + lane]);
-            if (p.use_res) mma16816(dxc[mt][n], a3, wt_frag[((2 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
+            if (f_res) mma16816(dxc[mt][n], a3, wt_frag[((2 * H + h) * (KIN / 8) + n) * 32 + lane], 0u);
           }
           *reinterpret_cast<uint32_t*>(gqsm + (16 * mt + g) * 8 + 2 * t) = a12[0];
           *reinterpret_cast<uint32_t*>(gqsm + (16 * mt + g + 8) * 8 + 2 * t) = a12[1];
@@ -534,7 +537,7 @@ attn_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
             ldmatrix_x4_trans(axt, xsm + (16 * kk + 8 * (m >> 1) + (lane & 7)) * KIN + 16 * ks + 8 * (m & 1));
             mma16816(dwq[h][ks], axt, bq[0], bq[1]);
             mma16816(dwk[h][ks], axt, bk[0], bk[1]);
-            if (p.use_res) mma16816(dwr[h][ks], axt, br[0], br[1]);
+            if (f_res) mma16816(dwr[h][ks], axt, br[0], br[1]);
           }
         }
       }
@@ -642,12 +645,20 @@ int attn_tc_bwd(const float* x, const float* wq, const float* wk, const float* w
   grid = std::min(grid, max_grid);
   *grid_used = grid;
   ProfileScope ps("attn_tc_bwd_kernel", st);
+  const bool all_on = p.use_scale && p.use_res && p.use_ln && p.relu;
 #define KON_ATB(KS_, HT_)                                                                                   \
   do {                                                                                                      \
-    KON_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KS_, HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem));                                                              \
-    attn_tc_bwd_kernel<KS_, HT_><<<grid, kAtBwdThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, gy, dx,     \
-                                                                   partial, p);                             \
+    if (all_on) {                                                                                           \
+      KON_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KS_, HT_, true>,                                     \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+      attn_tc_bwd_kernel<KS_, HT_, true><<<grid, kAtBwdThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, gy, \
+                                                                           dx, partial, p);                 \
+    } else {                                                                                                \
+      KON_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KS_, HT_, false>,                                    \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+      attn_tc_bwd_kernel<KS_, HT_, false><<<grid, kAtBwdThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta,    \
+                                                                            gy, dx, partial, p);            \
+    }                                                                                                       \
   } while (0)
   if (KS == 1 && p.H <= 2) KON_ATB(1, 2);
   else if (KS == 1) KON_ATB(1, 4);
