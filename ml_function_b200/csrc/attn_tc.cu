@@ -69,11 +69,12 @@ __device__ __forceinline__ void pack_w_frags(const float* __restrict__ wq, const
   }
 }
 
-template <int KS>
+template <int KS, bool ALL>
 __global__ void __launch_bounds__(kAtThreads)
 attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, const float* __restrict__ wk,
                    const float* __restrict__ wr, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
                    const AttnDims p) {
+  const bool f_scale = ALL || p.use_scale, f_res = ALL || p.use_res, f_ln = ALL || p.use_ln, f_relu = ALL || p.relu;   // cf. attn_tc_bwd_kernel
   extern __shared__ __align__(16) uint32_t smem_w[];                 // [3*H*KS*64] W fragments
   __shared__ __align__(16) unsigned short s_k[kAtWarps][32 * 8];     // per warp: K (bf16) [j][e]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -81,10 +82,10 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
   const int H = p.H, F = p.F, kin = 16 * KS;
   pack_w_frags(wq, wk, wr, KS, H, smem_w, tid, kAtThreads);
   __syncthreads();
-  const float sc = p.use_scale ? rsqrtf(8.f) : 1.f;
+  const float sc = f_scale ? rsqrtf(8.f) : 1.f;
   float gam[2], bet[2];
-  gam[0] = p.use_ln ? gamma[2 * t] : 1.f;  gam[1] = p.use_ln ? gamma[2 * t + 1] : 1.f;
-  bet[0] = p.use_ln ? beta[2 * t] : 0.f;   bet[1] = p.use_ln ? beta[2 * t + 1] : 0.f;
+  gam[0] = f_ln ? gamma[2 * t] : 1.f;  gam[1] = f_ln ? gamma[2 * t + 1] : 1.f;
+  bet[0] = f_ln ? beta[2 * t] : 0.f;   bet[1] = f_ln ? beta[2 * t + 1] : 0.f;
   unsigned short* ksm = s_k[warp];
 
   for (long long b = (long long)blockIdx.x * kAtWarps + warp; b < p.B; b += (long long)gridDim.x * kAtWarps) {
@@ -130,7 +131,7 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
         for (int mt = 0; mt < 2; ++mt) {
           mma16816(qc[mt], ax[mt][ks], bq0, bq1);
           mma16816(kc[mt], ax[mt][ks], bk0, bk1);
-          if (p.use_res) mma16816(rc[mt], ax[mt][ks], br0, br1);
+          if (f_res) mma16816(rc[mt], ax[mt][ks], br0, br1);
         }
       }
       // ---- K (bf16) -> shared [j][e] for the transposed read; Q / K fragments for S = Q K^T ----
@@ -184,7 +185,7 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float v0 = o[mt][2 * half], v1 = o[mt][2 * half + 1];
-          if (p.use_ln) {
+          if (f_ln) {
             float sum = v0 + v1;
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -196,8 +197,8 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
             v0 = (v0 - mean) * rstd * gam[0] + bet[0];
             v1 = (v1 - mean) * rstd * gam[1] + bet[1];
           }
-          if (p.use_res) { v0 += rc[mt][2 * half]; v1 += rc[mt][2 * half + 1]; }
-          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          if (f_res) { v0 += rc[mt][2 * half]; v1 += rc[mt][2 * half + 1]; }
+          if (f_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
           const int row = 16 * mt + g + 8 * half;
           if (row < F)
             *reinterpret_cast<float2*>(y + h * p.ysh + b * p.ysb + row * p.ysf + 2 * t) = make_float2(v0, v1);
@@ -618,12 +619,17 @@ int attn_tc_fwd(const float* x, const float* wq, const float* wk, const float* w
   const size_t smem = (size_t)3 * p.H * KS * 64 * 4;
   const int grid = (int)std::max<long long>(1, std::min<long long>((p.B + kAtWarps - 1) / kAtWarps, (long long)sms * 6));
   ProfileScope ps("attn_tc_fwd_kernel", st);
+  const bool all_on = p.use_scale && p.use_res && p.use_ln && p.relu;
+#define KON_ATF(KS_)                                                                                       \
+  if (all_on) attn_tc_fwd_kernel<KS_, true><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); \
+  else attn_tc_fwd_kernel<KS_, false><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p)
   switch (KS) {
-    case 1: attn_tc_fwd_kernel<1><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
-    case 2: attn_tc_fwd_kernel<2><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
-    case 3: attn_tc_fwd_kernel<3><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
-    default: attn_tc_fwd_kernel<4><<<grid, kAtThreads, smem, st>>>(x, wq, wk, wr_, gamma, beta, y, p); break;
+    case 1: KON_ATF(1); break;
+    case 2: KON_ATF(2); break;
+    case 3: KON_ATF(3); break;
+    default: KON_ATF(4); break;
   }
+#undef KON_ATF
   KON_LAUNCH_CHECK("attn_tc_fwd_kernel");
   return KON_OK;
 }
