@@ -88,31 +88,40 @@ attn_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq, co
   bet[0] = f_ln ? beta[2 * t] : 0.f;   bet[1] = f_ln ? beta[2 * t + 1] : 0.f;
   unsigned short* ksm = s_k[warp];
 
-  for (long long b = (long long)blockIdx.x * kAtWarps + warp; b < p.B; b += (long long)gridDim.x * kAtWarps) {
-    // ---- A fragments of X: rows 16mt+g (+8), cols 16ks+2t (+8) ------------------------------
-    uint32_t ax[2][KS][4];
-    const float* xb = x + b * (long long)F * kin;
+  // X of the NEXT sample is loaded (raw fp32, 8 float2 per k-step) while the current one is processed: the loads at
+  // the top of an iteration were consumed at once (their F2FP pack carried 31 % of the stall samples)
+  float2 nx[2][KS][4];
+  auto load_x = [&](long long bb) {
+    const float* xb = x + min(bb, p.B - 1) * (long long)F * kin;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
-      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      const int q0 = min(16 * mt + g, F - 1), q1 = min(16 * mt + g + 8, F - 1);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const int c0 = 16 * ks + 2 * t;
-        float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
-        if (r0 < F) {
-          v00 = __ldg(reinterpret_cast<const float2*>(xb + r0 * kin + c0));
-          v01 = __ldg(reinterpret_cast<const float2*>(xb + r0 * kin + c0 + 8));
-        }
-        if (r1 < F) {
-          v10 = __ldg(reinterpret_cast<const float2*>(xb + r1 * kin + c0));
-          v11 = __ldg(reinterpret_cast<const float2*>(xb + r1 * kin + c0 + 8));
-        }
-        ax[mt][ks][0] = pack2(v00.x, v00.y);
-        ax[mt][ks][1] = pack2(v10.x, v10.y);
-        ax[mt][ks][2] = pack2(v01.x, v01.y);
-        ax[mt][ks][3] = pack2(v11.x, v11.y);
+        nx[mt][ks][0] = __ldg(reinterpret_cast<const float2*>(xb + q0 * kin + c0));
+        nx[mt][ks][1] = __ldg(reinterpret_cast<const float2*>(xb + q1 * kin + c0));
+        nx[mt][ks][2] = __ldg(reinterpret_cast<const float2*>(xb + q0 * kin + c0 + 8));
+        nx[mt][ks][3] = __ldg(reinterpret_cast<const float2*>(xb + q1 * kin + c0 + 8));
       }
     }
+  };
+  load_x((long long)blockIdx.x * kAtWarps + warp);
+  for (long long b = (long long)blockIdx.x * kAtWarps + warp; b < p.B; b += (long long)gridDim.x * kAtWarps) {
+    // ---- A fragments of X: rows 16mt+g (+8), cols 16ks+2t (+8); padded rows are exact zeros ----
+    uint32_t ax[2][KS][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const bool on0 = 16 * mt + g < F, on1 = 16 * mt + g + 8 < F;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        ax[mt][ks][0] = on0 ? pack2(nx[mt][ks][0].x, nx[mt][ks][0].y) : 0u;
+        ax[mt][ks][1] = on1 ? pack2(nx[mt][ks][1].x, nx[mt][ks][1].y) : 0u;
+        ax[mt][ks][2] = on0 ? pack2(nx[mt][ks][2].x, nx[mt][ks][2].y) : 0u;
+        ax[mt][ks][3] = on1 ? pack2(nx[mt][ks][3].x, nx[mt][ks][3].y) : 0u;
+      }
+    }
+    load_x(b + (long long)gridDim.x * kAtWarps);
     for (int h = 0; h < H; ++h) {
       // ---- projections ----------------------------------------------------------------------
       float qc[2][4], kc[2][4], rc[2][4];
