@@ -279,15 +279,27 @@ __global__ void __launch_bounds__(416) cin_last_dw_kernel(const LastDwArgs a) {
   const int h_lo = min(warp * 16 + g8, a.Hp - 1), h_hi = min(warp * 16 + g8 + 8, a.Hp - 1);
   const bool lo_on = warp * 16 + g8 < a.Hp, hi_on = warp * 16 + g8 + 8 < a.Hp;
   const int xi = tid / 16, xd = tid % 16;        // this thread's element of x0*g (416 = 26*16 threads)
-  auto fill = [&](long long bb, int buf) {
+  // x0 * g of a batch: the global loads (fetch) are issued one iteration before the values are rounded and
+  // stored (stash), so their latency overlaps the MMAs of the batch in between
+  float fg[kLdwBatch];
+  unsigned short fx[kLdwBatch];
+  auto fetch = [&](long long bb) {
+#pragma unroll
+    for (int u = 0; u < kLdwBatch; ++u) {
+      const long long b = min(bb + u, b1 - 1);
+      const int xc = min(xi, a.m - 1);
+      fg[u] = __ldg(a.gpool + b * a.gstride + a.gcol + xd);
+      fx[u] = __ldg(a.x0b + (b * a.m + xc) * 16 + xd);
+    }
+  };
+  auto stash = [&](long long bb, int buf) {
 #pragma unroll
     for (int u = 0; u < kLdwBatch; ++u) {
       const long long b = bb + u;
       float v = 0.f;
       if (b < b1 && xi < a.m) {
-        const float gv = a.gpool[b * a.gstride + a.gcol + xd];
-        v = bf16_to_f32(__ldg(a.x0b + (b * a.m + xi) * 16 + xd)) * gv;
-        if (xi == 0) gacc += gv;
+        v = bf16_to_f32(fx[u]) * fg[u];
+        if (xi == 0) gacc += fg[u];
       }
       const __nv_bfloat16 hv = __float2bfloat16_rn(v);
       sX[buf][u][xi * kLdwRow + xd] = *reinterpret_cast<const unsigned short*>(&hv);
@@ -307,8 +319,10 @@ __global__ void __launch_bounds__(416) cin_last_dw_kernel(const LastDwArgs a) {
   };
   uint32_t an[kLdwBatch][4];
   if (b0 < b1) {
-    fill(b0, 0);
+    fetch(b0);
     if (warp < n_mt) load_a(b0, an);
+    stash(b0, 0);
+    if (b0 + kLdwBatch < b1) fetch(b0 + kLdwBatch);
   }
   __syncthreads();
   int buf = 0;
@@ -318,10 +332,8 @@ __global__ void __launch_bounds__(416) cin_last_dw_kernel(const LastDwArgs a) {
     for (int u = 0; u < kLdwBatch; ++u)
 #pragma unroll
       for (int q = 0; q < 4; ++q) ac[u][q] = an[u][q];
-    if (bb + kLdwBatch < b1) {
-      fill(bb + kLdwBatch, buf ^ 1);
-      if (warp < n_mt) load_a(bb + kLdwBatch, an);
-    }
+    const bool more = bb + kLdwBatch < b1;
+    if (more && warp < n_mt) load_a(bb + kLdwBatch, an);
     if (warp < n_mt) {
 #pragma unroll
       for (int u = 0; u < kLdwBatch; ++u) {
@@ -336,6 +348,10 @@ __global__ void __launch_bounds__(416) cin_last_dw_kernel(const LastDwArgs a) {
           }
         }
       }
+    }
+    if (more) {
+      stash(bb + kLdwBatch, buf ^ 1);                                   // fetched one iteration ago
+      if (bb + 2 * kLdwBatch < b1) fetch(bb + 2 * kLdwBatch);
     }
     __syncthreads();
   }
