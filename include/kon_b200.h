@@ -125,6 +125,11 @@ int kon_embed_bwd_reuse(const DLTensor* d_out, const DLTensor* ids, const int64_
 int kon_embed_sort(const DLTensor* ids, const int64_t* field_row_offset, int32_t n_fields,
                    DLTensor* workspace, void* stream);
 
+/* The routing's pass plan for ONE table (no device work; diagnostics and host-side tests): a table of `rows` rows is
+ * sorted by a stable LSD counting sort with digits of at most 12 bits, its passes occupying the first slots of the
+ * job.  out[6] = {active in `slot`, first pass, last pass, shift, digits, mask}; returns the passes the table needs. */
+int kon_embed_route_plan(int64_t rows, int32_t slot, int32_t max_passes, int64_t* out);
+
 /* Two gradients over ONE routing, one pass: d_out [B,F,dim] (dim % 4 == 0) for the embedding arena and
  * d_lin [B,F,1] (any strides; stride_f = 0 for a sum-pooled first-order term) for the dim-1 "linear" arena that
  * FeatureInput(useLinear=True) (DP:65-76) looks up with the SAME ids and per-field row counts.  unique_rows /

@@ -143,6 +143,7 @@ def lib():
         "kon_embed_bwd_reuse": (ctypes.c_int, [T, T, i64p, i32, T, T, T, T, vp]),
         "kon_embed_bwd_pair": (ctypes.c_int, [T, T, T, i64p, i32, T, T, T, T, T, i32, vp]),
         "kon_embed_sort": (ctypes.c_int, [T, i64p, i32, T, vp]),
+        "kon_embed_route_plan": (ctypes.c_int, [i64, i32, i32, i64p]),
         "kon_embed_sgd": (ctypes.c_int, [T, T, T, T, f32, f32, vp]),
         "kon_embed_adam": (ctypes.c_int, [T, T, T, T, T, T, f32, f32, f32, f32, f32, i32, vp]),
         "kon_embed_adam_devstep": (ctypes.c_int, [T, T, T, T, T, T, f32, f32, f32, f32, f32, T, vp]),
@@ -194,7 +195,8 @@ def lib():
 EXPORTED_SYMBOLS = (
     "kon_abi_version", "kon_last_error", "kon_launch_count", "kon_profile_enable", "kon_profile_reset",
     "kon_profile_read", "kon_device_info", "kon_embed_fwd",
-    "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_bwd_reuse", "kon_embed_bwd_pair", "kon_embed_sort", "kon_embed_sgd", "kon_embed_adam",
+    "kon_embed_bwd_workspace_bytes", "kon_embed_bwd", "kon_embed_bwd_reuse", "kon_embed_bwd_pair", "kon_embed_sort",
+    "kon_embed_route_plan", "kon_embed_sgd", "kon_embed_adam",
     "kon_embed_adam_devstep",
     "kon_peer_alloc", "kon_peer_open", "kon_peer_close", "kon_peer_free", "kon_peer_barrier", "kon_peer_put2d",
     "kon_embed_fwd_peer", "kon_embed_fwd_peer_cols", "kon_embed_bwd_peer",

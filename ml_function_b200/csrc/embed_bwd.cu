@@ -1314,3 +1314,19 @@ extern "C" int kon_embed_bwd_peer(const void* const* peer_d_out, int32_t n_peers
   return embed_bwd_core(src, ids, field_row_offset, n_fields, unique_rows, grads, n_unique, workspace,
                         reuse_sort ? 1 : 0, stream);
 }
+
+// The pass plan of the routing for one table (diagnostics / host-side tests; no device work): for `rows` rows and
+// pass slot `slot` of a job with `max_passes` slots -> out = {active, first, last, shift, bins, mask (low 32 bits)}.
+// Returns the number of passes the table needs.
+extern "C" int kon_embed_route_plan(int64_t rows, int32_t slot, int32_t max_passes, int64_t* out) {
+  const FieldPass fp = field_pass(rows, slot, max_passes);
+  if (out) {
+    out[0] = fp.active;
+    out[1] = fp.first;
+    out[2] = fp.last;
+    out[3] = fp.shift;
+    out[4] = fp.bins;
+    out[5] = fp.mask;
+  }
+  return passes_for(bits_for(rows));
+}

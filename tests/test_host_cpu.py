@@ -126,3 +126,38 @@ def test_shard_plan_criteo_8_ranks():
     mixed = ShardPlan([10, 60_000_000, 20], 4)
     assert mixed.rw_fields == [1] and not mixed.identity_order and mixed.exchange_order == [0, 2, 1]
     assert [mixed.to_global[f] for f in range(3)] == [0, 2, 1]
+
+
+def test_routing_pass_plan_covers_every_id_bit_once():
+    """kon_embed_route_plan (host logic of the embedding backward's per-field counting sort, no GPU): the digits of a
+    table's passes tile its id bits exactly, no pass has more than 4096 digits, the last pass only has the digits the
+    row count can produce, and a table's passes sit in the first slots of the job."""
+    import ctypes
+    from ml_function_b200 import _lib as L
+    lib = L.lib()
+    out = (ctypes.c_int64 * 6)()
+    for rows in [0, 1, 2, 3, 4096, 4097, 65536, 10131227, (1 << 24), (1 << 24) + 1, 100_000_000, (1 << 31) - 2]:
+        P = lib.kon_embed_route_plan(rows, 0, 3, out)
+        bits = max(rows - 1, 0).bit_length() if rows > 1 else 0
+        assert P == (1 if bits <= 12 else -(-bits // 12)), rows
+        covered = 0
+        for slot in range(3):
+            lib.kon_embed_route_plan(rows, slot, 3, out)
+            active, first, last, shift, bins, mask = (int(v) for v in out)
+            assert active == (slot < P), (rows, slot)
+            if not active:
+                continue
+            assert first == (slot == 0) and last == (slot == P - 1)
+            assert 1 <= bins <= 4096
+            assert shift == covered
+            if last:
+                assert bins == ((max(rows - 1, 0) >> shift) + 1)          # only digits that can occur
+                covered = bits
+            else:
+                assert bins == mask + 1 and bins & (bins - 1) == 0
+                covered += bins.bit_length() - 1
+            # every id below `rows` lands in a digit of the pass
+            for idv in {0, max(rows - 1, 0), max(rows // 2, 0)}:
+                d = (idv >> shift) & mask
+                assert 0 <= d < bins
+        assert covered == bits, rows
