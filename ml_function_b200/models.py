@@ -157,6 +157,7 @@ class DeepFM(_CtrModel):
 
     def forward(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
+        ops.two_branch_input(xcat)            # FM + MLP: the FM gradient is added into the MLP's in place (ops._XGRAD)
         lin = self.linear_embed.lookup_sum(ids)
         fm_ = self.fm.on_concat(xcat, lin, self.F, self.k)     # = self.fm([v, lin]) on the window of xcat
         dnn_ = self.dnn(xcat)
@@ -188,6 +189,7 @@ class DCN(_CtrModel):
 
     def forward(self, dense_inputs, sparse_inputs):
         ids, xcat, v = self.front(dense_inputs, sparse_inputs)
+        ops.two_branch_input(xcat)            # cross + MLP
         cross_fea = self.cross(xcat)                       # [B,W,1]
         deep_fea = self.dnn(xcat)
         return self.head([cross_fea, deep_fea])

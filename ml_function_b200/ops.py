@@ -123,17 +123,30 @@ _STEP_PRESORT = True
 # produces a full-width fp32 gradient (the first Dense layer: its dgrad GEMM output) offers that buffer here; a later
 # branch finds it, adds its own gradient INTO it (kon_fm_bwd_acc / kon_cross_bwd_acc) and returns None to autograd.
 # Whichever order autograd picks is fine: a branch that finds nothing returns its gradient the ordinary way.
+# Only buffers a builder has declared to have EXACTLY two consumers take part (``two_branch_input``): with a third
+# consumer autograd would already have summed the offered gradient into a new tensor when the late branch adds into
+# the old one, and that contribution would be lost.
 ACC_XGRAD = os.environ.get("KON_ACC_XGRAD", "1") != "0"
 _XGRAD = {}
+_XGRAD_OK = set()
+
+
+def two_branch_input(x: torch.Tensor) -> torch.Tensor:
+    """Declare that ``x`` (the concat buffer) feeds exactly two branches in this forward -- the MLP, whose first Dense
+    layer offers its input gradient, and ONE of FM / cross, which adds into it (DeepFM MD:80-90, DCN MD:92-106)."""
+    if ACC_XGRAD and _SHARE_SORT:
+        _XGRAD_OK.add(xgrad_key(x))
+    return x
 
 
 def offer_xgrad(key, g: torch.Tensor):
-    if ACC_XGRAD and _SHARE_SORT and g is not None and g.dtype == torch.float32 and g.is_contiguous():
+    if ACC_XGRAD and _SHARE_SORT and key in _XGRAD_OK and g is not None and g.dtype == torch.float32 \
+            and g.is_contiguous():
         _XGRAD[key] = g
 
 
 def take_xgrad(key, shape):
-    g = _XGRAD.get(key) if (ACC_XGRAD and _SHARE_SORT) else None
+    g = _XGRAD.pop(key, None) if (ACC_XGRAD and _SHARE_SORT) else None      # one taker per offer
     if g is not None and tuple(g.shape) == tuple(shape):
         return g
     return None
@@ -151,6 +164,7 @@ def new_step(presort: bool = True):
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
     _XGRAD.clear()
+    _XGRAD_OK.clear()
     _SHARE_SORT = True
     _STEP_PRESORT = presort
 
@@ -166,6 +180,7 @@ def end_step():
     _SORT_CACHE.clear()
     _STEP_CACHE.clear()
     _XGRAD.clear()
+    _XGRAD_OK.clear()
     _SHARE_SORT = False
 
 
